@@ -1,0 +1,489 @@
+"""CPU restatement of the resetius/fdm hot path -- TEST INFRASTRUCTURE ONLY.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline /
+``--impl reference`` legs may import this module.  The product
+(``fdm_b200``) never does; it fails loudly when its CUDA library is missing.
+
+Parity status: PINNED.  Every function here is checked in
+``tests/test_oracle_cpu.py`` against (a) the unmodified reference compiled into
+``oracle/_ref/libfdm_ref.so`` (when present), (b) the golden vectors under
+``tests/golden`` that were generated from that library by
+``tests/golden/make_golden.py``, and (c) the reference's own known-answer
+constructions (ut/ut_fft.cpp round trips and O(N^2) definitions,
+ut/ut_lapl_cube.cpp analytic solution).
+
+All arithmetic is float64 numpy/scipy.  The 1-D transforms use the closed forms
+that the reference's FFTW backend defines unambiguously (src/fft_fftw3.cpp:8-64)
+instead of re-tracing the Samarskii-Nikolaev butterflies of src/fft.cpp; the two
+agree to ~1e-15 (probed, and asserted by the tests).
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import scipy.fft as sfft
+import scipy.linalg
+
+# --------------------------------------------------------------------------------------
+# 1-D transforms (reference: src/fft.cpp, definitions src/asp_fft.cpp:308-319,404-418)
+# --------------------------------------------------------------------------------------
+
+
+def sFFT(s: np.ndarray, dx: float, axis: int = -1) -> np.ndarray:
+    """DST-I.  ``s`` holds the N-1 interior values s[1..N-1] along ``axis``.
+
+    S[k] = dx * sum_{j=1}^{N-1} s[j] sin(pi k j / N), k = 1..N-1
+    (src/fft.cpp:294-365; FFTW RODFT00 * 0.5, src/fft_fftw3.cpp:45-53).
+    """
+    return sfft.dst(s, type=1, axis=axis) * (0.5 * dx)
+
+
+def cFFT(s: np.ndarray, dx: float, axis: int = -1) -> np.ndarray:
+    """DCT-I with halved end points over N+1 values s[0..N] (src/fft.cpp:368-445).
+
+    S[k] = dx * (s[0]/2 + sum_{j=1}^{N-1} s[j] cos(pi k j / N) + (-1)^k s[N]/2)
+    (src/asp_fft.cpp:404-418; FFTW REDFT00 * 0.5, src/fft_fftw3.cpp:55-64).
+    """
+    return sfft.dct(s, type=1, axis=axis) * (0.5 * dx)
+
+
+def pFFT_1(s: np.ndarray, dx: float, axis: int = -1) -> np.ndarray:
+    """Periodic forward transform, values -> coefficients (src/fft.cpp:109-193).
+
+    S[k]   = dx * sum_j s[j] cos(2 pi k j / N), k = 0..N/2
+    S[N-k] = dx * sum_j s[j] sin(2 pi k j / N), k = 1..N/2-1
+    (src/fft_fftw3.cpp:8-22).
+    """
+    s = np.moveaxis(np.asarray(s, dtype=np.float64), axis, -1)
+    N = s.shape[-1]
+    X = np.fft.rfft(s, axis=-1)
+    out = np.empty_like(s)
+    out[..., : N // 2 + 1] = X.real
+    if N > 2:
+        out[..., N // 2 + 1 :] = (-X.imag[..., 1 : N // 2])[..., ::-1]
+    return np.moveaxis(out * dx, -1, axis)
+
+
+def pFFT(s: np.ndarray, dx: float, axis: int = -1) -> np.ndarray:
+    """Periodic inverse transform, coefficients -> values (src/fft.cpp:196-212).
+
+    S[j] = dx * (s[0]/2 + sum_{k=1}^{N/2-1} (s[k] cos(2 pi j k/N) + s[N-k] sin(2 pi j k/N))
+                 + (-1)^j s[N/2]/2)            (src/fft_fftw3.cpp:25-42)
+    """
+    s = np.moveaxis(np.asarray(s, dtype=np.float64), axis, -1)
+    N = s.shape[-1]
+    X = np.zeros(s.shape[:-1] + (N // 2 + 1,), dtype=np.complex128)
+    X.real[...] = s[..., : N // 2 + 1]
+    if N > 2:
+        X.imag[..., 1 : N // 2] = -(s[..., N // 2 + 1 :][..., ::-1])
+    # irfft computes (1/N)(X0 + 2 sum Re(Xk e^{+i...}) + (-1)^j X_{N/2});  we want half of N*that.
+    out = np.fft.irfft(X, n=N, axis=-1) * (0.5 * N)
+    return np.moveaxis(out * dx, -1, axis)
+
+
+# --------------------------------------------------------------------------------------
+# LaplCube (reference: src/lapl_cube.h:58-100, src/lapl_cube.cpp:9-172)
+# --------------------------------------------------------------------------------------
+
+
+class LaplCube:
+    """3-D Poisson solve; all-Dirichlet (periodic=False) or all-periodic."""
+
+    def __init__(self, dx, dy, dz, lx, ly, lz, nx, ny, nz, periodic=False):
+        self.dx, self.dy, self.dz = dx, dy, dz
+        self.lx, self.ly, self.lz = lx, ly, lz
+        self.nx, self.ny, self.nz = nx, ny, nz
+        self.periodic = bool(periodic)
+        self.slx, self.sly, self.slz = (math.sqrt(2.0 / l) for l in (lx, ly, lz))
+        # lapl_cube.h:66-80 (x1/xn/xpoints test zflag, harmless: only all-D / all-P exist)
+        if periodic:
+            self.z1 = self.y1 = self.x1 = 0
+            self.zn, self.yn, self.xn = nz - 1, ny - 1, nx - 1
+            self.zpoints, self.ypoints, self.xpoints = nz, ny, nx
+        else:
+            self.z1 = self.y1 = self.x1 = 1
+            self.zn, self.yn, self.xn = nz, ny, nx
+            self.zpoints, self.ypoints, self.xpoints = nz + 1, ny + 1, nx + 1
+        self._init_lm()
+
+    def _init_lm(self):
+        # lapl_cube.cpp:145-172, including the aliasing quirk (:162,:171):
+        # lm_x := lm_y when xpoints == ypoints, lm_z := lm_y when zpoints == ypoints,
+        # regardless of the spacings.
+        def lm(n, d2, lo, hi):
+            k = np.arange(lo, hi + 1, dtype=np.float64)
+            if self.periodic:
+                return 4.0 / d2 * np.sin(k * math.pi / n) ** 2
+            return 4.0 / d2 * np.sin(k * math.pi * 0.5 / (n + 1)) ** 2
+
+        self.lm_y = lm(self.ny, self.dy * self.dy, self.y1, self.yn)
+        lm_x = lm(self.nx, self.dx * self.dx, self.x1, self.xn)
+        lm_z = lm(self.nz, self.dz * self.dz, self.z1, self.zn)
+        self.lm_x = self.lm_y if self.xpoints == self.ypoints else lm_x
+        self.lm_z = self.lm_y if self.zpoints == self.ypoints else lm_z
+
+    def solve(self, rhs: np.ndarray) -> np.ndarray:
+        """rhs: [nz][ny][nx] interior-only array (last index fastest).  Returns ans."""
+        a = np.asarray(rhs, dtype=np.float64).reshape(self.nz, self.ny, self.nx)
+        fwd = pFFT_1 if self.periodic else sFFT
+        inv = pFFT if self.periodic else sFFT
+        # forward z, y, x  (lapl_cube.cpp:13-68)
+        a = fwd(a, self.dz * self.slz, axis=0)
+        a = fwd(a, self.dy * self.sly, axis=1)
+        a = fwd(a, self.dx * self.slx, axis=2)
+        # divide by -(lm_z + lm_y + lm_x)  (lapl_cube.cpp:70-80)
+        k2 = self.lm_z[:, None, None] + self.lm_y[None, :, None] + self.lm_x[None, None, :]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            a = a / (-k2)
+        if self.periodic:
+            a[0, 0, 0] = 0.0  # lapl_cube.cpp:82-84
+        # inverse x, y, z  (lapl_cube.cpp:86-142)
+        a = inv(a, self.slx, axis=2)
+        a = inv(a, self.sly, axis=1)
+        a = inv(a, self.slz, axis=0)
+        return np.ascontiguousarray(a)
+
+
+# --------------------------------------------------------------------------------------
+# Tridiagonal solve (reference boundary: LAPACK gtsv / gttrf+gttrs, src/blas.h:65-91)
+# --------------------------------------------------------------------------------------
+
+
+def tridiag_solve(L, D, U, b):
+    """Solve the tridiagonal system along the last axis.
+
+    L[..., j] multiplies x[j-1] in row j (L[..., 0] ignored), U[..., j] multiplies
+    x[j+1] (U[..., n-1] ignored).  Thomas algorithm without pivoting -- the reference's
+    matrices are diagonally dominant (lapl_cyl.cpp:151-159, lapl_rect.cpp:44-60) so
+    LAPACK's partial pivoting never interchanges; ut/ut_tdiag.cpp:27-170 asserts
+    Thomas == gtsv == gttrs to 1e-15.
+    """
+    D = np.array(np.broadcast_to(D, b.shape), dtype=np.float64)
+    L = np.broadcast_to(L, b.shape)
+    U = np.broadcast_to(U, b.shape)
+    x = np.array(b, dtype=np.float64)
+    n = b.shape[-1]
+    for j in range(1, n):
+        f = L[..., j] / D[..., j - 1]
+        D[..., j] = D[..., j] - f * U[..., j - 1]
+        x[..., j] = x[..., j] - f * x[..., j - 1]
+    x[..., n - 1] = x[..., n - 1] / D[..., n - 1]
+    for j in range(n - 2, -1, -1):
+        x[..., j] = (x[..., j] - U[..., j] * x[..., j + 1]) / D[..., j]
+    return x
+
+
+# --------------------------------------------------------------------------------------
+# LaplRect / LaplRectFFT2 (reference: src/lapl_rect.h, src/lapl_rect.cpp)
+# --------------------------------------------------------------------------------------
+
+
+class LaplRect:
+    """y-transform + tridiagonal in x (lapl_rect.cpp:63-110).  x is always Dirichlet."""
+
+    def __init__(self, dx, dy, lx, ly, nx, ny, yperiodic=False):
+        self.dx, self.dy, self.lx, self.ly, self.nx, self.ny = dx, dy, lx, ly, nx, ny
+        self.yperiodic = bool(yperiodic)
+        self.slx, self.sly = math.sqrt(2.0 / lx), math.sqrt(2.0 / ly)
+        self.y1, self.yn = (0, ny - 1) if yperiodic else (1, ny)
+        self.ypoints = ny if yperiodic else ny + 1
+        k = np.arange(self.y1, self.yn + 1, dtype=np.float64)
+        if yperiodic:
+            self.lm_y = 4.0 / (dy * dy) * np.sin(k * math.pi / ny) ** 2
+        else:
+            self.lm_y = 4.0 / (dy * dy) * np.sin(k * math.pi * 0.5 / (ny + 1)) ** 2
+        # index 0 unused, 1..nx (lapl_rect.h:57-59)
+        self.lm_y_scale = np.ones(nx + 1)
+        self.L_scale = np.ones(nx + 1)
+        self.U_scale = np.ones(nx + 1)
+
+    def solve(self, rhs):
+        rows = self.yn - self.y1 + 1
+        a = np.asarray(rhs, dtype=np.float64).reshape(rows, self.nx)
+        fwd = pFFT_1 if self.yperiodic else sFFT
+        inv = pFFT if self.yperiodic else sFFT
+        a = fwd(a, self.dy * self.sly, axis=0)
+        dx2 = self.dx * self.dx
+        # init_Mat (lapl_rect.cpp:44-60)
+        D = -2.0 / dx2 - self.lm_y[:, None] * self.lm_y_scale[None, 1:]
+        L = np.broadcast_to(self.L_scale[None, 1:] / dx2, D.shape)
+        U = np.broadcast_to(self.U_scale[None, 1:] / dx2, D.shape)
+        a = tridiag_solve(L, D, U, a)
+        a = inv(a, self.sly, axis=0)
+        return np.ascontiguousarray(a)
+
+
+class LaplRectFFT2(LaplRect):
+    """Transforms on both axes (lapl_rect.cpp:113-207)."""
+
+    def __init__(self, dx, dy, lx, ly, nx, ny, yperiodic=False, xperiodic=False):
+        super().__init__(dx, dy, lx, ly, nx, ny, yperiodic)
+        self.xperiodic = bool(xperiodic)
+        self.x1, self.xn = (0, nx - 1) if xperiodic else (1, nx)
+        self.xpoints = nx if xperiodic else nx + 1
+        j = np.arange(self.x1, self.xn + 1, dtype=np.float64)
+        if xperiodic:
+            lm_x = 4.0 / (dx * dx) * np.sin(j * math.pi / self.xpoints) ** 2
+        else:
+            lm_x = 4.0 / (dx * dx) * np.sin(j * math.pi * 0.5 / self.xpoints) ** 2
+        # aliasing only in the all-Dirichlet instantiation (lapl_rect.cpp:36-40)
+        if not yperiodic and not xperiodic and self.xpoints == self.ypoints:
+            self.lm_x = self.lm_y
+        else:
+            self.lm_x = lm_x
+
+    def solve(self, rhs):
+        rows = self.yn - self.y1 + 1
+        cols = self.xn - self.x1 + 1
+        a = np.asarray(rhs, dtype=np.float64).reshape(rows, cols)
+        fy, iy = (pFFT_1, pFFT) if self.yperiodic else (sFFT, sFFT)
+        fx, ix = (pFFT_1, pFFT) if self.xperiodic else (sFFT, sFFT)
+        a = fy(a, self.dy * self.sly, axis=0)
+        a = fx(a, self.dx * self.slx, axis=1)
+        scale = self.lm_y_scale[self.x1 : self.xn + 1]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            a = a / (-self.lm_y[:, None] * scale[None, :] - self.lm_x[None, :])
+        if self.y1 == 0 and self.x1 == 0:
+            a[0, 0] = 1.0  # "hack for double-period", lapl_rect.cpp:169-172
+        a = ix(a, self.slx, axis=1)
+        a = iy(a, self.sly, axis=0)
+        return np.ascontiguousarray(a)
+
+
+# --------------------------------------------------------------------------------------
+# LaplCyl3FFT2 (reference: src/lapl_cyl.h:12-37,171-249, src/lapl_cyl.cpp:11-170)
+# --------------------------------------------------------------------------------------
+
+SQRT_M_1_PI = 0.56418958354775629  # lapl_cyl.h:174
+
+
+class LaplCyl3FFT2:
+    def __init__(self, dr, dz, r0, lr, lz, nr, nz, nphi, zperiodic=False):
+        self.dr, self.dz, self.r0, self.lr, self.lz = dr, dz, r0, lr, lz
+        self.nr, self.nz, self.nphi = nr, nz, nphi
+        self.zperiodic = bool(zperiodic)
+        self.dphi = 2 * math.pi / nphi
+        self.slz = math.sqrt(2.0 / lz)
+        self.zpoints = nz if zperiodic else nz + 1
+        self.z1, self.zn = (0, nz - 1) if zperiodic else (1, nz)
+        dphi2, dz2 = self.dphi * self.dphi, dz * dz
+        i = np.arange(nphi, dtype=np.float64)
+        self.lm_phi = 4.0 / dphi2 * np.sin(i * self.dphi * 0.5) ** 2  # lapl_cyl.cpp:132-134
+        k = np.arange(self.zpoints, dtype=np.float64)
+        if zperiodic:
+            self.lm_z = 4.0 / dz2 * np.sin(k * math.pi / self.zpoints) ** 2
+        else:
+            self.lm_z = 4.0 / dz2 * np.sin(k * math.pi * 0.5 / self.zpoints) ** 2
+
+    def solve(self, rhs):
+        nzr = self.zn - self.z1 + 1
+        a = np.asarray(rhs, dtype=np.float64).reshape(self.nphi, nzr, self.nr)
+        a = pFFT_1(a, self.dphi * SQRT_M_1_PI, axis=0)  # lapl_cyl.cpp:14-29
+        if self.zperiodic:
+            a = pFFT_1(a, self.dz * self.slz, axis=1)
+        else:
+            a = sFFT(a, self.dz * self.slz, axis=1)  # lapl_cyl.cpp:31-50
+        # tridiagonal in r, lapl_cyl.cpp:151-159
+        dr, dr2 = self.dr, self.dr * self.dr
+        j = np.arange(1, self.nr + 1, dtype=np.float64)
+        r = self.r0 + j * dr
+        lmz = self.lm_z[self.z1 : self.zn + 1]
+        D = -2.0 / dr2 - self.lm_phi[:, None, None] / r[None, None, :] / r[None, None, :] - lmz[None, :, None]
+        # LAPACK layout: L[j-1] is the sub-diagonal of row j (j>1); restated row-wise here
+        Lrow = (r - 0.5 * dr) / dr2 / r
+        Urow = (r + 0.5 * dr) / dr2 / r
+        a = tridiag_solve(Lrow[None, None, :], D, Urow[None, None, :], a)
+        if self.zperiodic:
+            a = pFFT(a, self.slz, axis=1)
+        else:
+            a = sFFT(a, self.slz, axis=1)
+        a = pFFT(a, SQRT_M_1_PI, axis=0)
+        return np.ascontiguousarray(a)
+
+
+# --------------------------------------------------------------------------------------
+# Offset-indexed helper (reference: src/tensor.h -- row-major, last index fastest)
+# --------------------------------------------------------------------------------------
+
+
+class OT:
+    """numpy array with per-axis inclusive [lo,hi] index ranges, like fdm::tensor."""
+
+    def __init__(self, ranges):
+        self.lo = [r[0] for r in ranges]
+        self.hi = [r[1] for r in ranges]
+        self.a = np.zeros([h - l + 1 for l, h in ranges], dtype=np.float64)
+
+    def v(self, *rng):
+        """View for inclusive reference-index ranges; an int selects one index (kept as len-1)."""
+        sl = []
+        for ax, r in enumerate(rng):
+            if isinstance(r, int):
+                r = (r, r)
+            sl.append(slice(r[0] - self.lo[ax], r[1] - self.lo[ax] + 1))
+        return self.a[tuple(sl)]
+
+    @property
+    def size(self):
+        return self.a.size
+
+
+def _sq(x):
+    return x * x
+
+
+# --------------------------------------------------------------------------------------
+# NSCube (reference: src/ns_cube.h:46-78, src/ns_cube.cpp:27-277)
+# --------------------------------------------------------------------------------------
+
+
+class NSCube:
+    def __init__(self, nx=32, nz=32, Re=1.0, dt=0.001, u0=1.0,
+                 x1=-math.pi, y1=-math.pi, z1=-math.pi, x2=math.pi, y2=math.pi, z2=math.pi):
+        self.x1, self.y1, self.z1, self.x2, self.y2, self.z2 = x1, y1, z1, x2, y2, z2
+        self.U0, self.Re, self.dt = u0, Re, dt
+        self.nx = nx
+        self.ny = nx  # ns_cube.h:58 -- ny is read from key "nx"
+        self.nz = nz
+        nx, ny, nz = self.nx, self.ny, self.nz
+        self.dx, self.dy, self.dz = (x2 - x1) / nx, (y2 - y1) / ny, (z2 - z1) / nz
+        self.dx2, self.dy2, self.dz2 = self.dx**2, self.dy**2, self.dz**2
+        self.u = OT([(0, nz + 1), (0, ny + 1), (-1, nx + 1)])
+        self.v = OT([(0, nz + 1), (-1, ny + 1), (0, nx + 1)])
+        self.w = OT([(-1, nz + 1), (0, ny + 1), (0, nx + 1)])
+        self.p = OT([(0, nz + 1), (0, ny + 1), (0, nx + 1)])
+        self.x = OT([(1, nz), (1, ny), (1, nx)])
+        self.F = OT([(1, nz), (1, ny), (0, nx)])
+        self.G = OT([(1, nz), (0, ny), (1, nx)])
+        self.H = OT([(0, nz), (1, ny), (1, nx)])
+        self.RHS = OT([(1, nz), (1, ny), (1, nx)])
+        self.lapl = LaplCube(self.dx, self.dy, self.dz,
+                             x2 - x1 + self.dx, y2 - y1 + self.dy, z2 - z1 + self.dz, nx, ny, nz)
+        self.time_index = 0
+
+    def fields(self):
+        return {"u": self.u.a, "v": self.v.a, "w": self.w.a, "p": self.p.a, "x": self.x.a,
+                "F": self.F.a, "G": self.G.a, "H": self.H.a, "RHS": self.RHS.a}
+
+    def step(self):
+        self.init_bound()
+        self.FGH()
+        self.poisson()
+        self.update_uvwp()
+        self.time_index += 1
+
+    def init_bound(self):  # ns_cube.cpp:65-122, statement order preserved
+        nx, ny, nz, U0, Re = self.nx, self.ny, self.nz, self.U0, self.Re
+        u, v, w, p = self.u, self.v, self.w, self.p
+        # lid: k=0..ny+1, j=-1..nz+1 (sic: nz used for the x extent, ns_cube.cpp:68)
+        u.v(nz + 1, (0, ny + 1), (-1, nz + 1))[...] = 2 * U0 - u.v(nz, (0, ny + 1), (-1, nz + 1))
+        u.v((0, nz + 1), (0, ny + 1), -1)[...] = u.v((0, nz + 1), (0, ny + 1), 1)
+        u.v((0, nz + 1), (0, ny + 1), nx + 1)[...] = u.v((0, nz + 1), (0, ny + 1), nx - 1)
+        v.v((0, nz + 1), -1, (0, nx + 1))[...] = v.v((0, nz + 1), 1, (0, nx + 1))
+        v.v((0, nz + 1), ny + 1, (0, nx + 1))[...] = v.v((0, nz + 1), ny - 1, (0, nx + 1))
+        w.v(-1, (0, ny + 1), (0, nx + 1))[...] = w.v(1, (0, ny + 1), (0, nx + 1))
+        w.v(nz + 1, (0, ny + 1), (0, nx + 1))[...] = w.v(nz - 1, (0, ny + 1), (0, nx + 1))
+        I, K, J = (1, nz), (1, ny), (1, nx)
+        dx, dy, dz = self.dx, self.dy, self.dz
+        p.v(I, K, 0)[...] = p.v(I, K, 1) - (u.v(I, K, 1) - 2 * u.v(I, K, 0) + u.v(I, K, -1)) / Re / dx
+        p.v(I, K, nx + 1)[...] = p.v(I, K, nx) - (u.v(I, K, nx + 1) - 2 * u.v(I, K, nx) + u.v(I, K, nx - 1)) / Re / dx
+        p.v(I, 0, J)[...] = p.v(I, 1, J) - (v.v(I, 1, J) - 2 * v.v(I, 0, J) + v.v(I, -1, J)) / Re / dy
+        p.v(I, ny + 1, J)[...] = p.v(I, ny, J) - (v.v(I, ny + 1, J) - 2 * v.v(I, ny, J) + v.v(I, ny - 1, J)) / Re / dy
+        p.v(0, K, J)[...] = p.v(1, K, J) - (w.v(1, K, J) - 2 * w.v(0, K, J) + w.v(-1, K, J)) / Re / dz
+        p.v(nz + 1, K, J)[...] = p.v(nz, K, J) - (w.v(nz + 1, K, J) - 2 * w.v(nz, K, J) + w.v(nz - 1, K, J)) / Re / dz
+
+    def FGH(self):  # ns_cube.cpp:126-200
+        nx, ny, nz, Re, dt = self.nx, self.ny, self.nz, self.Re, self.dt
+        dx, dy, dz, dx2, dy2, dz2 = self.dx, self.dy, self.dz, self.dx2, self.dy2, self.dz2
+        u, v, w = self.u, self.v, self.w
+
+        def sh(t, I, K, J, di=0, dk=0, dj=0):
+            return t.v((I[0] + di, I[1] + di), (K[0] + dk, K[1] + dk), (J[0] + dj, J[1] + dj))
+
+        # F: i=1..nz, k=1..ny, j=0..nx
+        I, K, J = (1, nz), (1, ny), (0, nx)
+        U = lambda di=0, dk=0, dj=0: sh(u, I, K, J, di, dk, dj)
+        V = lambda di=0, dk=0, dj=0: sh(v, I, K, J, di, dk, dj)
+        W = lambda di=0, dk=0, dj=0: sh(w, I, K, J, di, dk, dj)
+        self.F.a[...] = U() + dt * (
+            (U(dj=1) - 2 * U() + U(dj=-1)) / Re / dx2 +
+            (U(dk=1) - 2 * U() + U(dk=-1)) / Re / dy2 +
+            (U(di=1) - 2 * U() + U(di=-1)) / Re / dz2 -
+            (_sq(0.5 * (U() + U(dj=1))) - _sq(0.5 * (U(dj=-1) + U()))) / dx -
+            0.25 * ((U() + U(dk=1)) * (V(dj=1) + V()) -
+                    (U(dk=-1) + U()) * (V(dk=-1, dj=1) + V(dk=-1))) / dy -
+            0.25 * ((U() + U(di=1)) * (W(dj=1) + W()) -
+                    (U(di=-1) + U()) * (W(di=-1, dj=1) + W(di=-1))) / dz)
+        # G: i=1..nz, k=0..ny, j=1..nx
+        I, K, J = (1, nz), (0, ny), (1, nx)
+        self.G.a[...] = V() + dt * (
+            (V(dj=1) - 2 * V() + V(dj=-1)) / Re / dx2 +
+            (V(dk=1) - 2 * V() + V(dk=-1)) / Re / dy2 +
+            (V(di=1) - 2 * V() + V(di=-1)) / Re / dz2 -
+            (_sq(0.5 * (V() + V(dk=1))) - _sq(0.5 * (V(dk=-1) + V()))) / dy -
+            0.25 * ((U() + U(dk=1)) * (V(dj=1) + V()) -
+                    (U(dj=-1) + U(dk=1, dj=-1)) * (V() + V(dj=-1))) / dx -
+            0.25 * ((W() + W(dk=1)) * (V() + V(di=1)) -
+                    (W(di=-1) + W(di=-1, dk=1)) * (V(di=-1) + V())) / dz)
+        # H: i=0..nz, k=1..ny, j=1..nx
+        I, K, J = (0, nz), (1, ny), (1, nx)
+        self.H.a[...] = W() + dt * (
+            (W(dj=1) - 2 * W() + W(dj=-1)) / Re / dx2 +
+            (W(dk=1) - 2 * W() + W(dk=-1)) / Re / dy2 +
+            (W(di=1) - 2 * W() + W(di=-1)) / Re / dz2 -
+            (_sq(0.5 * (W(di=1) + W())) - _sq(0.5 * (W(di=-1) + W()))) / dz -
+            0.25 * ((U(di=1) + U()) * (W(dj=1) + W()) -
+                    (U(di=1, dj=-1) + U(dj=-1)) * (W() + W(dj=-1))) / dx -
+            0.25 * ((W() + W(dk=1)) * (V() + V(di=1)) -
+                    (W(dk=-1) + W()) * (V(dk=-1) + V(di=1, dk=-1))) / dy)
+
+    def poisson(self):  # ns_cube.cpp:204-238
+        nx, ny, nz, dt = self.nx, self.ny, self.nz, self.dt
+        dx, dy, dz, dx2, dy2, dz2 = self.dx, self.dy, self.dz, self.dx2, self.dy2, self.dz2
+        F, G, H, p, R = self.F, self.G, self.H, self.p, self.RHS
+        I, K, J = (1, nz), (1, ny), (1, nx)
+        R.a[...] = ((F.v(I, K, J) - F.v(I, K, (0, nx - 1))) / dx +
+                    (G.v(I, K, J) - G.v(I, (0, ny - 1), J)) / dy +
+                    (H.v(I, K, J) - H.v((0, nz - 1), K, J)) / dz) / dt
+        # the reference applies the six corrections in this order per point (:213-233)
+        R.v(1, K, J)[...] -= p.v(0, K, J) / dz2
+        R.v(I, 1, J)[...] -= p.v(I, 0, J) / dy2
+        R.v(I, K, 1)[...] -= p.v(I, K, 0) / dx2
+        R.v(I, K, nx)[...] -= p.v(I, K, nx + 1) / dx2
+        R.v(I, ny, J)[...] -= p.v(I, ny + 1, J) / dy2
+        R.v(nz, K, J)[...] -= p.v(nz + 1, K, J) / dz2
+        self.x.a[...] = self.lapl.solve(R.a)
+
+    def update_uvwp(self):  # ns_cube.cpp:241-277
+        nx, ny, nz, dt = self.nx, self.ny, self.nz, self.dt
+        dx, dy, dz = self.dx, self.dy, self.dz
+        u, v, w, p, x, F, G, H = self.u, self.v, self.w, self.p, self.x, self.F, self.G, self.H
+        I, K, J = (1, nz), (1, ny), (1, nx)
+        Jm, Km, Im = (1, nx - 1), (1, ny - 1), (1, nz - 1)
+        u.v(I, K, Jm)[...] = F.v(I, K, Jm) - dt / dx * (x.v(I, K, (2, nx)) - x.v(I, K, Jm))
+        v.v(I, Km, J)[...] = G.v(I, Km, J) - dt / dy * (x.v(I, (2, ny), J) - x.v(I, Km, J))
+        w.v(Im, K, J)[...] = H.v(Im, K, J) - dt / dz * (x.v((2, nz), K, J) - x.v(Im, K, J))
+        p.v(I, K, J)[...] = x.a  # tensor::operator= copies the index-range intersection
+
+
+# --------------------------------------------------------------------------------------
+# Convenience
+# --------------------------------------------------------------------------------------
+
+
+def rel_l2(a, b):
+    """||a-b||_2 / ||b||_2 with a 0/0 guard (both exactly zero -> 0)."""
+    a = np.asarray(a, dtype=np.float64).ravel()
+    b = np.asarray(b, dtype=np.float64).ravel()
+    nb = float(np.linalg.norm(b))
+    nd = float(np.linalg.norm(a - b))
+    if nb == 0.0:
+        return 0.0 if nd == 0.0 else float("inf")
+    return nd / nb
+
+
+def synthetic_rhs(shape, seed=1234):
+    """Counter-based synthetic RHS, uniform(-0.5, 0.5), identical on every box."""
+    rng = np.random.Generator(np.random.Philox(key=seed))
+    return rng.random(shape, dtype=np.float64) - 0.5
