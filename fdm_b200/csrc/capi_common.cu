@@ -1,0 +1,139 @@
+// Library-wide pieces of the C ABI: error string, device tables, raw memory helpers,
+// batched 1-D transforms (fdm::FFT<double>::{sFFT,pFFT_1,pFFT}).
+#include <cmath>
+#include <map>
+#include <mutex>
+#include <vector>
+
+#include "common.h"
+#include "lapl_cube.h"
+
+namespace fdmb {
+
+static thread_local std::string g_error;
+unsigned long long g_launch_count = 0;
+
+void set_error(const char* fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_error = buf;
+}
+const char* get_error() { return g_error.c_str(); }
+
+static std::mutex g_tab_mutex;
+static std::map<std::pair<int, int>, Tables> g_tables;
+
+int get_tables(int N, Tables* out)
+{
+    int dev = 0;
+    FDMB_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_tab_mutex);
+    auto it = g_tables.find({dev, N});
+    if (it != g_tables.end()) { *out = it->second; return FDMB_OK; }
+    const int M = N / 2;
+    std::vector<double> sn(N / 2 + 1);
+    std::vector<cd> wm(M);
+    const long double pi = 3.141592653589793238462643383279502884L;
+    for (int j = 0; j <= N / 2; j++) sn[j] = (double)sinl(pi * j / N);
+    sn[N / 2] = 1.0;
+    for (int t = 0; t < M; t++) {
+        // exact octant symmetries keep the table accurate to the last bit
+        long double ang = 2 * pi * t / M;
+        wm[t].x = (double)cosl(ang);
+        wm[t].y = (double)(-sinl(ang));
+    }
+    if (M >= 4) { wm[M / 4].x = 0.0; wm[M / 4].y = -1.0; wm[3 * M / 4].x = 0.0; wm[3 * M / 4].y = 1.0; }
+    if (M >= 2) { wm[M / 2].x = -1.0; wm[M / 2].y = 0.0; }
+    double* d_sn = nullptr;
+    cd* d_wm = nullptr;
+    FDMB_CUDA(cudaMalloc(&d_sn, sizeof(double) * sn.size()));
+    FDMB_CUDA(cudaMalloc(&d_wm, sizeof(cd) * wm.size()));
+    FDMB_CUDA(cudaMemcpy(d_sn, sn.data(), sizeof(double) * sn.size(), cudaMemcpyHostToDevice));
+    FDMB_CUDA(cudaMemcpy(d_wm, wm.data(), sizeof(cd) * wm.size(), cudaMemcpyHostToDevice));
+    Tables t{d_sn, d_wm};
+    g_tables[{dev, N}] = t;
+    *out = t;
+    return FDMB_OK;
+}
+
+}  // namespace fdmb
+
+using namespace fdmb;
+
+extern "C" {
+
+const char* fdmb_last_error(void) { return get_error(); }
+int fdmb_version(void) { return 100; }
+
+int fdmb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int fdmb_set_device(int device)
+{
+    FDMB_CUDA(cudaSetDevice(device));
+    return FDMB_OK;
+}
+
+unsigned long long fdmb_launch_count(void) { return g_launch_count; }
+
+int fdmb_malloc(void** dptr, unsigned long long bytes)
+{
+    FDMB_CUDA(cudaMalloc(dptr, bytes));
+    return FDMB_OK;
+}
+int fdmb_free(void* dptr)
+{
+    FDMB_CUDA(cudaFree(dptr));
+    return FDMB_OK;
+}
+int fdmb_memcpy_h2d(void* dst, const void* src, unsigned long long bytes)
+{
+    FDMB_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+    return FDMB_OK;
+}
+int fdmb_memcpy_d2h(void* dst, const void* src, unsigned long long bytes)
+{
+    FDMB_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+    return FDMB_OK;
+}
+int fdmb_device_synchronize(void)
+{
+    FDMB_CUDA(cudaDeviceSynchronize());
+    return FDMB_OK;
+}
+
+int fdmb_fft_batch(int kind, int N, long long batch, double dx, const double* in, double* out)
+{
+    if (kind < 0 || kind > 2 || !supported_N(N) || batch < 0 || !in || !out) {
+        set_error("fdmb_fft_batch: kind must be 0..2 and N a power of two in [4,2048] (got kind=%d N=%d)", kind, N);
+        return FDMB_ERR_INVALID;
+    }
+    if (batch == 0) return FDMB_OK;
+    const int nvalid = kind == XF_DST ? N - 1 : N;
+    const size_t bytes = sizeof(double) * (size_t)batch * nvalid;
+    Tables t;
+    int rc = get_tables(N, &t);
+    if (rc) return rc;
+    double *d_in = nullptr, *d_out = nullptr;
+    FDMB_CUDA(cudaMalloc(&d_in, bytes));
+    FDMB_CUDA(cudaMalloc(&d_out, bytes));
+    FDMB_CUDA(cudaMemcpy(d_in, in, bytes, cudaMemcpyHostToDevice));
+    RowsArgs r{};
+    r.in = d_in; r.out = d_out; r.nrows = batch; r.nvalid = nvalid;
+    r.in_pitch = r.out_pitch = nvalid; r.scale = dx; r.SN = t.SN; r.WM = t.WM;
+    cudaError_t e = launch_rows(N, kind, r, 0);
+    if (e == cudaSuccess) e = cudaMemcpy(out, d_out, bytes, cudaMemcpyDeviceToHost);
+    cudaFree(d_in); cudaFree(d_out);
+    if (e != cudaSuccess) { set_error("fdmb_fft_batch: %s", cudaGetErrorString(e)); return FDMB_ERR_CUDA; }
+    return FDMB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,195 @@
+// LaplCube on B200: 3-D Poisson solve, all-Dirichlet or all-periodic.
+// Replaces fdm::LaplCube<double,check,F>::solve (reference src/lapl_cube.cpp:9-142,
+// constructor src/lapl_cube.h:58-100, eigenvalues src/lapl_cube.cpp:145-172).
+//
+// Sweep structure (v1): x rows -> y columns -> [z forward, divide, z inverse] -> y -> x.
+// The work array is pitched to a multiple of 16 doubles in x so that every strided
+// tile segment is 128-byte aligned; the caller's arrays keep the reference layout.
+#include <cmath>
+#include <vector>
+#include <new>
+
+#include "common.h"
+#include "xform_kernels.cuh"
+#include "lapl_cube.h"
+
+namespace fdmb {
+
+template <int N, int KIND>
+static cudaError_t rows_n(const RowsArgs& a, cudaStream_t st) { return launch_rows_t<N, KIND>(a, st); }
+
+cudaError_t launch_rows(int N, int kind, const RowsArgs& a, cudaStream_t st)
+{
+    g_launch_count++;
+#define X(NN)                                                                  \
+    case NN:                                                                   \
+        if (kind == XF_DST) return launch_rows_t<NN, XF_DST>(a, st);           \
+        if (kind == XF_PFWD) return launch_rows_t<NN, XF_PFWD>(a, st);         \
+        return launch_rows_t<NN, XF_PINV>(a, st);
+    switch (N) { FDMB_FOR_EACH_N(X) }
+#undef X
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_cols(int N, int kind, const ColsArgs& a, cudaStream_t st)
+{
+    g_launch_count++;
+    MidNone mid;
+#define X(NN)                                                                            \
+    case NN:                                                                             \
+        if (kind == XF_DST) return launch_cols_t<NN, XF_DST, MidNone, XF_DST>(a, mid, st);   \
+        if (kind == XF_PFWD) return launch_cols_t<NN, XF_PFWD, MidNone, XF_DST>(a, mid, st); \
+        return launch_cols_t<NN, XF_PINV, MidNone, XF_DST>(a, mid, st);
+    switch (N) { FDMB_FOR_EACH_N(X) }
+#undef X
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_cols_cube_divide(int N, bool periodic, const ColsArgs& a, const MidCubeDivide& mid,
+                                    cudaStream_t st)
+{
+    g_launch_count++;
+#define X(NN)                                                                                   \
+    case NN:                                                                                    \
+        if (periodic) return launch_cols_t<NN, XF_PFWD, MidCubeDivide, XF_PINV>(a, mid, st);    \
+        return launch_cols_t<NN, XF_DST, MidCubeDivide, XF_DST>(a, mid, st);
+    switch (N) { FDMB_FOR_EACH_N(X) }
+#undef X
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace fdmb
+
+using namespace fdmb;
+
+static inline double sq(double x) { return x * x; }
+
+int fdmb_lapl_cube::init()
+{
+    // transform lengths: Dirichlet n+1, periodic n (lapl_cube.h:74-76)
+    Nx = periodic ? nx : nx + 1;
+    Ny = periodic ? ny : ny + 1;
+    Nz = periodic ? nz : nz + 1;
+    if (nx < 1 || ny < 1 || nz < 1 || !supported_N(Nx) || !supported_N(Ny) || !supported_N(Nz)) {
+        set_error("LaplCube: %s axis sizes (%d,%d,%d) need transform lengths that are powers of two in [4,2048] "
+                  "(reference: verify((1<<n) == N), src/fft.cpp:67)",
+                  periodic ? "periodic" : "Dirichlet", nx, ny, nz);
+        return FDMB_ERR_INVALID;
+    }
+    slx = std::sqrt(2. / lx); sly = std::sqrt(2. / ly); slz = std::sqrt(2. / lz);
+    px = (nx + 15) / 16 * 16;
+    int rc;
+    if ((rc = get_tables(Nx, &tx)) || (rc = get_tables(Ny, &ty)) || (rc = get_tables(Nz, &tz))) return rc;
+
+    // eigenvalues, including the aliasing quirk of lapl_cube.cpp:162,171
+    const int x1 = periodic ? 0 : 1, xn = periodic ? nx - 1 : nx;
+    const int y1 = periodic ? 0 : 1, yn = periodic ? ny - 1 : ny;
+    const int z1 = periodic ? 0 : 1, zn = periodic ? nz - 1 : nz;
+    const double dx2 = dx * dx, dy2 = dy * dy, dz2 = dz * dz;
+    std::vector<double> lm_y(ny + 1, 0.0), lm_x(nx + 1, 0.0), lm_z(nz + 1, 0.0);
+    for (int k = y1; k <= yn; k++)
+        lm_y[k] = periodic ? 4. / dy2 * sq(sin(k * M_PI / (ny))) : 4. / dy2 * sq(sin(k * M_PI * 0.5 / (ny + 1)));
+    for (int j = x1; j <= xn; j++)
+        lm_x[j] = periodic ? 4. / dx2 * sq(sin(j * M_PI / (nx))) : 4. / dx2 * sq(sin(j * M_PI * 0.5 / (nx + 1)));
+    for (int i = z1; i <= zn; i++)
+        lm_z[i] = periodic ? 4. / dz2 * sq(sin(i * M_PI / (nz))) : 4. / dz2 * sq(sin(i * M_PI * 0.5 / (nz + 1)));
+    if (Nx == Ny) lm_x = lm_y;   // lm_x = xpoints == ypoints ? &lm_y[0] : &lm_x_[0]
+    if (Nz == Ny) lm_z = lm_y;
+
+    FDMB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    FDMB_CUDA(cudaMalloc(&d_lmx, sizeof(double) * (nx + 1)));
+    FDMB_CUDA(cudaMalloc(&d_lmy, sizeof(double) * (ny + 1)));
+    FDMB_CUDA(cudaMalloc(&d_lmz, sizeof(double) * (nz + 1)));
+    FDMB_CUDA(cudaMemcpy(d_lmx, lm_x.data(), sizeof(double) * (nx + 1), cudaMemcpyHostToDevice));
+    FDMB_CUDA(cudaMemcpy(d_lmy, lm_y.data(), sizeof(double) * (ny + 1), cudaMemcpyHostToDevice));
+    FDMB_CUDA(cudaMemcpy(d_lmz, lm_z.data(), sizeof(double) * (nz + 1), cudaMemcpyHostToDevice));
+    FDMB_CUDA(cudaMalloc(&d_work, sizeof(double) * (size_t)nz * ny * px));
+    return FDMB_OK;
+}
+
+fdmb_lapl_cube::~fdmb_lapl_cube()
+{
+    cudaFree(d_lmx); cudaFree(d_lmy); cudaFree(d_lmz); cudaFree(d_work);
+    cudaFree(d_rhs); cudaFree(d_ans);
+    if (stream) cudaStreamDestroy(stream);
+}
+
+int fdmb_lapl_cube::solve_device(double* d_out, const double* d_in, cudaStream_t st)
+{
+    const int kf = periodic ? XF_PFWD : XF_DST;
+    const int ki = periodic ? XF_PINV : XF_DST;
+    const long long plane = (long long)ny * px;
+    // x forward: rhs rows -> pitched work
+    RowsArgs r{};
+    r.in = d_in; r.out = d_work; r.nrows = (long long)nz * ny; r.nvalid = nx;
+    r.in_pitch = nx; r.out_pitch = px; r.scale = dx * slx; r.SN = tx.SN; r.WM = tx.WM;
+    FDMB_CUDA(launch_rows(Nx, kf, r, st));
+    // y forward
+    ColsArgs c{};
+    c.in = d_work; c.out = d_work; c.nvalid = ny; c.in_sj = c.out_sj = px; c.nb = nx; c.no = nz;
+    c.in_so = c.out_so = plane; c.scale = dy * sly; c.SN = ty.SN; c.WM = ty.WM;
+    FDMB_CUDA(launch_cols(Ny, kf, c, st));
+    // z forward, divide by -(lm_z+lm_y+lm_x), z inverse
+    ColsArgs z{};
+    z.in = d_work; z.out = d_work; z.nvalid = nz; z.in_sj = z.out_sj = plane; z.nb = nx; z.no = ny;
+    z.in_so = z.out_so = px; z.scale = dz * slz; z.scale2 = slz; z.SN = tz.SN; z.WM = tz.WM;
+    MidCubeDivide mid{d_lmz, d_lmx, d_lmy, periodic ? 1 : 0};
+    FDMB_CUDA(launch_cols_cube_divide(Nz, periodic != 0, z, mid, st));
+    // y inverse
+    c.scale = sly;
+    FDMB_CUDA(launch_cols(Ny, ki, c, st));
+    // x inverse: pitched work -> ans rows
+    r.in = d_work; r.out = d_out; r.in_pitch = px; r.out_pitch = nx; r.scale = slx;
+    FDMB_CUDA(launch_rows(Nx, ki, r, st));
+    return FDMB_OK;
+}
+
+int fdmb_lapl_cube::solve_host(double* ans, const double* rhs)
+{
+    const size_t bytes = sizeof(double) * (size_t)nx * ny * nz;
+    if (!d_rhs) FDMB_CUDA(cudaMalloc(&d_rhs, bytes));
+    if (!d_ans) FDMB_CUDA(cudaMalloc(&d_ans, bytes));
+    FDMB_CUDA(cudaMemcpyAsync(d_rhs, rhs, bytes, cudaMemcpyHostToDevice, stream));
+    int rc = solve_device(d_ans, d_rhs, stream);
+    if (rc) return rc;
+    FDMB_CUDA(cudaMemcpyAsync(ans, d_ans, bytes, cudaMemcpyDeviceToHost, stream));
+    FDMB_CUDA(cudaStreamSynchronize(stream));
+    return FDMB_OK;
+}
+
+extern "C" {
+
+int fdmb_lapl_cube_create(fdmb_lapl_cube** out, double dx, double dy, double dz, double lx, double ly, double lz,
+                          int nx, int ny, int nz, int periodic)
+{
+    if (!out) { set_error("null handle pointer"); return FDMB_ERR_INVALID; }
+    *out = nullptr;
+    auto* h = new (std::nothrow) fdmb_lapl_cube();
+    if (!h) { set_error("out of host memory"); return FDMB_ERR_NOMEM; }
+    h->dx = dx; h->dy = dy; h->dz = dz; h->lx = lx; h->ly = ly; h->lz = lz;
+    h->nx = nx; h->ny = ny; h->nz = nz; h->periodic = periodic ? 1 : 0;
+    int rc = h->init();
+    if (rc) { delete h; return rc; }
+    *out = h;
+    return FDMB_OK;
+}
+
+int fdmb_lapl_cube_solve(fdmb_lapl_cube* h, double* ans, const double* rhs)
+{
+    if (!h || !ans || !rhs) { set_error("null argument"); return FDMB_ERR_INVALID; }
+    return h->solve_host(ans, rhs);
+}
+
+int fdmb_lapl_cube_solve_device(fdmb_lapl_cube* h, double* d_ans, const double* d_rhs, void* stream)
+{
+    if (!h || !d_ans || !d_rhs) { set_error("null argument"); return FDMB_ERR_INVALID; }
+    return h->solve_device(d_ans, d_rhs, stream ? (cudaStream_t)stream : h->stream);
+}
+
+int fdmb_lapl_cube_destroy(fdmb_lapl_cube* h)
+{
+    delete h;
+    return FDMB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,424 @@
+// Batched 1-D real transforms on shared-memory tiles (sm_100a).
+//
+// Transforms provided (reference: src/fft.h:47-98, src/fft.cpp; closed forms in
+// src/fft_fftw3.cpp:8-64 and src/asp_fft.cpp:308-319):
+//   DST   -- FFT<T>::sFFT   : S[k] = scale * sum_{j=1}^{N-1} s[j] sin(pi k j / N)
+//   PFWD  -- FFT<T>::pFFT_1 : S[k] = scale * sum s[j] cos(2 pi k j/N) (k=0..N/2),
+//                             S[N-k] = scale * sum s[j] sin(2 pi k j/N) (k=1..N/2-1)
+//   PINV  -- FFT<T>::pFFT   : S[j] = scale * (s[0]/2 + sum_{k=1}^{N/2-1}(s[k] cos + s[N-k] sin)
+//                                             + (-1)^j s[N/2]/2)
+//
+// This is NOT the reference's Samarskii-Nikolaev recursion.  Every transform is
+// mapped onto one complex FFT of length M = N/2 held in shared memory:
+//   DST : fold (sin-weighted symmetric + antisymmetric parts) -> real FFT(N) via
+//         complex FFT(M) -> untangle -> prefix sum of the odd outputs
+//   PFWD: complex FFT(M) of the even/odd packed sequence -> untangle
+//   PINV: inverse untangle -> conj -> complex FFT(M) -> conj
+// The complex FFT is an in-place mixed-radix (2/4/8/16) decimation-in-frequency
+// transform with radix butterflies held in registers; its output is left in
+// digit-reversed order and the consumers index through pos().
+//
+// Thread mapping: a tile holds B independent sequences ("columns"); element j of
+// column b lives at tile[j*sj + b*sb].  Thread (b, g) works on column b; the G
+// threads with the same b share the butterflies of that column.  Lanes of a warp
+// run over b, so every twiddle is warp-uniform and every shared-memory access is
+// conflict free when one of (sj, sb) is 1 and the other is odd or >= B.
+#pragma once
+#ifndef FDMB_HOST_EMUL   // tests/host_emul compiles this header for the CPU with thread-barrier shims
+#include <cuda_runtime.h>
+#endif
+
+namespace fdmb {
+
+enum XformKind { XF_DST = 0, XF_PFWD = 1, XF_PINV = 2 };
+
+struct cd { double x, y; };
+__device__ __forceinline__ cd operator+(cd a, cd b) { return {a.x + b.x, a.y + b.y}; }
+__device__ __forceinline__ cd operator-(cd a, cd b) { return {a.x - b.x, a.y - b.y}; }
+__device__ __forceinline__ cd cmul(cd a, cd w) { return {a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x}; }
+__device__ __forceinline__ cd mul_mi(cd a) { return {a.y, -a.x}; }  // a * (-i)
+
+// ---- register butterflies, forward (e^{-2 pi i jk/R}), natural in / natural out ----
+template <int R> struct Dft;
+
+template <> struct Dft<2> {
+    static __device__ __forceinline__ void run(cd* v) {
+        cd a = v[0] + v[1], b = v[0] - v[1];
+        v[0] = a; v[1] = b;
+    }
+};
+template <> struct Dft<4> {
+    static __device__ __forceinline__ void run(cd* v) {
+        cd t0 = v[0] + v[2], t1 = v[0] - v[2], t2 = v[1] + v[3], t3 = mul_mi(v[1] - v[3]);
+        v[0] = t0 + t2; v[2] = t0 - t2; v[1] = t1 + t3; v[3] = t1 - t3;
+    }
+};
+template <> struct Dft<8> {
+    static __device__ __forceinline__ void run(cd* v) {
+        constexpr double h = 0.70710678118654752440;
+        cd u[4], w[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) { u[j] = v[j] + v[j + 4]; w[j] = v[j] - v[j + 4]; }
+        w[1] = {h * (w[1].x + w[1].y), h * (w[1].y - w[1].x)};
+        w[2] = mul_mi(w[2]);
+        w[3] = {h * (w[3].y - w[3].x), -h * (w[3].x + w[3].y)};
+        Dft<4>::run(u); Dft<4>::run(w);
+#pragma unroll
+        for (int k = 0; k < 4; k++) { v[2 * k] = u[k]; v[2 * k + 1] = w[k]; }
+    }
+};
+template <> struct Dft<16> {
+    static __device__ __forceinline__ void run(cd* v) {
+        constexpr double h = 0.70710678118654752440;
+        constexpr double c1 = 0.92387953251128675613;  // cos(pi/8)
+        constexpr double s1 = 0.38268343236508977173;  // sin(pi/8)
+        cd u[8], w[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) { u[j] = v[j] + v[j + 8]; w[j] = v[j] - v[j + 8]; }
+        w[1] = cmul(w[1], cd{c1, -s1});
+        w[2] = {h * (w[2].x + w[2].y), h * (w[2].y - w[2].x)};
+        w[3] = cmul(w[3], cd{s1, -c1});
+        w[4] = mul_mi(w[4]);
+        w[5] = cmul(w[5], cd{-s1, -c1});
+        w[6] = {h * (w[6].y - w[6].x), -h * (w[6].x + w[6].y)};
+        w[7] = cmul(w[7], cd{-c1, -s1});
+        Dft<8>::run(u); Dft<8>::run(w);
+#pragma unroll
+        for (int k = 0; k < 8; k++) { v[2 * k] = u[k]; v[2 * k + 1] = w[k]; }
+    }
+};
+
+// ---- radix plans: M = N/2 complex points, up to three passes -------------------
+template <int N> struct Plan;
+#define FDMB_PLAN(N_, R0_, R1_, R2_, G_)                                          \
+    template <> struct Plan<N_> {                                                 \
+        static constexpr int M = N_ / 2;                                          \
+        static constexpr int R0 = R0_, R1 = R1_, R2 = R2_;                        \
+        static constexpr int G = G_; /* default threads per column */             \
+        static_assert(R0_ * R1_ * R2_ == N_ / 2, "radix plan");                   \
+    };
+FDMB_PLAN(4, 2, 1, 1, 1)
+FDMB_PLAN(8, 4, 1, 1, 1)
+FDMB_PLAN(16, 8, 1, 1, 1)
+FDMB_PLAN(32, 4, 4, 1, 4)
+FDMB_PLAN(64, 8, 4, 1, 4)
+FDMB_PLAN(128, 8, 8, 1, 8)
+FDMB_PLAN(256, 16, 8, 1, 8)
+FDMB_PLAN(512, 16, 16, 1, 16)
+FDMB_PLAN(1024, 8, 8, 8, 32)
+FDMB_PLAN(2048, 16, 8, 8, 64)
+#undef FDMB_PLAN
+
+// position of output bin k after the in-place DIF passes (digit reversal)
+template <int N> __device__ __forceinline__ int fft_pos(int k)
+{
+    using P = Plan<N>;
+    int pos = 0, L = P::M;
+    { int d = k % P::R0; k /= P::R0; L /= P::R0; pos += d * L; }
+    if constexpr (P::R1 > 1) { int d = k % P::R1; k /= P::R1; L /= P::R1; pos += d * L; }
+    if constexpr (P::R2 > 1) { int d = k % P::R2; L /= P::R2; pos += d * L; }
+    return pos;
+}
+
+// One in-place DIF pass over sub-blocks of length L with radix R.
+// WM[t] = (cos(2 pi t/M), -sin(2 pi t/M)), t = 0..M-1.
+template <int M, int L, int R, int G>
+__device__ __forceinline__ void fft_pass(double* col, int sj, int g, const cd* __restrict__ WM)
+{
+    constexpr int S = L / R;      // distance between butterfly legs (complex elements)
+    constexpr int NBF = M / R;    // butterflies per column
+    constexpr int IT = (NBF + G - 1) / G;
+#pragma unroll
+    for (int it = 0; it < IT; it++) {
+        int q = g + it * G;
+        if (NBF % G != 0 && q >= NBF) break;
+        int blk = q / S, n2 = q % S;
+        int base = blk * L + n2;
+        cd v[R];
+#pragma unroll
+        for (int n1 = 0; n1 < R; n1++) {
+            int idx = 2 * (base + n1 * S);
+            v[n1].x = col[idx * sj];
+            v[n1].y = col[(idx + 1) * sj];
+        }
+        Dft<R>::run(v);
+#pragma unroll
+        for (int k1 = 0; k1 < R; k1++) {
+            cd o = v[k1];
+            if (S > 1 && k1 > 0) {
+                cd w = WM[n2 * k1 * (M / L)];
+                o = cmul(o, w);
+            }
+            int idx = 2 * (base + k1 * S);
+            col[idx * sj] = o.x;
+            col[(idx + 1) * sj] = o.y;
+        }
+    }
+}
+
+// Complex FFT of length M = N/2 on (col[2m*sj], col[(2m+1)*sj]); output digit-reversed.
+// Ends with __syncthreads().
+template <int N, int G>
+__device__ __forceinline__ void fft_inplace(double* col, int sj, int g, const cd* __restrict__ WM)
+{
+    using P = Plan<N>;
+    constexpr int M = P::M;
+    fft_pass<M, M, P::R0, G>(col, sj, g, WM);
+    __syncthreads();
+    if constexpr (P::R1 > 1) {
+        fft_pass<M, M / P::R0, P::R1, G>(col, sj, g, WM);
+        __syncthreads();
+    }
+    if constexpr (P::R2 > 1) {
+        fft_pass<M, M / P::R0 / P::R1, P::R2, G>(col, sj, g, WM);
+        __syncthreads();
+    }
+}
+
+// Untangle one (k, M-k) pair of the half-length FFT of a real sequence.
+// Y[k] = A_k - i B_k is the length-N DFT bin; returns A_k, B_k, A_{M-k}, B_{M-k}.
+// SN[j] = sin(pi j / N), j = 0..N/2.
+template <int N>
+__device__ __forceinline__ void untangle(const double* col, int sj, int k, const double* __restrict__ SN,
+                                         double scale, double& Ak, double& Bk, double& Am, double& Bm)
+{
+    constexpr int M = N / 2;
+    int pk = fft_pos<N>(k), pm = fft_pos<N>((M - k) & (M - 1));
+    cd zk = {col[(2 * pk) * sj], col[(2 * pk + 1) * sj]};
+    cd zm = {col[(2 * pm) * sj], col[(2 * pm + 1) * sj]};
+    double c = SN[M - 2 * k], s = SN[2 * k];      // cos, sin of 2 pi k / N
+    double hs = 0.5 * scale;
+    double ex = hs * (zk.x + zm.x), ey = hs * (zk.y - zm.y);
+    double ox = hs * (zk.y + zm.y), oy = -hs * (zk.x - zm.x);
+    double wx = c * ox + s * oy, wy = c * oy - s * ox;
+    Ak = ex + wx; Bk = -(ey + wy);
+    Am = ex - wx; Bm = ey - wy;
+}
+
+// ---------------------------------------------------------------------------------
+// DST-I over slots 1..N-1 of every column (slot 0 is the implicit zero boundary and
+// is clobbered).  All threads of the CTA must call; ends with __syncthreads().
+// scr: scratch of at least (G + G/8 + 1) * scr_s doubles per CTA, column b at scr[b].
+// ---------------------------------------------------------------------------------
+template <int N, int G>
+__device__ __forceinline__ void dst_tile(double* col, int sj, int g, double scale,
+                                         const double* __restrict__ SN, const cd* __restrict__ WM,
+                                         double* scr, int scr_s)
+{
+    constexpr int M = N / 2;
+    static_assert(G <= M / 2 || M == 2, "too many threads per column");
+    // fold: y[j] = sin(pi j/N)(x[j]+x[N-j]) + (x[j]-x[N-j])/2
+#pragma unroll
+    for (int j = g + 1; j < M; j += G) {
+        double a = col[j * sj], c = col[(N - j) * sj];
+        double y1 = SN[j] * (a + c), y2 = 0.5 * (a - c);
+        col[j * sj] = y1 + y2;
+        col[(N - j) * sj] = y1 - y2;
+    }
+    if (g == 0) { col[0] = 0.0; col[M * sj] = 2.0 * col[M * sj]; }
+    __syncthreads();
+
+    fft_inplace<N, G>(col, sj, g, WM);
+
+    // untangle into natural order: even slot 2k <- S[2k] = B_k, odd slot 2k+1 <- A_k
+    constexpr int HP = (M / 2 >= G) ? (M / 2) / G : 1;   // pairs per thread
+    double r[HP][4];
+#pragma unroll
+    for (int i = 0; i < HP; i++) {
+        int k = g + i * G;
+        if (k < M / 2)
+            untangle<N>(col, sj, k, SN, scale, r[i][0], r[i][1], r[i][2], r[i][3]);
+    }
+    double zh_x = 0, zh_y = 0;   // bin M/2 (self-paired), handled by g == 0
+    if (g == 0) {
+        int ph = fft_pos<N>(M / 2);
+        zh_x = scale * col[(2 * ph) * sj];
+        zh_y = scale * col[(2 * ph + 1) * sj];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < HP; i++) {
+        int k = g + i * G;
+        if (k == 0) {
+            col[0] = 0.0;
+            col[sj] = 0.5 * r[i][0];             // A_0 / 2 seeds the running sum
+        } else if (k < M / 2) {
+            col[(2 * k) * sj] = r[i][1];
+            col[(2 * k + 1) * sj] = r[i][0];
+            col[(2 * (M - k)) * sj] = r[i][3];
+            col[(2 * (M - k) + 1) * sj] = r[i][2];
+        }
+    }
+    if (g == 0) {
+        col[M * sj] = zh_y;                       // S[M]   = -Im Y[M/2] = Im Z[M/2]
+        col[(M + 1) * sj] = zh_x;                 // A_{M/2} = Re Z[M/2]
+    }
+    __syncthreads();
+
+    // inclusive prefix sum over the odd slots: S[2k+1] = sum_{m<=k} A'_m
+    constexpr int CS = M / G;     // contiguous chunk per thread
+    double a[CS];
+    double run = 0.0;
+#pragma unroll
+    for (int i = 0; i < CS; i++) {
+        int k = g * CS + i;
+        run += col[(2 * k + 1) * sj];
+        a[i] = run;
+    }
+    double off = 0.0;
+    if constexpr (G > 1) {
+        scr[g * scr_s] = run;
+        __syncthreads();
+        if constexpr (G <= 8) {
+#pragma unroll
+            for (int q = 0; q < G; q++) if (q < g) off += scr[q * scr_s];
+        } else {
+            double* scr2 = scr + G * scr_s;
+            if ((g & 7) == 0) {
+                double t = 0.0;
+#pragma unroll
+                for (int q = 0; q < 8; q++) t += scr[(g + q) * scr_s];
+                scr2[(g >> 3) * scr_s] = t;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int q = 0; q < G / 8; q++) if (q < (g >> 3)) off += scr2[q * scr_s];
+#pragma unroll
+            for (int q = 0; q < 8; q++) if (q < (g & 7)) off += scr[((g & ~7) + q) * scr_s];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < CS; i++) {
+        int k = g * CS + i;
+        col[(2 * k + 1) * sj] = a[i] + off;
+    }
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------
+// Periodic forward transform (pFFT_1) over slots 0..N-1.  Ends with __syncthreads().
+// ---------------------------------------------------------------------------------
+template <int N, int G>
+__device__ __forceinline__ void pfwd_tile(double* col, int sj, int g, double scale,
+                                          const double* __restrict__ SN, const cd* __restrict__ WM)
+{
+    constexpr int M = N / 2;
+    fft_inplace<N, G>(col, sj, g, WM);
+    constexpr int HP = (M / 2 >= G) ? (M / 2) / G : 1;
+    double r[HP][4];
+#pragma unroll
+    for (int i = 0; i < HP; i++) {
+        int k = g + i * G;
+        if (k < M / 2)
+            untangle<N>(col, sj, k, SN, scale, r[i][0], r[i][1], r[i][2], r[i][3]);
+    }
+    double zh_x = 0, zh_y = 0;
+    if (g == 0) {
+        int ph = fft_pos<N>(M / 2);
+        zh_x = scale * col[(2 * ph) * sj];
+        zh_y = scale * col[(2 * ph + 1) * sj];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < HP; i++) {
+        int k = g + i * G;
+        if (k == 0) {
+            col[0] = r[i][0];                       // S[0]   = Re Y[0]
+            col[M * sj] = r[i][2];                  // S[N/2] = Re Y[M]
+        } else if (k < M / 2) {
+            col[k * sj] = r[i][0];                  // S[k]     = A_k
+            col[(N - k) * sj] = r[i][1];            // S[N-k]   = B_k
+            col[(M - k) * sj] = r[i][2];            // S[M-k]   = A_{M-k}
+            col[(M + k) * sj] = r[i][3];            // S[N-(M-k)] = B_{M-k}
+        }
+    }
+    if (g == 0 && M >= 2) {
+        col[(M / 2) * sj] = zh_x;                   // S[N/4]   = Re Z[M/2]
+        col[(N - M / 2) * sj] = zh_y;               // S[3N/4]  = Im Z[M/2]
+    }
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------
+// Periodic inverse transform (pFFT) over slots 0..N-1.  Ends with __syncthreads().
+// ---------------------------------------------------------------------------------
+template <int N, int G>
+__device__ __forceinline__ void pinv_tile(double* col, int sj, int g, double scale,
+                                          const double* __restrict__ SN, const cd* __restrict__ WM)
+{
+    constexpr int M = N / 2;
+    constexpr int HP = (M / 2 >= G) ? (M / 2) / G : 1;
+    // inverse untangle: build conj(Z[k]), Z[k] = Ze[k] + i Zo[k]
+    double r[HP][4];
+#pragma unroll
+    for (int i = 0; i < HP; i++) {
+        int k = g + i * G;
+        if (k == 0) {
+            double a0 = col[0], aM = col[M * sj];
+            r[i][0] = a0 + aM; r[i][1] = -(a0 - aM);
+        } else if (k < M / 2) {
+            double ak = col[k * sj], bk = col[(N - k) * sj];
+            double am = col[(M - k) * sj], bm = col[(M + k) * sj];
+            // X_k = ak - i bk ; conj X_{M-k} = am + i bm
+            double ex = ak + am, ey = -bk + bm;          // Ze = X_k + conj X_{M-k}
+            double dx_ = ak - am, dy_ = -bk - bm;        // X_k - conj X_{M-k}
+            double c = SN[M - 2 * k], s = SN[2 * k];     // e^{+2 pi i k/N} = c + i s
+            double ox = dx_ * c - dy_ * s, oy = dx_ * s + dy_ * c;   // Zo
+            // Z[k] = Ze + i Zo = (ex - oy) + i (ey + ox); Z[M-k] = conj(Ze) + i conj(Zo) = (ex + oy) + i(-ey + ox)
+            r[i][0] = ex - oy; r[i][1] = -(ey + ox);     // conj Z[k]
+            r[i][2] = ex + oy; r[i][3] = -(-ey + ox);    // conj Z[M-k]
+        }
+    }
+    double zh_x = 0, zh_y = 0;
+    if (g == 0 && M >= 2) {
+        double a = col[(M / 2) * sj], b = col[(N - M / 2) * sj];
+        zh_x = 2.0 * a; zh_y = -2.0 * b;                 // conj(2a + 2ib)
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < HP; i++) {
+        int k = g + i * G;
+        if (k == 0) {
+            col[0] = r[i][0]; col[sj] = r[i][1];
+        } else if (k < M / 2) {
+            col[(2 * k) * sj] = r[i][0]; col[(2 * k + 1) * sj] = r[i][1];
+            col[(2 * (M - k)) * sj] = r[i][2]; col[(2 * (M - k) + 1) * sj] = r[i][3];
+        }
+    }
+    if (g == 0 && M >= 2) { col[M * sj] = zh_x; col[(M + 1) * sj] = zh_y; }
+    __syncthreads();
+
+    fft_inplace<N, G>(col, sj, g, WM);
+
+    // undo the digit reversal: y[2m] = Re F[pos(m)], y[2m+1] = -Im F[pos(m)]
+    constexpr int CS = M / G;
+    double o[CS][2];
+    double hs = 0.5 * scale;
+#pragma unroll
+    for (int i = 0; i < CS; i++) {
+        int m = g + i * G;
+        int p = fft_pos<N>(m);
+        o[i][0] = hs * col[(2 * p) * sj];
+        o[i][1] = -hs * col[(2 * p + 1) * sj];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < CS; i++) {
+        int m = g + i * G;
+        col[(2 * m) * sj] = o[i][0];
+        col[(2 * m + 1) * sj] = o[i][1];
+    }
+    __syncthreads();
+}
+
+template <int N, int G, int KIND>
+__device__ __forceinline__ void xform_tile(double* col, int sj, int g, double scale,
+                                           const double* __restrict__ SN, const cd* __restrict__ WM,
+                                           double* scr, int scr_s)
+{
+    if constexpr (KIND == XF_DST) dst_tile<N, G>(col, sj, g, scale, SN, WM, scr, scr_s);
+    else if constexpr (KIND == XF_PFWD) pfwd_tile<N, G>(col, sj, g, scale, SN, WM);
+    else pinv_tile<N, G>(col, sj, g, scale, SN, WM);
+}
+
+}  // namespace fdmb

@@ -1,0 +1,170 @@
+// Global-memory kernels around the shared-memory tile transforms of xform.cuh.
+//
+//   k_rows : transform along the CONTIGUOUS axis.  A CTA stages BR consecutive rows
+//            in a [BR][N+1] tile (odd pitch -> conflict-free for thread-per-row access),
+//            transforms every row, writes them back.  Row loads are fully coalesced.
+//   k_cols : transform along a STRIDED axis.  A CTA stages a [N][B] tile: all entries
+//            along the transform axis for B consecutive positions of the contiguous
+//            axis (B*8 = 128 or 256 byte segments).  An optional "mid" functor and
+//            second transform fuse  forward -> spectral multiply -> inverse  into one
+//            read+write sweep (the third-axis sweep of LaplCube).
+#pragma once
+#include "xform.cuh"
+
+namespace fdmb {
+
+template <int N> struct TileCfg {
+    // columns per CTA in k_cols / rows per CTA in k_rows
+    static constexpr int B = (N <= 64) ? 32 : (N <= 1024 ? 16 : 8);
+    static constexpr int G = Plan<N>::G;
+    static constexpr int THREADS = B * G;
+    static constexpr int SCR = (G + G / 8 + 1) * B;                  // scan scratch (doubles)
+    static constexpr size_t SMEM_COLS = sizeof(double) * (size_t)(N * B + SCR);
+    static constexpr size_t SMEM_ROWS = sizeof(double) * (size_t)((N + 1) * B + SCR);
+};
+
+struct RowsArgs {
+    const double* in;
+    double* out;
+    long long nrows;       // total rows
+    int nvalid;            // meaningful entries per row (N-1 for DST, N for periodic)
+    long long in_pitch;    // doubles between consecutive rows
+    long long out_pitch;
+    double scale;
+    const double* SN;
+    const cd* WM;
+};
+
+template <int N, int KIND>
+__global__ void __launch_bounds__(TileCfg<N>::THREADS) k_rows(RowsArgs a)
+{
+    using C = TileCfg<N>;
+    constexpr int BR = C::B, G = C::G, P = N + 1;
+    constexpr int J0 = (KIND == XF_DST) ? 1 : 0;
+    extern __shared__ double smem[];
+    double* tile = smem;
+    double* scr = smem + P * BR;
+    const int tid = threadIdx.x;
+    const long long row0 = (long long)blockIdx.x * BR;
+    constexpr int NW = C::THREADS / 32 > 0 ? C::THREADS / 32 : 1;
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int r = warp; r < BR; r += NW) {
+        long long row = row0 + r;
+        const double* src = a.in + row * a.in_pitch;
+        bool ok = row < a.nrows;
+        for (int x = lane; x < a.nvalid; x += 32)
+            tile[r * P + x + J0] = ok ? src[x] : 0.0;
+    }
+    __syncthreads();
+    const int b = tid % BR, g = tid / BR;
+    xform_tile<N, G, KIND>(tile + b * P, 1, g, a.scale, a.SN, a.WM, scr + b, BR);
+    for (int r = warp; r < BR; r += NW) {
+        long long row = row0 + r;
+        if (row >= a.nrows) continue;
+        double* dst = a.out + row * a.out_pitch;
+        for (int x = lane; x < a.nvalid; x += 32) dst[x] = tile[r * P + x + J0];
+    }
+}
+
+// mid functors: applied to tile value at (slot j, column index bb, outer index o)
+struct MidNone {
+    static constexpr bool active = false;
+    __device__ __forceinline__ double operator()(double v, int, int, int) const { return v; }
+};
+
+// v / -(lm_j[j] + lm_b[b] + lm_o[o]); optional zeroing of the (0,0,0) mode (lapl_cube.cpp:70-84)
+struct MidCubeDivide {
+    static constexpr bool active = true;
+    const double* lm_j;
+    const double* lm_b;
+    const double* lm_o;
+    int zero_null;
+    __device__ __forceinline__ double operator()(double v, int j, int b, int o) const
+    {
+        if (zero_null && j == 0 && b == 0 && o == 0) return 0.0;
+        return v / -(lm_j[j] + lm_b[b] + lm_o[o]);
+    }
+};
+
+struct ColsArgs {
+    const double* in;
+    double* out;
+    int nvalid;               // entries along the transform axis
+    long long in_sj, out_sj;  // stride (doubles) along the transform axis
+    int nb;                   // extent of the contiguous axis
+    int no;                   // extent of the outer axis
+    long long in_so, out_so;  // stride along the outer axis
+    double scale, scale2;     // forward / second transform scale
+    const double* SN;
+    const cd* WM;
+};
+
+template <int N, int KIND, typename MID, int KIND2>
+__global__ void __launch_bounds__(TileCfg<N>::THREADS) k_cols(ColsArgs a, MID mid)
+{
+    using C = TileCfg<N>;
+    constexpr int B = C::B, G = C::G;
+    constexpr int J0 = (KIND == XF_DST) ? 1 : 0;
+    extern __shared__ double smem[];
+    double* tile = smem;
+    double* scr = smem + N * B;
+    const int tid = threadIdx.x;
+    const int b0 = blockIdx.x * B;
+    const int o = blockIdx.y;
+    const int b = tid % B, g = tid / B;
+    const bool bok = b0 + b < a.nb;
+    {
+        const double* src = a.in + (long long)o * a.in_so + b0 + b;
+        for (int j = g; j < a.nvalid; j += G)
+            tile[(j + J0) * B + b] = bok ? src[j * a.in_sj] : 0.0;
+    }
+    __syncthreads();
+    xform_tile<N, G, KIND>(tile + b, B, g, a.scale, a.SN, a.WM, scr + b, B);
+    if constexpr (MID::active) {
+        for (int j = g; j < a.nvalid; j += G) {
+            double v = tile[(j + J0) * B + b];
+            tile[(j + J0) * B + b] = bok ? mid(v, j + J0, b0 + b + J0, o + J0) : 0.0;
+        }
+        __syncthreads();
+        xform_tile<N, G, KIND2>(tile + b, B, g, a.scale2, a.SN, a.WM, scr + b, B);
+    }
+    if (bok) {
+        double* dst = a.out + (long long)o * a.out_so + b0 + b;
+        for (int j = g; j < a.nvalid; j += G) dst[j * a.out_sj] = tile[(j + J0) * B + b];
+    }
+}
+
+// ---- host-side dispatch over the instantiated transform lengths -----------------
+#define FDMB_FOR_EACH_N(X) X(4) X(8) X(16) X(32) X(64) X(128) X(256) X(512) X(1024) X(2048)
+
+template <int N, int KIND>
+inline cudaError_t launch_rows_t(const RowsArgs& a, cudaStream_t st)
+{
+    using C = TileCfg<N>;
+    auto kern = k_rows<N, KIND>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_ROWS);
+        attr_set = true;
+    }
+    unsigned grid = (unsigned)((a.nrows + C::B - 1) / C::B);
+    kern<<<grid, C::THREADS, C::SMEM_ROWS, st>>>(a);
+    return cudaGetLastError();
+}
+
+template <int N, int KIND, typename MID, int KIND2>
+inline cudaError_t launch_cols_t(const ColsArgs& a, const MID& mid, cudaStream_t st)
+{
+    using C = TileCfg<N>;
+    auto kern = k_cols<N, KIND, MID, KIND2>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_COLS);
+        attr_set = true;
+    }
+    dim3 grid((a.nb + C::B - 1) / C::B, a.no);
+    kern<<<grid, C::THREADS, C::SMEM_COLS, st>>>(a, mid);
+    return cudaGetLastError();
+}
+
+}  // namespace fdmb

@@ -1,0 +1,80 @@
+/*
+ * fdm_b200 -- C ABI of the B200-native fast Poisson / Navier-Stokes projection path.
+ *
+ * This header is the drop-in boundary.  The reference (resetius/fdm) has no FFI
+ * or plugin registry: its boundary is a set of C++ class templates explicitly
+ * instantiated in libfdm.  Each group of entry points below replaces the body
+ * of one of those classes; the header-compatible C++ shims in fdm_b200/cxx/
+ * (namespace fdm, same class names, constructor and method signatures) call
+ * these functions, so existing callers recompile unchanged.
+ *
+ * Conventions
+ *   - plain C, no CUDA or torch types in any signature; `stream` arguments are a
+ *     cudaStream_t passed as void* (NULL = the handle's own stream).
+ *   - every function returns 0 on success or a negative FDMB_ERR_* code;
+ *     fdmb_last_error() returns a thread-local description.  The reference
+ *     aborts via verify() (src/verify.h:10-18) where we return an error; the
+ *     C++ shims turn non-zero codes back into that abort.
+ *   - arrays follow the reference layout: row-major, last index fastest,
+ *     interior points only, contiguous (src/tensor.h:207-219).
+ *   - `*_solve` / `*_step` take HOST pointers exactly like the reference
+ *     methods and copy across PCIe/NVLink-C2C internally; `*_device` variants
+ *     take device pointers and are asynchronous on `stream`.
+ *   - a handle owns one CUDA stream and its scratch; calls on one handle are
+ *     not re-entrant (same as the reference, whose solvers share member scratch).
+ *   - there is no CPU fallback: without a CUDA device every create fails.
+ */
+#ifndef FDM_B200_H
+#define FDM_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FDMB_OK 0
+#define FDMB_ERR_INVALID (-1)  /* bad argument / unsupported size (reference: verify((1<<n)==N), src/fft.cpp:67) */
+#define FDMB_ERR_CUDA (-2)     /* CUDA runtime error */
+#define FDMB_ERR_NOMEM (-3)
+#define FDMB_ERR_COMM (-4)     /* multi-GPU exchange error */
+
+/* ---- library ------------------------------------------------------------------ */
+const char* fdmb_last_error(void);
+int fdmb_version(void);
+int fdmb_device_count(void);
+int fdmb_set_device(int device);
+/* number of kernels this library has launched so far in this process */
+unsigned long long fdmb_launch_count(void);
+
+/* raw device memory helpers for hosts that have no CUDA runtime of their own */
+int fdmb_malloc(void** dptr, unsigned long long bytes);
+int fdmb_free(void* dptr);
+int fdmb_memcpy_h2d(void* dst, const void* src, unsigned long long bytes);
+int fdmb_memcpy_d2h(void* dst, const void* src, unsigned long long bytes);
+int fdmb_device_synchronize(void);
+
+/* ---- 1-D transforms ------------------------------------------------------------
+ * Batched fdm::FFT<double>::{sFFT,pFFT_1,pFFT}  (src/fft.h:82-90, src/fft.cpp:109-212,294-365).
+ * kind: 0 sFFT (DST-I over indices 1..N-1), 1 pFFT_1 (periodic, values->coefficients),
+ *       2 pFFT (periodic, coefficients->values).
+ * in/out: HOST arrays of `batch` rows; a row holds the N-1 (kind 0) or N (kind 1,2)
+ * meaningful entries, contiguous.  out[k] = dx * (...) exactly as the reference.     */
+int fdmb_fft_batch(int kind, int N, long long batch, double dx, const double* in, double* out);
+
+/* ---- LaplCube -------------------------------------------------------------------
+ * Replaces fdm::LaplCube<double,check,F> (src/lapl_cube.h:9-106, src/lapl_cube.cpp:9-172).
+ * create   <-> constructor (dx,dy,dz,lx,ly,lz,nx,ny,nz)   src/lapl_cube.h:58-100
+ * periodic <-> F = tensor_flags<periodic,periodic,periodic> (1) or tensor_flags<> (0),
+ *              the two instantiations of src/lapl_cube.cpp:174-182
+ * solve    <-> void solve(T* ans, T* rhs)                  src/lapl_cube.cpp:9-142
+ * Dirichlet axes need n+1 = 2^k, periodic axes n = 2^k (src/fft.cpp:60-67).          */
+typedef struct fdmb_lapl_cube fdmb_lapl_cube;
+int fdmb_lapl_cube_create(fdmb_lapl_cube** h, double dx, double dy, double dz,
+                          double lx, double ly, double lz, int nx, int ny, int nz, int periodic);
+int fdmb_lapl_cube_solve(fdmb_lapl_cube* h, double* ans, const double* rhs);
+int fdmb_lapl_cube_solve_device(fdmb_lapl_cube* h, double* d_ans, const double* d_rhs, void* stream);
+int fdmb_lapl_cube_destroy(fdmb_lapl_cube* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FDM_B200_H */

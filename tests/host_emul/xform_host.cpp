@@ -1,0 +1,64 @@
+// Host emulation of fdm_b200/csrc/xform.cuh: the device tile transforms are compiled
+// for the CPU with __syncthreads() mapped onto a std::barrier over G host threads
+// (one emulated column at a time).  Lets the CPU test-suite check the transform
+// algebra for every instantiated length without a GPU.  Test infrastructure only.
+#include <barrier>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <thread>
+#include <vector>
+#include <functional>
+
+#define FDMB_HOST_EMUL 1
+#define __device__
+#define __forceinline__ inline
+static thread_local std::barrier<>* tl_barrier = nullptr;
+static inline void __syncthreads() { tl_barrier->arrive_and_wait(); }
+
+#include "../../fdm_b200/csrc/xform.cuh"
+
+using namespace fdmb;
+
+static void make_tables(int N, std::vector<double>& sn, std::vector<cd>& wm)
+{
+    const int M = N / 2;
+    sn.resize(N / 2 + 1); wm.resize(M);
+    const long double pi = 3.141592653589793238462643383279502884L;
+    for (int j = 0; j <= N / 2; j++) sn[j] = (double)sinl(pi * j / N);
+    sn[N / 2] = 1.0;
+    for (int t = 0; t < M; t++) { wm[t].x = (double)cosl(2 * pi * t / M); wm[t].y = (double)(-sinl(2 * pi * t / M)); }
+    if (M >= 4) { wm[M / 4] = {0.0, -1.0}; wm[3 * M / 4] = {0.0, 1.0}; }
+    if (M >= 2) wm[M / 2] = {-1.0, 0.0};
+}
+
+template <int N, int KIND>
+static void run_one(double* data, int sj, double scale)
+{
+    constexpr int G = Plan<N>::G;
+    std::vector<double> sn; std::vector<cd> wm;
+    make_tables(N, sn, wm);
+    std::vector<double> scr((G + G / 8 + 2));
+    std::barrier<> bar(G);
+    std::vector<std::thread> th;
+    for (int g = 0; g < G; g++)
+        th.emplace_back([&, g] {
+            tl_barrier = &bar;
+            xform_tile<N, G, KIND>(data, sj, g, scale, sn.data(), wm.data(), scr.data(), 1);
+        });
+    for (auto& t : th) t.join();
+}
+
+// data: N slots with stride sj (slot 0 unused for kind 0)
+extern "C" int emul_xform(int kind, int N, double* data, int sj, double scale)
+{
+#define X(NN)                                                      \
+    case NN:                                                       \
+        if (kind == 0) run_one<NN, XF_DST>(data, sj, scale);       \
+        else if (kind == 1) run_one<NN, XF_PFWD>(data, sj, scale); \
+        else run_one<NN, XF_PINV>(data, sj, scale);                \
+        return 0;
+    switch (N) { X(4) X(8) X(16) X(32) X(64) X(128) X(256) X(512) X(1024) X(2048) }
+#undef X
+    return -1;
+}
