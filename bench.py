@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the fdm_b200 hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl ours|reference]
+
+A "step" is one pass of the hot path over one batch of synthetic input:
+  cube127  (default) one LaplCube Dirichlet solve, 127^3 fp64   (BASELINE.json configs[1])
+  cube255            one LaplCube Dirichlet solve, 255^3 fp64
+  nscube255          one NSCube lid-driven-cavity step, 255^3   (configs[2])
+  nscube31           one NSCube step, 31^3                      (configs[0])
+N>1: every rank runs its own independent problem (weak scaling, no data-path collective).
+
+Prints ONE JSON line (rank 0).  `value` is device-resident throughput; `e2e` goes through the
+host-pointer C-ABI entry point with pinned host buffers (H2D + solve + D2H inside the timed
+region); `roofline` is for the dominant kernel, timed live with CUDA events; `cpu_baseline` is the
+UNMODIFIED reference (oracle/_ref) on this box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+ALGO_BYTES_PER_SWEEP = 16.0      # one fp64 read + one fp64 write per grid point
+SOLVE_BYTES_PER_PT = 48.0        # 3 sweeps
+NS_BYTES_PER_PT = 168.0
+
+WORKLOADS = {
+    "cube127": dict(kind="cube", n=127, label="LaplCube Dirichlet 127^3 fp64 solve (BASELINE configs[1])"),
+    "cube255": dict(kind="cube", n=255, label="LaplCube Dirichlet 255^3 fp64 solve"),
+    "cube511": dict(kind="cube", n=511, label="LaplCube Dirichlet 511^3 fp64 solve"),
+    "nscube31": dict(kind="ns", n=31, Re=250.0, dt=0.01, label="NSCube 31^3 Re=250 dt=0.01 step (configs[0])"),
+    "nscube255": dict(kind="ns", n=255, Re=1000.0, dt=0.005, label="NSCube 255^3 Re=1000 dt=0.005 step (configs[2])"),
+}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            d = json.load(open(path))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index),
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            p = [x.strip() for x in r.split(",")]
+            if len(p) < 6:
+                continue
+            try:
+                sm.append(float(p[0])); mx.append(float(p[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, p[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cube_geometry(n):
+    # unit-cube convention of ut/ut_lapl_cube.cpp:56-61
+    dx = 1.0 / n
+    return dict(dx=dx, l=1.0 + dx)
+
+
+def run_reference(args, wl):
+    """--impl reference: the reference's own CPU implementation (oracle/_ref) on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import ref, fdm_oracle as O
+    if not ref.available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libfdm_ref.so not built"}))
+        return
+    n = wl["n"]
+    cores = ref.num_threads()
+    if wl["kind"] == "cube":
+        g = cube_geometry(n)
+        S = ref.LaplCube(g["dx"], g["dx"], g["dx"], g["l"], g["l"], g["l"], n, n, n)
+        rhs = O.synthetic_rhs((n, n, n), seed=1234)
+        step = lambda: S.solve(rhs)
+        units = n ** 3 / 1e9
+        metric, unit = "poisson_solve_gpts_per_s", "Gpts/s"
+        sample = f"full {n}^3 solve per step"
+    else:
+        ns = ref.NSCube(nx=n, nz=n, Re=wl["Re"], dt=wl["dt"])
+        step = lambda: ns.step(1)
+        units = 1.0
+        metric, unit = "ns_steps_per_s", "steps/s"
+        sample = f"full {n}^3 step per step"
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = units * args.steps / dt
+    print(json.dumps({
+        "impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl["label"]},
+        "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "reference", "sample": sample},
+        "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def cpu_baseline(wl):
+    """The unmodified reference on the host cores, bounded sample (rank 0, N=1 only)."""
+    try:
+        from oracle import ref, fdm_oracle as O
+        if not ref.available():
+            return {"value": None, "unit": "", "cores": 0, "kind": "reference", "sample": "oracle/_ref not built"}
+        n = wl["n"]
+        cores = ref.num_threads()
+        if wl["kind"] == "cube":
+            nn = min(n, 255)
+            g = cube_geometry(nn)
+            S = ref.LaplCube(g["dx"], g["dx"], g["dx"], g["l"], g["l"], g["l"], nn, nn, nn)
+            rhs = O.synthetic_rhs((nn, nn, nn), seed=1234)
+            S.solve(rhs)
+            reps = 10 if nn <= 127 else 3
+            best = 1e30
+            for _ in range(reps):
+                t0 = time.perf_counter(); S.solve(rhs); best = min(best, time.perf_counter() - t0)
+            return {"value": nn ** 3 / 1e9 / best, "unit": "Gpts/s", "cores": cores, "kind": "reference",
+                    "sample": f"best of {reps} full {nn}^3 solves, {best * 1e3:.1f} ms each"}
+        nn = min(n, 127)
+        ns = ref.NSCube(nx=nn, nz=nn, Re=wl["Re"], dt=wl["dt"])
+        ns.step(1)
+        reps = 20 if nn <= 63 else 5
+        t0 = time.perf_counter(); ns.step(reps); dt = (time.perf_counter() - t0) / reps
+        val = 1.0 / dt
+        note = f"{reps} steps at {nn}^3, {dt * 1e3:.1f} ms each"
+        if nn != n:
+            val *= (nn / n) ** 3
+            note += f"; scaled by ({nn}/{n})^3 to the {n}^3 workload"
+        return {"value": val, "unit": "steps/s", "cores": cores, "kind": "reference", "sample": note}
+    except Exception as e:  # never let the baseline kill the bench line
+        return {"value": None, "unit": "", "cores": 0, "kind": "reference", "sample": f"failed: {e}"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--workload", default="cube127", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import fdm_b200
+    from fdm_b200 import capi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    L = fdm_b200.lib()
+    capi.check(L.fdmb_set_device(local), "set_device")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    # a non-default stream: the C ABI treats a NULL stream as "the handle's own stream"
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    sptr = stream.cuda_stream
+    assert sptr != 0
+    W = max(args.warmup, 3)
+    K = args.steps
+    n = wl["n"]
+    peak, peak_src = measured_peaks()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    if wl["kind"] == "cube":
+        g = cube_geometry(n)
+        S = fdm_b200.LaplCube(g["dx"], g["dx"], g["dx"], g["l"], g["l"], g["l"], n, n, n)
+        pts = n ** 3
+        pair_bytes = 2 * 8 * pts
+        nbuf = max(2, int(np.ceil(2.2 * 126e6 / pair_bytes)))       # rotate > 2x L2 worth of rhs/ans pairs
+        rhs = [torch.rand(pts, dtype=torch.float64, device=dev) - 0.5 for _ in range(nbuf)]
+        ans = [torch.empty(pts, dtype=torch.float64, device=dev) for _ in range(nbuf)]
+        l2_policy = f"rotating {nbuf} rhs/ans pairs ({nbuf * pair_bytes / 1e6:.0f} MB > 126 MB L2)"
+
+        def step(i):
+            b = i % nbuf
+            S.solve_device(ans[b].data_ptr(), rhs[b].data_ptr(), sptr)
+        units_per_step = pts / 1e9
+        metric, unit = "poisson_solve_gpts_per_s", "Gpts/s"
+        algo_bytes_step = SOLVE_BYTES_PER_PT * pts
+        # e2e: host-pointer entry point, pinned buffers
+        h_rhs = torch.rand(pts, dtype=torch.float64).pin_memory()
+        h_ans = torch.empty(pts, dtype=torch.float64).pin_memory()
+        dp = C.POINTER(C.c_double)
+
+        def e2e_step():
+            capi.check(L.fdmb_lapl_cube_solve(S._h, C.cast(h_ans.data_ptr(), dp), C.cast(h_rhs.data_ptr(), dp)), "solve")
+        h2d = d2h = 8 * pts
+    else:
+        if not hasattr(fdm_b200, "NSCube"):
+            raise SystemExit("NSCube workload not built")
+        ns = fdm_b200.NSCube(nx=n, nz=n, Re=wl["Re"], dt=wl["dt"])
+        pts = n ** 3
+        l2_policy = f"state of 13 arrays = {13 * 8 * pts / 1e6:.0f} MB" + (" > 126 MB L2" if 13 * 8 * pts > 126e6 else " (fits L2; launch-bound size)")
+
+        def step(i):
+            ns.step_device(1, sptr)
+        units_per_step = 1.0
+        metric, unit = "ns_steps_per_s", "steps/s"
+        algo_bytes_step = NS_BYTES_PER_PT * pts
+        ns2 = fdm_b200.NSCube(nx=n, nz=n, Re=wl["Re"], dt=wl["dt"])
+
+        def e2e_step():
+            ns2.step_host_roundtrip()
+        h2d = d2h = ns2.state_bytes()
+
+    # ---- device-resident timing --------------------------------------------------
+    for i in range(W):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = L.fdmb_launch_count()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for i in range(K):
+        step(W + i)
+    e1.record(stream)
+    barrier()
+    launches = L.fdmb_launch_count() - launches0
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = units_per_step * K * world / (ms * 1e-3)
+
+    # ---- per-kernel live timing for the roofline (separate pass, same steps) -----
+    L.fdmb_profile_begin.restype = C.c_int
+    L.fdmb_profile_end.argtypes = [C.c_char_p, C.c_int]
+    capi.check(L.fdmb_profile_begin(), "profile_begin")
+    for i in range(K):
+        step(W + i)
+    buf = C.create_string_buffer(1 << 16)
+    capi.check(L.fdmb_profile_end(buf, len(buf)), "profile_end")
+    kern = []
+    for line in buf.value.decode().splitlines():
+        tag, cnt, tot = line.split()
+        kern.append((tag, int(cnt), float(tot)))
+    tot_kernel_ms = sum(k[2] for k in kern) or 1.0
+    top = max(kern, key=lambda k: k[2])
+    per_launch_ms = top[2] / top[1]
+    # algorithmic bytes of one launch of the dominant kernel: one read+write sweep over the grid
+    algo_launch = ALGO_BYTES_PER_SWEEP * pts * kernel_sweeps(top[0])
+    achieved = algo_launch / (per_launch_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": top[0], "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": load_traffic(top[0], args.workload), "peak_source": peak_src,
+                "kernel_share_of_step": top[2] / tot_kernel_ms,
+                "step_achieved_gbs": algo_bytes_step / (ms / K * 1e-3) / 1e9,
+                "step_frac": algo_bytes_step / (ms / K * 1e-3) / 1e9 / peak,
+                "kernels": {k[0]: {"launches_per_step": k[1] / K, "ms_per_launch": k[2] / k[1]} for k in kern}}
+
+    # ---- e2e through the host-pointer C ABI -----------------------------------------
+    Ke = max(3, min(K, 50))
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(Ke):
+        e2e_step()
+    torch.cuda.synchronize()
+    te = time.perf_counter() - t0
+    t = torch.tensor([te], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    te = float(t.item())
+    e2e = {"value": units_per_step * Ke * world / te, "unit": unit, "h2d_bytes_per_step": h2d,
+           "d2h_bytes_per_step": d2h, "steps": Ke, "ms_per_step": 1e3 * te / Ke}
+
+    if rank == 0:
+        out = {
+            "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl["label"], "l2_policy": l2_policy,
+                       "parallelism": "independent replicas per rank" if world > 1 else "single GPU"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(wl)
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def kernel_sweeps(tag):
+    """How many read+write sweeps over the grid one launch of this kernel stands for."""
+    return {"ns_fgh": 3.0, "ns_rhs": 2.0, "ns_fgh_rhs": 3.5, "ns_update": 4.0}.get(tag, 1.0)
+
+
+def load_traffic(tag, workload):
+    """dram bytes per launch from the committed ncu --set full capture, or None."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(path)).get(workload, {}).get(tag)
+    except Exception:
+        return None
+
+
+if __name__ == "__main__":
+    main()

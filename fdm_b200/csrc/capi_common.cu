@@ -24,6 +24,26 @@ void set_error(const char* fmt, ...)
 }
 const char* get_error() { return g_error.c_str(); }
 
+struct ProfRec { const char* tag; cudaEvent_t e0, e1; };
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+
+LaunchScope::LaunchScope(const char* tag_, cudaStream_t st_) : tag(tag_), st(st_), slot(-1)
+{
+    g_launch_count++;
+    if (g_prof_on) {
+        ProfRec r{tag, nullptr, nullptr};
+        cudaEventCreate(&r.e0); cudaEventCreate(&r.e1);
+        cudaEventRecord(r.e0, st);
+        slot = (int)g_prof.size();
+        g_prof.push_back(r);
+    }
+}
+LaunchScope::~LaunchScope()
+{
+    if (slot >= 0) cudaEventRecord(g_prof[slot].e1, st);
+}
+
 static std::mutex g_tab_mutex;
 static std::map<std::pair<int, int>, Tables> g_tables;
 
@@ -110,6 +130,41 @@ int fdmb_device_synchronize(void)
     return FDMB_OK;
 }
 
+int fdmb_profile_begin(void)
+{
+    for (auto& r : g_prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    g_prof.clear();
+    g_prof_on = true;
+    return FDMB_OK;
+}
+
+int fdmb_profile_end(char* buf, int buflen)
+{
+    g_prof_on = false;
+    FDMB_CUDA(cudaDeviceSynchronize());
+    std::map<std::string, std::pair<int, double>> agg;
+    std::vector<std::string> order;
+    for (auto& r : g_prof) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, r.e0, r.e1);
+        if (!agg.count(r.tag)) order.push_back(r.tag);
+        agg[r.tag].first++;
+        agg[r.tag].second += ms;
+        cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);
+    }
+    g_prof.clear();
+    std::string out;
+    for (auto& t : order) {
+        char line[256];
+        snprintf(line, sizeof(line), "%s %d %.6f\n", t.c_str(), agg[t].first, agg[t].second);
+        out += line;
+    }
+    if (buf && buflen > 0) {
+        snprintf(buf, buflen, "%s", out.c_str());
+    }
+    return FDMB_OK;
+}
+
 int fdmb_fft_batch(int kind, int N, long long batch, double dx, const double* in, double* out)
 {
     if (kind < 0 || kind > 2 || !supported_N(N) || batch < 0 || !in || !out) {
@@ -129,7 +184,7 @@ int fdmb_fft_batch(int kind, int N, long long batch, double dx, const double* in
     RowsArgs r{};
     r.in = d_in; r.out = d_out; r.nrows = batch; r.nvalid = nvalid;
     r.in_pitch = r.out_pitch = nvalid; r.scale = dx; r.SN = t.SN; r.WM = t.WM;
-    cudaError_t e = launch_rows(N, kind, r, 0);
+    cudaError_t e = launch_rows(N, kind, r, 0, "fft_batch");
     if (e == cudaSuccess) e = cudaMemcpy(out, d_out, bytes, cudaMemcpyDeviceToHost);
     cudaFree(d_in); cudaFree(d_out);
     if (e != cudaSuccess) { set_error("fdmb_fft_batch: %s", cudaGetErrorString(e)); return FDMB_ERR_CUDA; }

@@ -49,4 +49,14 @@ inline bool supported_N(int N) { return is_pow2(N) && N >= 4 && N <= 2048; }
 // counts kernel launches issued by this library (bench.py reports it as gpu_launches)
 extern unsigned long long g_launch_count;
 
+// Optional per-launch CUDA-event timing (fdmb_profile_begin/end).  Every launch site
+// wraps its kernel in a LaunchScope; outside profiling it only bumps the counter.
+struct LaunchScope {
+    const char* tag;
+    cudaStream_t st;
+    int slot;
+    LaunchScope(const char* tag, cudaStream_t st);
+    ~LaunchScope();
+};
+
 }  // namespace fdmb

@@ -18,9 +18,9 @@ namespace fdmb {
 template <int N, int KIND>
 static cudaError_t rows_n(const RowsArgs& a, cudaStream_t st) { return launch_rows_t<N, KIND>(a, st); }
 
-cudaError_t launch_rows(int N, int kind, const RowsArgs& a, cudaStream_t st)
+cudaError_t launch_rows(int N, int kind, const RowsArgs& a, cudaStream_t st, const char* tag)
 {
-    g_launch_count++;
+    LaunchScope scope(tag, st);
 #define X(NN)                                                                  \
     case NN:                                                                   \
         if (kind == XF_DST) return launch_rows_t<NN, XF_DST>(a, st);           \
@@ -31,9 +31,9 @@ cudaError_t launch_rows(int N, int kind, const RowsArgs& a, cudaStream_t st)
     return cudaErrorInvalidValue;
 }
 
-cudaError_t launch_cols(int N, int kind, const ColsArgs& a, cudaStream_t st)
+cudaError_t launch_cols(int N, int kind, const ColsArgs& a, cudaStream_t st, const char* tag)
 {
-    g_launch_count++;
+    LaunchScope scope(tag, st);
     MidNone mid;
 #define X(NN)                                                                            \
     case NN:                                                                             \
@@ -46,9 +46,9 @@ cudaError_t launch_cols(int N, int kind, const ColsArgs& a, cudaStream_t st)
 }
 
 cudaError_t launch_cols_cube_divide(int N, bool periodic, const ColsArgs& a, const MidCubeDivide& mid,
-                                    cudaStream_t st)
+                                    cudaStream_t st, const char* tag)
 {
-    g_launch_count++;
+    LaunchScope scope(tag, st);
 #define X(NN)                                                                                   \
     case NN:                                                                                    \
         if (periodic) return launch_cols_t<NN, XF_PFWD, MidCubeDivide, XF_PINV>(a, mid, st);    \
@@ -123,24 +123,24 @@ int fdmb_lapl_cube::solve_device(double* d_out, const double* d_in, cudaStream_t
     RowsArgs r{};
     r.in = d_in; r.out = d_work; r.nrows = (long long)nz * ny; r.nvalid = nx;
     r.in_pitch = nx; r.out_pitch = px; r.scale = dx * slx; r.SN = tx.SN; r.WM = tx.WM;
-    FDMB_CUDA(launch_rows(Nx, kf, r, st));
+    FDMB_CUDA(launch_rows(Nx, kf, r, st, "cube_x_fwd"));
     // y forward
     ColsArgs c{};
     c.in = d_work; c.out = d_work; c.nvalid = ny; c.in_sj = c.out_sj = px; c.nb = nx; c.no = nz;
     c.in_so = c.out_so = plane; c.scale = dy * sly; c.SN = ty.SN; c.WM = ty.WM;
-    FDMB_CUDA(launch_cols(Ny, kf, c, st));
+    FDMB_CUDA(launch_cols(Ny, kf, c, st, "cube_y_fwd"));
     // z forward, divide by -(lm_z+lm_y+lm_x), z inverse
     ColsArgs z{};
     z.in = d_work; z.out = d_work; z.nvalid = nz; z.in_sj = z.out_sj = plane; z.nb = nx; z.no = ny;
     z.in_so = z.out_so = px; z.scale = dz * slz; z.scale2 = slz; z.SN = tz.SN; z.WM = tz.WM;
     MidCubeDivide mid{d_lmz, d_lmx, d_lmy, periodic ? 1 : 0};
-    FDMB_CUDA(launch_cols_cube_divide(Nz, periodic != 0, z, mid, st));
+    FDMB_CUDA(launch_cols_cube_divide(Nz, periodic != 0, z, mid, st, "cube_z_fwd_div_inv"));
     // y inverse
     c.scale = sly;
-    FDMB_CUDA(launch_cols(Ny, ki, c, st));
+    FDMB_CUDA(launch_cols(Ny, ki, c, st, "cube_y_inv"));
     // x inverse: pitched work -> ans rows
     r.in = d_work; r.out = d_out; r.in_pitch = px; r.out_pitch = nx; r.scale = slx;
-    FDMB_CUDA(launch_rows(Nx, ki, r, st));
+    FDMB_CUDA(launch_rows(Nx, ki, r, st, "cube_x_inv"));
     return FDMB_OK;
 }
 

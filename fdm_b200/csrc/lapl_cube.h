@@ -4,10 +4,10 @@
 #include "xform_kernels.cuh"
 
 namespace fdmb {
-cudaError_t launch_rows(int N, int kind, const RowsArgs& a, cudaStream_t st);
-cudaError_t launch_cols(int N, int kind, const ColsArgs& a, cudaStream_t st);
+cudaError_t launch_rows(int N, int kind, const RowsArgs& a, cudaStream_t st, const char* tag);
+cudaError_t launch_cols(int N, int kind, const ColsArgs& a, cudaStream_t st, const char* tag);
 cudaError_t launch_cols_cube_divide(int N, bool periodic, const ColsArgs& a, const MidCubeDivide& mid,
-                                    cudaStream_t st);
+                                    cudaStream_t st, const char* tag);
 }  // namespace fdmb
 
 struct fdmb_lapl_cube {

@@ -45,6 +45,12 @@ int fdmb_set_device(int device);
 /* number of kernels this library has launched so far in this process */
 unsigned long long fdmb_launch_count(void);
 
+/* Per-launch CUDA-event timing of this library's kernels (used by bench.py for the roofline).
+ * begin() starts recording; end() synchronises and writes one line per kernel tag:
+ * "<tag> <launches> <total_ms>\n".                                                   */
+int fdmb_profile_begin(void);
+int fdmb_profile_end(char* buf, int buflen);
+
 /* raw device memory helpers for hosts that have no CUDA runtime of their own */
 int fdmb_malloc(void** dptr, unsigned long long bytes);
 int fdmb_free(void* dptr);
@@ -73,6 +79,34 @@ int fdmb_lapl_cube_create(fdmb_lapl_cube** h, double dx, double dy, double dz,
 int fdmb_lapl_cube_solve(fdmb_lapl_cube* h, double* ans, const double* rhs);
 int fdmb_lapl_cube_solve_device(fdmb_lapl_cube* h, double* d_ans, const double* d_rhs, void* stream);
 int fdmb_lapl_cube_destroy(fdmb_lapl_cube* h);
+
+/* ---- NSCube ---------------------------------------------------------------------
+ * Replaces fdm::NSCube<double,check> (src/ns_cube.h:13-92, src/ns_cube.cpp:27-277).
+ * params   <-> the [ns] config keys read by the constructor (src/ns_cube.h:47-61);
+ *              ny is taken from nx exactly like the reference (src/ns_cube.h:58).
+ * step     <-> void step()  (src/ns_cube.cpp:27-62), nsteps times, state stays on the device
+ * fields   <-> the public tensors u,v,w,p,x,F,G,H,RHS (src/ns_cube.h:31-33) with the
+ *              reference's extents, ghosts included (src/ns_cube.h:66-75); get/set copy
+ *              exactly what the reference exposes as ns.u.vec etc. (test/test_ns_cube.cpp:39). */
+typedef struct fdmb_ns_cube fdmb_ns_cube;
+typedef struct fdmb_ns_cube_params {
+    double x1, y1, z1, x2, y2, z2;
+    double u0, Re, dt;
+    int nx, nz;
+    int verbose;
+} fdmb_ns_cube_params;
+enum { FDMB_FIELD_U = 0, FDMB_FIELD_V, FDMB_FIELD_W, FDMB_FIELD_P, FDMB_FIELD_X,
+       FDMB_FIELD_F, FDMB_FIELD_G, FDMB_FIELD_H, FDMB_FIELD_RHS };
+int fdmb_ns_cube_default_params(fdmb_ns_cube_params* p);
+int fdmb_ns_cube_create(fdmb_ns_cube** h, const fdmb_ns_cube_params* p);
+int fdmb_ns_cube_step(fdmb_ns_cube* h, int nsteps);
+int fdmb_ns_cube_step_async(fdmb_ns_cube* h, int nsteps, void* stream);
+int fdmb_ns_cube_field_size(fdmb_ns_cube* h, int field, long long* count);
+int fdmb_ns_cube_get_field(fdmb_ns_cube* h, int field, double* host);
+int fdmb_ns_cube_set_field(fdmb_ns_cube* h, int field, const double* host);
+int fdmb_ns_cube_field_device_ptr(fdmb_ns_cube* h, int field, void** dptr);
+long long fdmb_ns_cube_time_index(fdmb_ns_cube* h);
+int fdmb_ns_cube_destroy(fdmb_ns_cube* h);
 
 #ifdef __cplusplus
 }
