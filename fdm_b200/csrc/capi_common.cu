@@ -1,12 +1,14 @@
 // Library-wide pieces of the C ABI: error string, device tables, raw memory helpers,
 // batched 1-D transforms (fdm::FFT<double>::{sFFT,pFFT_1,pFFT}).
 #include <cmath>
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <vector>
 
 #include "common.h"
 #include "lapl_cube.h"
+#include "pipe.cuh"
 
 namespace fdmb {
 
@@ -77,6 +79,63 @@ int get_tables(int N, Tables* out)
     Tables t{d_sn, d_wm};
     g_tables[{dev, N}] = t;
     *out = t;
+    return FDMB_OK;
+}
+
+int device_sm_count()
+{
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (!cached[dev]) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1) n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
+bool pipe_enabled()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("FDMB_PIPE");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v != 0;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int make_tensor_map_3d(CUtensorMap* tm, const void* base, unsigned long long e0, unsigned long long e1,
+                       unsigned long long e2, unsigned long long s1, unsigned long long s2, unsigned b0, unsigned b1,
+                       unsigned b2)
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        FDMB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+        if (!p || q != cudaDriverEntryPointSuccess) {
+            set_error("cuTensorMapEncodeTiled is not available from this driver");
+            return FDMB_ERR_CUDA;
+        }
+        fn = (EncodeTiledFn)p;
+    }
+    cuuint64_t dims[3] = {e0, e1, e2};
+    cuuint64_t strides[2] = {s1, s2};
+    cuuint32_t box[3] = {b0, b1, b2};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with code %d (dims %llu,%llu,%llu strides %llu,%llu box %u,%u,%u)", (int)r,
+                  e0, e1, e2, s1, s2, b0, b1, b2);
+        return FDMB_ERR_CUDA;
+    }
     return FDMB_OK;
 }
 

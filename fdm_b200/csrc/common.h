@@ -46,6 +46,9 @@ inline bool is_pow2(int n) { return n > 0 && (n & (n - 1)) == 0; }
 // transform lengths for which kernels are instantiated
 inline bool supported_N(int N) { return is_pow2(N) && N >= 4 && N <= 2048; }
 
+bool pipe_enabled();     // FDMB_PIPE=0 selects the synchronous sweep kernels (A/B measurements)
+int device_sm_count();
+
 // counts kernel launches issued by this library (bench.py reports it as gpu_launches)
 extern unsigned long long g_launch_count;
 

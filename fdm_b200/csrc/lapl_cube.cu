@@ -6,6 +6,7 @@
 // The work array is pitched to a multiple of 16 doubles in x so that every strided
 // tile segment is 128-byte aligned; the caller's arrays keep the reference layout.
 #include <cmath>
+#include <cstdint>
 #include <vector>
 #include <new>
 
@@ -58,6 +59,48 @@ cudaError_t launch_cols_cube_divide(int N, bool periodic, const ColsArgs& a, con
     return cudaErrorInvalidValue;
 }
 
+#define FDMB_FOR_EACH_PIPE_N(X) X(32) X(64) X(128) X(256) X(512) X(1024) X(2048)
+
+cudaError_t launch_rows_pipe(int N, int kind, const RowsPipeArgs& a, cudaStream_t st, const char* tag)
+{
+    LaunchScope scope(tag, st);
+#define X(NN)                                                                       \
+    case NN:                                                                        \
+        if (kind == XF_DST) return launch_rows_pipe_t<NN, XF_DST>(a, st);           \
+        if (kind == XF_PFWD) return launch_rows_pipe_t<NN, XF_PFWD>(a, st);         \
+        return launch_rows_pipe_t<NN, XF_PINV>(a, st);
+    switch (N) { FDMB_FOR_EACH_PIPE_N(X) }
+#undef X
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_cols_pipe(int N, int kind, const CUtensorMap& tm, const ColsPipeArgs& a, cudaStream_t st, const char* tag)
+{
+    LaunchScope scope(tag, st);
+    MidNone mid;
+#define X(NN)                                                                                      \
+    case NN:                                                                                       \
+        if (kind == XF_DST) return launch_cols_pipe_t<NN, XF_DST, MidNone, XF_DST>(tm, a, mid, st);    \
+        if (kind == XF_PFWD) return launch_cols_pipe_t<NN, XF_PFWD, MidNone, XF_DST>(tm, a, mid, st);  \
+        return launch_cols_pipe_t<NN, XF_PINV, MidNone, XF_DST>(tm, a, mid, st);
+    switch (N) { FDMB_FOR_EACH_PIPE_N(X) }
+#undef X
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_cols_pipe_cube_divide(int N, bool periodic, const CUtensorMap& tm, const ColsPipeArgs& a,
+                                         const MidCubeDivide& mid, cudaStream_t st, const char* tag)
+{
+    LaunchScope scope(tag, st);
+#define X(NN)                                                                                          \
+    case NN:                                                                                           \
+        if (periodic) return launch_cols_pipe_t<NN, XF_PFWD, MidCubeDivide, XF_PINV>(tm, a, mid, st);  \
+        return launch_cols_pipe_t<NN, XF_DST, MidCubeDivide, XF_DST>(tm, a, mid, st);
+    switch (N) { FDMB_FOR_EACH_PIPE_N(X) }
+#undef X
+    return cudaErrorInvalidValue;
+}
+
 }  // namespace fdmb
 
 using namespace fdmb;
@@ -104,6 +147,20 @@ int fdmb_lapl_cube::init()
     FDMB_CUDA(cudaMemcpy(d_lmy, lm_y.data(), sizeof(double) * (ny + 1), cudaMemcpyHostToDevice));
     FDMB_CUDA(cudaMemcpy(d_lmz, lm_z.data(), sizeof(double) * (nz + 1), cudaMemcpyHostToDevice));
     FDMB_CUDA(cudaMalloc(&d_work, sizeof(double) * (size_t)nz * ny * px));
+    if (pipe_enabled()) {
+        // tensor maps over the pitched work array: dims (x, y, z), tiles [N][B] along y or z
+        const unsigned long long s1 = 8ull * px, s2 = 8ull * (unsigned long long)ny * px;
+        if (pipe_supported_N(Ny)) {
+            boxrows_y = ny < 256 ? ny : 256; nchunk_y = (ny + boxrows_y - 1) / boxrows_y;
+            if ((rc = make_tensor_map_3d(&tm_y, d_work, nx, ny, nz, s1, s2, pipe_B(Ny), boxrows_y, 1))) return rc;
+            pipe_y = true;
+        }
+        if (pipe_supported_N(Nz)) {
+            boxrows_z = nz < 256 ? nz : 256; nchunk_z = (nz + boxrows_z - 1) / boxrows_z;
+            if ((rc = make_tensor_map_3d(&tm_z, d_work, nx, ny, nz, s1, s2, pipe_B(Nz), 1, boxrows_z))) return rc;
+            pipe_z = true;
+        }
+    }
     return FDMB_OK;
 }
 
@@ -123,24 +180,52 @@ int fdmb_lapl_cube::solve_device(double* d_out, const double* d_in, cudaStream_t
     RowsArgs r{};
     r.in = d_in; r.out = d_work; r.nrows = (long long)nz * ny; r.nvalid = nx;
     r.in_pitch = nx; r.out_pitch = px; r.scale = dx * slx; r.SN = tx.SN; r.WM = tx.WM;
-    FDMB_CUDA(launch_rows(Nx, kf, r, st, "cube_x_fwd"));
+    const bool pipe_x = pipe_enabled() && pipe_supported_N(Nx);
+    auto rows = [&](const RowsArgs& q, int kind, const char* tag, int reverse) -> cudaError_t {
+        if (pipe_x && (reinterpret_cast<uintptr_t>(q.in) & 15) == 0) {
+            RowsPipeArgs p{};
+            p.in = q.in; p.out = q.out; p.nrows = q.nrows; p.nvalid = q.nvalid; p.in_pitch = (int)q.in_pitch;
+            p.out_pitch = (int)q.out_pitch; p.reverse = reverse; p.scale = q.scale; p.SN = q.SN; p.WM = q.WM;
+            return launch_rows_pipe(Nx, kind, p, st, tag);
+        }
+        return launch_rows(Nx, kind, q, st, tag);
+    };
+    auto cols_y = [&](const ColsArgs& q, int kind, const char* tag, int reverse) -> cudaError_t {
+        if (pipe_y) {
+            ColsPipeArgs p{};
+            p.out = q.out; p.out_sj = q.out_sj; p.out_so = q.out_so; p.nvalid = q.nvalid; p.nb = q.nb; p.no = q.no;
+            p.taxis = 1; p.boxrows = boxrows_y; p.nchunk = nchunk_y; p.reverse = reverse; p.scale = q.scale;
+            p.scale2 = q.scale2; p.SN = q.SN; p.WM = q.WM;
+            return launch_cols_pipe(Ny, kind, tm_y, p, st, tag);
+        }
+        return launch_cols(Ny, kind, q, st, tag);
+    };
+    FDMB_CUDA(rows(r, kf, "cube_x_fwd", 0));
     // y forward
     ColsArgs c{};
     c.in = d_work; c.out = d_work; c.nvalid = ny; c.in_sj = c.out_sj = px; c.nb = nx; c.no = nz;
     c.in_so = c.out_so = plane; c.scale = dy * sly; c.SN = ty.SN; c.WM = ty.WM;
-    FDMB_CUDA(launch_cols(Ny, kf, c, st, "cube_y_fwd"));
+    FDMB_CUDA(cols_y(c, kf, "cube_y_fwd", 1));
     // z forward, divide by -(lm_z+lm_y+lm_x), z inverse
     ColsArgs z{};
     z.in = d_work; z.out = d_work; z.nvalid = nz; z.in_sj = z.out_sj = plane; z.nb = nx; z.no = ny;
     z.in_so = z.out_so = px; z.scale = dz * slz; z.scale2 = slz; z.SN = tz.SN; z.WM = tz.WM;
     MidCubeDivide mid{d_lmz, d_lmx, d_lmy, periodic ? 1 : 0};
-    FDMB_CUDA(launch_cols_cube_divide(Nz, periodic != 0, z, mid, st, "cube_z_fwd_div_inv"));
+    if (pipe_z) {
+        ColsPipeArgs p{};
+        p.out = z.out; p.out_sj = z.out_sj; p.out_so = z.out_so; p.nvalid = z.nvalid; p.nb = z.nb; p.no = z.no;
+        p.taxis = 2; p.boxrows = boxrows_z; p.nchunk = nchunk_z; p.reverse = 0; p.scale = z.scale; p.scale2 = z.scale2;
+        p.SN = z.SN; p.WM = z.WM;
+        FDMB_CUDA(launch_cols_pipe_cube_divide(Nz, periodic != 0, tm_z, p, mid, st, "cube_z_fwd_div_inv"));
+    } else {
+        FDMB_CUDA(launch_cols_cube_divide(Nz, periodic != 0, z, mid, st, "cube_z_fwd_div_inv"));
+    }
     // y inverse
     c.scale = sly;
-    FDMB_CUDA(launch_cols(Ny, ki, c, st, "cube_y_inv"));
+    FDMB_CUDA(cols_y(c, ki, "cube_y_inv", 0));
     // x inverse: pitched work -> ans rows
     r.in = d_work; r.out = d_out; r.in_pitch = px; r.out_pitch = nx; r.scale = slx;
-    FDMB_CUDA(launch_rows(Nx, ki, r, st, "cube_x_inv"));
+    FDMB_CUDA(rows(r, ki, "cube_x_inv", 1));
     return FDMB_OK;
 }
 

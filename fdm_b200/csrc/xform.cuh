@@ -200,23 +200,26 @@ __device__ __forceinline__ void untangle(const double* col, int sj, int k, const
 // is clobbered).  All threads of the CTA must call; ends with __syncthreads().
 // scr: scratch of at least (G + G/8 + 1) * scr_s doubles per CTA, column b at scr[b].
 // ---------------------------------------------------------------------------------
-template <int N, int G>
+// PREFOLD: the caller already applied the fold below while staging the tile (k_rows_pipe).
+template <int N, int G, bool PREFOLD = false>
 __device__ __forceinline__ void dst_tile(double* col, int sj, int g, double scale,
                                          const double* __restrict__ SN, const cd* __restrict__ WM,
                                          double* scr, int scr_s)
 {
     constexpr int M = N / 2;
     static_assert(G <= M / 2 || M == 2, "too many threads per column");
-    // fold: y[j] = sin(pi j/N)(x[j]+x[N-j]) + (x[j]-x[N-j])/2
+    if constexpr (!PREFOLD) {
+        // fold: y[j] = sin(pi j/N)(x[j]+x[N-j]) + (x[j]-x[N-j])/2
 #pragma unroll
-    for (int j = g + 1; j < M; j += G) {
-        double a = col[j * sj], c = col[(N - j) * sj];
-        double y1 = SN[j] * (a + c), y2 = 0.5 * (a - c);
-        col[j * sj] = y1 + y2;
-        col[(N - j) * sj] = y1 - y2;
+        for (int j = g + 1; j < M; j += G) {
+            double a = col[j * sj], c = col[(N - j) * sj];
+            double y1 = SN[j] * (a + c), y2 = 0.5 * (a - c);
+            col[j * sj] = y1 + y2;
+            col[(N - j) * sj] = y1 - y2;
+        }
+        if (g == 0) { col[0] = 0.0; col[M * sj] = 2.0 * col[M * sj]; }
+        __syncthreads();
     }
-    if (g == 0) { col[0] = 0.0; col[M * sj] = 2.0 * col[M * sj]; }
-    __syncthreads();
 
     fft_inplace<N, G>(col, sj, g, WM);
 
@@ -411,12 +414,12 @@ __device__ __forceinline__ void pinv_tile(double* col, int sj, int g, double sca
     __syncthreads();
 }
 
-template <int N, int G, int KIND>
+template <int N, int G, int KIND, bool PREFOLD = false>
 __device__ __forceinline__ void xform_tile(double* col, int sj, int g, double scale,
                                            const double* __restrict__ SN, const cd* __restrict__ WM,
                                            double* scr, int scr_s)
 {
-    if constexpr (KIND == XF_DST) dst_tile<N, G>(col, sj, g, scale, SN, WM, scr, scr_s);
+    if constexpr (KIND == XF_DST) dst_tile<N, G, PREFOLD>(col, sj, g, scale, SN, WM, scr, scr_s);
     else if constexpr (KIND == XF_PFWD) pfwd_tile<N, G>(col, sj, g, scale, SN, WM);
     else pinv_tile<N, G>(col, sj, g, scale, SN, WM);
 }

@@ -1,0 +1,294 @@
+// Persistent, asynchronously fed versions of the sweep kernels (sm_100a).
+//
+//   k_cols_pipe : strided-axis sweep.  Each CTA walks a static stride of [N][B] tiles.  One elected
+//                 thread arms an mbarrier and issues tensor-map tile copies (UTMALDG) into a ring of
+//                 NSTAGE shared-memory buffers; the CTA transforms a buffer in place, writes it back
+//                 with coalesced stores, and re-arms the buffer for the tile NSTAGE strides ahead.
+//                 Loads of tile i+1.. are in flight while tile i is transformed.
+//   k_rows_pipe : contiguous-axis sweep.  BR consecutive rows are ONE contiguous global chunk (also
+//                 for the caller's unpitched arrays), fetched with a 1-D bulk copy (UBLKCP) into a
+//                 dense staging ring; the first pass of the transform (the DST fold) reads the
+//                 staging buffer with lanes along the row and writes the odd-pitch compute tile, so
+//                 the repack is free.
+// Twiddle tables live in shared memory (warp-uniform broadcast reads).
+#pragma once
+#include "pipe.cuh"
+#include "xform_kernels.cuh"
+
+namespace fdmb {
+
+template <int N> struct PipeCfg {
+    static constexpr int B = (N <= 512) ? 16 : 8;      // sequences per tile
+    static constexpr int G = Plan<N>::G;
+    static constexpr int THREADS = B * G;
+    static constexpr int SCR = (G + G / 8 + 1) * B;
+    static constexpr int TAB = (N / 2 + 1) + 2 * (N / 2);               // SN + WM (doubles)
+    static constexpr int COLS_BUF = ((N + 1) * B + 15) / 16 * 16;      // doubles per stage buffer (128-B multiple)
+    static constexpr int COLS_STAGES = (N <= 256) ? 3 : (N <= 1024 ? 2 : 1);
+    static constexpr size_t cols_smem(int nstage)
+    {
+        return 8 * (size_t)(16 + nstage * COLS_BUF + SCR + TAB + 2) + 8 * 8 + 128;
+    }
+    static constexpr int BR = B;
+    static constexpr int ROWS_STAGES = (N <= 256) ? 2 : 1;
+    static constexpr size_t rows_smem(int nstage)
+    {
+        return 8 * (size_t)(nstage * BR * N + BR * (N + 1) + SCR + TAB + 2) + 8 * 8 + 128;
+    }
+};
+
+template <int N>
+__device__ __forceinline__ void load_tables(double* SNs, cd* WMs, const double* __restrict__ SN, const cd* __restrict__ WM)
+{
+    for (int i = threadIdx.x; i <= N / 2; i += blockDim.x) SNs[i] = SN[i];
+    for (int i = threadIdx.x; i < N / 2; i += blockDim.x) WMs[i] = WM[i];
+}
+
+struct ColsPipeArgs {
+    double* out;
+    long long out_sj, out_so;   // output strides (doubles) along the transform / outer axis
+    int nvalid;                 // entries along the transform axis
+    int nb, no;                 // extents of the contiguous / outer axis
+    int taxis;                  // tensor-map dimension of the transform axis (1 or 2)
+    int boxrows, nchunk;        // rows per tensor-map box, boxes per tile
+    int reverse;                // walk the tiles back to front (L2 reuse against the previous sweep)
+    double scale, scale2;
+    const double* SN;
+    const cd* WM;
+};
+
+template <int N, int KIND, typename MID, int KIND2, int NSTAGE>
+__global__ void __launch_bounds__(PipeCfg<N>::THREADS)
+k_cols_pipe(const __grid_constant__ CUtensorMap tm, ColsPipeArgs a, MID mid)
+{
+    using C = PipeCfg<N>;
+    constexpr int B = C::B, G = C::G;
+    constexpr int J0 = (KIND == XF_DST) ? 1 : 0;
+    constexpr int BUF = C::COLS_BUF;
+    constexpr int PRE = (J0 * B) % 16 ? 16 - (J0 * B) % 16 : 0;   // keeps the first loaded slot 128-B aligned
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    double* sm = reinterpret_cast<double*>(smem_raw);
+    double* bufs = sm + PRE;
+    double* scr = bufs + NSTAGE * BUF;
+    double* SNs = scr + C::SCR;
+    cd* WMs = reinterpret_cast<cd*>(SNs + (N / 2 + 2));
+    uint64_t* full = reinterpret_cast<uint64_t*>(WMs + N / 2);
+
+    const int tid = threadIdx.x;
+    const int b = tid % B, g = tid / B;
+    const int nbt = (a.nb + B - 1) / B;
+    const int ntiles = nbt * a.no;
+    const unsigned tx_bytes = (unsigned)a.nchunk * a.boxrows * B * 8;
+
+    auto issue = [&](int t, int s) {
+        if (a.reverse) t = ntiles - 1 - t;
+        const int o = t / nbt, b0 = (t % nbt) * B;
+        mbar_expect_tx(&full[s], tx_bytes);
+        double* dst = bufs + s * BUF + J0 * B;
+        for (int c = 0; c < a.nchunk; c++) {
+            const int r0 = c * a.boxrows;
+            if (a.taxis == 1) tma_load_3d(dst + r0 * B, &tm, b0, r0, o, &full[s]);
+            else tma_load_3d(dst + r0 * B, &tm, b0, o, r0, &full[s]);
+        }
+    };
+
+    if (tid == 0) {
+        tma_prefetch_desc(&tm);
+        for (int s = 0; s < NSTAGE; s++) mbar_init(&full[s], 1);
+        mbar_init_fence();
+    }
+    load_tables<N>(SNs, WMs, a.SN, a.WM);
+    __syncthreads();
+    if (tid == 0) {
+        for (int s = 0; s < NSTAGE; s++) {
+            int t = blockIdx.x + s * gridDim.x;
+            if (t < ntiles) issue(t, s);
+        }
+    }
+
+    int it = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, it++) {
+        const int s = it % NSTAGE;
+        const unsigned parity = (it / NSTAGE) & 1;
+        const int tt = a.reverse ? ntiles - 1 - t : t;
+        const int o = tt / nbt, b0 = (tt % nbt) * B;
+        const bool bok = b0 + b < a.nb;
+        double* tile = bufs + s * BUF;
+        mbar_wait(&full[s], parity);
+
+        xform_tile<N, G, KIND>(tile + b, B, g, a.scale, SNs, WMs, scr + b, B);
+        if constexpr (MID::active) {
+            for (int j = g; j < a.nvalid; j += G) {
+                double v = tile[(j + J0) * B + b];
+                tile[(j + J0) * B + b] = bok ? mid(v, j + J0, b0 + b + J0, o + J0) : 0.0;
+            }
+            __syncthreads();
+            xform_tile<N, G, KIND2>(tile + b, B, g, a.scale2, SNs, WMs, scr + b, B);
+        }
+        if (bok) {
+            double* dst = a.out + (long long)o * a.out_so + b0 + b;
+#pragma unroll 4
+            for (int j = g; j < a.nvalid; j += G) dst[j * a.out_sj] = tile[(j + J0) * B + b];
+        }
+        // the buffer is free once every thread has read it; order those generic reads/writes before
+        // the async-proxy writes of the next tile
+        fence_proxy_async();
+        __syncthreads();
+        const int tn = t + NSTAGE * gridDim.x;
+        if (tid == 0 && tn < ntiles) issue(tn, s);
+    }
+}
+
+struct RowsPipeArgs {
+    const double* in;
+    double* out;
+    long long nrows;
+    int nvalid;
+    int in_pitch, out_pitch;    // doubles; BR*in_pitch*8 is a multiple of 16, in is 16-byte aligned
+    int reverse;
+    double scale;
+    const double* SN;
+    const cd* WM;
+};
+
+template <int N, int KIND, int NSTAGE>
+__global__ void __launch_bounds__(PipeCfg<N>::THREADS) k_rows_pipe(RowsPipeArgs a)
+{
+    using C = PipeCfg<N>;
+    constexpr int BR = C::BR, G = C::G, P = N + 1, M = N / 2;
+    constexpr int J0 = (KIND == XF_DST) ? 1 : 0;
+    constexpr int NW = C::THREADS / 32;
+    static_assert(C::THREADS % 32 == 0, "whole warps");
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    double* sm = reinterpret_cast<double*>(smem_raw);
+    double* stage = sm;                               // [NSTAGE][BR * N] dense
+    double* tile = stage + NSTAGE * BR * N;           // [BR][N + 1]
+    double* scr = tile + BR * P;
+    double* SNs = scr + C::SCR;
+    cd* WMs = reinterpret_cast<cd*>(SNs + (N / 2 + 2));
+    uint64_t* full = reinterpret_cast<uint64_t*>(WMs + N / 2);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long ntiles = (a.nrows + BR - 1) / BR;
+
+    auto issue = [&](long long t, int s) {
+        if (a.reverse) t = ntiles - 1 - t;
+        const long long row0 = t * BR;
+        const int rows = (int)((a.nrows - row0) < BR ? (a.nrows - row0) : BR);
+        const unsigned bytes = ((unsigned)rows * a.in_pitch * 8u) & ~15u;
+        mbar_expect_tx(&full[s], bytes);
+        bulk_load_1d(stage + s * BR * N, a.in + row0 * a.in_pitch, bytes, &full[s]);
+    };
+
+    if (tid == 0) {
+        for (int s = 0; s < NSTAGE; s++) mbar_init(&full[s], 1);
+        mbar_init_fence();
+    }
+    load_tables<N>(SNs, WMs, a.SN, a.WM);
+    __syncthreads();
+    if (tid == 0) {
+        for (int s = 0; s < NSTAGE; s++) {
+            long long t = blockIdx.x + (long long)s * gridDim.x;
+            if (t < ntiles) issue(t, s);
+        }
+    }
+
+    const int b = tid % BR, g = tid / BR;
+    int it = 0;
+    for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, it++) {
+        const int s = it % NSTAGE;
+        const unsigned parity = (it / NSTAGE) & 1;
+        const long long tt = a.reverse ? ntiles - 1 - t : t;
+        const long long row0 = tt * BR;
+        const int rows = (int)((a.nrows - row0) < BR ? (a.nrows - row0) : BR);
+        double* st = stage + s * BR * N;
+        mbar_wait(&full[s], parity);
+        {   // an odd tail (rows*pitch odd) leaves one double outside the 16-byte granularity of the bulk copy
+            const long long cnt = (long long)rows * a.in_pitch;
+            if ((cnt & 1) && tid == 0) st[cnt - 1] = a.in[row0 * a.in_pitch + cnt - 1];
+            if (cnt & 1) __syncthreads();
+        }
+        // first touch: staging (dense, lanes along the row) -> odd-pitch compute tile
+        for (int r = warp; r < BR; r += NW) {
+            const double* src = st + r * a.in_pitch;
+            double* dst = tile + r * P;
+            const bool ok = r < rows;
+            if constexpr (KIND == XF_DST) {
+                for (int j = 1 + lane; j < M; j += 32) {
+                    double x1 = ok ? src[j - 1] : 0.0, x2 = ok ? src[N - j - 1] : 0.0;
+                    double y1 = SNs[j] * (x1 + x2), y2 = 0.5 * (x1 - x2);
+                    dst[j] = y1 + y2;
+                    dst[N - j] = y1 - y2;
+                }
+                if (lane == 0) { dst[0] = 0.0; dst[M] = ok ? 2.0 * src[M - 1] : 0.0; }
+            } else {
+                for (int j = lane; j < N; j += 32) dst[j] = ok ? src[j] : 0.0;
+            }
+        }
+        fence_proxy_async();
+        __syncthreads();
+        {   // staging buffer s is free again: fetch the tile NSTAGE strides ahead
+            const long long tn = t + (long long)NSTAGE * gridDim.x;
+            if (tid == 0 && tn < ntiles) issue(tn, s);
+        }
+        xform_tile<N, G, KIND, true>(tile + b * P, 1, g, a.scale, SNs, WMs, scr + b, BR);
+        for (int r = warp; r < rows; r += NW) {
+            double* dst = a.out + (row0 + r) * a.out_pitch;
+            const double* src = tile + r * P + J0;
+#pragma unroll 4
+            for (int x = lane; x < a.nvalid; x += 32) dst[x] = src[x];
+        }
+        __syncthreads();   // the compute tile is rewritten by the next first touch
+    }
+}
+
+// ---- host-side launchers ----------------------------------------------------------------------
+int device_sm_count();
+
+template <int N, int KIND, typename MID, int KIND2>
+inline cudaError_t launch_cols_pipe_t(const CUtensorMap& tm, const ColsPipeArgs& a, const MID& mid, cudaStream_t st)
+{
+    using C = PipeCfg<N>;
+    constexpr int NSTAGE = C::COLS_STAGES;
+    auto kern = k_cols_pipe<N, KIND, MID, KIND2, NSTAGE>;
+    constexpr size_t smem = C::cols_smem(NSTAGE);
+    static int per_sm = 0;
+    if (!per_sm) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, C::THREADS, smem);
+        if (e != cudaSuccess) return e;
+        if (per_sm < 1) per_sm = 1;
+    }
+    const long long ntiles = (long long)((a.nb + C::B - 1) / C::B) * a.no;
+    long long grid = (long long)device_sm_count() * per_sm;
+    if (grid > ntiles) grid = ntiles;
+    if (grid < 1) return cudaSuccess;
+    kern<<<(unsigned)grid, C::THREADS, smem, st>>>(tm, a, mid);
+    return cudaGetLastError();
+}
+
+template <int N, int KIND>
+inline cudaError_t launch_rows_pipe_t(const RowsPipeArgs& a, cudaStream_t st)
+{
+    using C = PipeCfg<N>;
+    constexpr int NSTAGE = C::ROWS_STAGES;
+    auto kern = k_rows_pipe<N, KIND, NSTAGE>;
+    constexpr size_t smem = C::rows_smem(NSTAGE);
+    static int per_sm = 0;
+    if (!per_sm) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, C::THREADS, smem);
+        if (e != cudaSuccess) return e;
+        if (per_sm < 1) per_sm = 1;
+    }
+    const long long ntiles = (a.nrows + C::BR - 1) / C::BR;
+    long long grid = (long long)device_sm_count() * per_sm;
+    if (grid > ntiles) grid = ntiles;
+    if (grid < 1) return cudaSuccess;
+    kern<<<(unsigned)grid, C::THREADS, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace fdmb
