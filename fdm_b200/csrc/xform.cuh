@@ -103,9 +103,10 @@ FDMB_PLAN(16, 8, 1, 1, 1)
 FDMB_PLAN(32, 4, 4, 1, 4)
 FDMB_PLAN(64, 8, 4, 1, 4)
 FDMB_PLAN(128, 8, 8, 1, 8)
-FDMB_PLAN(256, 16, 8, 1, 8)
-FDMB_PLAN(512, 16, 16, 1, 16)
-FDMB_PLAN(1024, 8, 8, 8, 32)
+// radix <= 8 keeps the butterflies near 64 registers, so 24+ warps per SM stay resident
+FDMB_PLAN(256, 8, 4, 4, 16)
+FDMB_PLAN(512, 8, 8, 4, 32)
+FDMB_PLAN(1024, 8, 8, 8, 64)
 FDMB_PLAN(2048, 16, 8, 8, 64)
 #undef FDMB_PLAN
 
@@ -422,6 +423,224 @@ __device__ __forceinline__ void xform_tile(double* col, int sj, int g, double sc
     if constexpr (KIND == XF_DST) dst_tile<N, G, PREFOLD>(col, sj, g, scale, SN, WM, scr, scr_s);
     else if constexpr (KIND == XF_PFWD) pfwd_tile<N, G>(col, sj, g, scale, SN, WM);
     else pinv_tile<N, G>(col, sj, g, scale, SN, WM);
+}
+
+// =====================================================================================
+// Shared-memory-traffic-lean DST-I ("fused" variant).
+//
+// The sweeps are bound by the shared-memory data pipe (ncu: l1tex__data_pipe_lsu_wavefronts at
+// ~80 % of peak with the straightforward staging above), so this variant touches the tile as
+// little as possible:
+//   stage A  fold + first radix pass: every thread reads its own and the mirrored inputs straight
+//            from the landed tile, folds in registers, runs the radix-R0 butterfly, stores once
+//   stage B  middle radix pass (if the plan has three passes)
+//   stage C  last radix pass + untangle: a thread processes a frequency block together with its
+//            mirror block (k <-> M-k live in the same thread), so the untangled A_k/B_k come out of
+//            registers; even output slots (S[2k] = B_k) leave through the OUT policy at once, the
+//            odd-slot seeds A'_k go back to the tile
+//   stage D  running sum over the odd slots, emitted through the OUT policy
+// OUT policies decide where a finished spectral value goes: back into the tile (rows kernel, and the
+// z sweep's first transform, scaled by the spectral multiplier) or directly to global memory with
+// coalesced stores (strided-axis kernels), which removes the final tile write + read.
+// Requirements: G == M / R0 (one first-pass butterfly per thread).
+// =====================================================================================
+
+struct OutTile {
+    double* col; int sj;
+    __device__ __forceinline__ void emit(int j, double v) const { col[j * sj] = v; }
+};
+// direct, coalesced store: lanes run over the contiguous axis, slot j -> row j-1 of the output
+struct OutGlobal {
+    double* dst; long long stride; bool ok;
+    __device__ __forceinline__ void emit(int j, double v) const { if (ok) dst[(long long)(j - 1) * stride] = v; }
+};
+template <typename MID> struct OutMidTile {
+    double* col; int sj; MID mid; int bidx, oidx; bool ok;
+    __device__ __forceinline__ void emit(int j, double v) const { col[j * sj] = ok ? mid(v, j, bidx, oidx) : 0.0; }
+};
+
+template <int N> struct PlanInfo {
+    using P = Plan<N>;
+    static constexpr int M = P::M;
+    static constexpr int NP = (P::R2 > 1) ? 3 : ((P::R1 > 1) ? 2 : 1);
+    static constexpr int RL = (NP == 3) ? P::R2 : P::R1;   // radix of the last pass (NP >= 2)
+    static constexpr int LB = M / RL;                       // frequency blocks of the last pass
+};
+
+template <int N, int G, bool PREFOLD, typename OUT>
+__device__ __forceinline__ void dst_tile_fused(double* col, int sj, int g, double scale,
+                                               const double* __restrict__ SN, const cd* __restrict__ WM,
+                                               double* scr, int scr_s, const OUT& out)
+{
+    using P = Plan<N>;
+    using I = PlanInfo<N>;
+    constexpr int M = N / 2, R0 = P::R0, S0 = M / R0;
+    static_assert(I::NP >= 2, "fused DST needs at least two radix passes");
+    static_assert(G == S0, "fused DST: one first-pass butterfly per thread");
+
+    // ---- stage A -------------------------------------------------------------------------
+    if constexpr (!PREFOLD) {
+        cd v[R0];
+#pragma unroll
+        for (int n1 = 0; n1 < R0; n1++) {
+            const int m = g + n1 * S0;
+            const int j0 = 2 * m, j1 = 2 * m + 1;
+            // y[j] = sin(pi j/N)(x[j]+x[N-j]) + (x[j]-x[N-j])/2 for every j in 1..N-1, y[0] = 0
+            double a0 = (m == 0) ? 0.0 : col[j0 * sj], c0 = (m == 0) ? 0.0 : col[(N - j0) * sj];
+            double a1 = col[j1 * sj], c1 = col[(N - j1) * sj];
+            double s0 = (n1 < R0 / 2) ? SN[j0] : SN[N - j0];
+            double s1 = (n1 < R0 / 2) ? SN[j1] : SN[N - j1];
+            v[n1].x = s0 * (a0 + c0) + 0.5 * (a0 - c0);
+            v[n1].y = s1 * (a1 + c1) + 0.5 * (a1 - c1);
+        }
+        __syncthreads();     // every mirrored read is done before anyone overwrites the inputs
+        Dft<R0>::run(v);
+#pragma unroll
+        for (int k1 = 0; k1 < R0; k1++) {
+            cd o = v[k1];
+            if (k1 > 0) o = cmul(o, WM[g * k1]);
+            const int idx = 2 * (g + k1 * S0);
+            col[idx * sj] = o.x;
+            col[(idx + 1) * sj] = o.y;
+        }
+        __syncthreads();
+    } else {
+        fft_pass<M, M, R0, G>(col, sj, g, WM);
+        __syncthreads();
+    }
+    // ---- stage B -------------------------------------------------------------------------
+    if constexpr (I::NP == 3) {
+        fft_pass<M, M / R0, P::R1, G>(col, sj, g, WM);
+        __syncthreads();
+    }
+    // ---- stage C: last pass on a block and its mirror block, untangle in registers -------------
+    constexpr int RL = I::RL, LB = I::LB;
+    constexpr int NU = (LB >= 2) ? LB / 2 : 1;            // units: {0, LB/2} and (u, LB-u), u = 1..LB/2-1
+    constexpr int ITC = (NU + G - 1) / G;
+    static_assert(LB >= 2, "last pass must leave at least two frequency blocks");
+    double rA[ITC][RL], rB[ITC][RL], rC[ITC][RL], rD[ITC][RL];   // A_k, B_k (block lo) / A, B (mirror block)
+    const double hs = 0.5 * scale;
+#pragma unroll
+    for (int it = 0; it < ITC; it++) {
+        const int u = g + it * G;
+        if (NU % G != 0 && u >= NU) break;
+        const int lo = u, hi = (u == 0) ? LB / 2 : LB - u;
+        cd va[RL], vb[RL];
+        {
+            const int ba = fft_pos<N>(lo), bb = fft_pos<N>(hi);
+#pragma unroll
+            for (int n1 = 0; n1 < RL; n1++) {
+                va[n1].x = col[(2 * (ba + n1)) * sj]; va[n1].y = col[(2 * (ba + n1) + 1) * sj];
+                vb[n1].x = col[(2 * (bb + n1)) * sj]; vb[n1].y = col[(2 * (bb + n1) + 1) * sj];
+            }
+        }
+        Dft<RL>::run(va);
+        Dft<RL>::run(vb);
+        if (u == 0) {
+            // block 0 holds k = LB*d: d = 0 (DC), d = RL/2 (k = M/2), pairs (d, RL-d);
+            // block LB/2 holds k = LB/2 + LB*d, pairs (d, RL-1-d)
+            rA[it][0] = scale * (va[0].x + va[0].y);   // A_0
+            rB[it][0] = 0.0;
+            rA[it][RL / 2] = scale * va[RL / 2].x;     // A_{M/2} = Re Z[M/2]
+            rB[it][RL / 2] = scale * va[RL / 2].y;     // S[M]    = Im Z[M/2]
+#pragma unroll
+            for (int d = 1; d < RL / 2; d++) {
+                const int k = LB * d;
+                const cd zk = va[d], zm = va[RL - d];
+                const double c = SN[M - 2 * k], s = SN[2 * k];
+                const double ex = hs * (zk.x + zm.x), ey = hs * (zk.y - zm.y);
+                const double ox = hs * (zk.y + zm.y), oy = -hs * (zk.x - zm.x);
+                const double wx = c * ox + s * oy, wy = c * oy - s * ox;
+                rA[it][d] = ex + wx; rB[it][d] = -(ey + wy);
+                rA[it][RL - d] = ex - wx; rB[it][RL - d] = ey - wy;
+            }
+#pragma unroll
+            for (int d = 0; d < RL / 2; d++) {
+                const int k = LB / 2 + LB * d;
+                const cd zk = vb[d], zm = vb[RL - 1 - d];
+                const double c = SN[M - 2 * k], s = SN[2 * k];
+                const double ex = hs * (zk.x + zm.x), ey = hs * (zk.y - zm.y);
+                const double ox = hs * (zk.y + zm.y), oy = -hs * (zk.x - zm.x);
+                const double wx = c * ox + s * oy, wy = c * oy - s * ox;
+                rC[it][d] = ex + wx; rD[it][d] = -(ey + wy);
+                rC[it][RL - 1 - d] = ex - wx; rD[it][RL - 1 - d] = ey - wy;
+            }
+        } else {
+            // block lo: k = lo + LB*d; its partner M-k sits in block hi at d' = RL-1-d
+#pragma unroll
+            for (int d = 0; d < RL; d++) {
+                const bool lower = d < RL / 2;                       // k < M/2 ?
+                const int k = lower ? lo + LB * d : hi + LB * (RL - 1 - d);
+                const cd zk = lower ? va[d] : vb[RL - 1 - d];
+                const cd zm = lower ? vb[RL - 1 - d] : va[d];
+                const double c = SN[M - 2 * k], s = SN[2 * k];
+                const double ex = hs * (zk.x + zm.x), ey = hs * (zk.y - zm.y);
+                const double ox = hs * (zk.y + zm.y), oy = -hs * (zk.x - zm.x);
+                const double wx = c * ox + s * oy, wy = c * oy - s * ox;
+                const double Ak = ex + wx, Bk = -(ey + wy), Am = ex - wx, Bm = ey - wy;
+                if (lower) { rA[it][d] = Ak; rB[it][d] = Bk; rC[it][RL - 1 - d] = Am; rD[it][RL - 1 - d] = Bm; }
+                else { rC[it][RL - 1 - d] = Ak; rD[it][RL - 1 - d] = Bk; rA[it][d] = Am; rB[it][d] = Bm; }
+            }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < ITC; it++) {
+        const int u = g + it * G;
+        if (NU % G != 0 && u >= NU) break;
+        const int lo = u, hi = (u == 0) ? LB / 2 : LB - u;
+#pragma unroll
+        for (int d = 0; d < RL; d++) {
+            const int ka = lo + LB * d, kb = hi + LB * d;
+            if (u == 0 && d == 0) {
+                col[sj] = 0.5 * rA[it][0];                 // A_0 / 2 seeds the running sum
+            } else {
+                out.emit(2 * ka, rB[it][d]);
+                col[(2 * ka + 1) * sj] = rA[it][d];
+            }
+            out.emit(2 * kb, rD[it][d]);
+            col[(2 * kb + 1) * sj] = rC[it][d];
+        }
+    }
+    __syncthreads();
+    // ---- stage D: inclusive prefix sum over the odd slots: S[2k+1] = sum_{m<=k} A'_m ------------
+    constexpr int CS = M / G;
+    double a[CS];
+    double run = 0.0;
+#pragma unroll
+    for (int i = 0; i < CS; i++) {
+        int k = g * CS + i;
+        run += col[(2 * k + 1) * sj];
+        a[i] = run;
+    }
+    double off = 0.0;
+    if constexpr (G > 1) {
+        scr[g * scr_s] = run;
+        __syncthreads();
+        if constexpr (G <= 8) {
+#pragma unroll
+            for (int q = 0; q < G; q++) if (q < g) off += scr[q * scr_s];
+        } else {
+            double* scr2 = scr + G * scr_s;
+            if ((g & 7) == 0) {
+                double t = 0.0;
+#pragma unroll
+                for (int q = 0; q < 8; q++) t += scr[(g + q) * scr_s];
+                scr2[(g >> 3) * scr_s] = t;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int q = 0; q < G / 8; q++) if (q < (g >> 3)) off += scr2[q * scr_s];
+#pragma unroll
+            for (int q = 0; q < 8; q++) if (q < (g & 7)) off += scr[((g & ~7) + q) * scr_s];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < CS; i++) {
+        int k = g * CS + i;
+        out.emit(2 * k + 1, a[i] + off);
+    }
+    __syncthreads();
 }
 
 }  // namespace fdmb

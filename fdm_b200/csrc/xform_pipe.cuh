@@ -24,13 +24,13 @@ template <int N> struct PipeCfg {
     static constexpr int SCR = (G + G / 8 + 1) * B;
     static constexpr int TAB = (N / 2 + 1) + 2 * (N / 2);               // SN + WM (doubles)
     static constexpr int COLS_BUF = ((N + 1) * B + 15) / 16 * 16;      // doubles per stage buffer (128-B multiple)
-    static constexpr int COLS_STAGES = (N <= 256) ? 3 : (N <= 1024 ? 2 : 1);
+    static constexpr int COLS_STAGES = (N <= 1024) ? 2 : 1;
     static constexpr size_t cols_smem(int nstage)
     {
         return 8 * (size_t)(16 + nstage * COLS_BUF + SCR + TAB + 2) + 8 * 8 + 128;
     }
     static constexpr int BR = B;
-    static constexpr int ROWS_STAGES = (N <= 256) ? 2 : 1;
+    static constexpr int ROWS_STAGES = 1;
     static constexpr size_t rows_smem(int nstage)
     {
         return 8 * (size_t)(nstage * BR * N + BR * (N + 1) + SCR + TAB + 2) + 8 * 8 + 128;
@@ -116,19 +116,31 @@ k_cols_pipe(const __grid_constant__ CUtensorMap tm, ColsPipeArgs a, MID mid)
         double* tile = bufs + s * BUF;
         mbar_wait(&full[s], parity);
 
-        xform_tile<N, G, KIND>(tile + b, B, g, a.scale, SNs, WMs, scr + b, B);
-        if constexpr (MID::active) {
-            for (int j = g; j < a.nvalid; j += G) {
-                double v = tile[(j + J0) * B + b];
-                tile[(j + J0) * B + b] = bok ? mid(v, j + J0, b0 + b + J0, o + J0) : 0.0;
+        if constexpr (KIND == XF_DST && (!MID::active || KIND2 == XF_DST)) {
+            // smem-lean path: finished spectral values leave the registers straight to global memory
+            const OutGlobal og{a.out + (long long)o * a.out_so + b0 + b, a.out_sj, bok};
+            if constexpr (MID::active) {
+                const OutMidTile<MID> om{tile + b, B, mid, b0 + b + 1, o + 1, bok};
+                dst_tile_fused<N, G, false>(tile + b, B, g, a.scale, SNs, WMs, scr + b, B, om);
+                dst_tile_fused<N, G, false>(tile + b, B, g, a.scale2, SNs, WMs, scr + b, B, og);
+            } else {
+                dst_tile_fused<N, G, false>(tile + b, B, g, a.scale, SNs, WMs, scr + b, B, og);
             }
-            __syncthreads();
-            xform_tile<N, G, KIND2>(tile + b, B, g, a.scale2, SNs, WMs, scr + b, B);
-        }
-        if (bok) {
-            double* dst = a.out + (long long)o * a.out_so + b0 + b;
+        } else {
+            xform_tile<N, G, KIND>(tile + b, B, g, a.scale, SNs, WMs, scr + b, B);
+            if constexpr (MID::active) {
+                for (int j = g; j < a.nvalid; j += G) {
+                    double v = tile[(j + J0) * B + b];
+                    tile[(j + J0) * B + b] = bok ? mid(v, j + J0, b0 + b + J0, o + J0) : 0.0;
+                }
+                __syncthreads();
+                xform_tile<N, G, KIND2>(tile + b, B, g, a.scale2, SNs, WMs, scr + b, B);
+            }
+            if (bok) {
+                double* dst = a.out + (long long)o * a.out_so + b0 + b;
 #pragma unroll 4
-            for (int j = g; j < a.nvalid; j += G) dst[j * a.out_sj] = tile[(j + J0) * B + b];
+                for (int j = g; j < a.nvalid; j += G) dst[j * a.out_sj] = tile[(j + J0) * B + b];
+            }
         }
         // the buffer is free once every thread has read it; order those generic reads/writes before
         // the async-proxy writes of the next tile
@@ -231,7 +243,10 @@ __global__ void __launch_bounds__(PipeCfg<N>::THREADS) k_rows_pipe(RowsPipeArgs 
             const long long tn = t + (long long)NSTAGE * gridDim.x;
             if (tid == 0 && tn < ntiles) issue(tn, s);
         }
-        xform_tile<N, G, KIND, true>(tile + b * P, 1, g, a.scale, SNs, WMs, scr + b, BR);
+        if constexpr (KIND == XF_DST)
+            dst_tile_fused<N, G, true>(tile + b * P, 1, g, a.scale, SNs, WMs, scr + b, BR, OutTile{tile + b * P, 1});
+        else
+            xform_tile<N, G, KIND, true>(tile + b * P, 1, g, a.scale, SNs, WMs, scr + b, BR);
         for (int r = warp; r < rows; r += NW) {
             double* dst = a.out + (row0 + r) * a.out_pitch;
             const double* src = tile + r * P + J0;

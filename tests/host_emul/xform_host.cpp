@@ -49,6 +49,49 @@ static void run_one(double* data, int sj, double scale)
     for (auto& t : th) t.join();
 }
 
+// fused DST (dst_tile_fused): mode 0 = OutTile, 1 = OutGlobal-like policy writing to a separate
+// array, 2 = PREFOLD (fold applied by the caller, like k_rows_pipe's first touch)
+struct OutSep {
+    double* dst;
+    void emit(int j, double v) const { dst[j - 1] = v; }
+};
+
+template <int N>
+static void run_fused(double* data, int sj, double scale, int mode, double* sep)
+{
+    constexpr int G = Plan<N>::G;
+    constexpr int M = N / 2;
+    std::vector<double> sn; std::vector<cd> wm;
+    make_tables(N, sn, wm);
+    if (mode == 2) {
+        for (int j = 1; j < M; j++) {
+            double a = data[j * sj], c = data[(N - j) * sj];
+            double y1 = sn[j] * (a + c), y2 = 0.5 * (a - c);
+            data[j * sj] = y1 + y2; data[(N - j) * sj] = y1 - y2;
+        }
+        data[0] = 0.0; data[M * sj] = 2.0 * data[M * sj];
+    }
+    std::vector<double> scr((G + G / 8 + 2));
+    std::barrier<> bar(G);
+    std::vector<std::thread> th;
+    for (int g = 0; g < G; g++)
+        th.emplace_back([&, g] {
+            tl_barrier = &bar;
+            if (mode == 0) dst_tile_fused<N, G, false>(data, sj, g, scale, sn.data(), wm.data(), scr.data(), 1, OutTile{data, sj});
+            else if (mode == 1) dst_tile_fused<N, G, false>(data, sj, g, scale, sn.data(), wm.data(), scr.data(), 1, OutSep{sep});
+            else dst_tile_fused<N, G, true>(data, sj, g, scale, sn.data(), wm.data(), scr.data(), 1, OutTile{data, sj});
+        });
+    for (auto& t : th) t.join();
+}
+
+extern "C" int emul_dst_fused(int N, double* data, int sj, double scale, int mode, double* sep)
+{
+#define X(NN) case NN: run_fused<NN>(data, sj, scale, mode, sep); return 0;
+    switch (N) { X(32) X(64) X(128) X(256) X(512) X(1024) X(2048) }
+#undef X
+    return -1;
+}
+
 // data: N slots with stride sj (slot 0 unused for kind 0)
 extern "C" int emul_xform(int kind, int N, double* data, int sj, double scale)
 {
