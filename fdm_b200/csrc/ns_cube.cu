@@ -100,18 +100,25 @@ __global__ void k_bound_p(Fld u, Fld v, Fld w, Fld p, NSGeom g)
 
 __device__ __forceinline__ double sq(double x) { return x * x; }
 
+// linear element offset of (i,k,j); every field of the graded sizes has < 2^31 elements per axis product
+__device__ __forceinline__ long long lin(const Fld& f, int i, int k, int j)
+{
+    return (long long)(i - f.lz) * f.sz + (long long)(k - f.ly) * f.sy + (j - f.lx);
+}
+
 // ---- FGH (ns_cube.cpp:126-200) ----------------------------------------------------------
 // One thread per (i,k,j) in [0..nz]x[0..ny]x[0..nx]; F where i,k>=1, G where i,j>=1, H where k,j>=1.
-__global__ void __launch_bounds__(256) k_fgh(Fld u, Fld v, Fld w, Fld F, Fld G, Fld H, NSGeom g)
+// Interior threads (i,k,j >= 1) read the 27 distinct taps of the three stencils once through
+// row pointers (immediate offsets, no per-tap address arithmetic) and produce F, G and H together;
+// the O(n^2) edge threads take the generic path.
+template <bool F_, bool G_, bool H_>
+__device__ __forceinline__ void fgh_generic(const Fld& u, const Fld& v, const Fld& w, const Fld& F, const Fld& G,
+                                            const Fld& H, const NSGeom& g, int i, int k, int j)
 {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    const int k = blockIdx.y * blockDim.y + threadIdx.y;
-    const int i = blockIdx.z;
-    if (j > g.nx || k > g.ny) return;
 #define U(a, b, c) u.at(a, b, c)
 #define V(a, b, c) v.at(a, b, c)
 #define W(a, b, c) w.at(a, b, c)
-    if (i >= 1 && k >= 1) {
+    if (F_) {
         const double uc = U(i, k, j);
         F.at(i, k, j) = uc + g.dt * (
             (U(i, k, j + 1) - 2 * uc + U(i, k, j - 1)) * g.cRx +
@@ -123,7 +130,7 @@ __global__ void __launch_bounds__(256) k_fgh(Fld u, Fld v, Fld w, Fld F, Fld G, 
             0.25 * ((uc + U(i + 1, k, j)) * (W(i, k, j + 1) + W(i, k, j)) -
                     (U(i - 1, k, j) + uc) * (W(i - 1, k, j + 1) + W(i - 1, k, j))) * g.idz);
     }
-    if (i >= 1 && j >= 1) {
+    if (G_) {
         const double vc = V(i, k, j);
         G.at(i, k, j) = vc + g.dt * (
             (V(i, k, j + 1) - 2 * vc + V(i, k, j - 1)) * g.cRx +
@@ -135,7 +142,7 @@ __global__ void __launch_bounds__(256) k_fgh(Fld u, Fld v, Fld w, Fld F, Fld G, 
             0.25 * ((W(i, k, j) + W(i, k + 1, j)) * (vc + V(i + 1, k, j)) -
                     (W(i - 1, k, j) + W(i - 1, k + 1, j)) * (V(i - 1, k, j) + vc)) * g.idz);
     }
-    if (k >= 1 && j >= 1) {
+    if (H_) {
         const double wc = W(i, k, j);
         H.at(i, k, j) = wc + g.dt * (
             (W(i, k, j + 1) - 2 * wc + W(i, k, j - 1)) * g.cRx +
@@ -152,6 +159,66 @@ __global__ void __launch_bounds__(256) k_fgh(Fld u, Fld v, Fld w, Fld F, Fld G, 
 #undef W
 }
 
+__global__ void __launch_bounds__(256) k_fgh(Fld u, Fld v, Fld w, Fld F, Fld G, Fld H, NSGeom g)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = blockIdx.y * blockDim.y + threadIdx.y;
+    const int i = blockIdx.z;
+    if (j > g.nx || k > g.ny) return;
+    if (i >= 1 && k >= 1 && j >= 1) {
+        const double* __restrict__ uc_ = u.p + lin(u, i, k, j);
+        const double* __restrict__ vc_ = v.p + lin(v, i, k, j);
+        const double* __restrict__ wc_ = w.p + lin(w, i, k, j);
+        const double* __restrict__ ukp = uc_ + u.sy; const double* __restrict__ ukm = uc_ - u.sy;
+        const double* __restrict__ uip = uc_ + u.sz; const double* __restrict__ uim = uc_ - u.sz;
+        const double* __restrict__ vkp = vc_ + v.sy; const double* __restrict__ vkm = vc_ - v.sy;
+        const double* __restrict__ vip = vc_ + v.sz; const double* __restrict__ vim = vc_ - v.sz;
+        const double* __restrict__ vipkm = vip - v.sy;
+        const double* __restrict__ wkp = wc_ + w.sy; const double* __restrict__ wkm = wc_ - w.sy;
+        const double* __restrict__ wip = wc_ + w.sz; const double* __restrict__ wim = wc_ - w.sz;
+        const double* __restrict__ wimkp = wim + w.sy;
+        // the 27 taps, named by (di,dk,dj) with m = -1, p = +1
+        const double u000 = uc_[0], u00p = uc_[1], u00m = uc_[-1], u0p0 = ukp[0], u0pm = ukp[-1], u0m0 = ukm[0];
+        const double up00 = uip[0], up0m = uip[-1], um00 = uim[0];
+        const double v000 = vc_[0], v00p = vc_[1], v00m = vc_[-1], v0p0 = vkp[0], v0m0 = vkm[0], v0mp = vkm[1];
+        const double vp00 = vip[0], vpm0 = vipkm[0], vm00 = vim[0];
+        const double w000 = wc_[0], w00p = wc_[1], w00m = wc_[-1], w0p0 = wkp[0], w0m0 = wkm[0];
+        const double wp00 = wip[0], wm00 = wim[0], wm0p = wim[1], wmp0 = wimkp[0];
+
+        F.p[lin(F, i, k, j)] = u000 + g.dt * (
+            (u00p - 2 * u000 + u00m) * g.cRx +
+            (u0p0 - 2 * u000 + u0m0) * g.cRy +
+            (up00 - 2 * u000 + um00) * g.cRz -
+            (sq(0.5 * (u000 + u00p)) - sq(0.5 * (u00m + u000))) * g.idx -
+            0.25 * ((u000 + u0p0) * (v00p + v000) -
+                    (u0m0 + u000) * (v0mp + v0m0)) * g.idy -
+            0.25 * ((u000 + up00) * (w00p + w000) -
+                    (um00 + u000) * (wm0p + wm00)) * g.idz);
+        G.p[lin(G, i, k, j)] = v000 + g.dt * (
+            (v00p - 2 * v000 + v00m) * g.cRx +
+            (v0p0 - 2 * v000 + v0m0) * g.cRy +
+            (vp00 - 2 * v000 + vm00) * g.cRz -
+            (sq(0.5 * (v000 + v0p0)) - sq(0.5 * (v0m0 + v000))) * g.idy -
+            0.25 * ((u000 + u0p0) * (v00p + v000) -
+                    (u00m + u0pm) * (v000 + v00m)) * g.idx -
+            0.25 * ((w000 + w0p0) * (v000 + vp00) -
+                    (wm00 + wmp0) * (vm00 + v000)) * g.idz);
+        H.p[lin(H, i, k, j)] = w000 + g.dt * (
+            (w00p - 2 * w000 + w00m) * g.cRx +
+            (w0p0 - 2 * w000 + w0m0) * g.cRy +
+            (wp00 - 2 * w000 + wm00) * g.cRz -
+            (sq(0.5 * (wp00 + w000)) - sq(0.5 * (wm00 + w000))) * g.idz -
+            0.25 * ((up00 + u000) * (w00p + w000) -
+                    (up0m + u00m) * (w000 + w00m)) * g.idx -
+            0.25 * ((w000 + w0p0) * (v000 + vp00) -
+                    (w0m0 + w000) * (v0m0 + vpm0)) * g.idy);
+        return;
+    }
+    if (i >= 1 && k >= 1) fgh_generic<true, false, false>(u, v, w, F, G, H, g, i, k, j);
+    if (i >= 1 && j >= 1) fgh_generic<false, true, false>(u, v, w, F, G, H, g, i, k, j);
+    if (k >= 1 && j >= 1) fgh_generic<false, false, true>(u, v, w, F, G, H, g, i, k, j);
+}
+
 // ---- poisson RHS (ns_cube.cpp:205-235) ---------------------------------------------------
 __global__ void __launch_bounds__(256) k_rhs(Fld F, Fld G, Fld H, Fld p, Fld R, NSGeom g)
 {
@@ -159,16 +226,19 @@ __global__ void __launch_bounds__(256) k_rhs(Fld F, Fld G, Fld H, Fld p, Fld R, 
     const int k = blockIdx.y * blockDim.y + threadIdx.y + 1;
     const int i = blockIdx.z + 1;
     if (j > g.nx || k > g.ny) return;
-    double r = ((F.at(i, k, j) - F.at(i, k, j - 1)) * g.idx +
-                (G.at(i, k, j) - G.at(i, k - 1, j)) * g.idy +
-                (H.at(i, k, j) - H.at(i - 1, k, j)) * g.idz) * g.idt;
-    if (i <= 1) r -= p.at(i - 1, k, j) * g.idz2;
-    if (k <= 1) r -= p.at(i, k - 1, j) * g.idy2;
-    if (j <= 1) r -= p.at(i, k, j - 1) * g.idx2;
-    if (j >= g.nx) r -= p.at(i, k, j + 1) * g.idx2;
-    if (k >= g.ny) r -= p.at(i, k + 1, j) * g.idy2;
-    if (i >= g.nz) r -= p.at(i + 1, k, j) * g.idz2;
-    R.at(i, k, j) = r;
+    const double* __restrict__ Fp = F.p + lin(F, i, k, j);
+    const double* __restrict__ Gp = G.p + lin(G, i, k, j);
+    const double* __restrict__ Hp = H.p + lin(H, i, k, j);
+    double r = ((Fp[0] - Fp[-1]) * g.idx + (Gp[0] - Gp[-G.sy]) * g.idy + (Hp[0] - Hp[-H.sz]) * g.idz) * g.idt;
+    if (i <= 1 || k <= 1 || j <= 1 || j >= g.nx || k >= g.ny || i >= g.nz) {
+        if (i <= 1) r -= p.at(i - 1, k, j) * g.idz2;
+        if (k <= 1) r -= p.at(i, k - 1, j) * g.idy2;
+        if (j <= 1) r -= p.at(i, k, j - 1) * g.idx2;
+        if (j >= g.nx) r -= p.at(i, k, j + 1) * g.idx2;
+        if (k >= g.ny) r -= p.at(i, k + 1, j) * g.idy2;
+        if (i >= g.nz) r -= p.at(i + 1, k, j) * g.idz2;
+    }
+    R.p[lin(R, i, k, j)] = r;
 }
 
 // ---- update_uvwp (ns_cube.cpp:241-277) ---------------------------------------------------
@@ -178,11 +248,12 @@ __global__ void __launch_bounds__(256) k_update(Fld u, Fld v, Fld w, Fld p, Fld 
     const int k = blockIdx.y * blockDim.y + threadIdx.y + 1;
     const int i = blockIdx.z + 1;
     if (j > g.nx || k > g.ny) return;
-    const double xc = x.at(i, k, j);
-    if (j < g.nx) u.at(i, k, j) = F.at(i, k, j) - g.dtdx * (x.at(i, k, j + 1) - xc);
-    if (k < g.ny) v.at(i, k, j) = G.at(i, k, j) - g.dtdy * (x.at(i, k + 1, j) - xc);
-    if (i < g.nz) w.at(i, k, j) = H.at(i, k, j) - g.dtdz * (x.at(i + 1, k, j) - xc);
-    p.at(i, k, j) = xc;   // p = x copies the index-range intersection (tensor.h:103-111)
+    const double* __restrict__ xp = x.p + lin(x, i, k, j);
+    const double xc = xp[0];
+    if (j < g.nx) u.p[lin(u, i, k, j)] = F.p[lin(F, i, k, j)] - g.dtdx * (xp[1] - xc);
+    if (k < g.ny) v.p[lin(v, i, k, j)] = G.p[lin(G, i, k, j)] - g.dtdy * (xp[x.sy] - xc);
+    if (i < g.nz) w.p[lin(w, i, k, j)] = H.p[lin(H, i, k, j)] - g.dtdz * (xp[x.sz] - xc);
+    p.p[lin(p, i, k, j)] = xc;   // p = x copies the index-range intersection (tensor.h:103-111)
 }
 
 }  // namespace fdmb
