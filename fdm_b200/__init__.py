@@ -8,6 +8,7 @@ object construction does, and fails loudly if it is missing.
 from .capi import FdmB200Error, lib  # noqa: F401
 from .lapl_cube import LaplCube  # noqa: F401
 from .ns_cube import NSCube  # noqa: F401
+from .lapl_cyl import LaplCyl3FFT2  # noqa: F401
 
 
 def fft_batch(kind, N, data, dx=1.0):

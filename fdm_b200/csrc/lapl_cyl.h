@@ -1,0 +1,26 @@
+// Internal definition of the LaplCyl3FFT2 handle (shared with ns_cyl.cu).
+#pragma once
+#include "lapl_cube.h"
+
+struct fdmb_lapl_cyl {
+    double dr, dz, r0, lr, lz;
+    int nr, nz, nphi, zperiodic;
+    double dphi = 0, slz = 0;
+    int Nz = 0;                        // z transform length (nz+1 Dirichlet, nz periodic)
+    int pr = 0;                        // r pitch of the work array (doubles)
+    fdmb::Tables tphi{}, tz{};
+    cudaStream_t stream = nullptr;
+    double *d_lmphi = nullptr, *d_lmz = nullptr;   // eigenvalues (lapl_cyl.cpp:132-141)
+    double *d_L = nullptr, *d_U = nullptr, *d_ir2 = nullptr;   // r-dependent matrix entries (lapl_cyl.cpp:151-159)
+    double* d_work = nullptr;
+    double *d_rhs = nullptr, *d_ans = nullptr;
+    bool pipe_z = false, pipe_phi = false;
+    CUtensorMap tm_z{}, tm_phi{}, tm_in{};
+    const void* tm_in_ptr = nullptr;
+    int boxrows_z = 0, nchunk_z = 0, boxrows_phi = 0, nchunk_phi = 0;
+
+    int init();
+    int solve_device(double* d_out, const double* d_in, cudaStream_t st);
+    int solve_host(double* ans, const double* rhs);
+    ~fdmb_lapl_cyl();
+};

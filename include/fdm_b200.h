@@ -80,6 +80,21 @@ int fdmb_lapl_cube_solve(fdmb_lapl_cube* h, double* ans, const double* rhs);
 int fdmb_lapl_cube_solve_device(fdmb_lapl_cube* h, double* d_ans, const double* d_rhs, void* stream);
 int fdmb_lapl_cube_destroy(fdmb_lapl_cube* h);
 
+/* ---- LaplCyl3FFT2 ---------------------------------------------------------------
+ * Replaces fdm::LaplCyl3FFT2<double,check,zflag> (src/lapl_cyl.h:172-249, src/lapl_cyl.cpp:11-170):
+ * Poisson equation in cylindrical coordinates, periodic in phi, Dirichlet (zperiodic=0) or
+ * periodic (1) in z, Dirichlet in r.
+ * create <-> constructor (dr,dz,r0,lr,lz,nr,nz,nphi)       src/lapl_cyl.h:212-245
+ * solve  <-> void solve(T* ans, T* rhs)                    src/lapl_cyl.cpp:11-128
+ * Arrays are [phi 0..nphi-1][z z1..zn][r 1..nr], r fastest (src/lapl_cyl.h:222).
+ * nphi and the z transform length (nz+1 Dirichlet, nz periodic) must be powers of two. */
+typedef struct fdmb_lapl_cyl fdmb_lapl_cyl;
+int fdmb_lapl_cyl_create(fdmb_lapl_cyl** h, double dr, double dz, double r0, double lr, double lz,
+                         int nr, int nz, int nphi, int zperiodic);
+int fdmb_lapl_cyl_solve(fdmb_lapl_cyl* h, double* ans, const double* rhs);
+int fdmb_lapl_cyl_solve_device(fdmb_lapl_cyl* h, double* d_ans, const double* d_rhs, void* stream);
+int fdmb_lapl_cyl_destroy(fdmb_lapl_cyl* h);
+
 /* ---- NSCube ---------------------------------------------------------------------
  * Replaces fdm::NSCube<double,check> (src/ns_cube.h:13-92, src/ns_cube.cpp:27-277).
  * params   <-> the [ns] config keys read by the constructor (src/ns_cube.h:47-61);
