@@ -4,11 +4,16 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl ours|reference]
 
 A "step" is one pass of the hot path over one batch of synthetic input:
-  cube127  (default) one LaplCube Dirichlet solve, 127^3 fp64   (BASELINE.json configs[1])
-  cube255            one LaplCube Dirichlet solve, 255^3 fp64
+  cube1023 (default) one LaplCube Dirichlet solve, 1023^3 fp64  (BASELINE.json configs[4]: the
+                     configuration the Gpts/s metric is quoted on "at 1/2/4/8 B200"; it fits one GPU)
+  cube127            one LaplCube Dirichlet solve, 127^3 fp64   (configs[1])
+  cube255 / cube511  one LaplCube Dirichlet solve, 255^3 / 511^3 fp64
   nscube255          one NSCube lid-driven-cavity step, 255^3   (configs[2])
   nscube31           one NSCube step, 31^3                      (configs[0])
-N>1: every rank runs its own independent problem (weak scaling, no data-path collective).
+N>1, cube workloads: ONE solve of the same grid, z-slab decomposed over the N ranks; the two
+slab<->pencil transposes are peer stores over NVLink fused into the y and z sweeps ("scaling":
+"strong").  N>1, NS workloads: independent replicas per rank ("weak"; the NS halo exchange is not
+built yet).
 
 Prints ONE JSON line (rank 0).  `value` is device-resident throughput; `e2e` goes through the
 host-pointer C-ABI entry point with pinned host buffers (H2D + solve + D2H inside the timed
@@ -39,6 +44,8 @@ WORKLOADS = {
     "cube127": dict(kind="cube", n=127, label="LaplCube Dirichlet 127^3 fp64 solve (BASELINE configs[1])"),
     "cube255": dict(kind="cube", n=255, label="LaplCube Dirichlet 255^3 fp64 solve"),
     "cube511": dict(kind="cube", n=511, label="LaplCube Dirichlet 511^3 fp64 solve"),
+    "cube1023": dict(kind="cube", n=1023, label="LaplCube Dirichlet 1023^3 fp64 solve, 1024 slots per axis "
+                                                "(BASELINE configs[4]; z-slab decomposed over the ranks when N>1)"),
     "nscube31": dict(kind="ns", n=31, Re=250.0, dt=0.01, label="NSCube 31^3 Re=250 dt=0.01 step (configs[0])"),
     "nscube255": dict(kind="ns", n=255, Re=1000.0, dt=0.005, label="NSCube 255^3 Re=1000 dt=0.005 step (configs[2])"),
 }
@@ -123,13 +130,14 @@ def run_reference(args, wl):
     n = wl["n"]
     cores = ref.num_threads()
     if wl["kind"] == "cube":
-        g = cube_geometry(n)
-        S = ref.LaplCube(g["dx"], g["dx"], g["dx"], g["l"], g["l"], g["l"], n, n, n)
-        rhs = O.synthetic_rhs((n, n, n), seed=1234)
+        nn = min(n, 255)      # bounded sample: the reference needs ~26 GB and ~30 s per 1023^3 solve
+        g = cube_geometry(nn)
+        S = ref.LaplCube(g["dx"], g["dx"], g["dx"], g["l"], g["l"], g["l"], nn, nn, nn)
+        rhs = O.synthetic_rhs((nn, nn, nn), seed=1234)
         step = lambda: S.solve(rhs)
-        units = n ** 3 / 1e9
+        units = nn ** 3 / 1e9
         metric, unit = "poisson_solve_gpts_per_s", "Gpts/s"
-        sample = f"full {n}^3 solve per step"
+        sample = f"full {nn}^3 solve per step" + ("" if nn == n else f" (bounded sample of the {n}^3 workload; Gpts/s is size-normalised)")
     else:
         ns = ref.NSCube(nx=n, nz=n, Re=wl["Re"], dt=wl["dt"])
         step = lambda: ns.step(1)
@@ -146,7 +154,8 @@ def run_reference(args, wl):
     print(json.dumps({
         "impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "higher_is_better": True, "scaling": "strong" if wl["kind"] == "cube" else "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
         "config": {"workload": wl["label"]},
         "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "reference", "sample": sample},
         "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -193,7 +202,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
-    ap.add_argument("--workload", default="cube127", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="cube1023", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -231,30 +240,39 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sharded = world > 1 and wl["kind"] == "cube"
     if wl["kind"] == "cube":
         g = cube_geometry(n)
-        S = fdm_b200.LaplCube(g["dx"], g["dx"], g["dx"], g["l"], g["l"], g["l"], n, n, n)
-        pts = n ** 3
-        pair_bytes = 2 * 8 * pts
+        if sharded:
+            S = fdm_b200.LaplCubeSharded(g["dx"], g["dx"], g["dx"], g["l"], g["l"], g["l"], n, n, n, rank=rank, nranks=world)
+            S.connect()
+            nz_local = S.nz_local
+        else:
+            S = fdm_b200.LaplCube(g["dx"], g["dx"], g["dx"], g["l"], g["l"], g["l"], n, n, n)
+            nz_local = n
+        pts = n ** 3                        # whole job
+        lpts = n * n * nz_local             # this rank's slab
+        pair_bytes = 2 * 8 * lpts
         nbuf = max(2, int(np.ceil(2.2 * 126e6 / pair_bytes)))       # rotate > 2x L2 worth of rhs/ans pairs
-        rhs = [torch.rand(pts, dtype=torch.float64, device=dev) - 0.5 for _ in range(nbuf)]
-        ans = [torch.empty(pts, dtype=torch.float64, device=dev) for _ in range(nbuf)]
+        rhs = [torch.rand(lpts, dtype=torch.float64, device=dev) - 0.5 for _ in range(nbuf)]
+        ans = [torch.empty(lpts, dtype=torch.float64, device=dev) for _ in range(nbuf)]
         l2_policy = f"rotating {nbuf} rhs/ans pairs ({nbuf * pair_bytes / 1e6:.0f} MB > 126 MB L2)"
 
         def step(i):
             b = i % nbuf
             S.solve_device(ans[b].data_ptr(), rhs[b].data_ptr(), sptr)
-        units_per_step = pts / 1e9
+        units_per_step = pts / 1e9 / (world if sharded else 1)       # x world below: one job over all ranks
         metric, unit = "poisson_solve_gpts_per_s", "Gpts/s"
-        algo_bytes_step = SOLVE_BYTES_PER_PT * pts
-        # e2e: host-pointer entry point, pinned buffers
-        h_rhs = torch.rand(pts, dtype=torch.float64).pin_memory()
-        h_ans = torch.empty(pts, dtype=torch.float64).pin_memory()
+        algo_bytes_step = SOLVE_BYTES_PER_PT * lpts
+        # e2e: host-pointer entry point, pinned buffers (this rank's slab)
+        h_rhs = torch.rand(lpts, dtype=torch.float64).pin_memory()
+        h_ans = torch.empty(lpts, dtype=torch.float64).pin_memory()
         dp = C.POINTER(C.c_double)
 
         def e2e_step():
             capi.check(L.fdmb_lapl_cube_solve(S._h, C.cast(h_ans.data_ptr(), dp), C.cast(h_rhs.data_ptr(), dp)), "solve")
-        h2d = d2h = 8 * pts
+        h2d = d2h = 8 * lpts
+        pts_kernel = lpts
     else:
         if not hasattr(fdm_b200, "NSCube"):
             raise SystemExit("NSCube workload not built")
@@ -272,6 +290,7 @@ def main():
         def e2e_step():
             ns2.step_host_roundtrip()
         h2d = d2h = ns2.state_bytes()
+        pts_kernel = pts
 
     # ---- device-resident timing --------------------------------------------------
     for i in range(W):
@@ -313,7 +332,7 @@ def main():
     top = max(kern, key=lambda k: k[2])
     per_launch_ms = top[2] / top[1]
     # algorithmic bytes of one launch of the dominant kernel: one read+write sweep over the grid
-    algo_launch = ALGO_BYTES_PER_SWEEP * pts * kernel_sweeps(top[0])
+    algo_launch = ALGO_BYTES_PER_SWEEP * pts_kernel * kernel_sweeps(top[0])
     achieved = algo_launch / (per_launch_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": top[0], "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": load_traffic(top[0], args.workload), "peak_source": peak_src,
@@ -323,8 +342,8 @@ def main():
                 "kernels": {k[0]: {"launches_per_step": k[1] / K, "ms_per_launch": k[2] / k[1]} for k in kern}}
 
     # ---- e2e through the host-pointer C ABI -----------------------------------------
-    Ke = max(3, min(K, 50))
-    for _ in range(3):
+    Ke = max(3, min(K, 50 if pts < 5e8 else 10))
+    for _ in range(2 if pts >= 5e8 else 3):
         e2e_step()
     barrier()
     t0 = time.perf_counter()
@@ -342,10 +361,13 @@ def main():
     if rank == 0:
         out = {
             "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong" if (sharded or wl["kind"] == "cube") else "weak",
+            "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": wl["label"], "l2_policy": l2_policy,
-                       "parallelism": "independent replicas per rank" if world > 1 else "single GPU"},
+                       "parallelism": ("single GPU" if world == 1 else
+                                       f"z-slabs over {world} GPUs, slab<->pencil transposes as peer stores over NVLink"
+                                       if sharded else "independent replicas per rank")},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
         }
         if world == 1 and not args.no_cpu_baseline:

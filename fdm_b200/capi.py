@@ -43,6 +43,13 @@ def lib():
     L.fdmb_lapl_cube_solve.argtypes = [C.c_void_p, dp, dp]
     L.fdmb_lapl_cube_solve_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.fdmb_lapl_cube_destroy.argtypes = [C.c_void_p]
+    ip = C.POINTER(C.c_int)
+    L.fdmb_slab_range.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, ip, ip]
+    L.fdmb_lapl_cube_create_sharded.argtypes = [C.POINTER(C.c_void_p)] + [C.c_double] * 6 + [C.c_int] * 6
+    L.fdmb_lapl_cube_local_slab.argtypes = [C.c_void_p, ip, ip]
+    L.fdmb_lapl_cube_export_ipc.argtypes = [C.c_void_p, C.c_void_p]
+    L.fdmb_lapl_cube_attach_ipc.argtypes = [C.c_void_p, C.c_void_p]
+    L.fdmb_lapl_cube_attach_local.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
     _lib = L
     return L
 

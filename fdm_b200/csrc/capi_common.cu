@@ -95,6 +95,13 @@ int device_sm_count()
     return cached[dev];
 }
 
+int current_device_slot()
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
+    return dev;
+}
+
 bool pipe_enabled()
 {
     static int v = -1;

@@ -48,6 +48,7 @@ inline bool supported_N(int N) { return is_pow2(N) && N >= 4 && N <= 2048; }
 
 bool pipe_enabled();     // FDMB_PIPE=0 selects the synchronous sweep kernels (A/B measurements)
 int device_sm_count();
+int current_device_slot();   // cudaGetDevice() clamped to [0, 63]
 
 // counts kernel launches issued by this library (bench.py reports it as gpu_launches)
 extern unsigned long long g_launch_count;

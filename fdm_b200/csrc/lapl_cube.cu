@@ -7,6 +7,7 @@
 // tile segment is 128-byte aligned; the caller's arrays keep the reference layout.
 #include <cmath>
 #include <cstdint>
+#include <cstring>
 #include <vector>
 #include <new>
 
@@ -101,6 +102,63 @@ cudaError_t launch_cols_pipe_cube_divide(int N, bool periodic, const CUtensorMap
     return cudaErrorInvalidValue;
 }
 
+cudaError_t launch_cols_pipe_shard(int N, int kind, const CUtensorMap& tm, const ColsPipeArgs& a, const OutShard& om,
+                                   cudaStream_t st, const char* tag)
+{
+    LaunchScope scope(tag, st);
+    MidNone mid;
+#define X(NN)                                                                                                     \
+    case NN:                                                                                                      \
+        if (kind == XF_DST) return launch_cols_pipe_t<NN, XF_DST, MidNone, XF_DST, OutShard>(tm, a, mid, st, om);   \
+        if (kind == XF_PFWD) return launch_cols_pipe_t<NN, XF_PFWD, MidNone, XF_DST, OutShard>(tm, a, mid, st, om); \
+        return launch_cols_pipe_t<NN, XF_PINV, MidNone, XF_DST, OutShard>(tm, a, mid, st, om);
+    switch (N) { FDMB_FOR_EACH_PIPE_N(X) }
+#undef X
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_cols_pipe_cube_divide_shard(int N, bool periodic, const CUtensorMap& tm, const ColsPipeArgs& a,
+                                               const MidCubeDivide& mid, const OutShard& om, cudaStream_t st,
+                                               const char* tag)
+{
+    LaunchScope scope(tag, st);
+#define X(NN)                                                                                                        \
+    case NN:                                                                                                         \
+        if (periodic) return launch_cols_pipe_t<NN, XF_PFWD, MidCubeDivide, XF_PINV, OutShard>(tm, a, mid, st, om);  \
+        return launch_cols_pipe_t<NN, XF_DST, MidCubeDivide, XF_DST, OutShard>(tm, a, mid, st, om);
+    switch (N) { FDMB_FOR_EACH_PIPE_N(X) }
+#undef X
+    return cudaErrorInvalidValue;
+}
+
+// ---- cross-GPU barrier on the handle's stream -----------------------------------------------------
+// Thread t publishes this rank's arrival epoch into rank t's flag array (release, system scope: all
+// peer stores of the kernels that ran before on this stream are complete at the kernel boundary),
+// then waits until rank t's epoch has arrived here.  A lost peer traps after ~30 s instead of hanging.
+struct PeerFlags { unsigned long long* f[FDMB_MAX_RANKS]; };
+
+__global__ void k_mg_barrier(PeerFlags pf, int rank, int nranks, unsigned long long epoch)
+{
+    const int t = threadIdx.x;
+    if (t < nranks) {
+        __threadfence_system();
+        unsigned long long* dst = pf.f[t] + rank;
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(epoch) : "memory");
+        const unsigned long long* src = pf.f[rank] + t;
+        unsigned long long t0, t1, seen;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(src) : "memory");
+            if (seen >= epoch) break;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > 30000000000ull) __trap();
+            __nanosleep(200);
+        }
+    }
+    __syncthreads();
+    __threadfence_system();
+}
+
 }  // namespace fdmb
 
 using namespace fdmb;
@@ -146,6 +204,8 @@ int fdmb_lapl_cube::init()
     FDMB_CUDA(cudaMemcpy(d_lmx, lm_x.data(), sizeof(double) * (nx + 1), cudaMemcpyHostToDevice));
     FDMB_CUDA(cudaMemcpy(d_lmy, lm_y.data(), sizeof(double) * (ny + 1), cudaMemcpyHostToDevice));
     FDMB_CUDA(cudaMemcpy(d_lmz, lm_z.data(), sizeof(double) * (nz + 1), cudaMemcpyHostToDevice));
+    FDMB_CUDA(cudaGetDevice(&device));
+    if (nranks > 1) return init_sharded();
     FDMB_CUDA(cudaMalloc(&d_work, sizeof(double) * (size_t)nz * ny * px));
     if (pipe_enabled()) {
         // tensor maps over the pitched work array: dims (x, y, z), tiles [N][B] along y or z
@@ -164,15 +224,141 @@ int fdmb_lapl_cube::init()
     return FDMB_OK;
 }
 
+static int ilog2(int v) { int l = 0; while ((1 << l) < v) l++; return l; }
+
+int fdmb_lapl_cube::init_sharded()
+{
+    const int J0 = periodic ? 0 : 1;
+    if (nranks != 2 && nranks != 4 && nranks != 8) {
+        set_error("LaplCube: nranks must be 1, 2, 4 or 8 (got %d)", nranks);
+        return FDMB_ERR_INVALID;
+    }
+    if (rank < 0 || rank >= nranks) { set_error("LaplCube: rank %d out of range", rank); return FDMB_ERR_INVALID; }
+    if (!pipe_supported_N(Ny) || !pipe_supported_N(Nz) || Ny / nranks < 2 || Nz / nranks < 2) {
+        set_error("LaplCube: the sharded solve needs y/z transform lengths >= 32 and >= 2*nranks (got %d, %d)", Ny, Nz);
+        return FDMB_ERR_INVALID;
+    }
+    Sy = Ny / nranks; Sz = Nz / nranks;
+    slab_range(nz, periodic, nranks, rank, &z_first, &nzl);
+    slab_range(ny, periodic, nranks, rank, &y_first, &nyl);
+    const size_t plane = (size_t)ny * px;
+    const size_t a_bytes = (sizeof(double) * (size_t)Sz * plane + 255) & ~(size_t)255;
+    const size_t t_bytes = (sizeof(double) * (size_t)nz * Sy * px + 255) & ~(size_t)255;
+    off_T = a_bytes; off_flags = a_bytes + t_bytes;
+    mg_bytes = off_flags + 256;
+    FDMB_CUDA(cudaMalloc(&mg_block, mg_bytes));
+    FDMB_CUDA(cudaMemset(mg_block, 0, mg_bytes));
+    d_A = reinterpret_cast<double*>(mg_block);
+    d_T = reinterpret_cast<double*>(reinterpret_cast<char*>(mg_block) + off_T);
+    d_flags = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(mg_block) + off_flags);
+    peer_block[rank] = mg_block;
+    // local views: the uniform allocations keep a slot-0 plane / row on rank 0 of a Dirichlet axis
+    d_work = d_A + (size_t)(z_first + J0 - rank * Sz) * plane;
+    double* t_loc = d_T + (size_t)(y_first + J0 - rank * Sy) * px;
+    int rc;
+    boxrows_y = ny < 256 ? ny : 256; nchunk_y = (ny + boxrows_y - 1) / boxrows_y;
+    if ((rc = make_tensor_map_3d(&tm_y, d_work, nx, ny, nzl, 8ull * px, 8ull * plane, pipe_B(Ny), boxrows_y, 1))) return rc;
+    boxrows_z = nz < 256 ? nz : 256; nchunk_z = (nz + boxrows_z - 1) / boxrows_z;
+    if ((rc = make_tensor_map_3d(&tm_z, t_loc, nx, nyl, nz, 8ull * px, 8ull * (unsigned long long)Sy * px, pipe_B(Nz), 1,
+                                 boxrows_z)))
+        return rc;
+    pipe_y = pipe_z = true;
+    return FDMB_OK;
+}
+
+int fdmb_lapl_cube::attach(void* const* bases)
+{
+    for (int q = 0; q < nranks; q++)
+        if (q != rank) peer_block[q] = bases[q];
+    attached = true;
+    return FDMB_OK;
+}
+
+int fdmb_lapl_cube::barrier(cudaStream_t st)
+{
+    PeerFlags pf{};
+    for (int q = 0; q < nranks; q++)
+        pf.f[q] = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(peer_block[q]) + off_flags);
+    epoch++;
+    LaunchScope scope("cube_mg_barrier", st);
+    k_mg_barrier<<<1, 32, 0, st>>>(pf, rank, nranks, epoch);
+    FDMB_CHECK_LAUNCH();
+    return FDMB_OK;
+}
+
 fdmb_lapl_cube::~fdmb_lapl_cube()
 {
-    cudaFree(d_lmx); cudaFree(d_lmy); cudaFree(d_lmz); cudaFree(d_work);
+    cudaFree(d_lmx); cudaFree(d_lmy); cudaFree(d_lmz);
+    if (nranks > 1) {
+        for (int q = 0; q < nranks; q++)
+            if (q != rank && peer_ipc[q] && peer_block[q]) cudaIpcCloseMemHandle(peer_block[q]);
+        cudaFree(mg_block);
+    } else {
+        cudaFree(d_work);
+    }
     cudaFree(d_rhs); cudaFree(d_ans);
     if (stream) cudaStreamDestroy(stream);
 }
 
+// Sharded solve: x rows (local) -> y columns, stores scattered into the peers' pencil buffers ->
+// barrier -> z forward, divide, z inverse on the local pencils, stores scattered back into the
+// peers' slabs -> barrier -> y columns, x rows (local).  d_in / d_out are this rank's z-slab.
+int fdmb_lapl_cube::solve_device_sharded(double* d_out, const double* d_in, cudaStream_t st)
+{
+    if (!attached) { set_error("LaplCube: sharded handle used before attach_ipc/attach_local"); return FDMB_ERR_COMM; }
+    const int kf = periodic ? XF_PFWD : XF_DST;
+    const int ki = periodic ? XF_PINV : XF_DST;
+    const long long plane = (long long)ny * px;
+    int rc;
+    auto rows = [&](const double* in, double* out, int in_pitch, int out_pitch, double scale, int kind, const char* tag,
+                    int reverse) -> cudaError_t {
+        if (pipe_supported_N(Nx) && (reinterpret_cast<uintptr_t>(in) & 15) == 0) {
+            RowsPipeArgs p{};
+            p.in = in; p.out = out; p.nrows = (long long)nzl * ny; p.nvalid = nx; p.in_pitch = in_pitch;
+            p.out_pitch = out_pitch; p.reverse = reverse; p.scale = scale; p.SN = tx.SN; p.WM = tx.WM;
+            return launch_rows_pipe(Nx, kind, p, st, tag);
+        }
+        RowsArgs r{};
+        r.in = in; r.out = out; r.nrows = (long long)nzl * ny; r.nvalid = nx; r.in_pitch = in_pitch;
+        r.out_pitch = out_pitch; r.scale = scale; r.SN = tx.SN; r.WM = tx.WM;
+        return launch_rows(Nx, kind, r, st, tag);
+    };
+    FDMB_CUDA(rows(d_in, d_work, nx, px, dx * slx, kf, "cube_x_fwd", 0));
+    {   // y forward, transposing into the pencil buffers T_q[z'][y slot & (Sy-1)][x]
+        ColsPipeArgs p{};
+        p.out = nullptr; p.nvalid = ny; p.nb = nx; p.no = nzl; p.taxis = 1; p.boxrows = boxrows_y; p.nchunk = nchunk_y;
+        p.reverse = 1; p.scale = dy * sly; p.SN = ty.SN; p.WM = ty.WM;
+        OutShard om{};
+        for (int q = 0; q < nranks; q++)
+            om.base[q] = reinterpret_cast<double*>(reinterpret_cast<char*>(peer_block[q]) + off_T);
+        om.logS = ilog2(Sy); om.maskS = Sy - 1; om.sj = px; om.so = (long long)Sy * px; om.o_off = z_first;
+        FDMB_CUDA(launch_cols_pipe_shard(Ny, kf, tm_y, p, om, st, "cube_y_fwd_xpose"));
+    }
+    if ((rc = barrier(st))) return rc;
+    {   // z forward, divide, z inverse; stores go back to the slabs A_r[z slot & (Sz-1)][y'][x]
+        ColsPipeArgs p{};
+        p.out = nullptr; p.nvalid = nz; p.nb = nx; p.no = nyl; p.taxis = 2; p.boxrows = boxrows_z; p.nchunk = nchunk_z;
+        p.reverse = 0; p.mid_o_off = y_first; p.scale = dz * slz; p.scale2 = slz; p.SN = tz.SN; p.WM = tz.WM;
+        MidCubeDivide mid{d_lmz, d_lmx, d_lmy, periodic ? 1 : 0};
+        OutShard om{};
+        for (int q = 0; q < nranks; q++) om.base[q] = reinterpret_cast<double*>(peer_block[q]);
+        om.logS = ilog2(Sz); om.maskS = Sz - 1; om.sj = plane; om.so = px; om.o_off = y_first;
+        FDMB_CUDA(launch_cols_pipe_cube_divide_shard(Nz, periodic != 0, tm_z, p, mid, om, st, "cube_z_fwd_div_inv_xpose"));
+    }
+    if ((rc = barrier(st))) return rc;
+    {   // y inverse (local)
+        ColsPipeArgs p{};
+        p.out = d_work; p.out_sj = px; p.out_so = plane; p.nvalid = ny; p.nb = nx; p.no = nzl; p.taxis = 1;
+        p.boxrows = boxrows_y; p.nchunk = nchunk_y; p.reverse = 0; p.scale = sly; p.SN = ty.SN; p.WM = ty.WM;
+        FDMB_CUDA(launch_cols_pipe(Ny, ki, tm_y, p, st, "cube_y_inv"));
+    }
+    FDMB_CUDA(rows(d_work, d_out, px, nx, slx, ki, "cube_x_inv", 1));
+    return FDMB_OK;
+}
+
 int fdmb_lapl_cube::solve_device(double* d_out, const double* d_in, cudaStream_t st)
 {
+    if (nranks > 1) return solve_device_sharded(d_out, d_in, st);
     const int kf = periodic ? XF_PFWD : XF_DST;
     const int ki = periodic ? XF_PINV : XF_DST;
     const long long plane = (long long)ny * px;
@@ -231,7 +417,7 @@ int fdmb_lapl_cube::solve_device(double* d_out, const double* d_in, cudaStream_t
 
 int fdmb_lapl_cube::solve_host(double* ans, const double* rhs)
 {
-    const size_t bytes = sizeof(double) * (size_t)nx * ny * nz;
+    const size_t bytes = sizeof(double) * (size_t)nx * ny * (nranks > 1 ? nzl : nz);   // this rank's slab
     if (!d_rhs) FDMB_CUDA(cudaMalloc(&d_rhs, bytes));
     if (!d_ans) FDMB_CUDA(cudaMalloc(&d_ans, bytes));
     FDMB_CUDA(cudaMemcpyAsync(d_rhs, rhs, bytes, cudaMemcpyHostToDevice, stream));
@@ -259,6 +445,99 @@ int fdmb_lapl_cube_create(fdmb_lapl_cube** out, double dx, double dy, double dz,
     return FDMB_OK;
 }
 
+int fdmb_slab_range(int n, int periodic, int nranks, int rank, int* first, int* count)
+{
+    const int N = periodic ? n : n + 1;
+    if (n < 1 || nranks < 1 || rank < 0 || rank >= nranks || !first || !count || !is_pow2(N) || !is_pow2(nranks) ||
+        N / nranks < 2) {
+        set_error("fdmb_slab_range: n=%d (transform length %d) cannot be split over %d ranks", n, N, nranks);
+        return FDMB_ERR_INVALID;
+    }
+    slab_range(n, periodic ? 1 : 0, nranks, rank, first, count);
+    return FDMB_OK;
+}
+
+int fdmb_lapl_cube_create_sharded(fdmb_lapl_cube** out, double dx, double dy, double dz, double lx, double ly, double lz,
+                                  int nx, int ny, int nz, int periodic, int rank, int nranks)
+{
+    if (!out) { set_error("null handle pointer"); return FDMB_ERR_INVALID; }
+    *out = nullptr;
+    auto* h = new (std::nothrow) fdmb_lapl_cube();
+    if (!h) { set_error("out of host memory"); return FDMB_ERR_NOMEM; }
+    h->dx = dx; h->dy = dy; h->dz = dz; h->lx = lx; h->ly = ly; h->lz = lz;
+    h->nx = nx; h->ny = ny; h->nz = nz; h->periodic = periodic ? 1 : 0;
+    h->rank = rank; h->nranks = nranks;
+    int rc = h->init();
+    if (rc) { delete h; return rc; }
+    *out = h;
+    return FDMB_OK;
+}
+
+int fdmb_lapl_cube_local_slab(fdmb_lapl_cube* h, int* z_first, int* nz_local)
+{
+    if (!h || !z_first || !nz_local) { set_error("null argument"); return FDMB_ERR_INVALID; }
+    *z_first = h->nranks > 1 ? h->z_first : 0;
+    *nz_local = h->nranks > 1 ? h->nzl : h->nz;
+    return FDMB_OK;
+}
+
+int fdmb_lapl_cube_export_ipc(fdmb_lapl_cube* h, void* handle)
+{
+    if (!h || !handle || h->nranks < 2) { set_error("export_ipc needs a sharded handle"); return FDMB_ERR_INVALID; }
+    static_assert(sizeof(cudaIpcMemHandle_t) == FDMB_IPC_HANDLE_BYTES, "IPC handle size");
+    cudaIpcMemHandle_t ih;
+    FDMB_CUDA(cudaIpcGetMemHandle(&ih, h->mg_block));
+    memcpy(handle, &ih, sizeof(ih));
+    return FDMB_OK;
+}
+
+int fdmb_lapl_cube_attach_ipc(fdmb_lapl_cube* h, const void* handles)
+{
+    if (!h || !handles || h->nranks < 2) { set_error("attach_ipc needs a sharded handle"); return FDMB_ERR_INVALID; }
+    void* bases[FDMB_MAX_RANKS] = {};
+    for (int q = 0; q < h->nranks; q++) {
+        if (q == h->rank) continue;
+        cudaIpcMemHandle_t ih;
+        memcpy(&ih, (const char*)handles + (size_t)q * FDMB_IPC_HANDLE_BYTES, sizeof(ih));
+        cudaError_t e = cudaIpcOpenMemHandle(&bases[q], ih, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            set_error("cudaIpcOpenMemHandle for rank %d failed: %s", q, cudaGetErrorString(e));
+            return FDMB_ERR_COMM;
+        }
+        h->peer_ipc[q] = true;
+    }
+    return h->attach(bases);
+}
+
+int fdmb_lapl_cube_attach_local(fdmb_lapl_cube* h, fdmb_lapl_cube* const* all)
+{
+    if (!h || !all || h->nranks < 2) { set_error("attach_local needs a sharded handle"); return FDMB_ERR_INVALID; }
+    void* bases[FDMB_MAX_RANKS] = {};
+    int cur = 0;
+    FDMB_CUDA(cudaGetDevice(&cur));
+    FDMB_CUDA(cudaSetDevice(h->device));
+    for (int q = 0; q < h->nranks; q++) {
+        if (q == h->rank) continue;
+        if (!all[q] || all[q]->nranks != h->nranks || all[q]->rank != q || all[q]->mg_bytes != h->mg_bytes) {
+            set_error("attach_local: handle %d does not belong to this sharded solve", q);
+            cudaSetDevice(cur);
+            return FDMB_ERR_INVALID;
+        }
+        if (all[q]->device != h->device) {
+            cudaError_t e = cudaDeviceEnablePeerAccess(all[q]->device, 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+            else if (e != cudaSuccess) {
+                set_error("cudaDeviceEnablePeerAccess(%d -> %d) failed: %s", h->device, all[q]->device, cudaGetErrorString(e));
+                cudaSetDevice(cur);
+                return FDMB_ERR_COMM;
+            }
+        }
+        bases[q] = all[q]->mg_block;
+    }
+    FDMB_CUDA(cudaSetDevice(cur));
+    return h->attach(bases);
+}
+
 int fdmb_lapl_cube_solve(fdmb_lapl_cube* h, double* ans, const double* rhs)
 {
     if (!h || !ans || !rhs) { set_error("null argument"); return FDMB_ERR_INVALID; }
@@ -268,6 +547,14 @@ int fdmb_lapl_cube_solve(fdmb_lapl_cube* h, double* ans, const double* rhs)
 int fdmb_lapl_cube_solve_device(fdmb_lapl_cube* h, double* d_ans, const double* d_rhs, void* stream)
 {
     if (!h || !d_ans || !d_rhs) { set_error("null argument"); return FDMB_ERR_INVALID; }
+    if (h->nranks > 1) {   // several ranks may share one process: launch on the handle's device
+        int cur = 0;
+        FDMB_CUDA(cudaGetDevice(&cur));
+        if (cur != h->device) FDMB_CUDA(cudaSetDevice(h->device));
+        int rc = h->solve_device(d_ans, d_rhs, stream ? (cudaStream_t)stream : h->stream);
+        if (cur != h->device) cudaSetDevice(cur);
+        return rc;
+    }
     return h->solve_device(d_ans, d_rhs, stream ? (cudaStream_t)stream : h->stream);
 }
 

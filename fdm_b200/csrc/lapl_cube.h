@@ -16,6 +16,23 @@ cudaError_t launch_rows_pipe(int N, int kind, const RowsPipeArgs& a, cudaStream_
 cudaError_t launch_cols_pipe(int N, int kind, const CUtensorMap& tm, const ColsPipeArgs& a, cudaStream_t st, const char* tag);
 cudaError_t launch_cols_pipe_cube_divide(int N, bool periodic, const CUtensorMap& tm, const ColsPipeArgs& a,
                                          const MidCubeDivide& mid, cudaStream_t st, const char* tag);
+// multi-GPU variants: the sweep's stores scatter over the peers' buffers (slab <-> pencil transpose)
+cudaError_t launch_cols_pipe_shard(int N, int kind, const CUtensorMap& tm, const ColsPipeArgs& a, const OutShard& om,
+                                   cudaStream_t st, const char* tag);
+cudaError_t launch_cols_pipe_cube_divide_shard(int N, bool periodic, const CUtensorMap& tm, const ColsPipeArgs& a,
+                                               const MidCubeDivide& mid, const OutShard& om, cudaStream_t st,
+                                               const char* tag);
+
+// Even split of the N index slots of one axis over P ranks (N, P powers of two).  Slot 0 of a
+// Dirichlet axis is the implicit zero boundary, so rank 0 owns one interior entry fewer.
+// first/count are in 0-based interior entries (what the caller's arrays hold).
+inline void slab_range(int n, int periodic, int nranks, int rank, int* first, int* count)
+{
+    const int N = periodic ? n : n + 1, S = N / nranks, J0 = periodic ? 0 : 1;
+    const int lo = rank * S < J0 ? J0 : rank * S;   // first slot owned
+    *first = lo - J0;
+    *count = (rank + 1) * S - lo;
+}
 }  // namespace fdmb
 
 struct fdmb_lapl_cube {
@@ -33,8 +50,30 @@ struct fdmb_lapl_cube {
     CUtensorMap tm_y{}, tm_z{};
     int boxrows_y = 0, nchunk_y = 0, boxrows_z = 0, nchunk_z = 0;
 
+    // ---- z-slab sharding over `nranks` GPUs (nranks == 1: everything above is the whole problem) ----
+    // Rank r owns the z slots [r*Sz, (r+1)*Sz) of the caller's arrays and, between the two transposes,
+    // the y slots [r*Sy, (r+1)*Sy) of the pencil buffer.  d_A ([Sz][ny][px]) and d_T ([nz][Sy][px]) are
+    // carved out of one allocation that the peers map (IPC or same-process peer access).
+    int rank = 0, nranks = 1;
+    int Sy = 0, Sz = 0;                 // slots per rank along y / z
+    int z_first = 0, nzl = 0;           // local interior planes: global z' in [z_first, z_first + nzl)
+    int y_first = 0, nyl = 0;           // local pencil rows
+    void* mg_block = nullptr;           // A | T | flags
+    size_t mg_bytes = 0, off_T = 0, off_flags = 0;
+    double *d_A = nullptr, *d_T = nullptr;                 // uniform allocations (slot 0 row/plane included)
+    unsigned long long* d_flags = nullptr;                 // [FDMB_MAX_RANKS] arrival epochs, written by the peers
+    void* peer_block[fdmb::FDMB_MAX_RANKS] = {};           // mapped bases of every rank's mg_block (own included)
+    bool peer_ipc[fdmb::FDMB_MAX_RANKS] = {};
+    bool attached = false;
+    unsigned long long epoch = 0;
+    int device = 0;
+
     int init();
+    int init_sharded();
+    int attach(void* const* bases);
+    int barrier(cudaStream_t st);
     int solve_device(double* d_out, const double* d_in, cudaStream_t st);
+    int solve_device_sharded(double* d_out, const double* d_in, cudaStream_t st);
     int solve_host(double* ans, const double* rhs);
     ~fdmb_lapl_cube();
 };

@@ -99,7 +99,8 @@ cudaError_t launch_tridiag_rows(const TridiagArgs& a, cudaStream_t st, const cha
     LaunchScope scope(tag, st);
     const int P = a.nr | 1;
     const size_t smem = sizeof(double) * (size_t)(2 * TS * P + 3 * (a.nr + 1));
-    static size_t set_smem = 0;
+    static size_t set_smem_dev[64] = {0};     // function attributes are per device
+    size_t& set_smem = set_smem_dev[current_device_slot()];
     if (smem > set_smem) {
         cudaError_t e = cudaFuncSetAttribute(k_tridiag_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;

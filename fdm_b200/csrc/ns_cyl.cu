@@ -1,0 +1,539 @@
+// NSCyl on B200: incompressible Navier-Stokes between two coaxial cylinders (Taylor-Couette) on a
+// staggered grid in (phi, z, r), explicit Euler predictor + pressure projection.  Replaces
+// fdm::NSCyl<double,check,zflag> (reference src/ns_cyl.h:17-132, src/ns_cyl.cpp:23-484).
+// The whole step is device resident; the state arrays keep the reference's extents and layout
+// (ghosts included, src/ns_cyl.h:80-93) so get/set_field are plain copies of ns.u.vec etc.
+//
+//   step()   = init_bound (ns_cyl.cpp:81-172)  -> k_cyl_bound_r, k_cyl_bound_z, k_cyl_bound_p
+//              FGH        (ns_cyl.cpp:175-277) -> k_cyl_fgh<false>
+//              poisson    (ns_cyl.cpp:408-442) -> k_cyl_rhs + LaplCyl3FFT2 solve
+//              update_uvwp(ns_cyl.cpp:445-484) -> k_cyl_update
+//   L_step() = the same with L_FGH (ns_cyl.cpp:280-405), linearised about u0, v0, w0 -> k_cyl_fgh<true>
+//
+// phi is periodic (slowest index), z is Dirichlet (zflag none) or periodic, r is fastest.
+// Index wrap follows the reference accessor (src/tensor.h:119-123).
+#include <cmath>
+#include <new>
+#include <random>
+#include <vector>
+
+#include "common.h"
+#include "lapl_cyl.h"
+
+namespace fdmb {
+
+// offset-indexed 3-D view [phi][z][r], row-major, last index fastest (src/tensor.h:207-219)
+struct CFld {
+    double* p;
+    int lz, lr;           // lowest z / r index
+    long long sp, sz;     // strides (doubles) of the phi and z axes
+    __host__ __device__ __forceinline__ double& at(int i, int k, int j) const
+    {
+        return p[(long long)i * sp + (long long)(k - lz) * sz + (j - lr)];
+    }
+};
+
+struct CylGeom {
+    int nr, nz, nphi;
+    int zper;                       // z periodic?
+    int z_, z0, z1, zn, znn;        // ns_cyl.h:71-75
+    double U0, dt;
+    double cRr, cRz, cRp;           // 1/Re/dr2, 1/Re/dz2, 1/Re/dphi2
+    double idr, idz, idphi;         // 1/dr, 1/dz, 1/dphi
+    double iRe;                     // 1/Re
+    double iRdr, iRdz;              // 1/Re/dr, 1/Re/dz
+    double iRdphi;                  // 1/dphi/Re
+    double idr2, idz2, idt;
+    double dtdr, dtdz, dtdphi;      // dt/dr, dt/dz, dt/dphi
+    // r-dependent factors (host tables, same formulas as the reference):
+    //   at u points r = r0 + dr*j (j = 0..nr):   fr2, fr1, firr (1/r^2), fir (1/r)
+    //   at cell centres r = r0 + dr*j - dr/2 (j = 0..nr+1):   cr2, cr1, cirr, cir, crp = r+dr/2, crm = r-dr/2
+    const double *fr2, *fr1, *firr, *fir;
+    const double *cr2, *cr1, *cirr, *cir, *crp, *crm;
+};
+
+// ---- init_bound (ns_cyl.cpp:81-172) --------------------------------------------------------------
+// r-direction ghosts of w, v, u (ns_cyl.cpp:83-104): one thread per (phi, z row)
+__global__ void k_cyl_bound_r(CFld u, CFld v, CFld w, CylGeom g)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x + g.z_;
+    const int i = blockIdx.y;
+    if (k > g.znn) return;
+    const int nr = g.nr;
+    if (k >= g.z0) {
+        w.at(i, k, 0) = 2 * g.U0 - w.at(i, k, 1);
+        w.at(i, k, nr + 1) = -w.at(i, k, nr);
+    }
+    v.at(i, k, 0) = -v.at(i, k, 1);
+    v.at(i, k, nr + 1) = -v.at(i, k, nr);
+    if (k >= g.z0) {
+        u.at(i, k, -1) = u.at(i, k, 1);
+        u.at(i, k, nr + 1) = u.at(i, k, nr - 1);
+    }
+}
+
+// z-direction ghosts, Dirichlet z only (ns_cyl.cpp:106-128).  The v mirror loops its r index over
+// z0..znn (ns_cyl.cpp:108) -- reproduced, clamped to the allocated r range.
+__global__ void k_cyl_bound_z(CFld u, CFld v, CFld w, CylGeom g, int jmax_v)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x - 1;   // -1 .. nr+1
+    const int i = blockIdx.y;
+    const int nr = g.nr, nz = g.nz;
+    if (j > nr + 1) return;
+    if (j >= g.z0 && j <= jmax_v) {
+        v.at(i, -1, j) = v.at(i, 1, j);
+        v.at(i, nz + 1, j) = v.at(i, nz - 1, j);
+    }
+    u.at(i, 0, j) = -u.at(i, 1, j);
+    u.at(i, nz + 1, j) = -u.at(i, nz, j);
+    if (j >= 0) {
+        w.at(i, 0, j) = -w.at(i, 1, j);
+        w.at(i, nz + 1, j) = -w.at(i, nz, j);
+    }
+}
+
+// pressure ghosts (ns_cyl.cpp:132-171); blockIdx.z = 0: r faces, 1: z faces (Dirichlet z)
+__global__ void k_cyl_bound_p(CFld u, CFld v, CFld p, CylGeom g)
+{
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y;
+    const int nr = g.nr, nz = g.nz;
+    if (blockIdx.z == 0) {
+        const int k = a + g.z1;
+        if (k > g.zn) return;
+        {
+            const int j = 0;
+            p.at(i, k, 0) = p.at(i, k, 1) -
+                (g.crp[j] * u.at(i, k, 1) * g.cir[j] - 2 * u.at(i, k, 0) + g.crm[j] * u.at(i, k, -1) * g.cir[j]) * g.iRdr;
+        }
+        {
+            const int j = nr;
+            p.at(i, k, nr + 1) = p.at(i, k, nr) +
+                (g.crp[j] * u.at(i, k, nr + 1) * g.cir[j] - 2 * u.at(i, k, nr) + g.crm[j] * u.at(i, k, nr - 1) * g.cir[j]) * g.iRdr;
+        }
+    } else {
+        const int j = a + 1;
+        if (j > nr) return;
+        p.at(i, 0, j) = p.at(i, 1, j) - (v.at(i, 1, j) - 2 * v.at(i, 0, j) + v.at(i, -1, j)) * g.iRdz;
+        p.at(i, nz + 1, j) = p.at(i, nz, j) + (v.at(i, nz + 1, j) - 2 * v.at(i, nz, j) + v.at(i, nz - 1, j)) * g.iRdz;
+    }
+}
+
+__device__ __forceinline__ double sq(double x) { return x * x; }
+
+// ---- FGH / L_FGH (ns_cyl.cpp:175-277, 280-405) ---------------------------------------------------
+// One thread per (i, k, j) in [0..nphi-1] x [z0..zn] x [0..nr]:
+//   F where k >= z1 (the reference loops i = 1..nphi and relies on the periodic wrap, :181),
+//   G where j >= 1, H where k >= z1 and j >= 1.
+template <bool LIN>
+__global__ void __launch_bounds__(256)
+k_cyl_fgh(CFld u, CFld v, CFld w, CFld u0, CFld v0, CFld w0, CFld F, CFld G, CFld H, CylGeom g)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = blockIdx.y * blockDim.y + threadIdx.y + g.z0;
+    const int i = blockIdx.z;
+    if (j > g.nr || k > g.zn) return;
+    const int ip = (i + 1 == g.nphi) ? 0 : i + 1, im = (i == 0) ? g.nphi - 1 : i - 1;
+    int kp = k + 1, km = k - 1;
+    if (g.zper) { if (kp == g.nz) kp = 0; if (km < 0) km = g.nz - 1; }
+#define U(a, b, c) u.at(a, b, c)
+#define V(a, b, c) v.at(a, b, c)
+#define W(a, b, c) w.at(a, b, c)
+#define U0(a, b, c) u0.at(a, b, c)
+#define V0(a, b, c) v0.at(a, b, c)
+#define W0(a, b, c) w0.at(a, b, c)
+    if (k >= g.z1) {
+        const double r2 = g.fr2[j], r1 = g.fr1[j], irr = g.firr[j], ir = g.fir[j];
+        const double uc = U(i, k, j);
+        double conv;
+        if (!LIN) {
+            conv =
+                (r2 * sq(0.5 * (uc + U(i, k, j + 1))) - r1 * sq(0.5 * (U(i, k, j - 1) + uc))) * g.idr +
+                0.25 * ((uc + U(i, kp, j)) * (V(i, k, j + 1) + V(i, k, j)) -
+                        (U(i, km, j) + uc) * (V(i, km, j + 1) + V(i, km, j))) * g.idz +
+                0.25 * ((uc + U(ip, k, j)) * (W(i, k, j + 1) + W(i, k, j)) -
+                        (U(im, k, j) + uc) * (W(im, k, j + 1) + W(im, k, j))) * g.idphi * ir -
+                sq(0.5 * (W(i, k, j + 1) + W(i, k, j))) * ir;
+        } else {
+            conv =
+                (r2 * (0.5 * uc + U(i, k, j + 1)) * (U0(i, k, j) + U0(i, k, j + 1)) -
+                 r1 * (0.5 * U(i, k, j - 1) + uc) * (U0(i, k, j - 1) + U0(i, k, j))) * g.idr +
+                0.25 * ((uc + U(i, kp, j)) * (V0(i, k, j + 1) + V0(i, k, j)) -
+                        (U(i, km, j) + uc) * (V0(i, km, j + 1) + V0(i, km, j))) * g.idz +
+                0.25 * ((U0(i, k, j) + U0(i, kp, j)) * (V(i, k, j + 1) + V(i, k, j)) -
+                        (U0(i, km, j) + U0(i, k, j)) * (V(i, km, j + 1) + V(i, km, j))) * g.idz +
+                0.25 * ((uc + U(ip, k, j)) * (W0(i, k, j + 1) + W0(i, k, j)) -
+                        (U(im, k, j) + uc) * (W0(im, k, j + 1) + W0(im, k, j))) * g.idphi * ir +
+                0.25 * ((U0(i, k, j) + U0(ip, k, j)) * (W(i, k, j + 1) + W(i, k, j)) -
+                        (U0(im, k, j) + U0(i, k, j)) * (W(im, k, j + 1) + W(im, k, j))) * g.idphi * ir -
+                0.5 * (W(i, k, j + 1) + W(i, k, j)) * (W0(i, k, j + 1) + W0(i, k, j)) * ir;
+        }
+        F.at(i, k, j) = uc + g.dt * (
+            (r2 * U(i, k, j + 1) - 2 * uc + r1 * U(i, k, j - 1)) * g.cRr +
+            (U(i, kp, j) - 2 * uc + U(i, km, j)) * g.cRz +
+            (U(ip, k, j) - 2 * uc + U(im, k, j)) * g.cRp * irr -
+            conv -
+            uc * irr * g.iRe -
+            2 * (0.5 * (W(i, k, j + 1) + W(i, k, j)) - 0.5 * (W(im, k, j + 1) + W(im, k, j))) * irr * g.iRdphi);
+    }
+    if (j >= 1) {
+        const double r2 = g.cr2[j], r1 = g.cr1[j], irr = g.cirr[j], ir = g.cir[j];
+        {
+            const double vc = V(i, k, j);
+            double conv;
+            if (!LIN) {
+                conv =
+                    (sq(0.5 * (vc + V(i, kp, j))) - sq(0.5 * (V(i, km, j) + vc))) * g.idz +
+                    0.25 * (r2 * (U(i, k, j) + U(i, kp, j)) * (V(i, k, j + 1) + vc) -
+                            r1 * (U(i, k, j - 1) + U(i, kp, j - 1)) * (vc + V(i, k, j - 1))) * g.idr +
+                    0.25 * ((W(i, k, j) + W(i, kp, j)) * (vc + V(ip, k, j)) -
+                            (W(im, k, j) + W(im, kp, j)) * (V(im, k, j) + vc)) * g.idphi * ir;
+            } else {
+                conv =
+                    (0.5 * (vc + V(i, kp, j)) * (V0(i, k, j) + V0(i, kp, j)) -
+                     0.5 * (V(i, km, j) + vc) * (V0(i, km, j) + V0(i, k, j))) * g.idz +
+                    0.25 * (r2 * (U(i, k, j) + U(i, kp, j)) * (V0(i, k, j + 1) + V0(i, k, j)) -
+                            r1 * (U(i, k, j - 1) + U(i, kp, j - 1)) * (V0(i, k, j) + V0(i, k, j - 1))) * g.idr +
+                    0.25 * (r2 * (U0(i, k, j) + U0(i, kp, j)) * (V(i, k, j + 1) + vc) -
+                            r1 * (U0(i, k, j - 1) + U0(i, kp, j - 1)) * (vc + V(i, k, j - 1))) * g.idr +
+                    0.25 * ((W(i, k, j) + W(i, kp, j)) * (V0(i, k, j) + V0(ip, k, j)) -
+                            (W(im, k, j) + W(im, kp, j)) * (V0(im, k, j) + V0(i, k, j))) * g.idphi * ir +
+                    0.25 * ((W0(i, k, j) + W0(i, kp, j)) * (vc + V(ip, k, j)) -
+                            (W0(im, k, j) + W0(im, kp, j)) * (V(im, k, j) + vc)) * g.idphi * ir;
+            }
+            G.at(i, k, j) = vc + g.dt * (
+                (r2 * V(i, k, j + 1) - 2 * vc + r1 * V(i, k, j - 1)) * g.cRr +
+                (V(i, kp, j) - 2 * vc + V(i, km, j)) * g.cRz +
+                (V(ip, k, j) - 2 * vc + V(im, k, j)) * g.cRp * irr -
+                conv);
+        }
+        if (k >= g.z1) {
+            const double wc = W(i, k, j);
+            double conv;
+            if (!LIN) {
+                conv =
+                    (sq(0.5 * (W(ip, k, j) + wc)) - sq(0.5 * (W(im, k, j) + wc))) * g.idphi * ir +
+                    0.25 * (r2 * (U(ip, k, j) + U(i, k, j)) * (W(i, k, j + 1) + wc) -
+                            r1 * (U(ip, k, j - 1) + U(i, k, j - 1)) * (wc + W(i, k, j - 1))) * g.idr +
+                    0.25 * ((wc + W(i, kp, j)) * (V(i, k, j) + V(ip, k, j)) -
+                            (W(i, km, j) + wc) * (V(i, km, j) + V(ip, km, j))) * g.idz +
+                    wc * 0.5 * (U(ip, k, j) + U(i, k, j)) * ir;
+            } else {
+                conv =
+                    (0.5 * (W(ip, k, j) + wc) * (W0(ip, k, j) + W0(i, k, j)) -
+                     0.5 * (W(im, k, j) + wc) * (W0(im, k, j) + W0(i, k, j))) * g.idphi * ir +
+                    0.25 * (r2 * (U(ip, k, j) + U(i, k, j)) * (W0(i, k, j + 1) + W0(i, k, j)) -
+                            r1 * (U(ip, k, j - 1) + U(i, k, j - 1)) * (W0(i, k, j) + W0(i, k, j - 1))) * g.idr +
+                    0.25 * (r2 * (U0(ip, k, j) + U0(i, k, j)) * (W(i, k, j + 1) + wc) -
+                            r1 * (U0(ip, k, j - 1) + U0(i, k, j - 1)) * (wc + W(i, k, j - 1))) * g.idr +
+                    0.25 * ((wc + W(i, kp, j)) * (V0(i, k, j) + V0(ip, k, j)) -
+                            (W(i, km, j) + wc) * (V0(i, km, j) + V0(ip, km, j))) * g.idz +
+                    0.25 * ((W0(i, k, j) + W0(i, kp, j)) * (V(i, k, j) + V(ip, k, j)) -
+                            (W0(i, km, j) + W0(i, k, j)) * (V(i, km, j) + V(ip, km, j))) * g.idz +
+                    W0(i, k, j) * 0.5 * (U(ip, k, j) + U(i, k, j)) * ir +
+                    wc * 0.5 * (U0(ip, k, j) + U0(i, k, j)) * ir;
+            }
+            H.at(i, k, j) = wc + g.dt * (
+                (r2 * W(i, k, j + 1) - 2 * wc + r1 * W(i, k, j - 1)) * g.cRr +
+                (W(i, kp, j) - 2 * wc + W(i, km, j)) * g.cRz +
+                (W(ip, k, j) - 2 * wc + W(im, k, j)) * g.cRp * irr -
+                conv -
+                wc * irr * g.iRe +
+                2 * (0.5 * (U(ip, k, j) + U(i, k, j)) - 0.5 * (U(i, k, j) + U(im, k, j))) * irr * g.iRdphi);
+        }
+    }
+#undef U
+#undef V
+#undef W
+#undef U0
+#undef V0
+#undef W0
+}
+
+// ---- poisson RHS (ns_cyl.cpp:408-439) --------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_cyl_rhs(CFld F, CFld G, CFld H, CFld p, CFld R, CylGeom g)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x + 1;
+    const int k = blockIdx.y * blockDim.y + threadIdx.y + g.z1;
+    const int i = blockIdx.z;
+    if (j > g.nr || k > g.zn) return;
+    const int im = (i == 0) ? g.nphi - 1 : i - 1;
+    int km = k - 1;
+    if (g.zper && km < 0) km = g.nz - 1;
+    const double ir = g.cir[j];
+    double r = ((g.crp[j] * F.at(i, k, j) - g.crm[j] * F.at(i, k, j - 1)) * ir * g.idr +
+                (G.at(i, k, j) - G.at(i, km, j)) * g.idz +
+                (H.at(i, k, j) - H.at(im, k, j)) * g.idphi * ir) * g.idt;
+    if (!g.zper && k <= 1) r -= p.at(i, k - 1, j) * g.idz2;
+    if (j <= 1) r -= g.crm[j] * ir * p.at(i, k, j - 1) * g.idr2;
+    if (j >= g.nr) r -= g.crp[j] * ir * p.at(i, k, j + 1) * g.idr2;
+    if (!g.zper && k >= g.nz) r -= p.at(i, k + 1, j) * g.idz2;
+    R.at(i, k, j) = r;
+}
+
+// ---- update_uvwp (ns_cyl.cpp:445-484) --------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_cyl_update(CFld u, CFld v, CFld w, CFld p, CFld x, CFld F, CFld G, CFld H, CylGeom g)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x + 1;
+    const int k = blockIdx.y * blockDim.y + threadIdx.y + g.z1;
+    const int i = blockIdx.z;
+    if (j > g.nr || k > g.zn) return;
+    const int ip = (i + 1 == g.nphi) ? 0 : i + 1;
+    const double xc = x.at(i, k, j);
+    if (j < g.nr) u.at(i, k, j) = F.at(i, k, j) - g.dtdr * (x.at(i, k, j + 1) - xc);
+    if (k < g.nz) {                                  // k = z1 .. nz-1 (ns_cyl.cpp:462)
+        int kp = k + 1;
+        if (g.zper && kp == g.nz) kp = 0;
+        v.at(i, k, j) = G.at(i, k, j) - g.dtdz * (x.at(i, kp, j) - xc);
+    }
+    w.at(i, k, j) = H.at(i, k, j) - g.dtdphi * g.cir[j] * (x.at(ip, k, j) - xc);
+    p.at(i, k, j) = xc;                              // p = x over the index-range intersection (tensor.h:103-111)
+}
+
+}  // namespace fdmb
+
+using namespace fdmb;
+
+struct fdmb_ns_cyl {
+    fdmb_ns_cyl_params prm{};
+    int nr = 0, nz = 0, nphi = 0, zper = 0;
+    double dr = 0, dz = 0, dphi = 0;
+    CylGeom g{};
+    CFld f[12]{};               // u v w p x F G H RHS u0 v0 w0
+    long long count[12]{};
+    double* d_tab = nullptr;    // r-dependent factor tables
+    fdmb_lapl_cyl* lapl = nullptr;
+    cudaStream_t stream = nullptr;
+    long long time_index = 0;
+
+    int init();
+    int step(int nsteps, int linear, cudaStream_t st);
+    ~fdmb_ns_cyl();
+};
+
+static int make_cfield(CFld& f, long long& count, int nphi, int z0, int z1, int r0, int r1)
+{
+    f.lz = z0; f.lr = r0;
+    f.sz = r1 - r0 + 1;
+    f.sp = (long long)(z1 - z0 + 1) * f.sz;
+    count = (long long)nphi * f.sp;
+    FDMB_CUDA(cudaMalloc(&f.p, sizeof(double) * count));
+    FDMB_CUDA(cudaMemset(f.p, 0, sizeof(double) * count));
+    return FDMB_OK;
+}
+
+int fdmb_ns_cyl::init()
+{
+    nr = prm.nr; nz = prm.nz; nphi = prm.nphi; zper = prm.zperiodic ? 1 : 0;
+    if (nr < 3 || nz < 3 || nphi < 4) { set_error("NSCyl: nr, nz >= 3 and nphi >= 4 required"); return FDMB_ERR_INVALID; }
+    const double R = prm.R, r0 = prm.r, h1 = prm.h1, h2 = prm.h2;
+    dr = (R - r0) / nr; dz = (h2 - h1) / nz; dphi = 2 * M_PI / nphi;          // ns_cyl.h:77
+    const double dr2 = dr * dr, dz2 = dz * dz, dphi2 = dphi * dphi;
+    // ns_cyl.h:95-97
+    int rc = fdmb_lapl_cyl_create(&lapl, dr, dz, r0 - dr / 2, R - r0 + dr, zper ? h2 - h1 : h2 - h1 + dz, nr, nz, nphi, zper);
+    if (rc) return rc;
+    FDMB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    g.nr = nr; g.nz = nz; g.nphi = nphi; g.zper = zper;
+    g.z_ = zper ? 0 : -1; g.z0 = 0; g.z1 = zper ? 0 : 1; g.zn = zper ? nz - 1 : nz; g.znn = zper ? nz - 1 : nz + 1;
+    const int z_ = g.z_, z0 = g.z0, z1 = g.z1, zn = g.zn, znn = g.znn;
+    // extents: ns_cyl.h:80-93
+    if ((rc = make_cfield(f[0], count[0], nphi, z0, znn, -1, nr + 1))) return rc;   // u
+    if ((rc = make_cfield(f[1], count[1], nphi, z_, znn, 0, nr + 1))) return rc;    // v
+    if ((rc = make_cfield(f[2], count[2], nphi, z0, znn, 0, nr + 1))) return rc;    // w
+    if ((rc = make_cfield(f[3], count[3], nphi, z0, znn, 0, nr + 1))) return rc;    // p
+    if ((rc = make_cfield(f[4], count[4], nphi, z1, zn, 1, nr))) return rc;         // x
+    if ((rc = make_cfield(f[5], count[5], nphi, z1, zn, 0, nr))) return rc;         // F
+    if ((rc = make_cfield(f[6], count[6], nphi, z0, zn, 1, nr))) return rc;         // G
+    if ((rc = make_cfield(f[7], count[7], nphi, z1, zn, 1, nr))) return rc;         // H
+    if ((rc = make_cfield(f[8], count[8], nphi, z1, zn, 1, nr))) return rc;         // RHS
+    if ((rc = make_cfield(f[9], count[9], nphi, z0, znn, -1, nr + 1))) return rc;   // u0
+    if ((rc = make_cfield(f[10], count[10], nphi, z_, znn, 0, nr + 1))) return rc;  // v0
+    if ((rc = make_cfield(f[11], count[11], nphi, z0, znn, 0, nr + 1))) return rc;  // w0
+    g.U0 = prm.u0; g.dt = prm.dt;
+    const double Re = prm.Re;
+    g.cRr = 1.0 / Re / dr2; g.cRz = 1.0 / Re / dz2; g.cRp = 1.0 / Re / dphi2;
+    g.idr = 1.0 / dr; g.idz = 1.0 / dz; g.idphi = 1.0 / dphi;
+    g.iRe = 1.0 / Re; g.iRdr = 1.0 / Re / dr; g.iRdz = 1.0 / Re / dz; g.iRdphi = 1.0 / dphi / Re;
+    g.idr2 = 1.0 / dr2; g.idz2 = 1.0 / dz2; g.idt = 1.0 / prm.dt;
+    g.dtdr = prm.dt / dr; g.dtdz = prm.dt / dz; g.dtdphi = prm.dt / dphi;
+    // r tables
+    const int T = nr + 2;
+    std::vector<double> tab(10 * (size_t)T, 0.0);
+    double *fr2 = &tab[0], *fr1 = &tab[T], *firr = &tab[2 * T], *fir = &tab[3 * T];
+    double *cr2 = &tab[4 * T], *cr1 = &tab[5 * T], *cirr = &tab[6 * T], *cir = &tab[7 * T], *crp = &tab[8 * T], *crm = &tab[9 * T];
+    for (int j = 0; j <= nr; j++) {
+        const double r = r0 + dr * j;                       // ns_cyl.cpp:184
+        fr2[j] = (r + 0.5 * dr) / r; fr1[j] = (r - 0.5 * dr) / r; firr[j] = 1.0 / (r * r); fir[j] = 1.0 / r;
+    }
+    for (int j = 0; j <= nr + 1; j++) {
+        const double r = r0 + dr * j - dr / 2;              // ns_cyl.cpp:217,246
+        cr2[j] = (r + 0.5 * dr) / r; cr1[j] = (r - 0.5 * dr) / r; cirr[j] = 1.0 / (r * r); cir[j] = 1.0 / r;
+        crp[j] = r + 0.5 * dr; crm[j] = r - 0.5 * dr;
+    }
+    FDMB_CUDA(cudaMalloc(&d_tab, sizeof(double) * tab.size()));
+    FDMB_CUDA(cudaMemcpy(d_tab, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice));
+    g.fr2 = d_tab; g.fr1 = d_tab + T; g.firr = d_tab + 2 * T; g.fir = d_tab + 3 * T;
+    g.cr2 = d_tab + 4 * T; g.cr1 = d_tab + 5 * T; g.cirr = d_tab + 6 * T; g.cir = d_tab + 7 * T;
+    g.crp = d_tab + 8 * T; g.crm = d_tab + 9 * T;
+    if (prm.vrandom == 1) {
+        // ns_cyl.h:99-108: default-seeded std::default_random_engine, uniform(-1e-3, 1e-3), drawn in
+        // (phi, z, r) order -- the same standard-library sequence as the reference build
+        std::vector<double> hv(count[1], 0.0);
+        std::default_random_engine generator;
+        std::uniform_real_distribution<double> distribution(-1e-3, 1e-3);
+        for (int i = 0; i < nphi; i++)
+            for (int k = z1; k <= zn; k++)
+                for (int j = 1; j <= nr; j++)
+                    hv[(size_t)i * f[1].sp + (size_t)(k - f[1].lz) * f[1].sz + (j - f[1].lr)] = distribution(generator);
+        FDMB_CUDA(cudaMemcpy(f[1].p, hv.data(), sizeof(double) * hv.size(), cudaMemcpyHostToDevice));
+    }
+    return FDMB_OK;
+}
+
+fdmb_ns_cyl::~fdmb_ns_cyl()
+{
+    for (auto& a : f) cudaFree(a.p);
+    cudaFree(d_tab);
+    if (lapl) fdmb_lapl_cyl_destroy(lapl);
+    if (stream) cudaStreamDestroy(stream);
+}
+
+int fdmb_ns_cyl::step(int nsteps, int linear, cudaStream_t st)
+{
+    const CFld &u = f[0], &v = f[1], &w = f[2], &p = f[3], &x = f[4], &F = f[5], &G = f[6], &H = f[7], &R = f[8];
+    const CFld &u0 = f[9], &v0 = f[10], &w0 = f[11];
+    const int nzrows = g.znn - g.z_ + 1;
+    for (int s = 0; s < nsteps; s++) {
+        {
+            LaunchScope sc("nscyl_bound_r", st);
+            dim3 grid((nzrows + 127) / 128, nphi);
+            k_cyl_bound_r<<<grid, 128, 0, st>>>(u, v, w, g);
+        }
+        if (!zper) {
+            LaunchScope sc("nscyl_bound_z", st);
+            const int jmax_v = g.znn < nr + 1 ? g.znn : nr + 1;
+            dim3 grid((nr + 3 + 127) / 128, nphi);
+            k_cyl_bound_z<<<grid, 128, 0, st>>>(u, v, w, g, jmax_v);
+        }
+        {
+            LaunchScope sc("nscyl_bound_p", st);
+            const int na = (g.zn - g.z1 + 1) > nr ? (g.zn - g.z1 + 1) : nr;
+            dim3 grid((na + 127) / 128, nphi, zper ? 1 : 2);
+            k_cyl_bound_p<<<grid, 128, 0, st>>>(u, v, p, g);
+        }
+        {
+            LaunchScope sc(linear ? "nscyl_lfgh" : "nscyl_fgh", st);
+            dim3 block(64, 4);
+            dim3 grid((nr + 1 + 63) / 64, (g.zn - g.z0 + 1 + 3) / 4, nphi);
+            if (linear) k_cyl_fgh<true><<<grid, block, 0, st>>>(u, v, w, u0, v0, w0, F, G, H, g);
+            else k_cyl_fgh<false><<<grid, block, 0, st>>>(u, v, w, u0, v0, w0, F, G, H, g);
+        }
+        {
+            LaunchScope sc("nscyl_rhs", st);
+            dim3 block(64, 4);
+            dim3 grid((nr + 63) / 64, (g.zn - g.z1 + 1 + 3) / 4, nphi);
+            k_cyl_rhs<<<grid, block, 0, st>>>(F, G, H, p, R, g);
+        }
+        FDMB_CHECK_LAUNCH();
+        int rc = lapl->solve_device(x.p, R.p, st);      // ns_cyl.cpp:441
+        if (rc) return rc;
+        {
+            LaunchScope sc("nscyl_update", st);
+            dim3 block(64, 4);
+            dim3 grid((nr + 63) / 64, (g.zn - g.z1 + 1 + 3) / 4, nphi);
+            k_cyl_update<<<grid, block, 0, st>>>(u, v, w, p, x, F, G, H, g);
+        }
+        FDMB_CHECK_LAUNCH();
+        time_index++;
+    }
+    return FDMB_OK;
+}
+
+extern "C" {
+
+int fdmb_ns_cyl_default_params(fdmb_ns_cyl_params* p)
+{
+    if (!p) { set_error("null argument"); return FDMB_ERR_INVALID; }
+    // defaults of ns_cyl.h:57-68
+    p->R = M_PI; p->r = M_PI / 2; p->h1 = 0; p->h2 = 10; p->u0 = 1.0; p->Re = 1.0; p->dt = 0.001;
+    p->nr = 32; p->nz = 31; p->nphi = 32; p->verbose = 0; p->vrandom = 0; p->zperiodic = 0;
+    return FDMB_OK;
+}
+
+int fdmb_ns_cyl_create(fdmb_ns_cyl** out, const fdmb_ns_cyl_params* p)
+{
+    if (!out || !p) { set_error("null argument"); return FDMB_ERR_INVALID; }
+    *out = nullptr;
+    auto* h = new (std::nothrow) fdmb_ns_cyl();
+    if (!h) { set_error("out of host memory"); return FDMB_ERR_NOMEM; }
+    h->prm = *p;
+    int rc = h->init();
+    if (rc) { delete h; return rc; }
+    *out = h;
+    return FDMB_OK;
+}
+
+int fdmb_ns_cyl_step(fdmb_ns_cyl* h, int nsteps)
+{
+    if (!h || nsteps < 0) { set_error("bad argument"); return FDMB_ERR_INVALID; }
+    int rc = h->step(nsteps, 0, h->stream);
+    if (rc) return rc;
+    FDMB_CUDA(cudaStreamSynchronize(h->stream));
+    return FDMB_OK;
+}
+
+int fdmb_ns_cyl_lstep(fdmb_ns_cyl* h, int nsteps)
+{
+    if (!h || nsteps < 0) { set_error("bad argument"); return FDMB_ERR_INVALID; }
+    int rc = h->step(nsteps, 1, h->stream);
+    if (rc) return rc;
+    FDMB_CUDA(cudaStreamSynchronize(h->stream));
+    return FDMB_OK;
+}
+
+int fdmb_ns_cyl_step_async(fdmb_ns_cyl* h, int nsteps, int linear, void* stream)
+{
+    if (!h || nsteps < 0) { set_error("bad argument"); return FDMB_ERR_INVALID; }
+    return h->step(nsteps, linear ? 1 : 0, stream ? (cudaStream_t)stream : h->stream);
+}
+
+int fdmb_ns_cyl_field_size(fdmb_ns_cyl* h, int field, long long* count)
+{
+    if (!h || field < 0 || field > 11 || !count) { set_error("bad field id"); return FDMB_ERR_INVALID; }
+    *count = h->count[field];
+    return FDMB_OK;
+}
+
+int fdmb_ns_cyl_get_field(fdmb_ns_cyl* h, int field, double* host)
+{
+    if (!h || field < 0 || field > 11 || !host) { set_error("bad field id"); return FDMB_ERR_INVALID; }
+    FDMB_CUDA(cudaMemcpyAsync(host, h->f[field].p, sizeof(double) * h->count[field], cudaMemcpyDeviceToHost, h->stream));
+    FDMB_CUDA(cudaStreamSynchronize(h->stream));
+    return FDMB_OK;
+}
+
+int fdmb_ns_cyl_set_field(fdmb_ns_cyl* h, int field, const double* host)
+{
+    if (!h || field < 0 || field > 11 || !host) { set_error("bad field id"); return FDMB_ERR_INVALID; }
+    FDMB_CUDA(cudaMemcpyAsync(h->f[field].p, host, sizeof(double) * h->count[field], cudaMemcpyHostToDevice, h->stream));
+    FDMB_CUDA(cudaStreamSynchronize(h->stream));
+    return FDMB_OK;
+}
+
+int fdmb_ns_cyl_field_device_ptr(fdmb_ns_cyl* h, int field, void** dptr)
+{
+    if (!h || field < 0 || field > 11 || !dptr) { set_error("bad field id"); return FDMB_ERR_INVALID; }
+    *dptr = h->f[field].p;
+    return FDMB_OK;
+}
+
+long long fdmb_ns_cyl_time_index(fdmb_ns_cyl* h) { return h ? h->time_index : -1; }
+
+int fdmb_ns_cyl_destroy(fdmb_ns_cyl* h)
+{
+    delete h;
+    return FDMB_OK;
+}
+
+}  // extern "C"

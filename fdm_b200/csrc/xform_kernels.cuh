@@ -134,6 +134,8 @@ __global__ void __launch_bounds__(TileCfg<N>::THREADS) k_cols(ColsArgs a, MID mi
     }
 }
 
+int current_device_slot();   // cudaGetDevice() clamped to [0, 63]
+
 // ---- host-side dispatch over the instantiated transform lengths -----------------
 #define FDMB_FOR_EACH_N(X) X(4) X(8) X(16) X(32) X(64) X(128) X(256) X(512) X(1024) X(2048)
 
@@ -142,7 +144,8 @@ inline cudaError_t launch_rows_t(const RowsArgs& a, cudaStream_t st)
 {
     using C = TileCfg<N>;
     auto kern = k_rows<N, KIND>;
-    static bool attr_set = false;
+    static bool attr_set_dev[64] = {false};   // function attributes are per device
+    bool& attr_set = attr_set_dev[current_device_slot()];
     if (!attr_set) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_ROWS);
         attr_set = true;
@@ -157,7 +160,8 @@ inline cudaError_t launch_cols_t(const ColsArgs& a, const MID& mid, cudaStream_t
 {
     using C = TileCfg<N>;
     auto kern = k_cols<N, KIND, MID, KIND2>;
-    static bool attr_set = false;
+    static bool attr_set_dev[64] = {false};   // function attributes are per device
+    bool& attr_set = attr_set_dev[current_device_slot()];
     if (!attr_set) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_COLS);
         attr_set = true;

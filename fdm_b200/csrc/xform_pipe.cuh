@@ -44,6 +44,44 @@ __device__ __forceinline__ void load_tables(double* SNs, cd* WMs, const double* 
     for (int i = threadIdx.x; i < N / 2; i += blockDim.x) WMs[i] = WM[i];
 }
 
+// ---- output maps of the strided-axis sweep ----------------------------------------------------
+// A map turns (transform slot, outer index, contiguous index) into a destination address.
+//   OutLinear : one pitched array on this GPU (slot j -> row j - J0)
+//   OutShard  : the slab <-> pencil transpose of the multi-GPU solve fused into the sweep's stores:
+//               slot j belongs to rank j >> logS and lands in that rank's buffer through its
+//               peer-mapped base pointer (NVLink stores, 128-byte segments along the contiguous axis)
+constexpr int FDMB_MAX_RANKS = 8;
+
+struct EmitLinear {
+    double* dst; long long stride; bool ok;
+    __device__ __forceinline__ void emit(int j, double v) const { if (ok) dst[(long long)j * stride] = v; }
+};
+struct OutLinear {
+    static constexpr bool sharded = false;
+    __device__ __forceinline__ EmitLinear emitter(double* out, long long sj, long long so, int j0, int o, int x, bool ok) const
+    {
+        return EmitLinear{out + (long long)o * so + x - (long long)j0 * sj, sj, ok};
+    }
+};
+struct EmitShard {
+    double* const* base; int logS, maskS; long long sj, off; bool ok;
+    __device__ __forceinline__ void emit(int j, double v) const
+    {
+        if (ok) base[j >> logS][(long long)(j & maskS) * sj + off] = v;
+    }
+};
+struct OutShard {
+    static constexpr bool sharded = true;
+    double* base[FDMB_MAX_RANKS];   // peer-mapped destination buffers, indexed by owning rank
+    int logS, maskS;                // slots per rank = 1 << logS
+    long long sj, so;               // destination strides (doubles) along the transform / outer axis
+    int o_off;                      // destination outer index of this rank's first outer entry
+    __device__ __forceinline__ EmitShard emitter(double*, long long, long long, int, int o, int x, bool ok) const
+    {
+        return EmitShard{base, logS, maskS, sj, (long long)(o + o_off) * so + x, ok};
+    }
+};
+
 struct ColsPipeArgs {
     double* out;
     long long out_sj, out_so;   // output strides (doubles) along the transform / outer axis
@@ -52,14 +90,15 @@ struct ColsPipeArgs {
     int taxis;                  // tensor-map dimension of the transform axis (1 or 2)
     int boxrows, nchunk;        // rows per tensor-map box, boxes per tile
     int reverse;                // walk the tiles back to front (L2 reuse against the previous sweep)
+    int mid_o_off;              // added to the outer index handed to the mid functor (sharded sweeps)
     double scale, scale2;
     const double* SN;
     const cd* WM;
 };
 
-template <int N, int KIND, typename MID, int KIND2, int NSTAGE>
+template <int N, int KIND, typename MID, int KIND2, int NSTAGE, typename OMAP>
 __global__ void __launch_bounds__(PipeCfg<N>::THREADS)
-k_cols_pipe(const __grid_constant__ CUtensorMap tm, ColsPipeArgs a, MID mid)
+k_cols_pipe(const __grid_constant__ CUtensorMap tm, ColsPipeArgs a, MID mid, const __grid_constant__ OMAP omap)
 {
     using C = PipeCfg<N>;
     constexpr int B = C::B, G = C::G;
@@ -118,9 +157,9 @@ k_cols_pipe(const __grid_constant__ CUtensorMap tm, ColsPipeArgs a, MID mid)
 
         if constexpr (KIND == XF_DST && (!MID::active || KIND2 == XF_DST)) {
             // smem-lean path: finished spectral values leave the registers straight to global memory
-            const OutGlobal og{a.out + (long long)o * a.out_so + b0 + b, a.out_sj, bok};
+            const auto og = omap.emitter(a.out, a.out_sj, a.out_so, J0, o, b0 + b, bok);
             if constexpr (MID::active) {
-                const OutMidTile<MID> om{tile + b, B, mid, b0 + b + 1, o + 1, bok};
+                const OutMidTile<MID> om{tile + b, B, mid, b0 + b + 1, o + a.mid_o_off + 1, bok};
                 dst_tile_fused<N, G, false>(tile + b, B, g, a.scale, SNs, WMs, scr + b, B, om);
                 dst_tile_fused<N, G, false>(tile + b, B, g, a.scale2, SNs, WMs, scr + b, B, og);
             } else {
@@ -131,15 +170,15 @@ k_cols_pipe(const __grid_constant__ CUtensorMap tm, ColsPipeArgs a, MID mid)
             if constexpr (MID::active) {
                 for (int j = g; j < a.nvalid; j += G) {
                     double v = tile[(j + J0) * B + b];
-                    tile[(j + J0) * B + b] = bok ? mid(v, j + J0, b0 + b + J0, o + J0) : 0.0;
+                    tile[(j + J0) * B + b] = bok ? mid(v, j + J0, b0 + b + J0, o + a.mid_o_off + J0) : 0.0;
                 }
                 __syncthreads();
                 xform_tile<N, G, KIND2>(tile + b, B, g, a.scale2, SNs, WMs, scr + b, B);
             }
-            if (bok) {
-                double* dst = a.out + (long long)o * a.out_so + b0 + b;
+            {
+                const auto og = omap.emitter(a.out, a.out_sj, a.out_so, J0, o, b0 + b, bok);
 #pragma unroll 4
-                for (int j = g; j < a.nvalid; j += G) dst[j * a.out_sj] = tile[(j + J0) * B + b];
+                for (int j = g; j < a.nvalid; j += G) og.emit(j + J0, tile[(j + J0) * B + b]);
             }
         }
         // the buffer is free once every thread has read it; order those generic reads/writes before
@@ -259,15 +298,18 @@ __global__ void __launch_bounds__(PipeCfg<N>::THREADS) k_rows_pipe(RowsPipeArgs 
 
 // ---- host-side launchers ----------------------------------------------------------------------
 int device_sm_count();
+int current_device_slot();   // cudaGetDevice() clamped to [0, 63]
 
-template <int N, int KIND, typename MID, int KIND2>
-inline cudaError_t launch_cols_pipe_t(const CUtensorMap& tm, const ColsPipeArgs& a, const MID& mid, cudaStream_t st)
+template <int N, int KIND, typename MID, int KIND2, typename OMAP = OutLinear>
+inline cudaError_t launch_cols_pipe_t(const CUtensorMap& tm, const ColsPipeArgs& a, const MID& mid, cudaStream_t st,
+                                      const OMAP& omap = OMAP{})
 {
     using C = PipeCfg<N>;
     constexpr int NSTAGE = C::COLS_STAGES;
-    auto kern = k_cols_pipe<N, KIND, MID, KIND2, NSTAGE>;
+    auto kern = k_cols_pipe<N, KIND, MID, KIND2, NSTAGE, OMAP>;
     constexpr size_t smem = C::cols_smem(NSTAGE);
-    static int per_sm = 0;
+    static int per_sm_dev[64] = {0};     // function attributes are per device
+    int& per_sm = per_sm_dev[current_device_slot()];
     if (!per_sm) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -279,7 +321,7 @@ inline cudaError_t launch_cols_pipe_t(const CUtensorMap& tm, const ColsPipeArgs&
     long long grid = (long long)device_sm_count() * per_sm;
     if (grid > ntiles) grid = ntiles;
     if (grid < 1) return cudaSuccess;
-    kern<<<(unsigned)grid, C::THREADS, smem, st>>>(tm, a, mid);
+    kern<<<(unsigned)grid, C::THREADS, smem, st>>>(tm, a, mid, omap);
     return cudaGetLastError();
 }
 
@@ -290,7 +332,8 @@ inline cudaError_t launch_rows_pipe_t(const RowsPipeArgs& a, cudaStream_t st)
     constexpr int NSTAGE = C::ROWS_STAGES;
     auto kern = k_rows_pipe<N, KIND, NSTAGE>;
     constexpr size_t smem = C::rows_smem(NSTAGE);
-    static int per_sm = 0;
+    static int per_sm_dev[64] = {0};     // function attributes are per device
+    int& per_sm = per_sm_dev[current_device_slot()];
     if (!per_sm) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;

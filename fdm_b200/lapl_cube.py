@@ -68,3 +68,88 @@ class LaplCube:
             self.close()
         except Exception:
             pass
+
+
+IPC_HANDLE_BYTES = 64
+
+
+def slab_range(n, periodic, nranks, rank):
+    """(first, count) of the 0-based interior entries of an axis of ``n`` points that ``rank`` owns
+    (``fdmb_slab_range``; host-only arithmetic, usable without a GPU)."""
+    first, count = C.c_int(), C.c_int()
+    capi.check(capi.lib().fdmb_slab_range(int(n), int(bool(periodic)), int(nranks), int(rank),
+                                          C.byref(first), C.byref(count)), "slab_range")
+    return first.value, count.value
+
+
+class LaplCubeSharded(LaplCube):
+    """One rank of the z-slab decomposed LaplCube solve (include/fdm_b200.h).
+
+    Same constructor as :class:`LaplCube` plus ``rank``/``nranks``; ``solve`` takes and returns this
+    rank's slab ``[nz_local][ny][nx]``.  Before the first solve the ranks must be connected:
+    ``connect(group)`` (one process per GPU, handles exchanged through ``torch.distributed``) or
+    ``LaplCubeSharded.connect_local(solvers)`` (all ranks in one process).
+    """
+
+    def __init__(self, dx, dy, dz, lx, ly, lz, nx, ny, nz, rank, nranks, periodic=False):
+        self.dx, self.dy, self.dz = float(dx), float(dy), float(dz)
+        self.lx, self.ly, self.lz = float(lx), float(ly), float(lz)
+        self.nx, self.ny, self.nz = int(nx), int(ny), int(nz)
+        self.periodic = bool(periodic)
+        self.rank, self.nranks = int(rank), int(nranks)
+        self._h = C.c_void_p()
+        L = capi.lib()
+        capi.check(L.fdmb_lapl_cube_create_sharded(C.byref(self._h), self.dx, self.dy, self.dz, self.lx, self.ly,
+                                                   self.lz, self.nx, self.ny, self.nz, int(self.periodic),
+                                                   self.rank, self.nranks), "LaplCube create_sharded")
+        zf, nzl = C.c_int(), C.c_int()
+        capi.check(L.fdmb_lapl_cube_local_slab(self._h, C.byref(zf), C.byref(nzl)), "local_slab")
+        self.z_first, self.nz_local = zf.value, nzl.value
+
+    @property
+    def shape(self):
+        return (self.nz_local, self.ny, self.nx)
+
+    def export_ipc(self) -> bytes:
+        buf = C.create_string_buffer(IPC_HANDLE_BYTES)
+        capi.check(capi.lib().fdmb_lapl_cube_export_ipc(self._h, buf), "export_ipc")
+        return buf.raw
+
+    def attach_ipc(self, handles):
+        """``handles``: the exported handles of all ranks, ordered by rank."""
+        blob = b"".join(handles)
+        if len(blob) != IPC_HANDLE_BYTES * self.nranks:
+            raise ValueError("need one IPC handle per rank")
+        capi.check(capi.lib().fdmb_lapl_cube_attach_ipc(self._h, C.create_string_buffer(blob, len(blob))), "attach_ipc")
+
+    def connect(self, group=None):
+        """Exchange the IPC handles over ``torch.distributed`` (any backend) and attach the peers."""
+        if self.nranks == 1:
+            return
+        import torch
+        import torch.distributed as dist
+        mine = self.export_ipc()
+        gathered = [None] * self.nranks
+        dist.all_gather_object(gathered, mine, group=group)
+        self.attach_ipc(gathered)
+        dist.barrier(group=group)
+        del torch
+
+    @staticmethod
+    def connect_local(solvers):
+        """All ranks live in this process (one handle per device): enable peer access both ways."""
+        arr = (C.c_void_p * len(solvers))(*[s._h for s in solvers])
+        for s in solvers:
+            capi.check(capi.lib().fdmb_lapl_cube_attach_local(s._h, arr), "attach_local")
+
+    def solve(self, ans, rhs=None):
+        if rhs is None:
+            rhs, ans = ans, None
+        rhs = np.ascontiguousarray(rhs, dtype=np.float64)
+        want = self.nx * self.ny * self.nz_local
+        if rhs.size != want:
+            raise ValueError(f"rhs slab has {rhs.size} elements, expected {want}")
+        if ans is None:
+            ans = np.empty(self.shape, dtype=np.float64)
+        capi.check(capi.lib().fdmb_lapl_cube_solve(self._h, capi.as_dp(ans), capi.as_dp(rhs)), "LaplCube solve (slab)")
+        return ans

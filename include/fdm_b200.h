@@ -80,6 +80,33 @@ int fdmb_lapl_cube_solve(fdmb_lapl_cube* h, double* ans, const double* rhs);
 int fdmb_lapl_cube_solve_device(fdmb_lapl_cube* h, double* d_ans, const double* d_rhs, void* stream);
 int fdmb_lapl_cube_destroy(fdmb_lapl_cube* h);
 
+/* Multi-GPU LaplCube: the grid is cut into z-slabs, one rank (= one GPU, normally one process) per
+ * slab.  The reference has no distributed solver; this is the slab decomposition of the same
+ * solve() (src/lapl_cube.cpp:9-142): x and y transforms are local to a slab, the z transform runs
+ * on y-pencils, and the two slab<->pencil transposes are fused into the stores of the y and z sweeps
+ * (peer stores over NVLink into buffers the ranks map from each other).
+ *   fdmb_slab_range        which 0-based interior entries of an axis of n points rank owns
+ *                          (host-only arithmetic; Dirichlet axes: slot 0 is the boundary, so rank 0
+ *                          owns one entry fewer)
+ *   create_sharded         same arguments as create + (rank, nranks); nranks in {1,2,4,8}; call with
+ *                          the rank's device current
+ *   export_ipc/attach_ipc  one process per GPU: every rank exports FDMB_IPC_HANDLE_BYTES bytes, the
+ *                          host exchanges them (torch.distributed / MPI all-gather), every rank
+ *                          attaches the concatenation ordered by rank
+ *   attach_local           all ranks in one process: pass the handles ordered by rank
+ *   solve / solve_device   on a sharded handle take this rank's slab [nz_local][ny][nx]; every rank
+ *                          must call them the same number of times (they meet in two device-side
+ *                          barriers per solve)                                                     */
+#define FDMB_IPC_HANDLE_BYTES 64
+int fdmb_slab_range(int n, int periodic, int nranks, int rank, int* first, int* count);
+int fdmb_lapl_cube_create_sharded(fdmb_lapl_cube** h, double dx, double dy, double dz,
+                                  double lx, double ly, double lz, int nx, int ny, int nz, int periodic,
+                                  int rank, int nranks);
+int fdmb_lapl_cube_local_slab(fdmb_lapl_cube* h, int* z_first, int* nz_local);
+int fdmb_lapl_cube_export_ipc(fdmb_lapl_cube* h, void* handle);
+int fdmb_lapl_cube_attach_ipc(fdmb_lapl_cube* h, const void* handles);
+int fdmb_lapl_cube_attach_local(fdmb_lapl_cube* h, fdmb_lapl_cube* const* all);
+
 /* ---- LaplCyl3FFT2 ---------------------------------------------------------------
  * Replaces fdm::LaplCyl3FFT2<double,check,zflag> (src/lapl_cyl.h:172-249, src/lapl_cyl.cpp:11-170):
  * Poisson equation in cylindrical coordinates, periodic in phi, Dirichlet (zperiodic=0) or
@@ -122,6 +149,38 @@ int fdmb_ns_cube_set_field(fdmb_ns_cube* h, int field, const double* host);
 int fdmb_ns_cube_field_device_ptr(fdmb_ns_cube* h, int field, void** dptr);
 long long fdmb_ns_cube_time_index(fdmb_ns_cube* h);
 int fdmb_ns_cube_destroy(fdmb_ns_cube* h);
+
+/* ---- NSCyl ----------------------------------------------------------------------
+ * Replaces fdm::NSCyl<double,check,zflag> (src/ns_cyl.h:17-132, src/ns_cyl.cpp:23-484): flow between
+ * two coaxial cylinders, inner one rotating with speed u0, on a staggered grid in (phi, z, r).
+ * params   <-> the [ns] config keys read by the constructor (src/ns_cyl.h:57-68); zperiodic selects
+ *              zflag = tensor_flag::periodic (1) or none (0), the instantiations of
+ *              src/ns_cyl.cpp:486-494; vrandom = 1 seeds v like src/ns_cyl.h:99-108
+ * step     <-> void step()    (src/ns_cyl.cpp:23-63), nsteps times, state stays on the device
+ * lstep    <-> void L_step()  (src/ns_cyl.cpp:66-78): the step linearised about u0, v0, w0
+ * fields   <-> the public tensors u,v,w,p,x,F,G,H,RHS,u0,v0,w0 (src/ns_cyl.h:40-46) with the
+ *              reference's extents [phi][z][r], ghosts included (src/ns_cyl.h:80-93).
+ * The reference's verify() wall invariants inside init_bound (src/ns_cyl.cpp:136-163) are not
+ * re-checked on the device.                                                                    */
+typedef struct fdmb_ns_cyl fdmb_ns_cyl;
+typedef struct fdmb_ns_cyl_params {
+    double R, r, h1, h2;      /* outer / inner radius, z range */
+    double u0, Re, dt;
+    int nr, nz, nphi;
+    int verbose, vrandom, zperiodic;
+} fdmb_ns_cyl_params;
+enum { FDMB_FIELD_U0 = 9, FDMB_FIELD_V0, FDMB_FIELD_W0 };
+int fdmb_ns_cyl_default_params(fdmb_ns_cyl_params* p);
+int fdmb_ns_cyl_create(fdmb_ns_cyl** h, const fdmb_ns_cyl_params* p);
+int fdmb_ns_cyl_step(fdmb_ns_cyl* h, int nsteps);
+int fdmb_ns_cyl_lstep(fdmb_ns_cyl* h, int nsteps);
+int fdmb_ns_cyl_step_async(fdmb_ns_cyl* h, int nsteps, int linear, void* stream);
+int fdmb_ns_cyl_field_size(fdmb_ns_cyl* h, int field, long long* count);
+int fdmb_ns_cyl_get_field(fdmb_ns_cyl* h, int field, double* host);
+int fdmb_ns_cyl_set_field(fdmb_ns_cyl* h, int field, const double* host);
+int fdmb_ns_cyl_field_device_ptr(fdmb_ns_cyl* h, int field, void** dptr);
+long long fdmb_ns_cyl_time_index(fdmb_ns_cyl* h);
+int fdmb_ns_cyl_destroy(fdmb_ns_cyl* h);
 
 #ifdef __cplusplus
 }

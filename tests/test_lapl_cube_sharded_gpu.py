@@ -1,0 +1,123 @@
+"""GPU parity tests for the z-slab decomposed LaplCube solve through the C ABI.
+
+Needs >= 2 visible B200s (`gpurun --gpus 2|4|8`); skipped on a single-GPU box.  Two ways of wiring
+the ranks are covered: all ranks in this process (attach_local) and one process per GPU launched
+with torch.distributed.run (IPC handles exchanged through the process group).
+Bar: relative L2 <= 1e-12 (fp64) of the gathered slabs against the oracle's full solve."""
+import math
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import fdm_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def fb():
+    import fdm_b200
+    if fdm_b200.lib().fdmb_device_count() < 2:
+        pytest.skip("the sharded solve needs at least 2 GPUs")
+    return fdm_b200
+
+
+def solve_in_process(fb, args, rhs, P, periodic=False, repeats=1):
+    import torch
+    L = fb.lib()
+    solvers, bufs = [], []
+    for r in range(P):
+        fb.capi.check(L.fdmb_set_device(r), "set_device")
+        s = fb.LaplCubeSharded(*args, rank=r, nranks=P, periodic=periodic)
+        solvers.append(s)
+        with torch.cuda.device(r):
+            slab = np.ascontiguousarray(rhs[s.z_first:s.z_first + s.nz_local])
+            d_rhs = torch.from_numpy(slab).cuda(r)
+            d_ans = torch.full_like(d_rhs, float("nan"))
+        bufs.append((d_rhs, d_ans))
+    fb.LaplCubeSharded.connect_local(solvers)
+    for _ in range(repeats):
+        for s, (d_rhs, d_ans) in zip(solvers, bufs):
+            s.solve_device(d_ans.data_ptr(), d_rhs.data_ptr())      # asynchronous on the handle's stream
+    for r in range(P):
+        fb.capi.check(L.fdmb_set_device(r), "set_device")
+        fb.capi.check(L.fdmb_device_synchronize(), "sync")
+    out = np.concatenate([b[1].cpu().numpy() for b in bufs], axis=0)
+    for s in solvers:
+        s.close()
+    fb.capi.check(L.fdmb_set_device(0), "set_device")
+    return out
+
+
+def ranks_available(fb):
+    n = fb.lib().fdmb_device_count()
+    return [p for p in (2, 4, 8) if p <= n]
+
+
+@pytest.mark.parametrize("n", [31, 63, 127])
+def test_sharded_dirichlet_vs_oracle(fb, n):
+    dx = 1.0 / n; l = 1 + dx
+    args = (dx, dx, dx, l, l, l, n, n, n)
+    rhs = O.synthetic_rhs((n, n, n), seed=n)
+    want = O.LaplCube(*args).solve(rhs)
+    for P in ranks_available(fb):
+        got = solve_in_process(fb, args, rhs, P, repeats=3)       # repeats exercise the barrier epochs
+        assert got.shape == want.shape
+        assert O.rel_l2(got, want) < TOL, f"P={P}"
+
+
+def test_sharded_ragged_vs_oracle(fb):
+    nz, ny, nx = 63, 31, 127
+    rhs = O.synthetic_rhs((nz, ny, nx), seed=5)
+    args = (0.1, 0.2, 0.3, 0.1 * (nx + 1), 0.2 * (ny + 1), 0.3 * (nz + 1), nx, ny, nz)
+    want = O.LaplCube(*args).solve(rhs)
+    for P in ranks_available(fb):
+        assert O.rel_l2(solve_in_process(fb, args, rhs, P), want) < TOL, f"P={P}"
+
+
+@pytest.mark.parametrize("n", [32, 64])
+def test_sharded_periodic_vs_oracle(fb, n):
+    dx = 2 * math.pi / n; l = 2 * math.pi
+    args = (dx, dx, dx, l, l, l, n, n, n)
+    rhs = O.synthetic_rhs((n, n, n), seed=n + 1)
+    want = O.LaplCube(*args, periodic=True).solve(rhs)
+    for P in ranks_available(fb):
+        assert O.rel_l2(solve_in_process(fb, args, rhs, P, periodic=True), want) < TOL, f"P={P}"
+
+
+def test_sharded_matches_single_gpu_255(fb):
+    # full-size property: the sharded solve reproduces the single-GPU solve
+    n = 255; dx = 1.0 / n; l = 1 + dx
+    args = (dx, dx, dx, l, l, l, n, n, n)
+    rhs = O.synthetic_rhs((n, n, n), seed=9)
+    single = fb.LaplCube(*args).solve(rhs)
+    for P in ranks_available(fb):
+        assert O.rel_l2(solve_in_process(fb, args, rhs, P), single) < 1e-13, f"P={P}"
+
+
+def test_sharded_rejects_bad_split(fb):
+    with pytest.raises(fb.FdmB200Error):
+        fb.LaplCubeSharded(1, 1, 1, 16, 16, 16, 15, 15, 15, rank=0, nranks=2)     # transform length 16 < 32
+    with pytest.raises(fb.FdmB200Error):
+        fb.LaplCubeSharded(1, 1, 1, 64, 64, 64, 63, 63, 63, rank=0, nranks=3)
+    s = fb.LaplCubeSharded(1, 1, 1, 64, 64, 64, 63, 63, 63, rank=0, nranks=2)
+    with pytest.raises(fb.FdmB200Error):                                           # not connected yet
+        s.solve(np.zeros(s.shape))
+
+
+def test_sharded_one_process_per_gpu(fb, tmp_path):
+    """torch.distributed.run, one rank per GPU, IPC handles exchanged through the process group."""
+    P = 2
+    out = tmp_path / "res.txt"
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={P}",
+           "--master-addr", "127.0.0.1", "--master-port", "29731",
+           os.path.join(ROOT, "tests", "mp", "sharded_worker.py"), "--size", "127", "--out", str(out)]
+    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    err = float(out.read_text())
+    assert err < TOL
