@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <cstdlib>
 #include <vector>
 #include <new>
 
@@ -402,6 +403,8 @@ int fdmb_lapl_cube::solve_device(double* d_out, const double* d_in, cudaStream_t
         p.out = z.out; p.out_sj = z.out_sj; p.out_so = z.out_so; p.nvalid = z.nvalid; p.nb = z.nb; p.no = z.no;
         p.taxis = 2; p.boxrows = boxrows_z; p.nchunk = nchunk_z; p.reverse = 0; p.scale = z.scale; p.scale2 = z.scale2;
         p.SN = z.SN; p.WM = z.WM;
+        if (getenv("FDMB_ZEXP")) FDMB_CUDA(launch_cols_pipe(Nz, kf, tm_z, p, st, "cube_z_single_EXPERIMENT"));
+        else
         FDMB_CUDA(launch_cols_pipe_cube_divide(Nz, periodic != 0, tm_z, p, mid, st, "cube_z_fwd_div_inv"));
     } else {
         FDMB_CUDA(launch_cols_cube_divide(Nz, periodic != 0, z, mid, st, "cube_z_fwd_div_inv"));

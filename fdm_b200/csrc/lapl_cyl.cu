@@ -23,21 +23,6 @@ namespace fdmb {
 // A CTA stages TS systems (rows of nr doubles) in an odd-pitch shared-memory tile with coalesced
 // loads; thread s then runs the Thomas recurrence of system s (conflict-free: consecutive lanes sit
 // one odd pitch apart), keeping the reciprocal pivots in a second tile; coalesced store.
-struct TridiagArgs {
-    double* data;             // [nsys rows][pitch], solved in place
-    long long pitch;
-    int nr;
-    int nmid;                 // systems are (outer, mid) pairs: row = outer * nmid + mid
-    long long nsys;
-    const double* lm_outer;   // eigenvalue by outer index (phi mode), scaled by ir2[j]
-    const double* lm_mid;     // eigenvalue by mid index (z mode), offset by mid0
-    int mid0;
-    double c0;                // -2/dr^2
-    const double* L;          // L[j], U[j], ir2[j], j = 1..nr
-    const double* U;
-    const double* ir2;
-};
-
 constexpr int TS = 32;
 
 __global__ void __launch_bounds__(128) k_tridiag_rows(TridiagArgs a)
@@ -94,11 +79,12 @@ __global__ void __launch_bounds__(128) k_tridiag_rows(TridiagArgs a)
     }
 }
 
+size_t tridiag_rows_smem(int nr) { return sizeof(double) * (size_t)(2 * TS * (nr | 1) + 3 * (nr + 1)); }
+
 cudaError_t launch_tridiag_rows(const TridiagArgs& a, cudaStream_t st, const char* tag)
 {
     LaunchScope scope(tag, st);
-    const int P = a.nr | 1;
-    const size_t smem = sizeof(double) * (size_t)(2 * TS * P + 3 * (a.nr + 1));
+    const size_t smem = tridiag_rows_smem(a.nr);
     static size_t set_smem_dev[64] = {0};     // function attributes are per device
     size_t& set_smem = set_smem_dev[current_device_slot()];
     if (smem > set_smem) {
@@ -125,7 +111,7 @@ int fdmb_lapl_cyl::init()
                   "(reference: verify((1<<n) == N), src/fft.cpp:67)", nphi, Nz, zperiodic ? "" : "+1");
         return FDMB_ERR_INVALID;
     }
-    if ((size_t)(2 * TS * (nr | 1) + 3 * (nr + 1)) * 8 > 220 * 1024) {
+    if (tridiag_rows_smem(nr) > 220 * 1024) {
         set_error("LaplCyl3FFT2: nr=%d exceeds the shared-memory tile of the tridiagonal kernel", nr);
         return FDMB_ERR_INVALID;
     }

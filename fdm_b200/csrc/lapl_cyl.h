@@ -2,6 +2,25 @@
 #pragma once
 #include "lapl_cube.h"
 
+namespace fdmb {
+struct TridiagArgs {
+    double* data;             // [nsys rows][pitch], solved in place
+    long long pitch;
+    int nr;
+    int nmid;                 // systems are (outer, mid) pairs: row = outer * nmid + mid
+    long long nsys;
+    const double* lm_outer;   // eigenvalue by outer index (phi mode), scaled by ir2[j]
+    const double* lm_mid;     // eigenvalue by mid index (z mode), offset by mid0
+    int mid0;
+    double c0;                // -2/dr^2
+    const double* L;          // L[j], U[j], ir2[j], j = 1..nr
+    const double* U;
+    const double* ir2;
+};
+cudaError_t launch_tridiag_rows(const TridiagArgs& a, cudaStream_t st, const char* tag);
+size_t tridiag_rows_smem(int nr);
+}  // namespace fdmb
+
 struct fdmb_lapl_cyl {
     double dr, dz, r0, lr, lz;
     int nr, nz, nphi, zperiodic;

@@ -107,6 +107,27 @@ int fdmb_lapl_cube_export_ipc(fdmb_lapl_cube* h, void* handle);
 int fdmb_lapl_cube_attach_ipc(fdmb_lapl_cube* h, const void* handles);
 int fdmb_lapl_cube_attach_local(fdmb_lapl_cube* h, fdmb_lapl_cube* const* all);
 
+/* ---- LaplRect / LaplRectFFT2 -----------------------------------------------------
+ * Replaces fdm::LaplRect<double,check,F> (src/lapl_rect.h:11-78, src/lapl_rect.cpp:44-110) and
+ * fdm::LaplRectFFT2<double,check,F> (src/lapl_rect.h:80-116, src/lapl_rect.cpp:113-207).
+ * create     <-> constructor (dx,dy,lx,ly,nx,ny); kind 0 = LaplRect (y transform + tridiagonal in x,
+ *                x always Dirichlet), 1 = LaplRectFFT2 (transforms on both axes);
+ *                yperiodic / xperiodic <-> F = tensor_flags<>, <periodic>, <periodic,periodic>
+ *                (instantiations src/lapl_rect.cpp:209-238; kind 0 ignores xperiodic, :47)
+ * set_scales <-> the public members lm_y_scale, L_scale, U_scale (src/lapl_rect.h:57-59; nx+1 host
+ *                doubles each, entry j for column j; NULL keeps the current values) that the
+ *                cylindrical slice plotter overwrites (src/velocity_plot.h:113-127)
+ * solve      <-> void solve(T* ans, T* rhs); arrays are [ny rows][nx], x fastest.
+ * Dirichlet axes need n+1 = 2^k, periodic axes n = 2^k on every transformed axis.          */
+typedef struct fdmb_lapl_rect fdmb_lapl_rect;
+int fdmb_lapl_rect_create(fdmb_lapl_rect** h, int kind, int yperiodic, int xperiodic,
+                          double dx, double dy, double lx, double ly, int nx, int ny);
+int fdmb_lapl_rect_set_scales(fdmb_lapl_rect* h, const double* lm_y_scale, const double* L_scale,
+                              const double* U_scale);
+int fdmb_lapl_rect_solve(fdmb_lapl_rect* h, double* ans, const double* rhs);
+int fdmb_lapl_rect_solve_device(fdmb_lapl_rect* h, double* d_ans, const double* d_rhs, void* stream);
+int fdmb_lapl_rect_destroy(fdmb_lapl_rect* h);
+
 /* ---- LaplCyl3FFT2 ---------------------------------------------------------------
  * Replaces fdm::LaplCyl3FFT2<double,check,zflag> (src/lapl_cyl.h:172-249, src/lapl_cyl.cpp:11-170):
  * Poisson equation in cylindrical coordinates, periodic in phi, Dirichlet (zperiodic=0) or
