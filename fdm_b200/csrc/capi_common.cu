@@ -146,6 +146,35 @@ int make_tensor_map_3d(CUtensorMap* tm, const void* base, unsigned long long e0,
     return FDMB_OK;
 }
 
+int make_cols_maps(ColsMaps* m, const void* base, int N, int taxis, unsigned long long e0, unsigned long long e1,
+                   unsigned long long e2, unsigned long long s1, unsigned long long s2, unsigned B)
+{
+    const unsigned long long n = taxis == 1 ? e1 : e2;       // entries along the transform axis
+    int rc;
+    m->boxrows = n < 256 ? (int)n : 256;
+    m->nchunk = (int)((n + m->boxrows - 1) / m->boxrows);
+    if (taxis == 1) rc = make_tensor_map_3d(&m->nat, base, e0, e1, e2, s1, s2, B, m->boxrows, 1);
+    else rc = make_tensor_map_3d(&m->nat, base, e0, e1, e2, s1, s2, B, 1, m->boxrows);
+    if (rc) return rc;
+    m->planar = false;
+    if ((int)n == N - 1 && N >= 32) {
+        const int M = N / 2;
+        m->boxrows_p = M < 256 ? M : 256;
+        m->nchunk_p = M / m->boxrows_p;
+        const unsigned long long no = (n + 1) / 2, ne = n / 2;     // even rows 0,2,.. / odd rows 1,3,..
+        const char* b1 = static_cast<const char*>(base) + (taxis == 1 ? s1 : s2);
+        if (taxis == 1) {
+            if ((rc = make_tensor_map_3d(&m->podd, base, e0, no, e2, 2 * s1, s2, B, m->boxrows_p, 1))) return rc;
+            if ((rc = make_tensor_map_3d(&m->peven, b1, e0, ne, e2, 2 * s1, s2, B, m->boxrows_p, 1))) return rc;
+        } else {
+            if ((rc = make_tensor_map_3d(&m->podd, base, e0, e1, no, s1, 2 * s2, B, 1, m->boxrows_p))) return rc;
+            if ((rc = make_tensor_map_3d(&m->peven, b1, e0, e1, ne, s1, 2 * s2, B, 1, m->boxrows_p))) return rc;
+        }
+        m->planar = true;
+    }
+    return FDMB_OK;
+}
+
 }  // namespace fdmb
 
 using namespace fdmb;

@@ -61,6 +61,16 @@ cudaError_t launch_cols_cube_divide(int N, bool periodic, const ColsArgs& a, con
     return cudaErrorInvalidValue;
 }
 
+
+// picks the tensor maps and box shape a sweep kernel expects: planar pair for the fused DST kernels
+#define FDMB_PICK_MAPS(fused)                                                                     \
+    const bool use_p = (fused);                                                                   \
+    if (use_p && !tm.planar) return cudaErrorInvalidValue;                                        \
+    const CUtensorMap& m1 = use_p ? tm.podd : tm.nat;                                             \
+    const CUtensorMap& m2 = use_p ? tm.peven : tm.nat;                                            \
+    a.boxrows = use_p ? tm.boxrows_p : tm.boxrows;                                                \
+    a.nchunk = use_p ? tm.nchunk_p : tm.nchunk;
+
 #define FDMB_FOR_EACH_PIPE_N(X) X(32) X(64) X(128) X(256) X(512) X(1024) X(2048)
 
 cudaError_t launch_rows_pipe(int N, int kind, const RowsPipeArgs& a, cudaStream_t st, const char* tag)
@@ -76,57 +86,61 @@ cudaError_t launch_rows_pipe(int N, int kind, const RowsPipeArgs& a, cudaStream_
     return cudaErrorInvalidValue;
 }
 
-cudaError_t launch_cols_pipe(int N, int kind, const CUtensorMap& tm, const ColsPipeArgs& a, cudaStream_t st, const char* tag)
+cudaError_t launch_cols_pipe(int N, int kind, const ColsMaps& tm, ColsPipeArgs a, cudaStream_t st, const char* tag)
 {
     LaunchScope scope(tag, st);
     MidNone mid;
-#define X(NN)                                                                                      \
-    case NN:                                                                                       \
-        if (kind == XF_DST) return launch_cols_pipe_t<NN, XF_DST, MidNone, XF_DST>(tm, a, mid, st);    \
-        if (kind == XF_PFWD) return launch_cols_pipe_t<NN, XF_PFWD, MidNone, XF_DST>(tm, a, mid, st);  \
-        return launch_cols_pipe_t<NN, XF_PINV, MidNone, XF_DST>(tm, a, mid, st);
+    FDMB_PICK_MAPS(kind == XF_DST)
+#define X(NN)                                                                                          \
+    case NN:                                                                                           \
+        if (kind == XF_DST) return launch_cols_pipe_t<NN, XF_DST, MidNone, XF_DST>(m1, m2, a, mid, st);    \
+        if (kind == XF_PFWD) return launch_cols_pipe_t<NN, XF_PFWD, MidNone, XF_DST>(m1, m2, a, mid, st);  \
+        return launch_cols_pipe_t<NN, XF_PINV, MidNone, XF_DST>(m1, m2, a, mid, st);
     switch (N) { FDMB_FOR_EACH_PIPE_N(X) }
 #undef X
     return cudaErrorInvalidValue;
 }
 
-cudaError_t launch_cols_pipe_cube_divide(int N, bool periodic, const CUtensorMap& tm, const ColsPipeArgs& a,
+cudaError_t launch_cols_pipe_cube_divide(int N, bool periodic, const ColsMaps& tm, ColsPipeArgs a,
                                          const MidCubeDivide& mid, cudaStream_t st, const char* tag)
 {
     LaunchScope scope(tag, st);
-#define X(NN)                                                                                          \
-    case NN:                                                                                           \
-        if (periodic) return launch_cols_pipe_t<NN, XF_PFWD, MidCubeDivide, XF_PINV>(tm, a, mid, st);  \
-        return launch_cols_pipe_t<NN, XF_DST, MidCubeDivide, XF_DST>(tm, a, mid, st);
+    FDMB_PICK_MAPS(!periodic)
+#define X(NN)                                                                                              \
+    case NN:                                                                                               \
+        if (periodic) return launch_cols_pipe_t<NN, XF_PFWD, MidCubeDivide, XF_PINV>(m1, m2, a, mid, st);  \
+        return launch_cols_pipe_t<NN, XF_DST, MidCubeDivide, XF_DST>(m1, m2, a, mid, st);
     switch (N) { FDMB_FOR_EACH_PIPE_N(X) }
 #undef X
     return cudaErrorInvalidValue;
 }
 
-cudaError_t launch_cols_pipe_shard(int N, int kind, const CUtensorMap& tm, const ColsPipeArgs& a, const OutShard& om,
+cudaError_t launch_cols_pipe_shard(int N, int kind, const ColsMaps& tm, ColsPipeArgs a, const OutShard& om,
                                    cudaStream_t st, const char* tag)
 {
     LaunchScope scope(tag, st);
     MidNone mid;
-#define X(NN)                                                                                                     \
-    case NN:                                                                                                      \
-        if (kind == XF_DST) return launch_cols_pipe_t<NN, XF_DST, MidNone, XF_DST, OutShard>(tm, a, mid, st, om);   \
-        if (kind == XF_PFWD) return launch_cols_pipe_t<NN, XF_PFWD, MidNone, XF_DST, OutShard>(tm, a, mid, st, om); \
-        return launch_cols_pipe_t<NN, XF_PINV, MidNone, XF_DST, OutShard>(tm, a, mid, st, om);
+    FDMB_PICK_MAPS(kind == XF_DST)
+#define X(NN)                                                                                                         \
+    case NN:                                                                                                          \
+        if (kind == XF_DST) return launch_cols_pipe_t<NN, XF_DST, MidNone, XF_DST, OutShard>(m1, m2, a, mid, st, om);   \
+        if (kind == XF_PFWD) return launch_cols_pipe_t<NN, XF_PFWD, MidNone, XF_DST, OutShard>(m1, m2, a, mid, st, om); \
+        return launch_cols_pipe_t<NN, XF_PINV, MidNone, XF_DST, OutShard>(m1, m2, a, mid, st, om);
     switch (N) { FDMB_FOR_EACH_PIPE_N(X) }
 #undef X
     return cudaErrorInvalidValue;
 }
 
-cudaError_t launch_cols_pipe_cube_divide_shard(int N, bool periodic, const CUtensorMap& tm, const ColsPipeArgs& a,
+cudaError_t launch_cols_pipe_cube_divide_shard(int N, bool periodic, const ColsMaps& tm, ColsPipeArgs a,
                                                const MidCubeDivide& mid, const OutShard& om, cudaStream_t st,
                                                const char* tag)
 {
     LaunchScope scope(tag, st);
-#define X(NN)                                                                                                        \
-    case NN:                                                                                                         \
-        if (periodic) return launch_cols_pipe_t<NN, XF_PFWD, MidCubeDivide, XF_PINV, OutShard>(tm, a, mid, st, om);  \
-        return launch_cols_pipe_t<NN, XF_DST, MidCubeDivide, XF_DST, OutShard>(tm, a, mid, st, om);
+    FDMB_PICK_MAPS(!periodic)
+#define X(NN)                                                                                                            \
+    case NN:                                                                                                             \
+        if (periodic) return launch_cols_pipe_t<NN, XF_PFWD, MidCubeDivide, XF_PINV, OutShard>(m1, m2, a, mid, st, om);  \
+        return launch_cols_pipe_t<NN, XF_DST, MidCubeDivide, XF_DST, OutShard>(m1, m2, a, mid, st, om);
     switch (N) { FDMB_FOR_EACH_PIPE_N(X) }
 #undef X
     return cudaErrorInvalidValue;
@@ -212,13 +226,11 @@ int fdmb_lapl_cube::init()
         // tensor maps over the pitched work array: dims (x, y, z), tiles [N][B] along y or z
         const unsigned long long s1 = 8ull * px, s2 = 8ull * (unsigned long long)ny * px;
         if (pipe_supported_N(Ny)) {
-            boxrows_y = ny < 256 ? ny : 256; nchunk_y = (ny + boxrows_y - 1) / boxrows_y;
-            if ((rc = make_tensor_map_3d(&tm_y, d_work, nx, ny, nz, s1, s2, pipe_B(Ny), boxrows_y, 1))) return rc;
+            if ((rc = make_cols_maps(&tm_y, d_work, Ny, 1, nx, ny, nz, s1, s2, pipe_B(Ny)))) return rc;
             pipe_y = true;
         }
         if (pipe_supported_N(Nz)) {
-            boxrows_z = nz < 256 ? nz : 256; nchunk_z = (nz + boxrows_z - 1) / boxrows_z;
-            if ((rc = make_tensor_map_3d(&tm_z, d_work, nx, ny, nz, s1, s2, pipe_B(Nz), 1, boxrows_z))) return rc;
+            if ((rc = make_cols_maps(&tm_z, d_work, Nz, 2, nx, ny, nz, s1, s2, pipe_B(Nz)))) return rc;
             pipe_z = true;
         }
     }
@@ -257,11 +269,8 @@ int fdmb_lapl_cube::init_sharded()
     d_work = d_A + (size_t)(z_first + J0 - rank * Sz) * plane;
     double* t_loc = d_T + (size_t)(y_first + J0 - rank * Sy) * px;
     int rc;
-    boxrows_y = ny < 256 ? ny : 256; nchunk_y = (ny + boxrows_y - 1) / boxrows_y;
-    if ((rc = make_tensor_map_3d(&tm_y, d_work, nx, ny, nzl, 8ull * px, 8ull * plane, pipe_B(Ny), boxrows_y, 1))) return rc;
-    boxrows_z = nz < 256 ? nz : 256; nchunk_z = (nz + boxrows_z - 1) / boxrows_z;
-    if ((rc = make_tensor_map_3d(&tm_z, t_loc, nx, nyl, nz, 8ull * px, 8ull * (unsigned long long)Sy * px, pipe_B(Nz), 1,
-                                 boxrows_z)))
+    if ((rc = make_cols_maps(&tm_y, d_work, Ny, 1, nx, ny, nzl, 8ull * px, 8ull * plane, pipe_B(Ny)))) return rc;
+    if ((rc = make_cols_maps(&tm_z, t_loc, Nz, 2, nx, nyl, nz, 8ull * px, 8ull * (unsigned long long)Sy * px, pipe_B(Nz))))
         return rc;
     pipe_y = pipe_z = true;
     return FDMB_OK;
@@ -327,7 +336,7 @@ int fdmb_lapl_cube::solve_device_sharded(double* d_out, const double* d_in, cuda
     FDMB_CUDA(rows(d_in, d_work, nx, px, dx * slx, kf, "cube_x_fwd", 0));
     {   // y forward, transposing into the pencil buffers T_q[z'][y slot & (Sy-1)][x]
         ColsPipeArgs p{};
-        p.out = nullptr; p.nvalid = ny; p.nb = nx; p.no = nzl; p.taxis = 1; p.boxrows = boxrows_y; p.nchunk = nchunk_y;
+        p.out = nullptr; p.nvalid = ny; p.nb = nx; p.no = nzl; p.taxis = 1;
         p.reverse = 1; p.scale = dy * sly; p.SN = ty.SN; p.WM = ty.WM;
         OutShard om{};
         for (int q = 0; q < nranks; q++)
@@ -338,7 +347,7 @@ int fdmb_lapl_cube::solve_device_sharded(double* d_out, const double* d_in, cuda
     if ((rc = barrier(st))) return rc;
     {   // z forward, divide, z inverse; stores go back to the slabs A_r[z slot & (Sz-1)][y'][x]
         ColsPipeArgs p{};
-        p.out = nullptr; p.nvalid = nz; p.nb = nx; p.no = nyl; p.taxis = 2; p.boxrows = boxrows_z; p.nchunk = nchunk_z;
+        p.out = nullptr; p.nvalid = nz; p.nb = nx; p.no = nyl; p.taxis = 2;
         p.reverse = 0; p.mid_o_off = y_first; p.scale = dz * slz; p.scale2 = slz; p.SN = tz.SN; p.WM = tz.WM;
         MidCubeDivide mid{d_lmz, d_lmx, d_lmy, periodic ? 1 : 0};
         OutShard om{};
@@ -350,7 +359,7 @@ int fdmb_lapl_cube::solve_device_sharded(double* d_out, const double* d_in, cuda
     {   // y inverse (local)
         ColsPipeArgs p{};
         p.out = d_work; p.out_sj = px; p.out_so = plane; p.nvalid = ny; p.nb = nx; p.no = nzl; p.taxis = 1;
-        p.boxrows = boxrows_y; p.nchunk = nchunk_y; p.reverse = 0; p.scale = sly; p.SN = ty.SN; p.WM = ty.WM;
+        p.reverse = 0; p.scale = sly; p.SN = ty.SN; p.WM = ty.WM;
         FDMB_CUDA(launch_cols_pipe(Ny, ki, tm_y, p, st, "cube_y_inv"));
     }
     FDMB_CUDA(rows(d_work, d_out, px, nx, slx, ki, "cube_x_inv", 1));
@@ -381,7 +390,7 @@ int fdmb_lapl_cube::solve_device(double* d_out, const double* d_in, cudaStream_t
         if (pipe_y) {
             ColsPipeArgs p{};
             p.out = q.out; p.out_sj = q.out_sj; p.out_so = q.out_so; p.nvalid = q.nvalid; p.nb = q.nb; p.no = q.no;
-            p.taxis = 1; p.boxrows = boxrows_y; p.nchunk = nchunk_y; p.reverse = reverse; p.scale = q.scale;
+            p.taxis = 1; p.reverse = reverse; p.scale = q.scale;
             p.scale2 = q.scale2; p.SN = q.SN; p.WM = q.WM;
             return launch_cols_pipe(Ny, kind, tm_y, p, st, tag);
         }
@@ -401,10 +410,8 @@ int fdmb_lapl_cube::solve_device(double* d_out, const double* d_in, cudaStream_t
     if (pipe_z) {
         ColsPipeArgs p{};
         p.out = z.out; p.out_sj = z.out_sj; p.out_so = z.out_so; p.nvalid = z.nvalid; p.nb = z.nb; p.no = z.no;
-        p.taxis = 2; p.boxrows = boxrows_z; p.nchunk = nchunk_z; p.reverse = 0; p.scale = z.scale; p.scale2 = z.scale2;
+        p.taxis = 2; p.reverse = 0; p.scale = z.scale; p.scale2 = z.scale2;
         p.SN = z.SN; p.WM = z.WM;
-        if (getenv("FDMB_ZEXP")) FDMB_CUDA(launch_cols_pipe(Nz, kf, tm_z, p, st, "cube_z_single_EXPERIMENT"));
-        else
         FDMB_CUDA(launch_cols_pipe_cube_divide(Nz, periodic != 0, tm_z, p, mid, st, "cube_z_fwd_div_inv"));
     } else {
         FDMB_CUDA(launch_cols_cube_divide(Nz, periodic != 0, z, mid, st, "cube_z_fwd_div_inv"));

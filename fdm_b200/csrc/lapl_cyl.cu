@@ -144,13 +144,11 @@ int fdmb_lapl_cyl::init()
     if (pipe_enabled()) {
         const unsigned long long s1 = 8ull * pr, s2 = 8ull * (unsigned long long)nz * pr;
         if (pipe_supported_N(Nz)) {
-            boxrows_z = nz < 256 ? nz : 256; nchunk_z = (nz + boxrows_z - 1) / boxrows_z;
-            if ((rc = make_tensor_map_3d(&tm_z, d_work, nr, nz, nphi, s1, s2, pipe_B(Nz), boxrows_z, 1))) return rc;
+            if ((rc = make_cols_maps(&tm_z, d_work, Nz, 1, nr, nz, nphi, s1, s2, pipe_B(Nz)))) return rc;
             pipe_z = true;
         }
         if (pipe_supported_N(nphi)) {
-            boxrows_phi = nphi < 256 ? nphi : 256; nchunk_phi = (nphi + boxrows_phi - 1) / boxrows_phi;
-            if ((rc = make_tensor_map_3d(&tm_phi, d_work, nr, nz, nphi, s1, s2, pipe_B(nphi), 1, boxrows_phi))) return rc;
+            if ((rc = make_cols_maps(&tm_phi, d_work, nphi, 2, nr, nz, nphi, s1, s2, pipe_B(nphi)))) return rc;
             pipe_phi = true;
         }
     }
@@ -175,14 +173,13 @@ int fdmb_lapl_cyl::solve_device(double* d_out, const double* d_in, cudaStream_t 
     {
         bool pipe_in = pipe_phi && (nr % 2 == 0) && ((reinterpret_cast<uintptr_t>(d_in) & 15) == 0);
         if (pipe_in && tm_in_ptr != d_in) {
-            if ((rc = make_tensor_map_3d(&tm_in, d_in, nr, nz, nphi, 8ull * nr, 8ull * uplane, pipe_B(nphi), 1, boxrows_phi)))
-                return rc;
+            if ((rc = make_cols_maps(&tm_in, d_in, nphi, 2, nr, nz, nphi, 8ull * nr, 8ull * uplane, pipe_B(nphi)))) return rc;
             tm_in_ptr = d_in;
         }
         if (pipe_in) {
             ColsPipeArgs p{};
             p.out = d_work; p.out_sj = wplane; p.out_so = pr; p.nvalid = nphi; p.nb = nr; p.no = nz; p.taxis = 2;
-            p.boxrows = boxrows_phi; p.nchunk = nchunk_phi; p.reverse = 0; p.scale = dphi * SQRT_M_1_PI;
+            p.reverse = 0; p.scale = dphi * SQRT_M_1_PI;
             p.SN = tphi.SN; p.WM = tphi.WM;
             FDMB_CUDA(launch_cols_pipe(nphi, XF_PFWD, tm_in, p, st, "cyl_phi_fwd"));
         } else {
@@ -197,7 +194,7 @@ int fdmb_lapl_cyl::solve_device(double* d_out, const double* d_in, cudaStream_t 
         if (pipe_z) {
             ColsPipeArgs p{};
             p.out = d_work; p.out_sj = pr; p.out_so = wplane; p.nvalid = nz; p.nb = nr; p.no = nphi; p.taxis = 1;
-            p.boxrows = boxrows_z; p.nchunk = nchunk_z; p.reverse = reverse; p.scale = scale; p.SN = tz.SN; p.WM = tz.WM;
+            p.reverse = reverse; p.scale = scale; p.SN = tz.SN; p.WM = tz.WM;
             return launch_cols_pipe(Nz, kind, tm_z, p, st, tag);
         }
         ColsArgs c{};
@@ -219,7 +216,7 @@ int fdmb_lapl_cyl::solve_device(double* d_out, const double* d_in, cudaStream_t 
     if (pipe_phi) {
         ColsPipeArgs p{};
         p.out = d_out; p.out_sj = uplane; p.out_so = nr; p.nvalid = nphi; p.nb = nr; p.no = nz; p.taxis = 2;
-        p.boxrows = boxrows_phi; p.nchunk = nchunk_phi; p.reverse = 0; p.scale = SQRT_M_1_PI; p.SN = tphi.SN; p.WM = tphi.WM;
+            p.reverse = 0; p.scale = SQRT_M_1_PI; p.SN = tphi.SN; p.WM = tphi.WM;
         FDMB_CUDA(launch_cols_pipe(nphi, XF_PINV, tm_phi, p, st, "cyl_phi_inv"));
     } else {
         ColsArgs c{};

@@ -34,9 +34,8 @@ struct fdmb_lapl_cyl {
     double* d_work = nullptr;
     double *d_rhs = nullptr, *d_ans = nullptr;
     bool pipe_z = false, pipe_phi = false;
-    CUtensorMap tm_z{}, tm_phi{}, tm_in{};
+    fdmb::ColsMaps tm_z{}, tm_phi{}, tm_in{};
     const void* tm_in_ptr = nullptr;
-    int boxrows_z = 0, nchunk_z = 0, boxrows_phi = 0, nchunk_phi = 0;
 
     int init();
     int solve_device(double* d_out, const double* d_in, cudaStream_t st);

@@ -103,4 +103,19 @@ int make_tensor_map_3d(CUtensorMap* tm, const void* base, unsigned long long e0,
                        unsigned long long e2, unsigned long long s1, unsigned long long s2, unsigned b0, unsigned b1,
                        unsigned b2);
 
+
+// Tensor maps of one strided-axis sweep over a 3-D fp64 array (x fastest; taxis = 1: tiles run along
+// dimension 1, taxis = 2: along dimension 2; B = tile width in x):
+//   nat          natural landing: row r of the transform axis -> tile row r (+ slot offset)
+//   podd / peven planar landing of the fused DST (built when the axis holds N-1 entries): the even
+//                global rows (odd slots) and the odd global rows (even slots) as two strided views
+struct ColsMaps {
+    CUtensorMap nat, podd, peven;
+    int boxrows = 0, nchunk = 0;          // natural
+    int boxrows_p = 0, nchunk_p = 0;      // planar, per parity
+    bool planar = false;
+};
+int make_cols_maps(ColsMaps* m, const void* base, int N, int taxis, unsigned long long e0, unsigned long long e1,
+                   unsigned long long e2, unsigned long long s1, unsigned long long s2, unsigned B);
+
 }  // namespace fdmb

@@ -426,37 +426,59 @@ __device__ __forceinline__ void xform_tile(double* col, int sj, int g, double sc
 }
 
 // =====================================================================================
-// Shared-memory-traffic-lean DST-I ("fused" variant).
+// Shared-memory-traffic-lean DST-I ("fused" variant) on a PLANAR tile.
 //
 // The sweeps are bound by the shared-memory data pipe (ncu: l1tex__data_pipe_lsu_wavefronts at
-// ~80 % of peak with the straightforward staging above), so this variant touches the tile as
-// little as possible:
+// 60-75 % of peak), so this variant touches the tile as little as possible and keeps every access
+// free of bank conflicts, also for 8-column tiles (64-byte rows) where two rows of equal parity
+// collide:
+//   layout   even slots and odd slots of a sequence live in two regions of the tile
+//            (Planar<N,GAP>: O[k] = slot 2k+1 at row k, E[k] = slot 2k at row M+GAP+k), which is
+//            also the layout of the half-length complex FFT (z[m] = y[2m] + i y[2m+1]: re = E[m],
+//            im = O[m]).  The strided-axis kernels land their tiles in this layout with two tensor
+//            maps (odd rows / even rows of the global array).
 //   stage A  fold + first radix pass: every thread reads its own and the mirrored inputs straight
 //            from the landed tile, folds in registers, runs the radix-R0 butterfly, stores once
 //   stage B  middle radix pass (if the plan has three passes)
 //   stage C  last radix pass + untangle: a thread processes a frequency block together with its
-//            mirror block (k <-> M-k live in the same thread), so the untangled A_k/B_k come out of
-//            registers; even output slots (S[2k] = B_k) leave through the OUT policy at once, the
-//            odd-slot seeds A'_k go back to the tile
+//            mirror block (k <-> M-k live in the same thread), the untangled A_k/B_k overwrite the
+//            registers that held Z[k]; even output slots (S[2k] = B_k) leave through the OUT policy
+//            at once, the odd-slot seeds A'_k go back to the O region
 //   stage D  running sum over the odd slots, emitted through the OUT policy
+// SWZ (8-column tiles): complex element s is stored at s ^ ((s / L1) & 1), L1 = M / R0, and seed k at
+// k ^ ((k / CS) & 1), so that the two thread groups sharing a half-warp always touch rows of different
+// parity.  Both swizzles only change per-thread base addresses.
+// The fold table SF[j] = (scale/2) sin(pi j/N) carries the transform's scale, so the untangle needs no
+// multiplications by it.
 // OUT policies decide where a finished spectral value goes: back into the tile (rows kernel, and the
 // z sweep's first transform, scaled by the spectral multiplier) or directly to global memory with
 // coalesced stores (strided-axis kernels), which removes the final tile write + read.
 // Requirements: G == M / R0 (one first-pass butterfly per thread).
 // =====================================================================================
 
-struct OutTile {
+template <int N, int GAP> struct Planar {
+    static constexpr int M = N / 2;
+    static constexpr int ROWS = N + GAP + 1;                        // O: [0,M), E: [M+GAP, M+GAP+M]
+    static __device__ __forceinline__ int O(int k) { return k; }               // slot 2k+1
+    static __device__ __forceinline__ int E(int k) { return M + GAP + k; }     // slot 2k
+    static __device__ __forceinline__ int row(int j) { return (j & 1) ? (j >> 1) : (M + GAP + (j >> 1)); }
+};
+
+template <int N, int GAP> struct OutTile {
     double* col; int sj;
-    __device__ __forceinline__ void emit(int j, double v) const { col[j * sj] = v; }
+    __device__ __forceinline__ void emit(int j, double v) const { col[Planar<N, GAP>::row(j) * sj] = v; }
 };
 // direct, coalesced store: lanes run over the contiguous axis, slot j -> row j-1 of the output
 struct OutGlobal {
     double* dst; long long stride; bool ok;
     __device__ __forceinline__ void emit(int j, double v) const { if (ok) dst[(long long)(j - 1) * stride] = v; }
 };
-template <typename MID> struct OutMidTile {
-    double* col; int sj; MID mid; int bidx, oidx; bool ok;
-    __device__ __forceinline__ void emit(int j, double v) const { col[j * sj] = ok ? mid(v, j, bidx, oidx) : 0.0; }
+template <int N, int GAP, typename MID> struct OutMidTile {
+    double* col; int sj; MID mid; typename MID::Ctx ctx; bool ok;
+    __device__ __forceinline__ void emit(int j, double v) const
+    {
+        col[Planar<N, GAP>::row(j) * sj] = ok ? mid.apply(v, j, ctx) : 0.0;
+    }
 };
 
 template <int N> struct PlanInfo {
@@ -465,33 +487,106 @@ template <int N> struct PlanInfo {
     static constexpr int NP = (P::R2 > 1) ? 3 : ((P::R1 > 1) ? 2 : 1);
     static constexpr int RL = (NP == 3) ? P::R2 : P::R1;   // radix of the last pass (NP >= 2)
     static constexpr int LB = M / RL;                       // frequency blocks of the last pass
+    static constexpr int L1 = M / P::R0;                    // sub-block length after the first pass
 };
 
-template <int N, int G, bool PREFOLD, typename OUT>
-__device__ __forceinline__ void dst_tile_fused(double* col, int sj, int g, double scale,
-                                               const double* __restrict__ SN, const cd* __restrict__ WM,
-                                               double* scr, int scr_s, const OUT& out)
+// One in-place DIF pass on the planar tile.  SWI / SWO: input / output stored with the block swizzle.
+template <int N, int GAP, int L, int R, int G, bool SWI, bool SWO>
+__device__ __forceinline__ void fft_pass_planar(double* col, int sj, int g, const cd* __restrict__ WM)
+{
+    using PL = Planar<N, GAP>;
+    constexpr int M = N / 2, L1 = PlanInfo<N>::L1;
+    constexpr int S = L / R;
+    constexpr int NBF = M / R;
+    constexpr int IT = (NBF + G - 1) / G;
+    static_assert(!(SWI || SWO) || ((L == M && S == L1) || (L == L1 && S % 2 == 0)), "swizzled pass shape");
+#pragma unroll
+    for (int it = 0; it < IT; it++) {
+        int q = g + it * G;
+        if (NBF % G != 0 && q >= NBF) break;
+        const int blk = q / S, n2 = q % S;
+        // swizzle bit of element base + n1*S: first pass -> n1 & 1, later passes -> blk & 1
+        const int cb = (L == M) ? 0 : (blk & 1);
+        cd v[R];
+#pragma unroll
+        for (int n1 = 0; n1 < R; n1++) {
+            const int bit = SWI ? ((L == M) ? (n1 & 1) : cb) : 0;
+            const int s = blk * L + (n2 ^ bit) + n1 * S;
+            v[n1].x = col[PL::E(s) * sj];
+            v[n1].y = col[PL::O(s) * sj];
+        }
+        Dft<R>::run(v);
+#pragma unroll
+        for (int k1 = 0; k1 < R; k1++) {
+            cd o = v[k1];
+            if (S > 1 && k1 > 0) o = cmul(o, WM[n2 * k1 * (M / L)]);
+            const int bit = SWO ? ((L == M) ? (k1 & 1) : cb) : 0;
+            const int s = blk * L + (n2 ^ bit) + k1 * S;
+            col[PL::E(s) * sj] = o.x;
+            col[PL::O(s) * sj] = o.y;
+        }
+    }
+}
+
+// Untangle one (k, M-k) pair of the (pre-scaled) half-length FFT in place:
+// zk = Z[k], zm = Z[M-k], 0 < k < M/2  ->  zk = (A_k, B_k), zm = (A_{M-k}, B_{M-k}).
+template <int N>
+__device__ __forceinline__ void untangle_inplace(cd& zk, cd& zm, int k, const double* __restrict__ SN)
+{
+    constexpr int M = N / 2;
+    const double c = SN[M - 2 * k], s = SN[2 * k];      // cos, sin of 2 pi k / N
+    const double ex = zk.x + zm.x, ey = zk.y - zm.y;
+    const double ox = zk.y + zm.y, oy = zm.x - zk.x;
+    const double wx = c * ox + s * oy, wy = c * oy - s * ox;
+    zk.x = ex + wx; zk.y = -(ey + wy);
+    zm.x = ex - wx; zm.y = ey - wy;
+}
+
+// Row of folded element y[j] for the PREFOLD entry of dst_tile_fused (the rows kernel's first touch).
+template <int N, int GAP, bool SWZ>
+__device__ __forceinline__ int prefold_row(int j)
+{
+    int m = j >> 1;
+    if (SWZ) m ^= (m / PlanInfo<N>::L1) & 1;
+    return (j & 1) ? Planar<N, GAP>::O(m) : Planar<N, GAP>::E(m);
+}
+
+// col: this thread's sequence in the planar tile (element row r at col[r * sj]); on entry the tile
+// holds the raw inputs x[1..N-1] (PREFOLD = false) or the folded, (scale/2)-scaled sequence y
+// (PREFOLD = true; y[0] = 0, y[M] = scale * x[M]).  SF[j] = (scale/2) * SN[j], hs = scale / 2.
+// SEP: finished values never go back into the working tile -- the seeds (and, for tile OUT policies, the
+// spectral values) are written to a second tile `ocol` that nobody reads during stage C, so the stage-C
+// results leave the registers at once (no barrier between the last loads and the first stores, half the
+// live registers).  ocol is this thread's column base in that tile (same sj); ignored when !SEP.
+template <int N, int G, int GAP, bool PREFOLD, bool SWZ, bool SEP = false, typename OUT>
+__device__ __forceinline__ void dst_tile_fused(double* col, int sj, int g, double hs,
+                                               const double* __restrict__ SN, const double* __restrict__ SF,
+                                               const cd* __restrict__ WM, double* scr, int scr_s, const OUT& out,
+                                               double* ocol = nullptr)
 {
     using P = Plan<N>;
     using I = PlanInfo<N>;
+    using PL = Planar<N, GAP>;
     constexpr int M = N / 2, R0 = P::R0, S0 = M / R0;
     static_assert(I::NP >= 2, "fused DST needs at least two radix passes");
     static_assert(G == S0, "fused DST: one first-pass butterfly per thread");
+    static_assert(!SWZ || I::NP == 3, "the block swizzle is defined for three-pass plans");
 
     // ---- stage A -------------------------------------------------------------------------
     if constexpr (!PREFOLD) {
         cd v[R0];
+        const double h2 = 0.5 * hs;
 #pragma unroll
         for (int n1 = 0; n1 < R0; n1++) {
             const int m = g + n1 * S0;
-            const int j0 = 2 * m, j1 = 2 * m + 1;
-            // y[j] = sin(pi j/N)(x[j]+x[N-j]) + (x[j]-x[N-j])/2 for every j in 1..N-1, y[0] = 0
-            double a0 = (m == 0) ? 0.0 : col[j0 * sj], c0 = (m == 0) ? 0.0 : col[(N - j0) * sj];
-            double a1 = col[j1 * sj], c1 = col[(N - j1) * sj];
-            double s0 = (n1 < R0 / 2) ? SN[j0] : SN[N - j0];
-            double s1 = (n1 < R0 / 2) ? SN[j1] : SN[N - j1];
-            v[n1].x = s0 * (a0 + c0) + 0.5 * (a0 - c0);
-            v[n1].y = s1 * (a1 + c1) + 0.5 * (a1 - c1);
+            // y[j] = hs * (sin(pi j/N)(x[j]+x[N-j]) + (x[j]-x[N-j])/2) for every j in 1..N-1, y[0] = 0;
+            // x[2m] = E[m], x[N-2m] = E[M-m], x[2m+1] = O[m], x[N-2m-1] = O[M-m-1]
+            double a0 = (m == 0) ? 0.0 : col[PL::E(m) * sj], c0 = (m == 0) ? 0.0 : col[PL::E(M - m) * sj];
+            double a1 = col[PL::O(m) * sj], c1 = col[PL::O(M - m - 1) * sj];
+            double s0 = (n1 < R0 / 2) ? SF[2 * m] : SF[N - 2 * m];
+            double s1 = (n1 < R0 / 2) ? SF[2 * m + 1] : SF[N - 2 * m - 1];
+            v[n1].x = s0 * (a0 + c0) + h2 * (a0 - c0);
+            v[n1].y = s1 * (a1 + c1) + h2 * (a1 - c1);
         }
         __syncthreads();     // every mirrored read is done before anyone overwrites the inputs
         Dft<R0>::run(v);
@@ -499,119 +594,92 @@ __device__ __forceinline__ void dst_tile_fused(double* col, int sj, int g, doubl
         for (int k1 = 0; k1 < R0; k1++) {
             cd o = v[k1];
             if (k1 > 0) o = cmul(o, WM[g * k1]);
-            const int idx = 2 * (g + k1 * S0);
-            col[idx * sj] = o.x;
-            col[(idx + 1) * sj] = o.y;
+            const int s = (g ^ (SWZ ? (k1 & 1) : 0)) + k1 * S0;
+            col[PL::E(s) * sj] = o.x;
+            col[PL::O(s) * sj] = o.y;
         }
         __syncthreads();
     } else {
-        fft_pass<M, M, R0, G>(col, sj, g, WM);
+        // the caller stored the folded sequence at prefold_row<N,GAP,SWZ>(j): already block-swizzled, so the
+        // first pass stays in place (every thread rewrites exactly the rows it read)
+        fft_pass_planar<N, GAP, M, R0, G, SWZ, SWZ>(col, sj, g, WM);
         __syncthreads();
     }
     // ---- stage B -------------------------------------------------------------------------
     if constexpr (I::NP == 3) {
-        fft_pass<M, M / R0, P::R1, G>(col, sj, g, WM);
+        fft_pass_planar<N, GAP, M / R0, P::R1, G, SWZ, SWZ>(col, sj, g, WM);
         __syncthreads();
     }
     // ---- stage C: last pass on a block and its mirror block, untangle in registers -------------
     constexpr int RL = I::RL, LB = I::LB;
-    constexpr int NU = (LB >= 2) ? LB / 2 : 1;            // units: {0, LB/2} and (u, LB-u), u = 1..LB/2-1
-    constexpr int ITC = (NU + G - 1) / G;
-    static_assert(LB >= 2, "last pass must leave at least two frequency blocks");
-    double rA[ITC][RL], rB[ITC][RL], rC[ITC][RL], rD[ITC][RL];   // A_k, B_k (block lo) / A, B (mirror block)
-    const double hs = 0.5 * scale;
+    constexpr int NU = LB / 2;            // units: {0, LB/2} and (u, LB-u), u = 1..LB/2-1
+    constexpr int CS = M / G;             // odd-slot chunk per thread in stage D
+    static_assert(LB >= 2 && NU <= G, "last pass: at most one unit per thread");
+    static_assert(!SWZ || (CS % 2 == 0 && (LB / CS) % 2 == 0 && LB % CS == 0), "seed swizzle shape");
+    const int u = g;
+    const bool active = (NU == G) || (u < NU);
+    const int lo = u, hi = (u == 0) ? LB / 2 : LB - u;
+    cd va[RL], vb[RL];
+    if (active) {
+        const int ba = fft_pos<N>(lo), bb = fft_pos<N>(hi);
+        const int ca = SWZ ? ((ba / I::L1) & 1) : 0, cb = SWZ ? ((bb / I::L1) & 1) : 0;
 #pragma unroll
-    for (int it = 0; it < ITC; it++) {
-        const int u = g + it * G;
-        if (NU % G != 0 && u >= NU) break;
-        const int lo = u, hi = (u == 0) ? LB / 2 : LB - u;
-        cd va[RL], vb[RL];
-        {
-            const int ba = fft_pos<N>(lo), bb = fft_pos<N>(hi);
-#pragma unroll
-            for (int n1 = 0; n1 < RL; n1++) {
-                va[n1].x = col[(2 * (ba + n1)) * sj]; va[n1].y = col[(2 * (ba + n1) + 1) * sj];
-                vb[n1].x = col[(2 * (bb + n1)) * sj]; vb[n1].y = col[(2 * (bb + n1) + 1) * sj];
-            }
+        for (int n1 = 0; n1 < RL; n1++) {
+            const int sa = ba + (n1 ^ ca), sb = bb + (n1 ^ cb);
+            va[n1].x = col[PL::E(sa) * sj]; va[n1].y = col[PL::O(sa) * sj];
+            vb[n1].x = col[PL::E(sb) * sj]; vb[n1].y = col[PL::O(sb) * sj];
         }
         Dft<RL>::run(va);
         Dft<RL>::run(vb);
         if (u == 0) {
             // block 0 holds k = LB*d: d = 0 (DC), d = RL/2 (k = M/2), pairs (d, RL-d);
             // block LB/2 holds k = LB/2 + LB*d, pairs (d, RL-1-d)
-            rA[it][0] = scale * (va[0].x + va[0].y);   // A_0
-            rB[it][0] = 0.0;
-            rA[it][RL / 2] = scale * va[RL / 2].x;     // A_{M/2} = Re Z[M/2]
-            rB[it][RL / 2] = scale * va[RL / 2].y;     // S[M]    = Im Z[M/2]
+            va[0].x = 2.0 * (va[0].x + va[0].y);     // A_0
+            va[0].y = 0.0;
+            va[RL / 2].x = 2.0 * va[RL / 2].x;        // A_{M/2} = Re Z[M/2]
+            va[RL / 2].y = 2.0 * va[RL / 2].y;        // S[M]    = Im Z[M/2]
 #pragma unroll
-            for (int d = 1; d < RL / 2; d++) {
-                const int k = LB * d;
-                const cd zk = va[d], zm = va[RL - d];
-                const double c = SN[M - 2 * k], s = SN[2 * k];
-                const double ex = hs * (zk.x + zm.x), ey = hs * (zk.y - zm.y);
-                const double ox = hs * (zk.y + zm.y), oy = -hs * (zk.x - zm.x);
-                const double wx = c * ox + s * oy, wy = c * oy - s * ox;
-                rA[it][d] = ex + wx; rB[it][d] = -(ey + wy);
-                rA[it][RL - d] = ex - wx; rB[it][RL - d] = ey - wy;
-            }
+            for (int d = 1; d < RL / 2; d++) untangle_inplace<N>(va[d], va[RL - d], LB * d, SN);
 #pragma unroll
-            for (int d = 0; d < RL / 2; d++) {
-                const int k = LB / 2 + LB * d;
-                const cd zk = vb[d], zm = vb[RL - 1 - d];
-                const double c = SN[M - 2 * k], s = SN[2 * k];
-                const double ex = hs * (zk.x + zm.x), ey = hs * (zk.y - zm.y);
-                const double ox = hs * (zk.y + zm.y), oy = -hs * (zk.x - zm.x);
-                const double wx = c * ox + s * oy, wy = c * oy - s * ox;
-                rC[it][d] = ex + wx; rD[it][d] = -(ey + wy);
-                rC[it][RL - 1 - d] = ex - wx; rD[it][RL - 1 - d] = ey - wy;
-            }
+            for (int d = 0; d < RL / 2; d++) untangle_inplace<N>(vb[d], vb[RL - 1 - d], LB / 2 + LB * d, SN);
         } else {
             // block lo: k = lo + LB*d; its partner M-k sits in block hi at d' = RL-1-d
 #pragma unroll
             for (int d = 0; d < RL; d++) {
-                const bool lower = d < RL / 2;                       // k < M/2 ?
-                const int k = lower ? lo + LB * d : hi + LB * (RL - 1 - d);
-                const cd zk = lower ? va[d] : vb[RL - 1 - d];
-                const cd zm = lower ? vb[RL - 1 - d] : va[d];
-                const double c = SN[M - 2 * k], s = SN[2 * k];
-                const double ex = hs * (zk.x + zm.x), ey = hs * (zk.y - zm.y);
-                const double ox = hs * (zk.y + zm.y), oy = -hs * (zk.x - zm.x);
-                const double wx = c * ox + s * oy, wy = c * oy - s * ox;
-                const double Ak = ex + wx, Bk = -(ey + wy), Am = ex - wx, Bm = ey - wy;
-                if (lower) { rA[it][d] = Ak; rB[it][d] = Bk; rC[it][RL - 1 - d] = Am; rD[it][RL - 1 - d] = Bm; }
-                else { rC[it][RL - 1 - d] = Ak; rD[it][RL - 1 - d] = Bk; rA[it][d] = Am; rB[it][d] = Bm; }
+                if (d < RL / 2) untangle_inplace<N>(va[d], vb[RL - 1 - d], lo + LB * d, SN);           // k < M/2
+                else untangle_inplace<N>(vb[RL - 1 - d], va[d], hi + LB * (RL - 1 - d), SN);
             }
         }
     }
-    __syncthreads();
-#pragma unroll
-    for (int it = 0; it < ITC; it++) {
-        const int u = g + it * G;
-        if (NU % G != 0 && u >= NU) break;
-        const int lo = u, hi = (u == 0) ? LB / 2 : LB - u;
+    if constexpr (!SEP) __syncthreads();
+    double* scol = SEP ? ocol : col;      // where the seeds live
+    if (active) {
+        // seed k lives at O[k ^ ((k / CS) & 1)] when swizzled: (k / CS) & 1 is a per-thread constant
+        const int za = SWZ ? ((lo / CS) & 1) : 0, zb = SWZ ? ((hi / CS) & 1) : 0;
 #pragma unroll
         for (int d = 0; d < RL; d++) {
             const int ka = lo + LB * d, kb = hi + LB * d;
             if (u == 0 && d == 0) {
-                col[sj] = 0.5 * rA[it][0];                 // A_0 / 2 seeds the running sum
+                scol[PL::O(0) * sj] = 0.5 * va[0].x;         // A_0 / 2 seeds the running sum
             } else {
-                out.emit(2 * ka, rB[it][d]);
-                col[(2 * ka + 1) * sj] = rA[it][d];
+                out.emit(2 * ka, va[d].y);
+                scol[PL::O((lo ^ za) + LB * d) * sj] = va[d].x;
             }
-            out.emit(2 * kb, rD[it][d]);
-            col[(2 * kb + 1) * sj] = rC[it][d];
+            out.emit(2 * kb, vb[d].y);
+            scol[PL::O((hi ^ zb) + LB * d) * sj] = vb[d].x;
         }
     }
     __syncthreads();
     // ---- stage D: inclusive prefix sum over the odd slots: S[2k+1] = sum_{m<=k} A'_m ------------
-    constexpr int CS = M / G;
     double a[CS];
     double run = 0.0;
+    {
+        const int zg = SWZ ? (g & 1) : 0;
 #pragma unroll
-    for (int i = 0; i < CS; i++) {
-        int k = g * CS + i;
-        run += col[(2 * k + 1) * sj];
-        a[i] = run;
+        for (int i = 0; i < CS; i++) {
+            run += scol[PL::O(g * CS + (i ^ zg)) * sj];
+            a[i] = run;
+        }
     }
     double off = 0.0;
     if constexpr (G > 1) {

@@ -66,11 +66,32 @@ __global__ void __launch_bounds__(TileCfg<N>::THREADS) k_rows(RowsArgs a)
     }
 }
 
-// mid functors: applied to tile value at (slot j, column index bb, outer index o)
+// mid functors: applied to tile value at (slot j, column index bb, outer index o).  The fused sweeps
+// hoist the (bb, o) part out of the per-slot work: ctx(bb, o) once per tile, apply(v, j, ctx) per slot.
 struct MidNone {
     static constexpr bool active = false;
+    struct Ctx {};
     __device__ __forceinline__ double operator()(double v, int, int, int) const { return v; }
+    __device__ __forceinline__ Ctx ctx(int, int) const { return Ctx{}; }
+    __device__ __forceinline__ double apply(double v, int, const Ctx&) const { return v; }
 };
+
+// 1/d to within an ulp: hardware seed (MUFU.RCP64H, ~20 bits) + two Newton steps.  d is a sum of
+// Laplacian eigenvalues: finite, positive, far from the subnormal and overflow ranges.
+__device__ __forceinline__ double rcp_newton(double d)
+{
+#ifdef FDMB_HOST_EMUL
+    return 1.0 / d;
+#else
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    double e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+#endif
+}
 
 // v / -(lm_j[j] + lm_b[b] + lm_o[o]); optional zeroing of the (0,0,0) mode (lapl_cube.cpp:70-84)
 struct MidCubeDivide {
@@ -79,10 +100,18 @@ struct MidCubeDivide {
     const double* lm_b;
     const double* lm_o;
     int zero_null;
+    struct Ctx { double s; bool null_bo; };
     __device__ __forceinline__ double operator()(double v, int j, int b, int o) const
     {
         if (zero_null && j == 0 && b == 0 && o == 0) return 0.0;
         return v / -(lm_j[j] + lm_b[b] + lm_o[o]);
+    }
+    __device__ __forceinline__ Ctx ctx(int b, int o) const { return Ctx{lm_b[b] + lm_o[o], zero_null && b == 0 && o == 0}; }
+    // the quotient as a product with a Newton reciprocal (<= 2 ulp from the division; parity bar is 1e-12)
+    __device__ __forceinline__ double apply(double v, int j, const Ctx& c) const
+    {
+        if (c.null_bo && j == 0) return 0.0;
+        return -v * rcp_newton(lm_j[j] + c.s);
     }
 };
 

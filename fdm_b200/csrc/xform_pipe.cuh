@@ -22,18 +22,28 @@ template <int N> struct PipeCfg {
     static constexpr int G = Plan<N>::G;
     static constexpr int THREADS = B * G;
     static constexpr int SCR = (G + G / 8 + 1) * B;
-    static constexpr int TAB = (N / 2 + 1) + 2 * (N / 2);               // SN + WM (doubles)
-    static constexpr int COLS_BUF = ((N + 1) * B + 15) / 16 * 16;      // doubles per stage buffer (128-B multiple)
+    static constexpr bool SWZ = (B == 8);              // 64-byte tile rows: keep half-warps on rows of different parity
+    // SN + WM + two fold tables SF (doubles)
+    static constexpr int TAB = (N / 2 + 2) + 2 * (N / 2) + 2 * (N / 2 + 2);
+    static constexpr int COLS_GAP = 1;                 // planar tile: E region starts one row late (128-B aligned landing)
+    static constexpr int COLS_BUF = ((N + 2) * B + 15) / 16 * 16;      // doubles per stage buffer (128-B multiple)
     static constexpr int COLS_STAGES = (N <= 1024) ? 2 : 1;
+    // fused DST sweeps write their results into a second tile instead of back into the working one
+    // (dst_tile_fused SEP); only where one CTA per SM is resident anyway and the tile still fits
+    static constexpr bool COLS_SEP = (N == 1024);
     static constexpr size_t cols_smem(int nstage)
     {
-        return 8 * (size_t)(16 + nstage * COLS_BUF + SCR + TAB + 2) + 8 * 8 + 128;
+        return 8 * (size_t)(16 + (nstage + (COLS_SEP ? 1 : 0)) * COLS_BUF + SCR + TAB + 2) + 8 * 8 + 128;
     }
     static constexpr int BR = B;
+    // planar rows tile: the E region starts 8 doubles after a multiple of 16 so that the 8 even + 8 odd slots a
+    // half-warp touches when it walks along a row fall into different banks (Planar<N, ROWS_GAP>)
+    static constexpr int ROWS_GAP = 8;
+    static constexpr int ROWS_P = (BR == 8) ? N + 18 : N + 9;   // tile pitch: = 2 (mod 16) for 8 rows, odd for 16 rows
     static constexpr int ROWS_STAGES = 1;
     static constexpr size_t rows_smem(int nstage)
     {
-        return 8 * (size_t)(nstage * BR * N + BR * (N + 1) + SCR + TAB + 2) + 8 * 8 + 128;
+        return 8 * (size_t)(nstage * BR * N + BR * ROWS_P + SCR + TAB + 2) + 8 * 8 + 128;
     }
 };
 
@@ -42,6 +52,12 @@ __device__ __forceinline__ void load_tables(double* SNs, cd* WMs, const double* 
 {
     for (int i = threadIdx.x; i <= N / 2; i += blockDim.x) SNs[i] = SN[i];
     for (int i = threadIdx.x; i < N / 2; i += blockDim.x) WMs[i] = WM[i];
+}
+// fold table of the fused DST: SF[j] = hs * sin(pi j / N)
+template <int N>
+__device__ __forceinline__ void load_fold_table(double* SFs, const double* __restrict__ SN, double hs)
+{
+    for (int i = threadIdx.x; i <= N / 2; i += blockDim.x) SFs[i] = hs * SN[i];
 }
 
 // ---- output maps of the strided-axis sweep ----------------------------------------------------
@@ -96,47 +112,74 @@ struct ColsPipeArgs {
     const cd* WM;
 };
 
+// FUSED (DST, and DST -> multiply -> DST): the tile lands in the planar layout of dst_tile_fused through two
+// tensor maps (tm: even global rows = odd slots, tm2: odd global rows = even slots); otherwise tm lands the
+// tile in natural order and tm2 is unused.
+template <int KIND, typename MID, int KIND2> struct ColsFused {
+    static constexpr bool value = (KIND == XF_DST) && (!MID::active || KIND2 == XF_DST);
+};
+
 template <int N, int KIND, typename MID, int KIND2, int NSTAGE, typename OMAP>
 __global__ void __launch_bounds__(PipeCfg<N>::THREADS)
-k_cols_pipe(const __grid_constant__ CUtensorMap tm, ColsPipeArgs a, MID mid, const __grid_constant__ OMAP omap)
+k_cols_pipe(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tm2, ColsPipeArgs a, MID mid,
+            const __grid_constant__ OMAP omap)
 {
     using C = PipeCfg<N>;
-    constexpr int B = C::B, G = C::G;
+    constexpr int B = C::B, G = C::G, M = N / 2, GAP = C::COLS_GAP;
+    constexpr bool FUSED = ColsFused<KIND, MID, KIND2>::value;
     constexpr int J0 = (KIND == XF_DST) ? 1 : 0;
     constexpr int BUF = C::COLS_BUF;
-    constexpr int PRE = (J0 * B) % 16 ? 16 - (J0 * B) % 16 : 0;   // keeps the first loaded slot 128-B aligned
+    // natural landing: keep the first loaded slot 128-B aligned
+    constexpr int PRE = FUSED ? 0 : ((J0 * B) % 16 ? 16 - (J0 * B) % 16 : 0);
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     double* sm = reinterpret_cast<double*>(smem_raw);
     double* bufs = sm + PRE;
-    double* scr = bufs + NSTAGE * BUF;
+    constexpr bool SEP = FUSED && C::COLS_SEP;
+    double* alt = bufs + NSTAGE * BUF;                         // second tile of the SEP variant
+    double* scr = sm + 16 + (NSTAGE + (C::COLS_SEP ? 1 : 0)) * BUF;
     double* SNs = scr + C::SCR;
     cd* WMs = reinterpret_cast<cd*>(SNs + (N / 2 + 2));
-    uint64_t* full = reinterpret_cast<uint64_t*>(WMs + N / 2);
+    double* SF1 = reinterpret_cast<double*>(WMs + N / 2);
+    double* SF2 = SF1 + (N / 2 + 2);
+    uint64_t* full = reinterpret_cast<uint64_t*>(SF2 + (N / 2 + 2));
 
     const int tid = threadIdx.x;
     const int b = tid % B, g = tid / B;
     const int nbt = (a.nb + B - 1) / B;
     const int ntiles = nbt * a.no;
-    const unsigned tx_bytes = (unsigned)a.nchunk * a.boxrows * B * 8;
+    const unsigned tx_bytes = (unsigned)a.nchunk * a.boxrows * B * 8 * (FUSED ? 2 : 1);
 
     auto issue = [&](int t, int s) {
         if (a.reverse) t = ntiles - 1 - t;
         const int o = t / nbt, b0 = (t % nbt) * B;
         mbar_expect_tx(&full[s], tx_bytes);
-        double* dst = bufs + s * BUF + J0 * B;
+        double* buf = bufs + s * BUF;
         for (int c = 0; c < a.nchunk; c++) {
             const int r0 = c * a.boxrows;
-            if (a.taxis == 1) tma_load_3d(dst + r0 * B, &tm, b0, r0, o, &full[s]);
-            else tma_load_3d(dst + r0 * B, &tm, b0, o, r0, &full[s]);
+            if constexpr (FUSED) {
+                double* dO = buf + r0 * B;                    // O[h]   <- global row 2h
+                double* dE = buf + (M + GAP + 1 + r0) * B;    // E[h+1] <- global row 2h + 1
+                if (a.taxis == 1) { tma_load_3d(dO, &tm, b0, r0, o, &full[s]); tma_load_3d(dE, &tm2, b0, r0, o, &full[s]); }
+                else { tma_load_3d(dO, &tm, b0, o, r0, &full[s]); tma_load_3d(dE, &tm2, b0, o, r0, &full[s]); }
+            } else {
+                double* dst = buf + J0 * B;
+                if (a.taxis == 1) tma_load_3d(dst + r0 * B, &tm, b0, r0, o, &full[s]);
+                else tma_load_3d(dst + r0 * B, &tm, b0, o, r0, &full[s]);
+            }
         }
     };
 
     if (tid == 0) {
         tma_prefetch_desc(&tm);
+        if constexpr (FUSED) tma_prefetch_desc(&tm2);
         for (int s = 0; s < NSTAGE; s++) mbar_init(&full[s], 1);
         mbar_init_fence();
     }
     load_tables<N>(SNs, WMs, a.SN, a.WM);
+    if constexpr (FUSED) {
+        load_fold_table<N>(SF1, a.SN, 0.5 * a.scale);
+        if constexpr (MID::active) load_fold_table<N>(SF2, a.SN, 0.5 * a.scale2);
+    }
     __syncthreads();
     if (tid == 0) {
         for (int s = 0; s < NSTAGE; s++) {
@@ -155,15 +198,20 @@ k_cols_pipe(const __grid_constant__ CUtensorMap tm, ColsPipeArgs a, MID mid, con
         double* tile = bufs + s * BUF;
         mbar_wait(&full[s], parity);
 
-        if constexpr (KIND == XF_DST && (!MID::active || KIND2 == XF_DST)) {
+        if constexpr (FUSED) {
             // smem-lean path: finished spectral values leave the registers straight to global memory
             const auto og = omap.emitter(a.out, a.out_sj, a.out_so, J0, o, b0 + b, bok);
             if constexpr (MID::active) {
-                const OutMidTile<MID> om{tile + b, B, mid, b0 + b + 1, o + a.mid_o_off + 1, bok};
-                dst_tile_fused<N, G, false>(tile + b, B, g, a.scale, SNs, WMs, scr + b, B, om);
-                dst_tile_fused<N, G, false>(tile + b, B, g, a.scale2, SNs, WMs, scr + b, B, og);
+                // forward -> multiply -> inverse; with SEP the two transforms ping-pong between the tiles
+                double* t2 = SEP ? alt : tile;
+                const OutMidTile<N, GAP, MID> om{t2 + b, B, mid, mid.ctx(bok ? b0 + b + 1 : 0, o + a.mid_o_off + 1), bok};
+                dst_tile_fused<N, G, GAP, false, C::SWZ, SEP>(tile + b, B, g, 0.5 * a.scale, SNs, SF1, WMs, scr + b, B, om,
+                                                              t2 + b);
+                dst_tile_fused<N, G, GAP, false, C::SWZ, SEP>(t2 + b, B, g, 0.5 * a.scale2, SNs, SF2, WMs, scr + b, B, og,
+                                                              tile + b);
             } else {
-                dst_tile_fused<N, G, false>(tile + b, B, g, a.scale, SNs, WMs, scr + b, B, og);
+                dst_tile_fused<N, G, GAP, false, C::SWZ, SEP>(tile + b, B, g, 0.5 * a.scale, SNs, SF1, WMs, scr + b, B, og,
+                                                              alt + b);
             }
         } else {
             xform_tile<N, G, KIND>(tile + b, B, g, a.scale, SNs, WMs, scr + b, B);
@@ -206,21 +254,26 @@ template <int N, int KIND, int NSTAGE>
 __global__ void __launch_bounds__(PipeCfg<N>::THREADS) k_rows_pipe(RowsPipeArgs a)
 {
     using C = PipeCfg<N>;
-    constexpr int BR = C::BR, G = C::G, P = N + 1, M = N / 2;
+    constexpr int RG = C::ROWS_GAP;
+    using PL = Planar<N, RG>;
+    constexpr int BR = C::BR, G = C::G, P = C::ROWS_P, M = N / 2;
+    static_assert(P >= PL::ROWS, "rows tile pitch");
     constexpr int J0 = (KIND == XF_DST) ? 1 : 0;
     constexpr int NW = C::THREADS / 32;
     static_assert(C::THREADS % 32 == 0, "whole warps");
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     double* sm = reinterpret_cast<double*>(smem_raw);
     double* stage = sm;                               // [NSTAGE][BR * N] dense
-    double* tile = stage + NSTAGE * BR * N;           // [BR][N + 1]
+    double* tile = stage + NSTAGE * BR * N;           // [BR][P]; DST: planar rows (Planar<N,0>)
     double* scr = tile + BR * P;
     double* SNs = scr + C::SCR;
     cd* WMs = reinterpret_cast<cd*>(SNs + (N / 2 + 2));
-    uint64_t* full = reinterpret_cast<uint64_t*>(WMs + N / 2);
+    double* SF1 = reinterpret_cast<double*>(WMs + N / 2);
+    uint64_t* full = reinterpret_cast<uint64_t*>(SF1 + 2 * (N / 2 + 2));
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long ntiles = (a.nrows + BR - 1) / BR;
+    const double hs = 0.5 * a.scale, h2 = 0.5 * hs;
 
     auto issue = [&](long long t, int s) {
         if (a.reverse) t = ntiles - 1 - t;
@@ -236,6 +289,7 @@ __global__ void __launch_bounds__(PipeCfg<N>::THREADS) k_rows_pipe(RowsPipeArgs 
         mbar_init_fence();
     }
     load_tables<N>(SNs, WMs, a.SN, a.WM);
+    if constexpr (KIND == XF_DST) load_fold_table<N>(SF1, a.SN, hs);
     __syncthreads();
     if (tid == 0) {
         for (int s = 0; s < NSTAGE; s++) {
@@ -259,7 +313,8 @@ __global__ void __launch_bounds__(PipeCfg<N>::THREADS) k_rows_pipe(RowsPipeArgs 
             if ((cnt & 1) && tid == 0) st[cnt - 1] = a.in[row0 * a.in_pitch + cnt - 1];
             if (cnt & 1) __syncthreads();
         }
-        // first touch: staging (dense, lanes along the row) -> odd-pitch compute tile
+        // first touch: staging (dense, lanes along the row) -> compute tile; the DST fold happens here and
+        // writes the planar layout (even / odd slots de-interleaved)
         for (int r = warp; r < BR; r += NW) {
             const double* src = st + r * a.in_pitch;
             double* dst = tile + r * P;
@@ -267,11 +322,14 @@ __global__ void __launch_bounds__(PipeCfg<N>::THREADS) k_rows_pipe(RowsPipeArgs 
             if constexpr (KIND == XF_DST) {
                 for (int j = 1 + lane; j < M; j += 32) {
                     double x1 = ok ? src[j - 1] : 0.0, x2 = ok ? src[N - j - 1] : 0.0;
-                    double y1 = SNs[j] * (x1 + x2), y2 = 0.5 * (x1 - x2);
-                    dst[j] = y1 + y2;
-                    dst[N - j] = y1 - y2;
+                    double y1 = SF1[j] * (x1 + x2), y2 = h2 * (x1 - x2);
+                    dst[prefold_row<N, RG, C::SWZ>(j)] = y1 + y2;
+                    dst[prefold_row<N, RG, C::SWZ>(N - j)] = y1 - y2;
                 }
-                if (lane == 0) { dst[0] = 0.0; dst[M] = ok ? 2.0 * src[M - 1] : 0.0; }
+                if (lane == 0) {
+                    dst[prefold_row<N, RG, C::SWZ>(0)] = 0.0;
+                    dst[prefold_row<N, RG, C::SWZ>(M)] = ok ? a.scale * src[M - 1] : 0.0;
+                }
             } else {
                 for (int j = lane; j < N; j += 32) dst[j] = ok ? src[j] : 0.0;
             }
@@ -283,14 +341,15 @@ __global__ void __launch_bounds__(PipeCfg<N>::THREADS) k_rows_pipe(RowsPipeArgs 
             if (tid == 0 && tn < ntiles) issue(tn, s);
         }
         if constexpr (KIND == XF_DST)
-            dst_tile_fused<N, G, true>(tile + b * P, 1, g, a.scale, SNs, WMs, scr + b, BR, OutTile{tile + b * P, 1});
+            dst_tile_fused<N, G, RG, true, C::SWZ>(tile + b * P, 1, g, hs, SNs, SF1, WMs, scr + b, BR,
+                                                   OutTile<N, RG>{tile + b * P, 1});
         else
             xform_tile<N, G, KIND, true>(tile + b * P, 1, g, a.scale, SNs, WMs, scr + b, BR);
         for (int r = warp; r < rows; r += NW) {
             double* dst = a.out + (row0 + r) * a.out_pitch;
-            const double* src = tile + r * P + J0;
+            const double* src = tile + r * P;
 #pragma unroll 4
-            for (int x = lane; x < a.nvalid; x += 32) dst[x] = src[x];
+            for (int x = lane; x < a.nvalid; x += 32) dst[x] = (KIND == XF_DST) ? src[PL::row(x + 1)] : src[x];
         }
         __syncthreads();   // the compute tile is rewritten by the next first touch
     }
@@ -301,8 +360,8 @@ int device_sm_count();
 int current_device_slot();   // cudaGetDevice() clamped to [0, 63]
 
 template <int N, int KIND, typename MID, int KIND2, typename OMAP = OutLinear>
-inline cudaError_t launch_cols_pipe_t(const CUtensorMap& tm, const ColsPipeArgs& a, const MID& mid, cudaStream_t st,
-                                      const OMAP& omap = OMAP{})
+inline cudaError_t launch_cols_pipe_t(const CUtensorMap& tm, const CUtensorMap& tm2, const ColsPipeArgs& a, const MID& mid,
+                                      cudaStream_t st, const OMAP& omap = OMAP{})
 {
     using C = PipeCfg<N>;
     constexpr int NSTAGE = C::COLS_STAGES;
@@ -321,7 +380,7 @@ inline cudaError_t launch_cols_pipe_t(const CUtensorMap& tm, const ColsPipeArgs&
     long long grid = (long long)device_sm_count() * per_sm;
     if (grid > ntiles) grid = ntiles;
     if (grid < 1) return cudaSuccess;
-    kern<<<(unsigned)grid, C::THREADS, smem, st>>>(tm, a, mid, omap);
+    kern<<<(unsigned)grid, C::THREADS, smem, st>>>(tm, tm2, a, mid, omap);
     return cudaGetLastError();
 }
 

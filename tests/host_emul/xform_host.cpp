@@ -49,44 +49,65 @@ static void run_one(double* data, int sj, double scale)
     for (auto& t : th) t.join();
 }
 
-// fused DST (dst_tile_fused): mode 0 = OutTile, 1 = OutGlobal-like policy writing to a separate
-// array, 2 = PREFOLD (fold applied by the caller, like k_rows_pipe's first touch)
+// fused DST (dst_tile_fused) on the planar tile layout: mode 0 = OutTile, 1 = OutGlobal-like policy
+// writing to a separate array, 2 = PREFOLD (fold applied by the caller, like k_rows_pipe's first touch).
+// swz selects the 8-column-tile swizzles (three-pass plans only).  data: natural slots 0..N-1, stride sj.
 struct OutSep {
     double* dst;
     void emit(int j, double v) const { dst[j - 1] = v; }
 };
 
-template <int N>
-static void run_fused(double* data, int sj, double scale, int mode, double* sep)
+template <int N, int GAP, bool SWZ>
+static void run_fused_t(double* data, int sj, double scale, int mode, double* sep)
 {
     constexpr int G = Plan<N>::G;
     constexpr int M = N / 2;
+    using PL = Planar<N, GAP>;
     std::vector<double> sn; std::vector<cd> wm;
     make_tables(N, sn, wm);
+    const double hs = 0.5 * scale;
+    std::vector<double> sf(M + 1);
+    for (int j = 0; j <= M; j++) sf[j] = hs * sn[j];
+    std::vector<double> tile((size_t)PL::ROWS * sj, 777.0);     // garbage in the unused rows
     if (mode == 2) {
         for (int j = 1; j < M; j++) {
             double a = data[j * sj], c = data[(N - j) * sj];
-            double y1 = sn[j] * (a + c), y2 = 0.5 * (a - c);
-            data[j * sj] = y1 + y2; data[(N - j) * sj] = y1 - y2;
+            double y1 = sf[j] * (a + c), y2 = 0.5 * hs * (a - c);
+            tile[prefold_row<N, GAP, SWZ>(j) * sj] = y1 + y2; tile[prefold_row<N, GAP, SWZ>(N - j) * sj] = y1 - y2;
         }
-        data[0] = 0.0; data[M * sj] = 2.0 * data[M * sj];
+        tile[prefold_row<N, GAP, SWZ>(0) * sj] = 0.0; tile[prefold_row<N, GAP, SWZ>(M) * sj] = scale * data[M * sj];
+    } else {
+        for (int j = 1; j < N; j++) tile[PL::row(j) * sj] = data[j * sj];
     }
     std::vector<double> scr((G + G / 8 + 2));
     std::barrier<> bar(G);
     std::vector<std::thread> th;
+    double* t = tile.data();
     for (int g = 0; g < G; g++)
         th.emplace_back([&, g] {
             tl_barrier = &bar;
-            if (mode == 0) dst_tile_fused<N, G, false>(data, sj, g, scale, sn.data(), wm.data(), scr.data(), 1, OutTile{data, sj});
-            else if (mode == 1) dst_tile_fused<N, G, false>(data, sj, g, scale, sn.data(), wm.data(), scr.data(), 1, OutSep{sep});
-            else dst_tile_fused<N, G, true>(data, sj, g, scale, sn.data(), wm.data(), scr.data(), 1, OutTile{data, sj});
+            if (mode == 0) dst_tile_fused<N, G, GAP, false, SWZ>(t, sj, g, hs, sn.data(), sf.data(), wm.data(), scr.data(), 1, OutTile<N, GAP>{t, sj});
+            else if (mode == 1) dst_tile_fused<N, G, GAP, false, SWZ>(t, sj, g, hs, sn.data(), sf.data(), wm.data(), scr.data(), 1, OutSep{sep});
+            else dst_tile_fused<N, G, GAP, true, SWZ>(t, sj, g, hs, sn.data(), sf.data(), wm.data(), scr.data(), 1, OutTile<N, GAP>{t, sj});
         });
-    for (auto& t : th) t.join();
+    for (auto& x : th) x.join();
+    if (mode != 1)
+        for (int j = 1; j < N; j++) data[j * sj] = tile[PL::row(j) * sj];
 }
 
-extern "C" int emul_dst_fused(int N, double* data, int sj, double scale, int mode, double* sep)
+template <int N>
+static void run_fused(double* data, int sj, double scale, int mode, double* sep, int swz)
 {
-#define X(NN) case NN: run_fused<NN>(data, sj, scale, mode, sep); return 0;
+    if constexpr (PlanInfo<N>::NP == 3) {
+        if (swz) { run_fused_t<N, 1, true>(data, sj, scale, mode, sep); return; }
+    }
+    if (mode == 2) run_fused_t<N, 0, false>(data, sj, scale, mode, sep);
+    else run_fused_t<N, 1, false>(data, sj, scale, mode, sep);
+}
+
+extern "C" int emul_dst_fused(int N, double* data, int sj, double scale, int mode, double* sep, int swz)
+{
+#define X(NN) case NN: run_fused<NN>(data, sj, scale, mode, sep, swz); return 0;
     switch (N) { X(32) X(64) X(128) X(256) X(512) X(1024) X(2048) }
 #undef X
     return -1;

@@ -66,7 +66,7 @@ def cyl_scales(nx, x1, dx):
 
 @pytest.mark.parametrize("kind", ["rect", "fft2"])
 def test_rect_cyl_scales_vs_compiled_reference(fb, ref, kind):
-    nx, ny = 64, 31
+    nx, ny = 63, 31
     dx = (math.pi / 2) / nx; dy = 10.0 / ny
     g = (dx, dy, math.pi / 2 + dx, 10.0 + dy, nx, ny)
     lm, L, U = cyl_scales(nx, math.pi / 2, dx)

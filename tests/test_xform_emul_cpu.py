@@ -24,7 +24,7 @@ def emul():
                        check=True)
     L = C.CDLL(LIB)
     L.emul_xform.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double), C.c_int, C.c_double]
-    L.emul_dst_fused.argtypes = [C.c_int, C.POINTER(C.c_double), C.c_int, C.c_double, C.c_int, C.POINTER(C.c_double)]
+    L.emul_dst_fused.argtypes = [C.c_int, C.POINTER(C.c_double), C.c_int, C.c_double, C.c_int, C.POINTER(C.c_double), C.c_int]
     return L
 
 
@@ -60,14 +60,16 @@ def test_roundtrip_identity(emul):
 
 @pytest.mark.parametrize("N", [32, 64, 128, 256, 512, 1024, 2048])
 @pytest.mark.parametrize("mode", [0, 1, 2])
-def test_fused_dst(emul, N, mode):
-    """dst_tile_fused (fold + first pass, last pass + untangle in registers, output policies)."""
+@pytest.mark.parametrize("swz", [0, 1])
+def test_fused_dst(emul, N, mode, swz):
+    """dst_tile_fused on the planar tile (fold + first pass, last pass + untangle in registers, output
+    policies); swz = 1 adds the 8-column-tile swizzles (ignored for two-pass plans)."""
     rng = np.random.default_rng(7 * N + mode)
     p = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
     sj = 3
     x = rng.uniform(-1, 1, N - 1)
     d = np.zeros(N * sj); d[sj::sj][: N - 1] = x; d[0] = 123.0     # slot 0 must be ignored
     sep = np.zeros(N - 1)
-    assert emul.emul_dst_fused(N, p(d), sj, 0.37, mode, p(sep)) == 0
+    assert emul.emul_dst_fused(N, p(d), sj, 0.37, mode, p(sep), swz) == 0
     got = sep if mode == 1 else d[sj::sj][: N - 1]
     assert O.rel_l2(got, O.sFFT(x, 0.37)) < 2e-14
