@@ -116,9 +116,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int make_tensor_map_3d(CUtensorMap* tm, const void* base, unsigned long long e0, unsigned long long e1,
-                       unsigned long long e2, unsigned long long s1, unsigned long long s2, unsigned b0, unsigned b1,
-                       unsigned b2)
+static int encode_tiled(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+                        const cuuint32_t* box)
 {
     static EncodeTiledFn fn = nullptr;
     if (!fn) {
@@ -131,17 +130,84 @@ int make_tensor_map_3d(CUtensorMap* tm, const void* base, unsigned long long e0,
         }
         fn = (EncodeTiledFn)p;
     }
-    cuuint64_t dims[3] = {e0, e1, e2};
-    cuuint64_t strides[2] = {s1, s2};
-    cuuint32_t box[3] = {b0, b1, b2};
-    cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<void*>(base), dims, strides, box, estr,
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, (cuuint32_t)rank, const_cast<void*>(base), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
-        set_error("cuTensorMapEncodeTiled failed with code %d (dims %llu,%llu,%llu strides %llu,%llu box %u,%u,%u)", (int)r,
-                  e0, e1, e2, s1, s2, b0, b1, b2);
+        set_error("cuTensorMapEncodeTiled failed with code %d (rank %d dims %llu,%llu,%llu,%llu strides %llu,%llu,%llu "
+                  "box %u,%u,%u,%u)", (int)r, rank, (unsigned long long)dims[0], (unsigned long long)dims[1],
+                  (unsigned long long)dims[2], rank > 3 ? (unsigned long long)dims[3] : 0ull,
+                  (unsigned long long)strides[0], (unsigned long long)strides[1], rank > 3 ? (unsigned long long)strides[2] : 0ull,
+                  box[0], box[1], box[2], rank > 3 ? box[3] : 0u);
         return FDMB_ERR_CUDA;
+    }
+    return FDMB_OK;
+}
+
+int make_tensor_map_3d(CUtensorMap* tm, const void* base, unsigned long long e0, unsigned long long e1,
+                       unsigned long long e2, unsigned long long s1, unsigned long long s2, unsigned b0, unsigned b1,
+                       unsigned b2)
+{
+    cuuint64_t dims[3] = {e0, e1, e2};
+    cuuint64_t strides[2] = {s1, s2};
+    cuuint32_t box[3] = {b0, b1, b2};
+    return encode_tiled(tm, base, 3, dims, strides, box);
+}
+
+int make_cols_maps_blocked(ColsMaps* m, const void* base, int N, bool pair_axis, int blog, unsigned long long e_x,
+                           unsigned long long n_lohi, unsigned long long n_mid, unsigned long long s_lo,
+                           unsigned long long s_mid, unsigned long long s_hi, unsigned B)
+{
+    const unsigned LO = 1u << blog;
+    const unsigned long long n_hi = (n_lohi + LO - 1) / LO;
+    const unsigned long long n = pair_axis ? n_lohi : n_mid;     // entries along the transform axis
+    const char* b = static_cast<const char*>(base);
+    int rc;
+    m->blog = blog;
+    m->planar = ((int)n == N - 1 && N >= 32 && LO >= 2);
+    if (pair_axis) {
+        m->taxis = 3;
+        m->boxhi = n_hi < 256 ? (int)n_hi : 256;
+        m->boxrows = m->boxhi * (int)LO;
+        m->nchunk = (int)((n_hi + m->boxhi - 1) / m->boxhi);
+        {
+            cuuint64_t dims[4] = {e_x, LO, n_mid, n_hi};
+            cuuint64_t strides[3] = {s_lo, s_mid, s_hi};
+            cuuint32_t box[4] = {B, LO, 1, (cuuint32_t)m->boxhi};
+            if ((rc = encode_tiled(&m->nat, base, 4, dims, strides, box))) return rc;
+        }
+        if (m->planar) {
+            m->boxhi_p = m->boxhi;
+            m->boxrows_p = m->boxhi * (int)(LO / 2);
+            m->nchunk_p = m->nchunk;
+            cuuint64_t dims[4] = {e_x, LO / 2, n_mid, n_hi};
+            cuuint64_t strides[3] = {2 * s_lo, s_mid, s_hi};
+            cuuint32_t box[4] = {B, LO / 2, 1, (cuuint32_t)m->boxhi};
+            if ((rc = encode_tiled(&m->podd, b, 4, dims, strides, box))) return rc;
+            if ((rc = encode_tiled(&m->peven, b + s_lo, 4, dims, strides, box))) return rc;
+        }
+    } else {
+        m->taxis = 4;
+        m->boxrows = n < 256 ? (int)n : 256;
+        m->nchunk = (int)((n + m->boxrows - 1) / m->boxrows);
+        {
+            cuuint64_t dims[4] = {e_x, LO, n_mid, n_hi};
+            cuuint64_t strides[3] = {s_lo, s_mid, s_hi};
+            cuuint32_t box[4] = {B, 1, (cuuint32_t)m->boxrows, 1};
+            if ((rc = encode_tiled(&m->nat, base, 4, dims, strides, box))) return rc;
+        }
+        m->planar = ((int)n == N - 1 && N >= 32);
+        if (m->planar) {
+            const int M = N / 2;
+            m->boxrows_p = M < 256 ? M : 256;
+            m->nchunk_p = M / m->boxrows_p;
+            cuuint64_t dO[4] = {e_x, LO, (n + 1) / 2, n_hi}, dE[4] = {e_x, LO, n / 2, n_hi};
+            cuuint64_t strides[3] = {s_lo, 2 * s_mid, s_hi};
+            cuuint32_t box[4] = {B, 1, (cuuint32_t)m->boxrows_p, 1};
+            if ((rc = encode_tiled(&m->podd, b, 4, dO, strides, box))) return rc;
+            if ((rc = encode_tiled(&m->peven, b + s_mid, 4, dE, strides, box))) return rc;
+        }
     }
     return FDMB_OK;
 }

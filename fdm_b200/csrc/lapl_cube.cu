@@ -69,7 +69,8 @@ cudaError_t launch_cols_cube_divide(int N, bool periodic, const ColsArgs& a, con
     const CUtensorMap& m1 = use_p ? tm.podd : tm.nat;                                             \
     const CUtensorMap& m2 = use_p ? tm.peven : tm.nat;                                            \
     a.boxrows = use_p ? tm.boxrows_p : tm.boxrows;                                                \
-    a.nchunk = use_p ? tm.nchunk_p : tm.nchunk;
+    a.nchunk = use_p ? tm.nchunk_p : tm.nchunk;                                                   \
+    if (tm.taxis) { a.taxis = tm.taxis; a.boxhi = use_p ? tm.boxhi_p : tm.boxhi; a.blog = tm.blog; }
 
 #define FDMB_FOR_EACH_PIPE_N(X) X(32) X(64) X(128) X(256) X(512) X(1024) X(2048)
 
@@ -96,6 +97,19 @@ cudaError_t launch_cols_pipe(int N, int kind, const ColsMaps& tm, ColsPipeArgs a
         if (kind == XF_DST) return launch_cols_pipe_t<NN, XF_DST, MidNone, XF_DST>(m1, m2, a, mid, st);    \
         if (kind == XF_PFWD) return launch_cols_pipe_t<NN, XF_PFWD, MidNone, XF_DST>(m1, m2, a, mid, st);  \
         return launch_cols_pipe_t<NN, XF_PINV, MidNone, XF_DST>(m1, m2, a, mid, st);
+    switch (N) { FDMB_FOR_EACH_PIPE_N(X) }
+#undef X
+    return cudaErrorInvalidValue;
+}
+
+// DST sweep along the blocked axis of a blocked work array (ColsMaps::taxis == 3), written back in place
+cudaError_t launch_cols_pipe_blocked(int N, const ColsMaps& tm, ColsPipeArgs a, const OutBlocked& ob, cudaStream_t st,
+                                     const char* tag)
+{
+    LaunchScope scope(tag, st);
+    MidNone mid;
+    FDMB_PICK_MAPS(true)
+#define X(NN) case NN: return launch_cols_pipe_t<NN, XF_DST, MidNone, XF_DST, OutBlocked>(m1, m2, a, mid, st, ob);
     switch (N) { FDMB_FOR_EACH_PIPE_N(X) }
 #undef X
     return cudaErrorInvalidValue;
@@ -221,6 +235,30 @@ int fdmb_lapl_cube::init()
     FDMB_CUDA(cudaMemcpy(d_lmz, lm_z.data(), sizeof(double) * (nz + 1), cudaMemcpyHostToDevice));
     FDMB_CUDA(cudaGetDevice(&device));
     if (nranks > 1) return init_sharded();
+    // Optional BLOCKED work array ([yb][z][yi][x], 64 rows per block; FDMB_BLOCKED=1).  In the natural layout the
+    // 1023 rows of a z tile at 1023^3 sit on 1023 different 2 MB pages and a plain copy with that access pattern
+    // runs at 2.4 TB/s against 5.0 TB/s with a short stride (profiles/r01g_access_pattern.md).  Blocking fixes the
+    // copy rate, but the z sweep is bound by the SMs' shared-memory pipe today, so the solve gains only ~1 %: off
+    // by default until the sweeps' compute side is faster.
+    {
+        const char* e = getenv("FDMB_BLOCKED");
+        const bool can = pipe_enabled() && !periodic && pipe_supported_N(Nx) && pipe_supported_N(Ny) && pipe_supported_N(Nz);
+        blog = (can && e && e[0] == '1') ? 6 : 0;
+        if (blog && (1 << blog) > Ny / 2) blog = 4;      // small grids (tests): keep at least two blocks
+        if (const char* b = getenv("FDMB_BLOG")) if (blog) blog = atoi(b);
+    }
+    if (blog) {
+        const int YB = 1 << blog;
+        nyb = (ny + YB - 1) / YB;
+        const size_t welems = (size_t)nyb * nz * YB * px;
+        FDMB_CUDA(cudaMalloc(&d_work, sizeof(double) * welems));
+        FDMB_CUDA(cudaMemset(d_work, 0, sizeof(double) * welems));      // the padding rows of the last block stay zero
+        const unsigned long long s_lo = 8ull * px, s_mid = s_lo * YB, s_hi = s_mid * (unsigned long long)nz;
+        if ((rc = make_cols_maps_blocked(&tm_y, d_work, Ny, true, blog, nx, ny, nz, s_lo, s_mid, s_hi, pipe_B(Ny)))) return rc;
+        if ((rc = make_cols_maps_blocked(&tm_z, d_work, Nz, false, blog, nx, ny, nz, s_lo, s_mid, s_hi, pipe_B(Nz)))) return rc;
+        pipe_y = pipe_z = true;
+        return FDMB_OK;
+    }
     FDMB_CUDA(cudaMalloc(&d_work, sizeof(double) * (size_t)nz * ny * px));
     if (pipe_enabled()) {
         // tensor maps over the pitched work array: dims (x, y, z), tiles [N][B] along y or z
@@ -269,8 +307,11 @@ int fdmb_lapl_cube::init_sharded()
     d_work = d_A + (size_t)(z_first + J0 - rank * Sz) * plane;
     double* t_loc = d_T + (size_t)(y_first + J0 - rank * Sy) * px;
     int rc;
+    // the transposing sweeps (y forward, z) use the wide tiles of PipeCfg<N, true>; the local y inverse the normal ones
     if ((rc = make_cols_maps(&tm_y, d_work, Ny, 1, nx, ny, nzl, 8ull * px, 8ull * plane, pipe_B(Ny)))) return rc;
-    if ((rc = make_cols_maps(&tm_z, t_loc, Nz, 2, nx, nyl, nz, 8ull * px, 8ull * (unsigned long long)Sy * px, pipe_B(Nz))))
+    if ((rc = make_cols_maps(&tm_yw, d_work, Ny, 1, nx, ny, nzl, 8ull * px, 8ull * plane, pipe_B_sharded(Ny)))) return rc;
+    if ((rc = make_cols_maps(&tm_z, t_loc, Nz, 2, nx, nyl, nz, 8ull * px, 8ull * (unsigned long long)Sy * px,
+                             pipe_B_sharded(Nz))))
         return rc;
     pipe_y = pipe_z = true;
     return FDMB_OK;
@@ -342,7 +383,7 @@ int fdmb_lapl_cube::solve_device_sharded(double* d_out, const double* d_in, cuda
         for (int q = 0; q < nranks; q++)
             om.base[q] = reinterpret_cast<double*>(reinterpret_cast<char*>(peer_block[q]) + off_T);
         om.logS = ilog2(Sy); om.maskS = Sy - 1; om.sj = px; om.so = (long long)Sy * px; om.o_off = z_first;
-        FDMB_CUDA(launch_cols_pipe_shard(Ny, kf, tm_y, p, om, st, "cube_y_fwd_xpose"));
+        FDMB_CUDA(launch_cols_pipe_shard(Ny, kf, tm_yw, p, om, st, "cube_y_fwd_xpose"));
     }
     if ((rc = barrier(st))) return rc;
     {   // z forward, divide, z inverse; stores go back to the slabs A_r[z slot & (Sz-1)][y'][x]
@@ -377,6 +418,34 @@ int fdmb_lapl_cube::solve_device(double* d_out, const double* d_in, cudaStream_t
     r.in = d_in; r.out = d_work; r.nrows = (long long)nz * ny; r.nvalid = nx;
     r.in_pitch = nx; r.out_pitch = px; r.scale = dx * slx; r.SN = tx.SN; r.WM = tx.WM;
     const bool pipe_x = pipe_enabled() && pipe_supported_N(Nx);
+    if (blog) {
+        // blocked work array W[yb][z][yi][x]
+        if ((reinterpret_cast<uintptr_t>(d_in) & 15) != 0) {
+            set_error("LaplCube: rhs must be 16-byte aligned for grids this large");
+            return FDMB_ERR_INVALID;
+        }
+        const int YB = 1 << blog;
+        const long long s_lo = px, s_mid = (long long)YB * px, s_hi = s_mid * nz;
+        RowsPipeArgs rp{};
+        rp.in = d_in; rp.out = d_work; rp.nrows = (long long)nz * ny; rp.nvalid = nx; rp.in_pitch = nx; rp.out_pitch = px;
+        rp.reverse = 0; rp.scale = dx * slx; rp.SN = tx.SN; rp.WM = tx.WM; rp.blk = 1; rp.blog = blog; rp.ny = ny; rp.nz = nz;
+        FDMB_CUDA(launch_rows_pipe(Nx, XF_DST, rp, st, "cube_x_fwd"));
+        ColsPipeArgs py{};
+        py.out = d_work; py.out_sj = s_lo; py.out_so = s_mid; py.nvalid = ny; py.nb = nx; py.no = nz;
+        py.reverse = 1; py.scale = dy * sly; py.SN = ty.SN; py.WM = ty.WM;
+        const OutBlocked ob{s_hi, blog};
+        FDMB_CUDA(launch_cols_pipe_blocked(Ny, tm_y, py, ob, st, "cube_y_fwd"));
+        ColsPipeArgs pz{};
+        pz.out = d_work; pz.out_sj = s_mid; pz.out_so = s_lo; pz.out_so_hi = s_hi; pz.nvalid = nz; pz.nb = nx; pz.no = ny;
+        pz.reverse = 0; pz.scale = dz * slz; pz.scale2 = slz; pz.SN = tz.SN; pz.WM = tz.WM;
+        MidCubeDivide midb{d_lmz, d_lmx, d_lmy, 0};
+        FDMB_CUDA(launch_cols_pipe_cube_divide(Nz, false, tm_z, pz, midb, st, "cube_z_fwd_div_inv"));
+        py.reverse = 0; py.scale = sly;
+        FDMB_CUDA(launch_cols_pipe_blocked(Ny, tm_y, py, ob, st, "cube_y_inv"));
+        rp.in = d_work; rp.out = d_out; rp.in_pitch = px; rp.out_pitch = nx; rp.reverse = 1; rp.scale = slx; rp.blk = 2;
+        FDMB_CUDA(launch_rows_pipe(Nx, XF_DST, rp, st, "cube_x_inv"));
+        return FDMB_OK;
+    }
     auto rows = [&](const RowsArgs& q, int kind, const char* tag, int reverse) -> cudaError_t {
         if (pipe_x && (reinterpret_cast<uintptr_t>(q.in) & 15) == 0) {
             RowsPipeArgs p{};

@@ -12,10 +12,13 @@ cudaError_t launch_cols_cube_divide(int N, bool periodic, const ColsArgs& a, con
 // persistent TMA-fed variants (transform lengths >= 32)
 inline bool pipe_supported_N(int N) { return supported_N(N) && N >= 32; }
 inline int pipe_B(int N) { return N <= 512 ? 16 : 8; }
+inline int pipe_B_sharded(int N) { return N <= 1024 ? 16 : 8; }     // PipeCfg<N, true>::B
 cudaError_t launch_rows_pipe(int N, int kind, const RowsPipeArgs& a, cudaStream_t st, const char* tag);
 cudaError_t launch_cols_pipe(int N, int kind, const ColsMaps& tm, ColsPipeArgs a, cudaStream_t st, const char* tag);
 cudaError_t launch_cols_pipe_cube_divide(int N, bool periodic, const ColsMaps& tm, ColsPipeArgs a,
                                          const MidCubeDivide& mid, cudaStream_t st, const char* tag);
+cudaError_t launch_cols_pipe_blocked(int N, const ColsMaps& tm, ColsPipeArgs a, const OutBlocked& ob, cudaStream_t st,
+                                     const char* tag);
 // multi-GPU variants: the sweep's stores scatter over the peers' buffers (slab <-> pencil transpose)
 cudaError_t launch_cols_pipe_shard(int N, int kind, const ColsMaps& tm, ColsPipeArgs a, const OutShard& om,
                                    cudaStream_t st, const char* tag);
@@ -47,7 +50,8 @@ struct fdmb_lapl_cube {
     double* d_work = nullptr;
     double *d_rhs = nullptr, *d_ans = nullptr;   // staging for the host-pointer entry point
     bool pipe_y = false, pipe_z = false;         // tensor maps over d_work are valid
-    fdmb::ColsMaps tm_y{}, tm_z{};
+    fdmb::ColsMaps tm_y{}, tm_z{}, tm_yw{};      // tm_yw: wide-tile maps of the sharded y forward sweep
+    int blog = 0, nyb = 0;                       // blocked work array [yb][z][yi][x], 1 << blog rows per block (0: natural)
 
     // ---- z-slab sharding over `nranks` GPUs (nranks == 1: everything above is the whole problem) ----
     // Rank r owns the z slots [r*Sz, (r+1)*Sz) of the caller's arrays and, between the two transposes,

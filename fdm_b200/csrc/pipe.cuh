@@ -65,6 +65,14 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* t
         "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
         : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, uint64_t* bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
+        : "memory");
+}
 __device__ __forceinline__ void tma_load_3d_hint(void* smem_dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar,
                                                  uint64_t pol)
 {
@@ -114,8 +122,23 @@ struct ColsMaps {
     int boxrows = 0, nchunk = 0;          // natural
     int boxrows_p = 0, nchunk_p = 0;      // planar, per parity
     bool planar = false;
+    int taxis = 0;                        // set by make_cols_maps_blocked: 3 (pair axis) or 4 (mid axis)
+    int boxhi = 0, boxhi_p = 0;           // taxis 3: blocks per box along the hi dimension
+    int blog = 0;                         // log2(block)
 };
 int make_cols_maps(ColsMaps* m, const void* base, int N, int taxis, unsigned long long e0, unsigned long long e1,
                    unsigned long long e2, unsigned long long s1, unsigned long long s2, unsigned B);
+
+
+// The same for a BLOCKED 4-D array (x, lo, mid, hi): an axis of n entries is split as index = hi * LO + lo with
+// LO = 1 << blog consecutive entries kept next to each other (stride s_lo) inside every `mid` slice:
+//   pair_axis = true  : tiles run along the blocked axis (n entries), outer index = mid
+//   pair_axis = false : tiles run along mid (n entries), outer index = hi * LO + lo
+// Keeps the 2 MB pages one tile touches to a few dozen for BOTH strided axes of a large 3-D array (a natural
+// layout puts the 1023 rows of a third-axis tile on 1023 different pages, which the TLBs do not cover).
+// Strides in BYTES.  n_lohi / n_mid are the real entry counts along the blocked axis / mid.
+int make_cols_maps_blocked(ColsMaps* m, const void* base, int N, bool pair_axis, int blog, unsigned long long e_x,
+                           unsigned long long n_lohi, unsigned long long n_mid, unsigned long long s_lo,
+                           unsigned long long s_mid, unsigned long long s_hi, unsigned B);
 
 }  // namespace fdmb

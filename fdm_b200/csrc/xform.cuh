@@ -28,6 +28,11 @@
 #include <cuda_runtime.h>
 #endif
 
+#ifndef FDMB_TW_POW
+#define FDMB_TW_POW 1     // fused DST passes, N >= 1024: twiddle powers by multiplication instead of table loads
+                          // (-5 % at 1023^3; at N <= 512 the extra registers cost a resident CTA)
+#endif
+
 namespace fdmb {
 
 enum XformKind { XF_DST = 0, XF_PFWD = 1, XF_PINV = 2 };
@@ -87,6 +92,20 @@ template <> struct Dft<16> {
         for (int k = 0; k < 8; k++) { v[2 * k] = u[k]; v[2 * k + 1] = w[k]; }
     }
 };
+
+// Twiddles of one radix-R butterfly: v[k1] *= w^k1, k1 = 1..R-1, from the single table entry w = w^1.
+// A warp holds several transform positions, so every twiddle load costs up to four shared-memory wavefronts;
+// the powers are cheaper as fp64 multiplies (a few ulp, far inside the 1e-12 parity bar).
+template <int R>
+__device__ __forceinline__ void apply_twiddle_powers(cd* v, cd w)
+{
+    cd p[R];
+    p[1] = w;
+#pragma unroll
+    for (int k = 2; k < R; k++) p[k] = (k & 1) ? cmul(p[k - 1], w) : cmul(p[k / 2], p[k / 2]);
+#pragma unroll
+    for (int k = 1; k < R; k++) v[k] = cmul(v[k], p[k]);
+}
 
 // ---- radix plans: M = N/2 complex points, up to three passes -------------------
 template <int N> struct Plan;
@@ -453,7 +472,8 @@ __device__ __forceinline__ void xform_tile(double* col, int sj, int g, double sc
 // OUT policies decide where a finished spectral value goes: back into the tile (rows kernel, and the
 // z sweep's first transform, scaled by the spectral multiplier) or directly to global memory with
 // coalesced stores (strided-axis kernels), which removes the final tile write + read.
-// Requirements: G == M / R0 (one first-pass butterfly per thread).
+// Requirements: G divides M / R0 (a whole number of first-pass butterflies per thread) and the last pass has
+// at most G units (block pairs).
 // =====================================================================================
 
 template <int N, int GAP> struct Planar {
@@ -516,10 +536,16 @@ __device__ __forceinline__ void fft_pass_planar(double* col, int sj, int g, cons
             v[n1].y = col[PL::O(s) * sj];
         }
         Dft<R>::run(v);
+        if constexpr (S > 1 && R > 1) {
+            if constexpr (FDMB_TW_POW && N >= 1024) apply_twiddle_powers<R>(v, WM[n2 * (M / L)]);
+            else {
+#pragma unroll
+                for (int k1 = 1; k1 < R; k1++) v[k1] = cmul(v[k1], WM[n2 * k1 * (M / L)]);
+            }
+        }
 #pragma unroll
         for (int k1 = 0; k1 < R; k1++) {
             cd o = v[k1];
-            if (S > 1 && k1 > 0) o = cmul(o, WM[n2 * k1 * (M / L)]);
             const int bit = SWO ? ((L == M) ? (k1 & 1) : cb) : 0;
             const int s = blk * L + (n2 ^ bit) + k1 * S;
             col[PL::E(s) * sj] = o.x;
@@ -569,34 +595,47 @@ __device__ __forceinline__ void dst_tile_fused(double* col, int sj, int g, doubl
     using PL = Planar<N, GAP>;
     constexpr int M = N / 2, R0 = P::R0, S0 = M / R0;
     static_assert(I::NP >= 2, "fused DST needs at least two radix passes");
-    static_assert(G == S0, "fused DST: one first-pass butterfly per thread");
+    static_assert(S0 % G == 0, "fused DST: a whole number of first-pass butterflies per thread");
     static_assert(!SWZ || I::NP == 3, "the block swizzle is defined for three-pass plans");
+    constexpr int NA = S0 / G;            // first-pass butterflies per thread
 
     // ---- stage A -------------------------------------------------------------------------
     if constexpr (!PREFOLD) {
-        cd v[R0];
+        cd v[NA][R0];
         const double h2 = 0.5 * hs;
 #pragma unroll
-        for (int n1 = 0; n1 < R0; n1++) {
-            const int m = g + n1 * S0;
-            // y[j] = hs * (sin(pi j/N)(x[j]+x[N-j]) + (x[j]-x[N-j])/2) for every j in 1..N-1, y[0] = 0;
-            // x[2m] = E[m], x[N-2m] = E[M-m], x[2m+1] = O[m], x[N-2m-1] = O[M-m-1]
-            double a0 = (m == 0) ? 0.0 : col[PL::E(m) * sj], c0 = (m == 0) ? 0.0 : col[PL::E(M - m) * sj];
-            double a1 = col[PL::O(m) * sj], c1 = col[PL::O(M - m - 1) * sj];
-            double s0 = (n1 < R0 / 2) ? SF[2 * m] : SF[N - 2 * m];
-            double s1 = (n1 < R0 / 2) ? SF[2 * m + 1] : SF[N - 2 * m - 1];
-            v[n1].x = s0 * (a0 + c0) + h2 * (a0 - c0);
-            v[n1].y = s1 * (a1 + c1) + h2 * (a1 - c1);
+        for (int it = 0; it < NA; it++) {
+            const int q = g + it * G;
+#pragma unroll
+            for (int n1 = 0; n1 < R0; n1++) {
+                const int m = q + n1 * S0;
+                // y[j] = hs * (sin(pi j/N)(x[j]+x[N-j]) + (x[j]-x[N-j])/2) for every j in 1..N-1, y[0] = 0;
+                // x[2m] = E[m], x[N-2m] = E[M-m], x[2m+1] = O[m], x[N-2m-1] = O[M-m-1]
+                double a0 = (m == 0) ? 0.0 : col[PL::E(m) * sj], c0 = (m == 0) ? 0.0 : col[PL::E(M - m) * sj];
+                double a1 = col[PL::O(m) * sj], c1 = col[PL::O(M - m - 1) * sj];
+                double s0 = (n1 < R0 / 2) ? SF[2 * m] : SF[N - 2 * m];
+                double s1 = (n1 < R0 / 2) ? SF[2 * m + 1] : SF[N - 2 * m - 1];
+                v[it][n1].x = s0 * (a0 + c0) + h2 * (a0 - c0);
+                v[it][n1].y = s1 * (a1 + c1) + h2 * (a1 - c1);
+            }
         }
         __syncthreads();     // every mirrored read is done before anyone overwrites the inputs
-        Dft<R0>::run(v);
 #pragma unroll
-        for (int k1 = 0; k1 < R0; k1++) {
-            cd o = v[k1];
-            if (k1 > 0) o = cmul(o, WM[g * k1]);
-            const int s = (g ^ (SWZ ? (k1 & 1) : 0)) + k1 * S0;
-            col[PL::E(s) * sj] = o.x;
-            col[PL::O(s) * sj] = o.y;
+        for (int it = 0; it < NA; it++) {
+            const int q = g + it * G;
+            Dft<R0>::run(v[it]);
+            if constexpr (FDMB_TW_POW && N >= 1024) apply_twiddle_powers<R0>(v[it], WM[q]);
+            else {
+#pragma unroll
+                for (int k1 = 1; k1 < R0; k1++) v[it][k1] = cmul(v[it][k1], WM[q * k1]);
+            }
+#pragma unroll
+            for (int k1 = 0; k1 < R0; k1++) {
+                cd o = v[it][k1];
+                const int s = (q ^ (SWZ ? (k1 & 1) : 0)) + k1 * S0;
+                col[PL::E(s) * sj] = o.x;
+                col[PL::O(s) * sj] = o.y;
+            }
         }
         __syncthreads();
     } else {

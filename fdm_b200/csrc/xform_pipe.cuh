@@ -17,20 +17,32 @@
 
 namespace fdmb {
 
-template <int N> struct PipeCfg {
-    static constexpr int B = (N <= 512) ? 16 : 8;      // sequences per tile
-    static constexpr int G = Plan<N>::G;
+// WIDE: the multi-GPU transposing sweeps.  Their stores cross NVLink, where 128-byte segments move at ~1.5x the
+// rate of 64-byte ones (measured: 620 vs 420 GB/s per direction), so N = 1024 keeps 16-column tiles there: one
+// 128 KB tile and one 512-thread CTA per SM, no second stage (those sweeps are NVLink-bound, not SM-bound).
+template <int N, bool WIDE = false> struct PipeCfg {
+    static constexpr int B = (N <= 512 || (WIDE && N == 1024)) ? 16 : 8;      // sequences per tile
+    static constexpr int G = Plan<N>::G;               // threads per sequence, contiguous-axis sweep
     static constexpr int THREADS = B * G;
+    // strided-axis sweeps at N = 1024: the last radix pass has only 32 units (block pairs) per sequence, so 64
+    // threads per sequence leave half the CTA idle in the heaviest stage.  32 threads per sequence (two
+    // first/middle-pass butterflies each) keep every warp busy, and two 256-thread CTAs share an SM, so one CTA's
+    // shared-memory phases overlap the other's fp64 phases.
+    static constexpr int GC = (N == 1024) ? 32 : G;
+    static constexpr int THREADS_COLS = B * GC;
+    // resident CTAs the register allocation must leave room for (plain sweep / fused forward-multiply-inverse sweep)
+    static constexpr int COLS_MIN_CTAS = (N == 1024 && !WIDE) ? 2 : (N == 256 ? 3 : 1);
+    static constexpr int COLS_MIN_CTAS_MID = (N == 1024 && !WIDE) ? 2 : (N == 256 ? 2 : 1);
     static constexpr int SCR = (G + G / 8 + 1) * B;
     static constexpr bool SWZ = (B == 8);              // 64-byte tile rows: keep half-warps on rows of different parity
     // SN + WM + two fold tables SF (doubles)
     static constexpr int TAB = (N / 2 + 2) + 2 * (N / 2) + 2 * (N / 2 + 2);
     static constexpr int COLS_GAP = 1;                 // planar tile: E region starts one row late (128-B aligned landing)
     static constexpr int COLS_BUF = ((N + 2) * B + 15) / 16 * 16;      // doubles per stage buffer (128-B multiple)
-    static constexpr int COLS_STAGES = (N <= 1024) ? 2 : 1;
+    static constexpr int COLS_STAGES = (N <= 512) ? 2 : 1;
     // fused DST sweeps write their results into a second tile instead of back into the working one
     // (dst_tile_fused SEP); only where one CTA per SM is resident anyway and the tile still fits
-    static constexpr bool COLS_SEP = (N == 1024);
+    static constexpr bool COLS_SEP = false;
     static constexpr size_t cols_smem(int nstage)
     {
         return 8 * (size_t)(16 + (nstage + (COLS_SEP ? 1 : 0)) * COLS_BUF + SCR + TAB + 2) + 8 * 8 + 128;
@@ -74,9 +86,27 @@ struct EmitLinear {
 };
 struct OutLinear {
     static constexpr bool sharded = false;
-    __device__ __forceinline__ EmitLinear emitter(double* out, long long sj, long long so, int j0, int o, int x, bool ok) const
+    // ooff: offset (doubles) of the tile's outer index, computed by the kernel (linear or blocked)
+    __device__ __forceinline__ EmitLinear emitter(double* out, long long sj, long long ooff, int j0, int, int x, bool ok) const
     {
-        return EmitLinear{out + (long long)o * so + x - (long long)j0 * sj, sj, ok};
+        return EmitLinear{out + ooff + x - (long long)j0 * sj, sj, ok};
+    }
+};
+// the transform axis itself is blocked in the destination (taxis 3): entry r = hi * LO + lo
+struct EmitBlocked {
+    double* dst; long long s_lo, s_hi; int j0, blog, bmask; bool ok;
+    __device__ __forceinline__ void emit(int j, double v) const
+    {
+        const int r = j - j0;
+        if (ok) dst[(long long)(r >> blog) * s_hi + (long long)(r & bmask) * s_lo] = v;
+    }
+};
+struct OutBlocked {
+    static constexpr bool sharded = false;
+    long long s_hi; int blog;
+    __device__ __forceinline__ EmitBlocked emitter(double* out, long long sj, long long ooff, int j0, int, int x, bool ok) const
+    {
+        return EmitBlocked{out + ooff + x, sj, s_hi, j0, blog, (1 << blog) - 1, ok};
     }
 };
 struct EmitShard {
@@ -93,7 +123,7 @@ struct OutShard {
     long long sj, so;               // destination strides (doubles) along the transform / outer axis
     int o_off;                      // destination outer index of this rank's first outer entry
     __device__ __forceinline__ EmitShard emitter(double*, long long, long long, int, int o, int x, bool ok) const
-    {
+    {   // (the kernel's outer offset is ignored: the destination buffers have their own strides)
         return EmitShard{base, logS, maskS, sj, (long long)(o + o_off) * so + x, ok};
     }
 };
@@ -103,8 +133,12 @@ struct ColsPipeArgs {
     long long out_sj, out_so;   // output strides (doubles) along the transform / outer axis
     int nvalid;                 // entries along the transform axis
     int nb, no;                 // extents of the contiguous / outer axis
-    int taxis;                  // tensor-map dimension of the transform axis (1 or 2)
+    int taxis;                  // 1 / 2: tensor-map dimension of the transform axis (3-D maps);
+                                // 3 / 4: blocked 4-D maps, tiles along the blocked axis / along mid (ColsMaps)
     int boxrows, nchunk;        // rows per tensor-map box, boxes per tile
+    int boxhi;                  // taxis 3: blocks per box
+    int blog;                   // blocked layouts: log2(block); taxis 4 splits the outer index with it
+    long long out_so_hi;        // taxis 4: output stride of the outer index's block number (out_so: within a block)
     int reverse;                // walk the tiles back to front (L2 reuse against the previous sweep)
     int mid_o_off;              // added to the outer index handed to the mid functor (sharded sweeps)
     double scale, scale2;
@@ -120,12 +154,14 @@ template <int KIND, typename MID, int KIND2> struct ColsFused {
 };
 
 template <int N, int KIND, typename MID, int KIND2, int NSTAGE, typename OMAP>
-__global__ void __launch_bounds__(PipeCfg<N>::THREADS)
+__global__ void __launch_bounds__(PipeCfg<N, OMAP::sharded>::THREADS_COLS,
+                                  MID::active ? PipeCfg<N, OMAP::sharded>::COLS_MIN_CTAS_MID
+                                              : PipeCfg<N, OMAP::sharded>::COLS_MIN_CTAS)
 k_cols_pipe(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tm2, ColsPipeArgs a, MID mid,
             const __grid_constant__ OMAP omap)
 {
-    using C = PipeCfg<N>;
-    constexpr int B = C::B, G = C::G, M = N / 2, GAP = C::COLS_GAP;
+    using C = PipeCfg<N, OMAP::sharded>;
+    constexpr int B = C::B, G = C::GC, M = N / 2, GAP = C::COLS_GAP;
     constexpr bool FUSED = ColsFused<KIND, MID, KIND2>::value;
     constexpr int J0 = (KIND == XF_DST) ? 1 : 0;
     constexpr int BUF = C::COLS_BUF;
@@ -156,15 +192,25 @@ k_cols_pipe(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUte
         double* buf = bufs + s * BUF;
         for (int c = 0; c < a.nchunk; c++) {
             const int r0 = c * a.boxrows;
-            if constexpr (FUSED) {
-                double* dO = buf + r0 * B;                    // O[h]   <- global row 2h
-                double* dE = buf + (M + GAP + 1 + r0) * B;    // E[h+1] <- global row 2h + 1
-                if (a.taxis == 1) { tma_load_3d(dO, &tm, b0, r0, o, &full[s]); tma_load_3d(dE, &tm2, b0, r0, o, &full[s]); }
-                else { tma_load_3d(dO, &tm, b0, o, r0, &full[s]); tma_load_3d(dE, &tm2, b0, o, r0, &full[s]); }
-            } else {
-                double* dst = buf + J0 * B;
-                if (a.taxis == 1) tma_load_3d(dst + r0 * B, &tm, b0, r0, o, &full[s]);
-                else tma_load_3d(dst + r0 * B, &tm, b0, o, r0, &full[s]);
+            double* dO = FUSED ? buf + r0 * B : buf + J0 * B + r0 * B;      // FUSED: O[h] <- global row 2h
+            double* dE = buf + (M + GAP + 1 + r0) * B;                       // FUSED: E[h+1] <- global row 2h + 1
+            switch (a.taxis) {
+            case 1:
+                tma_load_3d(dO, &tm, b0, r0, o, &full[s]);
+                if constexpr (FUSED) tma_load_3d(dE, &tm2, b0, r0, o, &full[s]);
+                break;
+            case 2:
+                tma_load_3d(dO, &tm, b0, o, r0, &full[s]);
+                if constexpr (FUSED) tma_load_3d(dE, &tm2, b0, o, r0, &full[s]);
+                break;
+            case 3:
+                tma_load_4d(dO, &tm, b0, 0, o, c * a.boxhi, &full[s]);
+                if constexpr (FUSED) tma_load_4d(dE, &tm2, b0, 0, o, c * a.boxhi, &full[s]);
+                break;
+            default:
+                tma_load_4d(dO, &tm, b0, o & ((1 << a.blog) - 1), r0, o >> a.blog, &full[s]);
+                if constexpr (FUSED) tma_load_4d(dE, &tm2, b0, o & ((1 << a.blog) - 1), r0, o >> a.blog, &full[s]);
+                break;
             }
         }
     };
@@ -195,12 +241,16 @@ k_cols_pipe(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUte
         const int tt = a.reverse ? ntiles - 1 - t : t;
         const int o = tt / nbt, b0 = (tt % nbt) * B;
         const bool bok = b0 + b < a.nb;
+        // offset of the outer index in the output: linear, or block number / position in block (taxis 4)
+        const long long ooff = (a.taxis == 4)
+                                   ? (long long)(o >> a.blog) * a.out_so_hi + (long long)(o & ((1 << a.blog) - 1)) * a.out_so
+                                   : (long long)o * a.out_so;
         double* tile = bufs + s * BUF;
         mbar_wait(&full[s], parity);
 
         if constexpr (FUSED) {
             // smem-lean path: finished spectral values leave the registers straight to global memory
-            const auto og = omap.emitter(a.out, a.out_sj, a.out_so, J0, o, b0 + b, bok);
+            const auto og = omap.emitter(a.out, a.out_sj, ooff, J0, o, b0 + b, bok);
             if constexpr (MID::active) {
                 // forward -> multiply -> inverse; with SEP the two transforms ping-pong between the tiles
                 double* t2 = SEP ? alt : tile;
@@ -224,7 +274,7 @@ k_cols_pipe(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUte
                 xform_tile<N, G, KIND2>(tile + b, B, g, a.scale2, SNs, WMs, scr + b, B);
             }
             {
-                const auto og = omap.emitter(a.out, a.out_sj, a.out_so, J0, o, b0 + b, bok);
+                const auto og = omap.emitter(a.out, a.out_sj, ooff, J0, o, b0 + b, bok);
 #pragma unroll 4
                 for (int j = g; j < a.nvalid; j += G) og.emit(j + J0, tile[(j + J0) * B + b]);
             }
@@ -248,6 +298,11 @@ struct RowsPipeArgs {
     double scale;
     const double* SN;
     const cd* WM;
+    // Blocked work-array layout [yb][z][yi][x] (make_cols_maps_blocked): rows are (z, y) pairs, y = yb * YB + yi.
+    //   blk = 0 : both sides natural (row = z * ny + y)
+    //   blk = 1 : natural in, blocked out (forward sweep: the caller's array -> work array)
+    //   blk = 2 : blocked in, natural out (inverse sweep); a tile is BR consecutive yi of one (yb, z) block
+    int blk, blog, ny, nz;
 };
 
 template <int N, int KIND, int NSTAGE>
@@ -272,16 +327,43 @@ __global__ void __launch_bounds__(PipeCfg<N>::THREADS) k_rows_pipe(RowsPipeArgs 
     uint64_t* full = reinterpret_cast<uint64_t*>(SF1 + 2 * (N / 2 + 2));
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const long long ntiles = (a.nrows + BR - 1) / BR;
+    const int YB = 1 << a.blog, SUB = YB / BR > 0 ? YB / BR : 1;   // blk = 2: BR divides YB
+    const int nyb = (a.ny + YB - 1) >> a.blog;
+    const long long ntiles = (a.blk == 2) ? (long long)a.nz * nyb * SUB : (a.nrows + BR - 1) / BR;
     const double hs = 0.5 * a.scale, h2 = 0.5 * hs;
 
-    auto issue = [&](long long t, int s) {
+    // tile -> first input row (in rows of in_pitch), first natural row, valid rows
+    auto locate = [&](long long t, long long& in_row0, long long& nat_row0, int& rows) {
         if (a.reverse) t = ntiles - 1 - t;
-        const long long row0 = t * BR;
-        const int rows = (int)((a.nrows - row0) < BR ? (a.nrows - row0) : BR);
+        if (a.blk == 2) {
+            const int sub = (int)(t % SUB);
+            const long long t2 = t / SUB;
+            const int yb = (int)(t2 % nyb);
+            const long long z = t2 / nyb;
+            const int y0 = yb * YB + sub * BR;
+            in_row0 = (((long long)yb * a.nz + z) << a.blog) + sub * BR;
+            nat_row0 = z * a.ny + y0;
+            rows = a.ny - y0 < BR ? a.ny - y0 : BR;
+            if (rows < 0) rows = 0;
+        } else {
+            in_row0 = nat_row0 = t * BR;
+            rows = (int)((a.nrows - nat_row0) < BR ? (a.nrows - nat_row0) : BR);
+        }
+    };
+    // natural row -> output row (in rows of out_pitch)
+    auto out_row = [&](long long row) -> long long {
+        if (a.blk != 1) return row;
+        const long long z = row / a.ny;
+        const int y = (int)(row - z * a.ny);
+        return ((((long long)(y >> a.blog)) * a.nz + z) << a.blog) + (y & (YB - 1));
+    };
+
+    auto issue = [&](long long t, int s) {
+        long long in_row0, nat_row0; int rows;
+        locate(t, in_row0, nat_row0, rows);
         const unsigned bytes = ((unsigned)rows * a.in_pitch * 8u) & ~15u;
         mbar_expect_tx(&full[s], bytes);
-        bulk_load_1d(stage + s * BR * N, a.in + row0 * a.in_pitch, bytes, &full[s]);
+        if (bytes) bulk_load_1d(stage + s * BR * N, a.in + in_row0 * a.in_pitch, bytes, &full[s]);
     };
 
     if (tid == 0) {
@@ -303,14 +385,13 @@ __global__ void __launch_bounds__(PipeCfg<N>::THREADS) k_rows_pipe(RowsPipeArgs 
     for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, it++) {
         const int s = it % NSTAGE;
         const unsigned parity = (it / NSTAGE) & 1;
-        const long long tt = a.reverse ? ntiles - 1 - t : t;
-        const long long row0 = tt * BR;
-        const int rows = (int)((a.nrows - row0) < BR ? (a.nrows - row0) : BR);
+        long long in_row0, row0; int rows;
+        locate(t, in_row0, row0, rows);
         double* st = stage + s * BR * N;
         mbar_wait(&full[s], parity);
         {   // an odd tail (rows*pitch odd) leaves one double outside the 16-byte granularity of the bulk copy
             const long long cnt = (long long)rows * a.in_pitch;
-            if ((cnt & 1) && tid == 0) st[cnt - 1] = a.in[row0 * a.in_pitch + cnt - 1];
+            if ((cnt & 1) && tid == 0) st[cnt - 1] = a.in[in_row0 * a.in_pitch + cnt - 1];
             if (cnt & 1) __syncthreads();
         }
         // first touch: staging (dense, lanes along the row) -> compute tile; the DST fold happens here and
@@ -346,7 +427,7 @@ __global__ void __launch_bounds__(PipeCfg<N>::THREADS) k_rows_pipe(RowsPipeArgs 
         else
             xform_tile<N, G, KIND, true>(tile + b * P, 1, g, a.scale, SNs, WMs, scr + b, BR);
         for (int r = warp; r < rows; r += NW) {
-            double* dst = a.out + (row0 + r) * a.out_pitch;
+            double* dst = a.out + out_row(row0 + r) * a.out_pitch;
             const double* src = tile + r * P;
 #pragma unroll 4
             for (int x = lane; x < a.nvalid; x += 32) dst[x] = (KIND == XF_DST) ? src[PL::row(x + 1)] : src[x];
@@ -363,7 +444,7 @@ template <int N, int KIND, typename MID, int KIND2, typename OMAP = OutLinear>
 inline cudaError_t launch_cols_pipe_t(const CUtensorMap& tm, const CUtensorMap& tm2, const ColsPipeArgs& a, const MID& mid,
                                       cudaStream_t st, const OMAP& omap = OMAP{})
 {
-    using C = PipeCfg<N>;
+    using C = PipeCfg<N, OMAP::sharded>;
     constexpr int NSTAGE = C::COLS_STAGES;
     auto kern = k_cols_pipe<N, KIND, MID, KIND2, NSTAGE, OMAP>;
     constexpr size_t smem = C::cols_smem(NSTAGE);
@@ -372,7 +453,7 @@ inline cudaError_t launch_cols_pipe_t(const CUtensorMap& tm, const CUtensorMap& 
     if (!per_sm) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, C::THREADS, smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, C::THREADS_COLS, smem);
         if (e != cudaSuccess) return e;
         if (per_sm < 1) per_sm = 1;
     }
@@ -380,7 +461,7 @@ inline cudaError_t launch_cols_pipe_t(const CUtensorMap& tm, const CUtensorMap& 
     long long grid = (long long)device_sm_count() * per_sm;
     if (grid > ntiles) grid = ntiles;
     if (grid < 1) return cudaSuccess;
-    kern<<<(unsigned)grid, C::THREADS, smem, st>>>(tm, tm2, a, mid, omap);
+    kern<<<(unsigned)grid, C::THREADS_COLS, smem, st>>>(tm, tm2, a, mid, omap);
     return cudaGetLastError();
 }
 

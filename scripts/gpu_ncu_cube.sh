@@ -1,6 +1,8 @@
-tag=${1:-r01b}
-out=gpurun_out/$tag
-mkdir -p $out
-ncu --set full --clock-control none --import-source on -k regex:'k_cols_pipe|k_rows_pipe' -s 20 -c 5 -o $out/full_cube255 -f \
-    python bench.py --workload cube255 --steps 2 --warmup 3 --no-cpu-baseline > $out/full_cube255.log 2>&1
-tail -3 $out/full_cube255.log
+# Usage (under gpurun): bash scripts/gpu_ncu_cube.sh <tag> [workloads]  -- ncu --set full of the 5 sweeps of one solve
+tag=${1:-exp}
+mkdir -p gpurun_out/$tag
+for w in ${2:-cube1023 cube255}; do
+ncu --set full --clock-control none --import-source on -k regex:'k_cols_pipe|k_rows_pipe' -s 15 -c 5 -o gpurun_out/$tag/full_$w -f \
+    python bench.py --workload $w --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/$tag/full_$w.log 2>&1
+tail -2 gpurun_out/$tag/full_$w.log | cut -c1-300
+done

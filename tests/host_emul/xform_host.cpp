@@ -57,10 +57,10 @@ struct OutSep {
     void emit(int j, double v) const { dst[j - 1] = v; }
 };
 
-template <int N, int GAP, bool SWZ>
+template <int N, int GAP, bool SWZ, int GDIV = 1>
 static void run_fused_t(double* data, int sj, double scale, int mode, double* sep)
 {
-    constexpr int G = Plan<N>::G;
+    constexpr int G = Plan<N>::G / GDIV;   // GDIV = 2: several first/middle-pass butterflies per thread
     constexpr int M = N / 2;
     using PL = Planar<N, GAP>;
     std::vector<double> sn; std::vector<cd> wm;
@@ -103,6 +103,14 @@ static void run_fused(double* data, int sj, double scale, int mode, double* sep,
     }
     if (mode == 2) run_fused_t<N, 0, false>(data, sj, scale, mode, sep);
     else run_fused_t<N, 1, false>(data, sj, scale, mode, sep);
+}
+
+// N = 1024 with 32 threads per sequence (the strided-axis sweeps' configuration, PipeCfg<1024>::GC)
+extern "C" int emul_dst_fused_half(double* data, int sj, double scale, int mode, double* sep, int swz)
+{
+    if (swz) run_fused_t<1024, 1, true, 2>(data, sj, scale, mode, sep);
+    else run_fused_t<1024, 1, false, 2>(data, sj, scale, mode, sep);
+    return 0;
 }
 
 extern "C" int emul_dst_fused(int N, double* data, int sj, double scale, int mode, double* sep, int swz)

@@ -25,6 +25,7 @@ def emul():
     L = C.CDLL(LIB)
     L.emul_xform.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double), C.c_int, C.c_double]
     L.emul_dst_fused.argtypes = [C.c_int, C.POINTER(C.c_double), C.c_int, C.c_double, C.c_int, C.POINTER(C.c_double), C.c_int]
+    L.emul_dst_fused_half.argtypes = [C.POINTER(C.c_double), C.c_int, C.c_double, C.c_int, C.POINTER(C.c_double), C.c_int]
     return L
 
 
@@ -71,5 +72,22 @@ def test_fused_dst(emul, N, mode, swz):
     d = np.zeros(N * sj); d[sj::sj][: N - 1] = x; d[0] = 123.0     # slot 0 must be ignored
     sep = np.zeros(N - 1)
     assert emul.emul_dst_fused(N, p(d), sj, 0.37, mode, p(sep), swz) == 0
+    got = sep if mode == 1 else d[sj::sj][: N - 1]
+    assert O.rel_l2(got, O.sFFT(x, 0.37)) < 2e-14
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("swz", [0, 1])
+def test_fused_dst_1024_half_threads(emul, mode, swz):
+    """N = 1024 with 32 threads per sequence (PipeCfg<1024>::GC): two first/middle-pass butterflies per
+    thread, one last-pass unit per thread."""
+    N = 1024
+    rng = np.random.default_rng(99 + mode)
+    p = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    sj = 3
+    x = rng.uniform(-1, 1, N - 1)
+    d = np.zeros(N * sj); d[sj::sj][: N - 1] = x; d[0] = 123.0
+    sep = np.zeros(N - 1)
+    assert emul.emul_dst_fused_half(p(d), sj, 0.37, mode, p(sep), swz) == 0
     got = sep if mode == 1 else d[sj::sj][: N - 1]
     assert O.rel_l2(got, O.sFFT(x, 0.37)) < 2e-14
