@@ -341,6 +341,22 @@ def main():
                 "step_frac": algo_bytes_step / (ms / K * 1e-3) / 1e9 / peak,
                 "kernels": {k[0]: {"launches_per_step": k[1] / K, "ms_per_launch": k[2] / k[1]} for k in kern}}
 
+    if sharded:
+        # per GPU 48 n^3 / P bytes of HBM traffic plus two slab<->pencil transposes, each sending (and
+        # receiving) 8 (n^3 / P) (P - 1) / P bytes over NVLink (900 GB/s per direction per GPU, nominal)
+        nvl = 900.0
+        t_hbm = SOLVE_BYTES_PER_PT * pts / world / (peak * 1e9) * 1e3
+        xpose_bytes = 8.0 * pts / world * (world - 1) / world
+        t_nvl = 2 * xpose_bytes / (nvl * 1e9) * 1e3
+        t_step = ms / K
+        roofline["sharded"] = {
+            "hbm_ms": t_hbm, "nvlink_ms": t_nvl, "nvlink_peak_gbs_per_dir": nvl,
+            "nvlink_bytes_per_gpu_per_transpose": xpose_bytes,
+            "t_roof_ms_no_overlap": t_hbm + t_nvl, "t_roof_ms_overlap": max(t_hbm, t_nvl),
+            "frac_no_overlap": (t_hbm + t_nvl) / t_step, "frac_overlap": max(t_hbm, t_nvl) / t_step,
+            "note": "step_frac above is the per-GPU HBM fraction alone; frac_no_overlap is the aggregate "
+                    "HBM + NVLink roofline of BASELINE.json's 8-GPU target (>= 0.5)"}
+
     # ---- e2e through the host-pointer C ABI -----------------------------------------
     Ke = max(3, min(K, 50 if pts < 5e8 else 10))
     for _ in range(2 if pts >= 5e8 else 3):

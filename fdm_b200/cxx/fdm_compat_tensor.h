@@ -27,11 +27,18 @@ template <tensor_flag first, tensor_flag... rest> struct tensor_flags<first, res
     using tail = tensor_flags<rest...>;
 };
 
+// src/tensor.h:34-59: trailing `none` flags dropped, so that e.g. <periodic, none> names the same type as <periodic>
+template <tensor_flag... flags> struct short_flags { using value = tensor_flags<flags...>; };
+template <> struct short_flags<tensor_flag::periodic, tensor_flag::none> { using value = tensor_flags<tensor_flag::periodic>; };
+template <> struct short_flags<tensor_flag::none, tensor_flag::none> { using value = tensor_flags<>; };
+template <> struct short_flags<tensor_flag::none, tensor_flag::none, tensor_flag::none> { using value = tensor_flags<>; };
+template <> struct short_flags<tensor_flag::none> { using value = tensor_flags<>; };
+
 template <typename T, int rank, bool check = true, typename F = tensor_flags<>>
 class tensor {
     template <int level, typename FF> struct cursor {
         T* base; const int* lo; const int* len; const long long* stride;
-        auto operator[](int i) const
+        decltype(auto) operator[](int i) const
         {
             int l = lo[level], n = len[level];
             if constexpr (has_tensor_flag(FF::head, tensor_flag::periodic)) i = ((i - l) % n + n) % n + l;
@@ -68,7 +75,7 @@ public:
     tensor(const tensor&) = delete;
     tensor& operator=(const tensor&) = delete;
 
-    auto operator[](int i) { return cursor<0, F>{vec, lo_, len_, stride_}[i]; }
+    decltype(auto) operator[](int i) { return cursor<0, F>{vec, lo_, len_, stride_}[i]; }
     void use(T* p) { vec = p; }
     T maxabs() const
     {

@@ -4,6 +4,10 @@
 //   shim_check cubep <n> <rhs.bin> <ans.bin>      LaplCube<double,true,periodic^3>
 //   shim_check cubef <n> <rhs.bin> <ans.bin>      LaplCube<float,false> (fp32 at the boundary)
 //   shim_check ns <n> <steps> <prefix> [--ns:...] NSCube<double,true>, dumps <prefix>_{u,v,w,p}.bin
+//   shim_check rect|rectfft2 <nx> <ny> <rhs.bin> <ans.bin>   LaplRect / LaplRectFFT2 <double,true>, cylindrical
+//                                                 column scales written through the public vectors
+//   shim_check cyl <nr> <nz> <nphi> <rhs.bin> <ans.bin>      LaplCyl3FFT2<double,true>
+//   shim_check nscyl <steps> <lsteps> <prefix> [--ns:...]    NSCyl<double,true>, dumps <prefix>_{u,v,w,p}.bin
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -12,6 +16,8 @@
 #include <vector>
 
 #include "ns_cube.h"
+#include "ns_cyl.h"
+#include "lapl_rect.h"
 
 using namespace fdm;
 
@@ -56,6 +62,64 @@ int main(int argc, char** argv)
             for (size_t i = 0; i < cnt; i++) ans[i] = a[i];
         }
         spit(argv[4], ans.data(), cnt);
+        return 0;
+    }
+    if (mode == "rect" || mode == "rectfft2") {
+        // the slice solver of the cylindrical plotter: src/velocity_plot.h:113-127
+        int nx = atoi(argv[2]), ny = atoi(argv[3]);
+        double x1 = M_PI / 2, dx = (M_PI / 2) / nx, dy = 10.0 / ny;
+        auto rhs = slurp(argv[4], (size_t)nx * ny);
+        std::vector<double> ans((size_t)nx * ny);
+        auto scales = [&](auto& lapl) {
+            for (int j = 1; j <= nx; j++) {
+                double r = x1 + j * dx - dx / 2;
+                lapl.lm_y_scale[j] = 1. / r / r; lapl.U_scale[j] = (r + dx / 2) / r; lapl.L_scale[j] = (r - dx / 2) / r;
+            }
+        };
+        if (mode == "rect") {
+            LaplRect<double, true> lapl(dx, dy, M_PI / 2 + dx, 10.0 + dy, nx, ny);
+            scales(lapl);
+            lapl.solve(ans.data(), rhs.data());
+        } else {
+            LaplRectFFT2<double, true> lapl(dx, dy, M_PI / 2 + dx, 10.0 + dy, nx, ny);
+            scales(lapl);
+            lapl.solve(ans.data(), rhs.data());
+        }
+        spit(argv[5], ans.data(), ans.size());
+        return 0;
+    }
+    if (mode == "cyl") {
+        if (argc < 7) return 1;
+        int nr = atoi(argv[2]), nz = atoi(argv[3]), nphi = atoi(argv[4]);
+        double R = M_PI, r0 = M_PI / 2, h = 10.0, dr = (R - r0) / nr, dz = h / nz;
+        size_t cnt = (size_t)nr * nz * nphi;
+        auto rhs = slurp(argv[5], cnt);
+        std::vector<double> ans(cnt);
+        LaplCyl3FFT2<double, true> lapl(dr, dz, r0 - dr / 2, R - r0 + dr, h + dz, nr, nz, nphi);   // src/ns_cyl.h:94-97
+        lapl.solve(ans.data(), rhs.data());
+        spit(argv[6], ans.data(), cnt);
+        return 0;
+    }
+    if (mode == "nscyl") {
+        int steps = atoi(argv[2]), lsteps = atoi(argv[3]);
+        std::string prefix = argv[4];
+        std::vector<char*> args{argv[0]};
+        for (int i = 5; i < argc; i++) args.push_back(argv[i]);
+        Config c;
+        c.rewrite((int)args.size(), args.data());
+        NSCyl<double, true> ns(c);
+        for (int i = 0; i < steps; i++) ns.step();
+        if (lsteps) {
+            // linearise about the current state, like test/test_ns_cyl_spectral.cpp:47-58
+            for (long long i = 0; i < (long long)ns.u.size; i++) ns.u0.vec[i] = ns.u.vec[i];
+            for (long long i = 0; i < (long long)ns.v.size; i++) ns.v0.vec[i] = ns.v.vec[i];
+            for (long long i = 0; i < (long long)ns.w.size; i++) ns.w0.vec[i] = ns.w.vec[i];
+            ns.sync_to_device();
+            for (int i = 0; i < lsteps; i++) ns.L_step();
+        }
+        spit(prefix + "_u.bin", ns.u.vec, ns.u.size); spit(prefix + "_v.bin", ns.v.vec, ns.v.size);
+        spit(prefix + "_w.bin", ns.w.vec, ns.w.size); spit(prefix + "_p.bin", ns.p.vec, ns.p.size);
+        printf("time_index %d size %d\n", ns.time_index, ns.size());
         return 0;
     }
     if (mode == "ns") {

@@ -8,13 +8,13 @@ LIBDIR = os.path.join(ROOT, "fdm_b200")
 
 
 def build(out, with_reference_headers=False):
-    inc = ["-I" + os.path.join(ROOT, "include")]
+    # the drop-in class headers shadow the reference's same-named ones (lapl_cube.h, ns_cube.h, ...)
+    inc = ["-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "fdm_b200", "cxx")]
     std = "-std=c++17"
     if with_reference_headers:
-        # the reference's own tensor.h / config.h are found first, like inside the reference tree
+        # ... while the reference's own tensor.h / config.h are picked up, like inside the reference tree
         inc += ["-I/root/reference/src", "-I" + os.path.join(ROOT, "oracle", "stub"), "-include", "cmath"]
         std = "-std=c++20"
-    inc += ["-I" + os.path.join(ROOT, "fdm_b200", "cxx")]
     cmd = ["/usr/bin/g++", std, "-O1", "-Wall", *inc, SRC, "-o", out]
     if with_reference_headers:
         cmd.append("-c")         # compile only: the reference's config.cpp is not linked here

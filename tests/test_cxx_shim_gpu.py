@@ -55,3 +55,51 @@ def test_cxx_ns_cube(exe, tmp_path):
     got = np.concatenate([np.fromfile(tmp_path / f"ns_{f}.bin") for f in "uvwp"])
     want = np.concatenate([po.fields()[f].ravel() for f in "uvwp"])
     assert O.rel_l2(got, want) < 1e-12
+
+
+@pytest.mark.parametrize("mode", ["rect", "rectfft2"])
+def test_cxx_lapl_rect_with_public_scales(exe, tmp_path, ref, mode):
+    # src/velocity_plot.h:113-127: the caller overwrites lm_y_scale / L_scale / U_scale after construction
+    nx, ny = 63, 31
+    dx = (math.pi / 2) / nx; dy = 10.0 / ny
+    rhs = O.synthetic_rhs((ny, nx), seed=21)
+    rhs.tofile(tmp_path / "rhs.bin")
+    subprocess.run([exe, mode, str(nx), str(ny), str(tmp_path / "rhs.bin"), str(tmp_path / "ans.bin")], check=True)
+    got = np.fromfile(tmp_path / "ans.bin").reshape(ny, nx)
+    j = np.arange(nx + 1, dtype=np.float64)
+    r = math.pi / 2 + j * dx - dx / 2
+    lm = 1.0 / r / r; U = (r + dx / 2) / r; L = (r - dx / 2) / r
+    lm[0] = U[0] = L[0] = 1.0
+    R = ref.LaplRect("rect" if mode == "rect" else "fft2", dx, dy, math.pi / 2 + dx, 10.0 + dy, nx, ny, 0)
+    R.set_scales(lm, L, U)
+    assert O.rel_l2(got, R.solve(rhs)) < 1e-12
+
+
+def test_cxx_lapl_cyl(exe, tmp_path, ref):
+    nr, nz, nphi = 32, 31, 32
+    rhs = O.synthetic_rhs((nphi, nz, nr), seed=22)
+    rhs.tofile(tmp_path / "rhs.bin")
+    subprocess.run([exe, "cyl", str(nr), str(nz), str(nphi), str(tmp_path / "rhs.bin"), str(tmp_path / "ans.bin")], check=True)
+    got = np.fromfile(tmp_path / "ans.bin").reshape(nphi, nz, nr)
+    R, r0, h = math.pi, math.pi / 2, 10.0
+    dr = (R - r0) / nr; dz = h / nz
+    want = ref.LaplCyl3FFT2(dr, dz, r0 - dr / 2, R - r0 + dr, h + dz, nr, nz, nphi).solve(rhs)
+    assert O.rel_l2(got, want) < 1e-12
+
+
+@pytest.mark.parametrize("lsteps", [0, 3])
+def test_cxx_ns_cyl(exe, tmp_path, ref, lsteps):
+    # README Taylor-vortex run (32 x 31 x 32, Re = 200, dt = 0.01), then optionally L_step about the current state
+    steps = 5
+    r = subprocess.run([exe, "nscyl", str(steps), str(lsteps), str(tmp_path / "nc"), "--ns:Re=200", "--ns:dt=0.01"],
+                       check=True, capture_output=True, text=True)
+    assert f"time_index {steps + lsteps}" in r.stdout
+    po = ref.NSCyl(nr=32, nz=31, nphi=32, Re=200.0, dt=0.01)
+    po.step(steps)
+    if lsteps:
+        for f in "uvw":
+            po.set_field(f + "0", po.field(f))
+        po.step(lsteps, linear=True)
+    got = np.concatenate([np.fromfile(tmp_path / f"nc_{f}.bin") for f in "uvwp"])
+    want = np.concatenate([po.field(f).ravel() for f in "uvwp"])
+    assert O.rel_l2(got, want) < 1e-12
