@@ -10,10 +10,9 @@ A "step" is one pass of the hot path over one batch of synthetic input:
   cube255 / cube511  one LaplCube Dirichlet solve, 255^3 / 511^3 fp64
   nscube255          one NSCube lid-driven-cavity step, 255^3   (configs[2])
   nscube31           one NSCube step, 31^3                      (configs[0])
-N>1, cube workloads: ONE solve of the same grid, z-slab decomposed over the N ranks; the two
-slab<->pencil transposes are peer stores over NVLink fused into the y and z sweeps ("scaling":
-"strong").  N>1, NS workloads: independent replicas per rank ("weak"; the NS halo exchange is not
-built yet).
+N>1: ONE solve / ONE time step of the same grid, z-slab decomposed over the N ranks ("scaling": "strong"); the
+two slab<->pencil transposes of the solve are peer stores over NVLink fused into the y and z sweeps, the NS
+stencils read their halo planes from the neighbours' memory.
 
 Prints ONE JSON line (rank 0).  `value` is device-resident throughput; `e2e` goes through the
 host-pointer C-ABI entry point with pinned host buffers (H2D + solve + D2H inside the timed
@@ -240,7 +239,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    sharded = world > 1 and wl["kind"] == "cube"
+    sharded = world > 1 and wl["kind"] == "cube"       # (the NS branch decides for itself below)
     if wl["kind"] == "cube":
         g = cube_geometry(n)
         if sharded:
@@ -276,21 +275,26 @@ def main():
     else:
         if not hasattr(fdm_b200, "NSCube"):
             raise SystemExit("NSCube workload not built")
-        ns = fdm_b200.NSCube(nx=n, nz=n, Re=wl["Re"], dt=wl["dt"])
+        sharded = world > 1 and (n + 1) // world >= 4
+        shard_kw = dict(rank=rank, nranks=world) if sharded else {}
+        ns = fdm_b200.NSCube(nx=n, nz=n, Re=wl["Re"], dt=wl["dt"], **shard_kw)
+        ns.connect()
         pts = n ** 3
-        l2_policy = f"state of 13 arrays = {13 * 8 * pts / 1e6:.0f} MB" + (" > 126 MB L2" if 13 * 8 * pts > 126e6 else " (fits L2; launch-bound size)")
+        lpts = n * n * (ns.local_planes("x")[1])
+        l2_policy = f"state of 13 arrays = {13 * 8 * lpts / 1e6:.0f} MB per GPU" + (" > 126 MB L2" if 13 * 8 * lpts > 126e6 else " (fits L2; launch-bound size)")
 
         def step(i):
             ns.step_device(1, sptr)
-        units_per_step = 1.0
+        units_per_step = 1.0 / (world if sharded else 1)      # x world below: one time step of the whole grid
         metric, unit = "ns_steps_per_s", "steps/s"
-        algo_bytes_step = NS_BYTES_PER_PT * pts
-        ns2 = fdm_b200.NSCube(nx=n, nz=n, Re=wl["Re"], dt=wl["dt"])
+        algo_bytes_step = NS_BYTES_PER_PT * lpts
+        ns2 = fdm_b200.NSCube(nx=n, nz=n, Re=wl["Re"], dt=wl["dt"], **shard_kw)
+        ns2.connect()
 
         def e2e_step():
             ns2.step_host_roundtrip()
         h2d = d2h = ns2.state_bytes()
-        pts_kernel = pts
+        pts_kernel = lpts
 
     # ---- device-resident timing --------------------------------------------------
     for i in range(W):
@@ -345,7 +349,7 @@ def main():
         # per GPU 48 n^3 / P bytes of HBM traffic plus two slab<->pencil transposes, each sending (and
         # receiving) 8 (n^3 / P) (P - 1) / P bytes over NVLink (900 GB/s per direction per GPU, nominal)
         nvl = 900.0
-        t_hbm = SOLVE_BYTES_PER_PT * pts / world / (peak * 1e9) * 1e3
+        t_hbm = (SOLVE_BYTES_PER_PT if wl["kind"] == "cube" else NS_BYTES_PER_PT) * pts / world / (peak * 1e9) * 1e3
         xpose_bytes = 8.0 * pts / world * (world - 1) / world
         t_nvl = 2 * xpose_bytes / (nvl * 1e9) * 1e3
         t_step = ms / K
@@ -377,12 +381,13 @@ def main():
     if rank == 0:
         out = {
             "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong" if (sharded or wl["kind"] == "cube") else "weak",
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong" if (sharded or world == 1) else "weak",
             "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": wl["label"], "l2_policy": l2_policy,
                        "parallelism": ("single GPU" if world == 1 else
                                        f"z-slabs over {world} GPUs, slab<->pencil transposes as peer stores over NVLink"
+                                       + ("" if wl["kind"] == "cube" else ", stencil halo planes pulled from the neighbours")
                                        if sharded else "independent replicas per rank")},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
         }

@@ -7,7 +7,7 @@ object construction does, and fails loudly if it is missing.
 """
 from .capi import FdmB200Error, lib  # noqa: F401
 from .lapl_cube import LaplCube, LaplCubeSharded, slab_range  # noqa: F401
-from .ns_cube import NSCube  # noqa: F401
+from .ns_cube import NSCube, owned_planes  # noqa: F401
 from .lapl_cyl import LaplCyl3FFT2  # noqa: F401
 from .lapl_rect import LaplRect, LaplRectFFT2  # noqa: F401
 from .ns_cyl import NSCyl  # noqa: F401

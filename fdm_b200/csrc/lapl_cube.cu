@@ -314,6 +314,16 @@ int fdmb_lapl_cube::init_sharded()
                              pipe_B_sharded(Nz))))
         return rc;
     pipe_y = pipe_z = true;
+    {   // load every kernel of the sharded solve on this device now (preload_only(), xform_pipe.cuh)
+        cudaFuncAttributes fa;
+        FDMB_CUDA(cudaFuncGetAttributes(&fa, k_mg_barrier));
+        preload_only() = true;
+        attached = true;
+        rc = solve_device_sharded(d_work, d_work, stream);
+        attached = false;
+        preload_only() = false;
+        if (rc) return rc;
+    }
     return FDMB_OK;
 }
 
@@ -327,6 +337,7 @@ int fdmb_lapl_cube::attach(void* const* bases)
 
 int fdmb_lapl_cube::barrier(cudaStream_t st)
 {
+    if (preload_only()) return FDMB_OK;
     PeerFlags pf{};
     for (int q = 0; q < nranks; q++)
         pf.f[q] = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(peer_block[q]) + off_flags);

@@ -4,11 +4,18 @@
 // resident; the state arrays keep the reference's extents and layout (ghosts included)
 // so get/set_field are plain copies of what the reference exposes as ns.u.vec etc.
 //
+// Multi-GPU: the same z-slabs as the sharded LaplCube.  Every rank keeps WINDOWS of the global
+// arrays (its own planes plus the halo planes its stencils read), all kernels index with GLOBAL (i,k,j), and the
+// halo planes are pulled from the neighbours' memory over NVLink (peer loads) after a cross-GPU barrier:
+//   barrier -> pull u,v,w halos -> init_bound -> FGH (H also on the plane below the slab, recomputed instead of
+//   exchanged) -> RHS -> sharded solve -> barrier -> pull the x plane above the slab -> update
+//
 //   step() = init_bound (ns_cube.cpp:65-122)  -> k_bound_lid, k_bound_mirror, k_bound_p
 //            FGH        (ns_cube.cpp:126-200) -> k_fgh
 //            poisson    (ns_cube.cpp:204-238) -> k_rhs + LaplCube solve
 //            update_uvwp(ns_cube.cpp:241-277) -> k_update
 #include <cmath>
+#include <cstring>
 #include <new>
 
 #include "common.h"
@@ -48,43 +55,49 @@ __global__ void k_bound_lid(Fld u, NSGeom g, int jmax)
     u.at(g.nz + 1, k, j) = 2 * g.U0 - u.at(g.nz, k, j);
 }
 
-// mirror ghosts (ns_cube.cpp:76-95).  blockIdx.z selects the field.
-__global__ void k_bound_mirror(Fld u, Fld v, Fld w, NSGeom g)
+// mirror ghosts (ns_cube.cpp:76-95).  blockIdx.z selects the field.  zlo..zhi: the z planes of u and v held by
+// this rank (0..nz+1 on one GPU; own planes + halos when sharded); wbot / wtop: this rank holds the bottom / top
+// z ghost plane of w.
+__global__ void k_bound_mirror(Fld u, Fld v, Fld w, NSGeom g, int zlo, int zhi, int wbot, int wtop)
 {
     int a = blockIdx.x * blockDim.x + threadIdx.x;   // fast index of the face
     int b = blockIdx.y;                              // slow index of the face
-    if (blockIdx.z == 0) {          // u: i = b in 0..nz+1, k = a in 0..ny+1
-        if (b <= g.nz + 1 && a <= g.ny + 1) {
+    if (blockIdx.z == 0) {          // u: i = b in zlo..zhi, k = a in 0..ny+1
+        b += zlo;
+        if (b <= zhi && a <= g.ny + 1) {
             u.at(b, a, -1) = u.at(b, a, 1);
             u.at(b, a, g.nx + 1) = u.at(b, a, g.nx - 1);
         }
-    } else if (blockIdx.z == 1) {   // v: i = b in 0..nz+1, j = a in 0..nx+1
-        if (b <= g.nz + 1 && a <= g.nx + 1) {
+    } else if (blockIdx.z == 1) {   // v: i = b in zlo..zhi, j = a in 0..nx+1
+        b += zlo;
+        if (b <= zhi && a <= g.nx + 1) {
             v.at(b, -1, a) = v.at(b, 1, a);
             v.at(b, g.ny + 1, a) = v.at(b, g.ny - 1, a);
         }
     } else {                        // w: k = b in 0..ny+1, j = a in 0..nx+1
         if (b <= g.ny + 1 && a <= g.nx + 1) {
-            w.at(-1, b, a) = w.at(1, b, a);
-            w.at(g.nz + 1, b, a) = w.at(g.nz - 1, b, a);
+            if (wbot) w.at(-1, b, a) = w.at(1, b, a);
+            if (wtop) w.at(g.nz + 1, b, a) = w.at(g.nz - 1, b, a);
         }
     }
 }
 
-// pressure ghosts (ns_cube.cpp:98-121)
-__global__ void k_bound_p(Fld u, Fld v, Fld w, Fld p, NSGeom g)
+// pressure ghosts (ns_cube.cpp:98-121).  ilo..ihi: this rank's interior planes (1..nz on one GPU).
+__global__ void k_bound_p(Fld u, Fld v, Fld w, Fld p, NSGeom g, int ilo, int ihi, int wbot, int wtop)
 {
     int a = blockIdx.x * blockDim.x + threadIdx.x + 1;
     int b = blockIdx.y + 1;
     const int nx = g.nx, ny = g.ny, nz = g.nz;
-    if (blockIdx.z == 0) {          // x faces: i = b in 1..nz, k = a in 1..ny
-        if (b <= nz && a <= ny) {
+    if (blockIdx.z == 0) {          // x faces: i = b in ilo..ihi, k = a in 1..ny
+        b += ilo - 1;
+        if (b <= ihi && a <= ny) {
             int i = b, k = a;
             p.at(i, k, 0) = p.at(i, k, 1) - (u.at(i, k, 1) - 2 * u.at(i, k, 0) + u.at(i, k, -1)) * g.iRdx;
             p.at(i, k, nx + 1) = p.at(i, k, nx) - (u.at(i, k, nx + 1) - 2 * u.at(i, k, nx) + u.at(i, k, nx - 1)) * g.iRdx;
         }
-    } else if (blockIdx.z == 1) {   // y faces: i = b in 1..nz, j = a in 1..nx
-        if (b <= nz && a <= nx) {
+    } else if (blockIdx.z == 1) {   // y faces: i = b in ilo..ihi, j = a in 1..nx
+        b += ilo - 1;
+        if (b <= ihi && a <= nx) {
             int i = b, j = a;
             p.at(i, 0, j) = p.at(i, 1, j) - (v.at(i, 1, j) - 2 * v.at(i, 0, j) + v.at(i, -1, j)) * g.iRdy;
             p.at(i, ny + 1, j) = p.at(i, ny, j) - (v.at(i, ny + 1, j) - 2 * v.at(i, ny, j) + v.at(i, ny - 1, j)) * g.iRdy;
@@ -92,8 +105,9 @@ __global__ void k_bound_p(Fld u, Fld v, Fld w, Fld p, NSGeom g)
     } else {                        // z faces: k = b in 1..ny, j = a in 1..nx
         if (b <= ny && a <= nx) {
             int k = b, j = a;
-            p.at(0, k, j) = p.at(1, k, j) - (w.at(1, k, j) - 2 * w.at(0, k, j) + w.at(-1, k, j)) * g.iRdz;
-            p.at(nz + 1, k, j) = p.at(nz, k, j) - (w.at(nz + 1, k, j) - 2 * w.at(nz, k, j) + w.at(nz - 1, k, j)) * g.iRdz;
+            if (wbot) p.at(0, k, j) = p.at(1, k, j) - (w.at(1, k, j) - 2 * w.at(0, k, j) + w.at(-1, k, j)) * g.iRdz;
+            if (wtop)
+                p.at(nz + 1, k, j) = p.at(nz, k, j) - (w.at(nz + 1, k, j) - 2 * w.at(nz, k, j) + w.at(nz - 1, k, j)) * g.iRdz;
         }
     }
 }
@@ -107,7 +121,8 @@ __device__ __forceinline__ long long lin(const Fld& f, int i, int k, int j)
 }
 
 // ---- FGH (ns_cube.cpp:126-200) ----------------------------------------------------------
-// One thread per (i,k,j) in [0..nz]x[0..ny]x[0..nx]; F where i,k>=1, G where i,j>=1, H where k,j>=1.
+// One thread per (i,k,j) in [i0..]x[0..ny]x[0..nx]; F where i>=iFG and k>=1, G where i>=iFG and j>=1, H where
+// k,j>=1 (one GPU: i0 = 0, iFG = 1; a sharded rank starts one plane below its slab and computes only H there).
 // Interior threads (i,k,j >= 1) read the 27 distinct taps of the three stencils once through
 // row pointers (immediate offsets, no per-tap address arithmetic) and produce F, G and H together;
 // the O(n^2) edge threads take the generic path.
@@ -159,13 +174,13 @@ __device__ __forceinline__ void fgh_generic(const Fld& u, const Fld& v, const Fl
 #undef W
 }
 
-__global__ void __launch_bounds__(256) k_fgh(Fld u, Fld v, Fld w, Fld F, Fld G, Fld H, NSGeom g)
+__global__ void __launch_bounds__(256) k_fgh(Fld u, Fld v, Fld w, Fld F, Fld G, Fld H, NSGeom g, int i0, int iFG)
 {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int k = blockIdx.y * blockDim.y + threadIdx.y;
-    const int i = blockIdx.z;
+    const int i = blockIdx.z + i0;
     if (j > g.nx || k > g.ny) return;
-    if (i >= 1 && k >= 1 && j >= 1) {
+    if (i >= iFG && k >= 1 && j >= 1) {
         const double* __restrict__ uc_ = u.p + lin(u, i, k, j);
         const double* __restrict__ vc_ = v.p + lin(v, i, k, j);
         const double* __restrict__ wc_ = w.p + lin(w, i, k, j);
@@ -214,17 +229,17 @@ __global__ void __launch_bounds__(256) k_fgh(Fld u, Fld v, Fld w, Fld F, Fld G, 
                     (w0m0 + w000) * (v0m0 + vpm0)) * g.idy);
         return;
     }
-    if (i >= 1 && k >= 1) fgh_generic<true, false, false>(u, v, w, F, G, H, g, i, k, j);
-    if (i >= 1 && j >= 1) fgh_generic<false, true, false>(u, v, w, F, G, H, g, i, k, j);
+    if (i >= iFG && k >= 1) fgh_generic<true, false, false>(u, v, w, F, G, H, g, i, k, j);
+    if (i >= iFG && j >= 1) fgh_generic<false, true, false>(u, v, w, F, G, H, g, i, k, j);
     if (k >= 1 && j >= 1) fgh_generic<false, false, true>(u, v, w, F, G, H, g, i, k, j);
 }
 
 // ---- poisson RHS (ns_cube.cpp:205-235) ---------------------------------------------------
-__global__ void __launch_bounds__(256) k_rhs(Fld F, Fld G, Fld H, Fld p, Fld R, NSGeom g)
+__global__ void __launch_bounds__(256) k_rhs(Fld F, Fld G, Fld H, Fld p, Fld R, NSGeom g, int ilo)
 {
     const int j = blockIdx.x * blockDim.x + threadIdx.x + 1;
     const int k = blockIdx.y * blockDim.y + threadIdx.y + 1;
-    const int i = blockIdx.z + 1;
+    const int i = blockIdx.z + ilo;
     if (j > g.nx || k > g.ny) return;
     const double* __restrict__ Fp = F.p + lin(F, i, k, j);
     const double* __restrict__ Gp = G.p + lin(G, i, k, j);
@@ -242,11 +257,11 @@ __global__ void __launch_bounds__(256) k_rhs(Fld F, Fld G, Fld H, Fld p, Fld R, 
 }
 
 // ---- update_uvwp (ns_cube.cpp:241-277) ---------------------------------------------------
-__global__ void __launch_bounds__(256) k_update(Fld u, Fld v, Fld w, Fld p, Fld x, Fld F, Fld G, Fld H, NSGeom g)
+__global__ void __launch_bounds__(256) k_update(Fld u, Fld v, Fld w, Fld p, Fld x, Fld F, Fld G, Fld H, NSGeom g, int ilo)
 {
     const int j = blockIdx.x * blockDim.x + threadIdx.x + 1;
     const int k = blockIdx.y * blockDim.y + threadIdx.y + 1;
-    const int i = blockIdx.z + 1;
+    const int i = blockIdx.z + ilo;
     if (j > g.nx || k > g.ny) return;
     const double* __restrict__ xp = x.p + lin(x, i, k, j);
     const double xc = xp[0];
@@ -256,57 +271,153 @@ __global__ void __launch_bounds__(256) k_update(Fld u, Fld v, Fld w, Fld p, Fld 
     p.p[lin(p, i, k, j)] = xc;   // p = x copies the index-range intersection (tensor.h:103-111)
 }
 
+// ---- halo pull: whole z planes copied from the neighbours' windows (peer loads over NVLink) ---------
+constexpr int NS_MAX_PULLS = 8;
+struct PullList {
+    const double* src[NS_MAX_PULLS];
+    double* dst[NS_MAX_PULLS];
+    long long n[NS_MAX_PULLS];     // doubles, even (planes of the graded sizes) or odd: handled element-wise
+    int count;
+};
+__global__ void __launch_bounds__(256) k_pull(PullList pl)
+{
+    const int s = blockIdx.y;
+    if (s >= pl.count) return;
+    const double* __restrict__ src = pl.src[s];
+    double* __restrict__ dst = pl.dst[s];
+    const long long n = pl.n[s];
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x)
+        dst[e] = src[e];
+}
+
 }  // namespace fdmb
 
 using namespace fdmb;
+
+// global z range of field `fld` (u v w p x F G H RHS), ns_cube.h:66-75
+static inline void field_zrange(int fld, int nz, int* lo, int* hi)
+{
+    static const int L[9] = {0, 0, -1, 0, 1, 1, 1, 0, 1};
+    static const int H1[9] = {1, 1, 1, 1, 0, 0, 0, 0, 0};      // hi = nz + H1
+    *lo = L[fld]; *hi = nz + H1[fld];
+}
+
+// Planes of field `fld` that rank `rank` of `nranks` HOLDS (window: own planes + halos) and OWNS (the planes it
+// reports through get_field; the owned ranges of all ranks tile the global range).  ilo..ihi = interior planes
+// of the rank's z-slab, the same slabs as the sharded LaplCube (fdmb_slab_range).
+static void ns_planes(int fld, int nz, int rank, int nranks, int* wlo, int* whi, int* olo, int* ohi)
+{
+    int first = 0, cnt = nz, glo, ghi;
+    if (nranks > 1) slab_range(nz, 0, nranks, rank, &first, &cnt);
+    const int ilo = first + 1, ihi = first + cnt;
+    const bool bot = rank == 0, top = rank == nranks - 1;
+    field_zrange(fld, nz, &glo, &ghi);
+    *olo = bot ? glo : ilo;
+    *ohi = top ? ghi : ihi;
+    switch (fld) {
+    case 0: case 1: case 3: *wlo = bot ? glo : ilo - 1; *whi = ihi + 1; break;            // u v p: one plane each side
+    case 2: *wlo = bot ? glo : ilo - 2; *whi = ihi + 1; break;                            // w: H below the slab reads i-1
+    case 4: *wlo = ilo; *whi = top ? ihi : ihi + 1; break;                                // x: update reads x[i+1]
+    case 7: *wlo = bot ? glo : ilo - 1; *whi = ihi; break;                                // H: divergence reads H[i-1]
+    default: *wlo = ilo; *whi = ihi; break;                                               // F G RHS
+    }
+}
+
+struct NSLayout {
+    int wlo[9], whi[9], olo[9], ohi[9];
+    long long sy[9], sz[9], count[9];
+    size_t off[9], bytes;
+};
+static void ns_layout(int nx, int ny, int nz, int rank, int nranks, NSLayout* L)
+{
+    // x/y extents: ns_cube.h:66-75
+    static const int Y0[9] = {0, -1, 0, 0, 1, 1, 0, 1, 1}, X0[9] = {-1, 0, 0, 0, 1, 0, 1, 1, 1};
+    const int Y1[9] = {ny + 1, ny + 1, ny + 1, ny + 1, ny, ny, ny, ny, ny};
+    const int X1[9] = {nx + 1, nx + 1, nx + 1, nx + 1, nx, nx, nx, nx, nx};
+    size_t o = 0;
+    for (int f = 0; f < 9; f++) {
+        ns_planes(f, nz, rank, nranks, &L->wlo[f], &L->whi[f], &L->olo[f], &L->ohi[f]);
+        L->sy[f] = X1[f] - X0[f] + 1;
+        L->sz[f] = (long long)(Y1[f] - Y0[f] + 1) * L->sy[f];
+        L->count[f] = (long long)(L->whi[f] - L->wlo[f] + 1) * L->sz[f];
+        L->off[f] = o;
+        o += (sizeof(double) * (size_t)L->count[f] + 255) & ~(size_t)255;
+    }
+    L->bytes = o;
+}
 
 struct fdmb_ns_cube {
     fdmb_ns_cube_params prm{};
     int nx = 0, ny = 0, nz = 0;
     double dx = 0, dy = 0, dz = 0;
     NSGeom g{};
-    Fld f[9]{};                 // u v w p x F G H RHS
-    long long count[9]{};
+    Fld f[9]{};                 // u v w p x F G H RHS: windows over the global arrays, indexed globally
+    NSLayout lay{};
     fdmb_lapl_cube* lapl = nullptr;
     cudaStream_t stream = nullptr;
     long long time_index = 0;
+    // z-slab sharding (nranks == 1: the windows are the whole arrays)
+    int rank = 0, nranks = 1, ilo = 1, ihi = 0, device = 0;
+    void* block = nullptr;                       // all nine windows in one allocation (one IPC handle)
+    void* peer_block[FDMB_MAX_RANKS] = {};
+    bool peer_ipc[FDMB_MAX_RANKS] = {};
+    bool attached = false;
 
     int init();
     int step(int nsteps, cudaStream_t st);
+    int pull(const int* flds, const int* lo, const int* hi, const int* from, int n, cudaStream_t st);
+    double* owned_ptr(int fld) const { return f[fld].p + (long long)(lay.olo[fld] - lay.wlo[fld]) * lay.sz[fld]; }
+    long long owned_count(int fld) const { return (long long)(lay.ohi[fld] - lay.olo[fld] + 1) * lay.sz[fld]; }
     ~fdmb_ns_cube();
 };
-
-static int make_field(Fld& f, long long& count, int z0, int z1, int y0, int y1, int x0, int x1)
-{
-    f.lz = z0; f.ly = y0; f.lx = x0;
-    f.sy = x1 - x0 + 1;
-    f.sz = (long long)(y1 - y0 + 1) * f.sy;
-    count = (long long)(z1 - z0 + 1) * f.sz;
-    FDMB_CUDA(cudaMalloc(&f.p, sizeof(double) * count));
-    FDMB_CUDA(cudaMemset(f.p, 0, sizeof(double) * count));
-    return FDMB_OK;
-}
 
 int fdmb_ns_cube::init()
 {
     nx = prm.nx; ny = prm.nx /* ns_cube.h:58: ny is read from key "nx" */; nz = prm.nz;
     if (nx < 3 || nz < 3) { set_error("NSCube: nx, nz must be >= 3"); return FDMB_ERR_INVALID; }
+    if (nranks > 1 && (nz + 1) / nranks < 4) {
+        set_error("NSCube: the sharded step needs at least 4 z planes per rank (nz=%d, %d ranks)", nz, nranks);
+        return FDMB_ERR_INVALID;
+    }
     dx = (prm.x2 - prm.x1) / nx; dy = (prm.y2 - prm.y1) / ny; dz = (prm.z2 - prm.z1) / nz;
     const double dx2 = dx * dx, dy2 = dy * dy, dz2 = dz * dz;
-    int rc = fdmb_lapl_cube_create(&lapl, dx, dy, dz, prm.x2 - prm.x1 + dx, prm.y2 - prm.y1 + dy,
+    int rc;
+    if (nranks > 1)
+        rc = fdmb_lapl_cube_create_sharded(&lapl, dx, dy, dz, prm.x2 - prm.x1 + dx, prm.y2 - prm.y1 + dy,
+                                           prm.z2 - prm.z1 + dz, nx, ny, nz, 0, rank, nranks);
+    else
+        rc = fdmb_lapl_cube_create(&lapl, dx, dy, dz, prm.x2 - prm.x1 + dx, prm.y2 - prm.y1 + dy,
                                    prm.z2 - prm.z1 + dz, nx, ny, nz, 0);   // ns_cube.h:77
     if (rc) return rc;
+    FDMB_CUDA(cudaGetDevice(&device));
     FDMB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-    // extents: ns_cube.h:66-75
-    if ((rc = make_field(f[0], count[0], 0, nz + 1, 0, ny + 1, -1, nx + 1))) return rc;  // u
-    if ((rc = make_field(f[1], count[1], 0, nz + 1, -1, ny + 1, 0, nx + 1))) return rc;  // v
-    if ((rc = make_field(f[2], count[2], -1, nz + 1, 0, ny + 1, 0, nx + 1))) return rc;  // w
-    if ((rc = make_field(f[3], count[3], 0, nz + 1, 0, ny + 1, 0, nx + 1))) return rc;   // p
-    if ((rc = make_field(f[4], count[4], 1, nz, 1, ny, 1, nx))) return rc;               // x
-    if ((rc = make_field(f[5], count[5], 1, nz, 1, ny, 0, nx))) return rc;               // F
-    if ((rc = make_field(f[6], count[6], 1, nz, 0, ny, 1, nx))) return rc;               // G
-    if ((rc = make_field(f[7], count[7], 0, nz, 1, ny, 1, nx))) return rc;               // H
-    if ((rc = make_field(f[8], count[8], 1, nz, 1, ny, 1, nx))) return rc;               // RHS
+    {
+        int first = 0, cnt = nz;
+        if (nranks > 1) slab_range(nz, 0, nranks, rank, &first, &cnt);
+        ilo = first + 1; ihi = first + cnt;
+    }
+    {   // Load this translation unit's kernels NOW.  With lazy module loading the first launch of a kernel may need a
+        // context synchronisation; a step starts with a cross-GPU barrier kernel that spins until the peers arrive,
+        // so a first-use load behind it deadlocks when several ranks are driven by one host thread.
+        cudaFuncAttributes fa;
+        FDMB_CUDA(cudaFuncGetAttributes(&fa, k_pull));
+        FDMB_CUDA(cudaFuncGetAttributes(&fa, k_fgh));
+        FDMB_CUDA(cudaFuncGetAttributes(&fa, k_rhs));
+        FDMB_CUDA(cudaFuncGetAttributes(&fa, k_update));
+        FDMB_CUDA(cudaFuncGetAttributes(&fa, k_bound_lid));
+        FDMB_CUDA(cudaFuncGetAttributes(&fa, k_bound_mirror));
+        FDMB_CUDA(cudaFuncGetAttributes(&fa, k_bound_p));
+    }
+    ns_layout(nx, ny, nz, rank, nranks, &lay);
+    FDMB_CUDA(cudaMalloc(&block, lay.bytes));
+    FDMB_CUDA(cudaMemset(block, 0, lay.bytes));
+    static const int Y0[9] = {0, -1, 0, 0, 1, 1, 0, 1, 1}, X0[9] = {-1, 0, 0, 0, 1, 0, 1, 1, 1};
+    for (int k = 0; k < 9; k++) {
+        f[k].p = reinterpret_cast<double*>(static_cast<char*>(block) + lay.off[k]);
+        f[k].lz = lay.wlo[k]; f[k].ly = Y0[k]; f[k].lx = X0[k];
+        f[k].sy = lay.sy[k]; f[k].sz = lay.sz[k];
+    }
+    peer_block[rank] = block;
     g.nx = nx; g.ny = ny; g.nz = nz; g.U0 = prm.u0; g.dt = prm.dt;
     const double Re = prm.Re;
     g.cRx = 1.0 / Re / dx2; g.cRy = 1.0 / Re / dy2; g.cRz = 1.0 / Re / dz2;
@@ -320,17 +431,62 @@ int fdmb_ns_cube::init()
 
 fdmb_ns_cube::~fdmb_ns_cube()
 {
-    for (auto& a : f) cudaFree(a.p);
+    for (int q = 0; q < nranks; q++)
+        if (q != rank && peer_ipc[q] && peer_block[q]) cudaIpcCloseMemHandle(peer_block[q]);
+    cudaFree(block);
     if (lapl) fdmb_lapl_cube_destroy(lapl);
     if (stream) cudaStreamDestroy(stream);
+}
+
+// copy planes lo[s]..hi[s] of field flds[s] from rank from[s]'s window into this rank's window
+int fdmb_ns_cube::pull(const int* flds, const int* lo, const int* hi, const int* from, int n, cudaStream_t st)
+{
+    PullList pl{};
+    long long nmax = 0;
+    for (int s = 0; s < n; s++) {
+        const int k = flds[s];
+        NSLayout q;
+        ns_layout(nx, ny, nz, from[s], nranks, &q);
+        pl.src[s] = reinterpret_cast<const double*>(static_cast<const char*>(peer_block[from[s]]) + q.off[k]) +
+                    (long long)(lo[s] - q.wlo[k]) * q.sz[k];
+        pl.dst[s] = f[k].p + (long long)(lo[s] - lay.wlo[k]) * lay.sz[k];
+        pl.n[s] = (long long)(hi[s] - lo[s] + 1) * lay.sz[k];
+        if (pl.n[s] > nmax) nmax = pl.n[s];
+    }
+    pl.count = n;
+    LaunchScope sc("ns_halo_pull", st);
+    long long bx = (nmax + 256 * 4 - 1) / (256 * 4);
+    if (bx > 1024) bx = 1024;
+    if (bx < 1) bx = 1;
+    k_pull<<<dim3((unsigned)bx, n), 256, 0, st>>>(pl);
+    FDMB_CHECK_LAUNCH();
+    return FDMB_OK;
 }
 
 int fdmb_ns_cube::step(int nsteps, cudaStream_t st)
 {
     const Fld &u = f[0], &v = f[1], &w = f[2], &p = f[3], &x = f[4], &F = f[5], &G = f[6], &H = f[7], &R = f[8];
     const int nmax = nx > ny ? (nx > nz ? nx : nz) : (ny > nz ? ny : nz);
+    const bool bot = rank == 0, top = rank == nranks - 1;
+    const int nzl = ihi - ilo + 1;
+    if (nranks > 1 && !attached) { set_error("NSCube: sharded handle used before attach_ipc/attach_local"); return FDMB_ERR_COMM; }
+    int rc;
     for (int s = 0; s < nsteps; s++) {
-        {   // the reference loops j = -1..nz+1 (ns_cube.cpp:68); clamp to the allocated x range
+        if (nranks > 1) {
+            // every rank has finished the previous update (or set_field): fetch the halo planes of u, v, w
+            if ((rc = lapl->barrier(st))) return rc;
+            int flds[6], lo[6], hi[6], from[6], n = 0;
+            if (!bot) {
+                flds[n] = 0; lo[n] = hi[n] = ilo - 1; from[n++] = rank - 1;
+                flds[n] = 1; lo[n] = hi[n] = ilo - 1; from[n++] = rank - 1;
+                flds[n] = 2; lo[n] = ilo - 2; hi[n] = ilo - 1; from[n++] = rank - 1;
+            }
+            if (!top) {
+                for (int k = 0; k < 3; k++) { flds[n] = k; lo[n] = hi[n] = ihi + 1; from[n++] = rank + 1; }
+            }
+            if ((rc = pull(flds, lo, hi, from, n, st))) return rc;
+        }
+        if (top) {   // the reference loops j = -1..nz+1 (ns_cube.cpp:68); clamp to the allocated x range
             int jmax = (nz + 1 < nx + 1) ? nz + 1 : nx + 1;
             LaunchScope sc("ns_bound_lid", st);
             dim3 grid((jmax + 2 + 127) / 128, ny + 2);
@@ -338,39 +494,62 @@ int fdmb_ns_cube::step(int nsteps, cudaStream_t st)
         }
         {
             LaunchScope sc("ns_bound_mirror", st);
-            dim3 grid((nmax + 2 + 127) / 128, nmax + 2, 3);
-            k_bound_mirror<<<grid, 128, 0, st>>>(u, v, w, g);
+            const int zlo = lay.wlo[0], zhi = lay.whi[0];
+            const int rows = (zhi - zlo + 1) > ny + 2 ? (zhi - zlo + 1) : ny + 2;
+            dim3 grid((nmax + 2 + 127) / 128, rows, 3);
+            k_bound_mirror<<<grid, 128, 0, st>>>(u, v, w, g, zlo, zhi, bot ? 1 : 0, top ? 1 : 0);
         }
         {
             LaunchScope sc("ns_bound_p", st);
-            dim3 grid((nmax + 127) / 128, nmax, 3);
-            k_bound_p<<<grid, 128, 0, st>>>(u, v, w, p, g);
+            const int rows = nzl > ny ? nzl : ny;
+            dim3 grid((nmax + 127) / 128, rows, 3);
+            k_bound_p<<<grid, 128, 0, st>>>(u, v, w, p, g, ilo, ihi, bot ? 1 : 0, top ? 1 : 0);
         }
         {
             LaunchScope sc("ns_fgh", st);
             dim3 block(64, 4);
-            dim3 grid((nx + 1 + 63) / 64, (ny + 1 + 3) / 4, nz + 1);
-            k_fgh<<<grid, block, 0, st>>>(u, v, w, F, G, H, g);
+            const int i0 = lay.wlo[7];                 // first plane of H
+            dim3 grid((nx + 1 + 63) / 64, (ny + 1 + 3) / 4, ihi - i0 + 1);
+            k_fgh<<<grid, block, 0, st>>>(u, v, w, F, G, H, g, i0, ilo);
         }
         {
             LaunchScope sc("ns_rhs", st);
             dim3 block(64, 4);
-            dim3 grid((nx + 63) / 64, (ny + 3) / 4, nz);
-            k_rhs<<<grid, block, 0, st>>>(F, G, H, p, R, g);
+            dim3 grid((nx + 63) / 64, (ny + 3) / 4, nzl);
+            k_rhs<<<grid, block, 0, st>>>(F, G, H, p, R, g, ilo);
         }
         FDMB_CHECK_LAUNCH();
-        int rc = lapl->solve_device(x.p, R.p, st);
+        rc = lapl->solve_device(x.p, R.p, st);
         if (rc) return rc;
+        if (nranks > 1) {
+            // the neighbour above has written its x slab: fetch the plane the w update reads
+            if ((rc = lapl->barrier(st))) return rc;
+            if (!top) {
+                int fld = 4, lo = ihi + 1, hi = ihi + 1, from = rank + 1;
+                if ((rc = pull(&fld, &lo, &hi, &from, 1, st))) return rc;
+            }
+        }
         {
             LaunchScope sc("ns_update", st);
             dim3 block(64, 4);
-            dim3 grid((nx + 63) / 64, (ny + 3) / 4, nz);
-            k_update<<<grid, block, 0, st>>>(u, v, w, p, x, F, G, H, g);
+            dim3 grid((nx + 63) / 64, (ny + 3) / 4, nzl);
+            k_update<<<grid, block, 0, st>>>(u, v, w, p, x, F, G, H, g, ilo);
         }
         FDMB_CHECK_LAUNCH();
         time_index++;
     }
     return FDMB_OK;
+}
+
+// runs `body` with the handle's device current (several ranks may share one process)
+template <typename Fn> static int on_device(fdmb_ns_cube* h, Fn body)
+{
+    int cur = 0;
+    FDMB_CUDA(cudaGetDevice(&cur));
+    if (cur != h->device) FDMB_CUDA(cudaSetDevice(h->device));
+    int rc = body();
+    if (cur != h->device) cudaSetDevice(cur);
+    return rc;
 }
 
 extern "C" {
@@ -386,61 +565,164 @@ int fdmb_ns_cube_default_params(fdmb_ns_cube_params* p)
     return FDMB_OK;
 }
 
-int fdmb_ns_cube_create(fdmb_ns_cube** out, const fdmb_ns_cube_params* p)
+static int ns_create(fdmb_ns_cube** out, const fdmb_ns_cube_params* p, int rank, int nranks)
 {
     if (!out || !p) { set_error("null argument"); return FDMB_ERR_INVALID; }
     *out = nullptr;
+    if (nranks != 1 && nranks != 2 && nranks != 4 && nranks != 8) {
+        set_error("NSCube: nranks must be 1, 2, 4 or 8 (got %d)", nranks);
+        return FDMB_ERR_INVALID;
+    }
+    if (rank < 0 || rank >= nranks) { set_error("NSCube: rank %d out of range", rank); return FDMB_ERR_INVALID; }
     auto* h = new (std::nothrow) fdmb_ns_cube();
     if (!h) { set_error("out of host memory"); return FDMB_ERR_NOMEM; }
-    h->prm = *p;
+    h->prm = *p; h->rank = rank; h->nranks = nranks;
     int rc = h->init();
     if (rc) { delete h; return rc; }
     *out = h;
     return FDMB_OK;
 }
 
+int fdmb_ns_cube_create(fdmb_ns_cube** out, const fdmb_ns_cube_params* p) { return ns_create(out, p, 0, 1); }
+
+int fdmb_ns_cube_create_sharded(fdmb_ns_cube** out, const fdmb_ns_cube_params* p, int rank, int nranks)
+{
+    return ns_create(out, p, rank, nranks);
+}
+
+int fdmb_ns_cube_owned_planes(int nz, int field, int rank, int nranks, int* z_first, int* nplanes)
+{
+    if (field < 0 || field > 8 || !z_first || !nplanes || nz < 3 || nranks < 1 || rank < 0 || rank >= nranks ||
+        (nranks > 1 && (!is_pow2(nz + 1) || !is_pow2(nranks) || (nz + 1) / nranks < 4))) {
+        set_error("fdmb_ns_cube_owned_planes: bad argument (nz=%d field=%d rank=%d/%d)", nz, field, rank, nranks);
+        return FDMB_ERR_INVALID;
+    }
+    int wlo, whi, olo, ohi;
+    ns_planes(field, nz, rank, nranks, &wlo, &whi, &olo, &ohi);
+    *z_first = olo; *nplanes = ohi - olo + 1;
+    return FDMB_OK;
+}
+
+int fdmb_ns_cube_local_planes(fdmb_ns_cube* h, int field, int* z_first, int* nplanes)
+{
+    if (!h || field < 0 || field > 8 || !z_first || !nplanes) { set_error("bad field id"); return FDMB_ERR_INVALID; }
+    *z_first = h->lay.olo[field]; *nplanes = h->lay.ohi[field] - h->lay.olo[field] + 1;
+    return FDMB_OK;
+}
+
+int fdmb_ns_cube_export_ipc(fdmb_ns_cube* h, void* handles)
+{
+    if (!h || !handles || h->nranks < 2) { set_error("export_ipc needs a sharded handle"); return FDMB_ERR_INVALID; }
+    int rc = fdmb_lapl_cube_export_ipc(h->lapl, handles);
+    if (rc) return rc;
+    cudaIpcMemHandle_t ih;
+    FDMB_CUDA(cudaIpcGetMemHandle(&ih, h->block));
+    memcpy(static_cast<char*>(handles) + FDMB_IPC_HANDLE_BYTES, &ih, sizeof(ih));
+    return FDMB_OK;
+}
+
+// handles: nranks records of 2 * FDMB_IPC_HANDLE_BYTES (solver block, field block), indexed by rank
+int fdmb_ns_cube_attach_ipc(fdmb_ns_cube* h, const void* handles)
+{
+    if (!h || !handles || h->nranks < 2) { set_error("attach_ipc needs a sharded handle"); return FDMB_ERR_INVALID; }
+    char solver[FDMB_MAX_RANKS * FDMB_IPC_HANDLE_BYTES];
+    for (int q = 0; q < h->nranks; q++)
+        memcpy(solver + (size_t)q * FDMB_IPC_HANDLE_BYTES, static_cast<const char*>(handles) + (size_t)q * 2 * FDMB_IPC_HANDLE_BYTES,
+               FDMB_IPC_HANDLE_BYTES);
+    int rc = fdmb_lapl_cube_attach_ipc(h->lapl, solver);
+    if (rc) return rc;
+    for (int q = 0; q < h->nranks; q++) {
+        if (q == h->rank) continue;
+        cudaIpcMemHandle_t ih;
+        memcpy(&ih, static_cast<const char*>(handles) + (size_t)q * 2 * FDMB_IPC_HANDLE_BYTES + FDMB_IPC_HANDLE_BYTES, sizeof(ih));
+        cudaError_t e = cudaIpcOpenMemHandle(&h->peer_block[q], ih, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            set_error("cudaIpcOpenMemHandle for rank %d failed: %s", q, cudaGetErrorString(e));
+            return FDMB_ERR_COMM;
+        }
+        h->peer_ipc[q] = true;
+    }
+    h->attached = true;
+    return FDMB_OK;
+}
+
+int fdmb_ns_cube_attach_local(fdmb_ns_cube* h, fdmb_ns_cube* const* all)
+{
+    if (!h || !all || h->nranks < 2) { set_error("attach_local needs a sharded handle"); return FDMB_ERR_INVALID; }
+    fdmb_lapl_cube* solvers[FDMB_MAX_RANKS] = {};
+    for (int q = 0; q < h->nranks; q++) {
+        if (!all[q] || all[q]->nranks != h->nranks || all[q]->rank != q || all[q]->nz != h->nz || all[q]->nx != h->nx) {
+            set_error("attach_local: handle %d does not belong to this sharded run", q);
+            return FDMB_ERR_INVALID;
+        }
+        solvers[q] = all[q]->lapl;
+    }
+    int rc = fdmb_lapl_cube_attach_local(h->lapl, solvers);      // also enables peer access between the devices
+    if (rc) return rc;
+    for (int q = 0; q < h->nranks; q++) h->peer_block[q] = all[q]->block;
+    h->attached = true;
+    return FDMB_OK;
+}
+
 int fdmb_ns_cube_step(fdmb_ns_cube* h, int nsteps)
 {
     if (!h || nsteps < 0) { set_error("bad argument"); return FDMB_ERR_INVALID; }
-    int rc = h->step(nsteps, h->stream);
-    if (rc) return rc;
-    FDMB_CUDA(cudaStreamSynchronize(h->stream));
-    return FDMB_OK;
+    return on_device(h, [&] {
+        int rc = h->step(nsteps, h->stream);
+        if (rc) return rc;
+        FDMB_CUDA(cudaStreamSynchronize(h->stream));
+        return (int)FDMB_OK;
+    });
 }
 
 int fdmb_ns_cube_step_async(fdmb_ns_cube* h, int nsteps, void* stream)
 {
     if (!h || nsteps < 0) { set_error("bad argument"); return FDMB_ERR_INVALID; }
-    return h->step(nsteps, stream ? (cudaStream_t)stream : h->stream);
+    return on_device(h, [&] { return h->step(nsteps, stream ? (cudaStream_t)stream : h->stream); });
+}
+
+int fdmb_ns_cube_synchronize(fdmb_ns_cube* h)
+{
+    if (!h) { set_error("null argument"); return FDMB_ERR_INVALID; }
+    return on_device(h, [&] {
+        FDMB_CUDA(cudaStreamSynchronize(h->stream));
+        return (int)FDMB_OK;
+    });
 }
 
 int fdmb_ns_cube_field_size(fdmb_ns_cube* h, int field, long long* count)
 {
     if (!h || field < 0 || field > 8 || !count) { set_error("bad field id"); return FDMB_ERR_INVALID; }
-    *count = h->count[field];
+    *count = h->owned_count(field);
     return FDMB_OK;
 }
 
 int fdmb_ns_cube_get_field(fdmb_ns_cube* h, int field, double* host)
 {
     if (!h || field < 0 || field > 8 || !host) { set_error("bad field id"); return FDMB_ERR_INVALID; }
-    FDMB_CUDA(cudaMemcpyAsync(host, h->f[field].p, sizeof(double) * h->count[field], cudaMemcpyDeviceToHost, h->stream));
-    FDMB_CUDA(cudaStreamSynchronize(h->stream));
-    return FDMB_OK;
+    return on_device(h, [&] {
+        FDMB_CUDA(cudaMemcpyAsync(host, h->owned_ptr(field), sizeof(double) * h->owned_count(field), cudaMemcpyDeviceToHost,
+                                  h->stream));
+        FDMB_CUDA(cudaStreamSynchronize(h->stream));
+        return (int)FDMB_OK;
+    });
 }
 
 int fdmb_ns_cube_set_field(fdmb_ns_cube* h, int field, const double* host)
 {
     if (!h || field < 0 || field > 8 || !host) { set_error("bad field id"); return FDMB_ERR_INVALID; }
-    FDMB_CUDA(cudaMemcpyAsync(h->f[field].p, host, sizeof(double) * h->count[field], cudaMemcpyHostToDevice, h->stream));
-    FDMB_CUDA(cudaStreamSynchronize(h->stream));
-    return FDMB_OK;
+    return on_device(h, [&] {
+        FDMB_CUDA(cudaMemcpyAsync(h->owned_ptr(field), host, sizeof(double) * h->owned_count(field), cudaMemcpyHostToDevice,
+                                  h->stream));
+        FDMB_CUDA(cudaStreamSynchronize(h->stream));
+        return (int)FDMB_OK;
+    });
 }
 
 int fdmb_ns_cube_field_device_ptr(fdmb_ns_cube* h, int field, void** dptr)
 {
     if (!h || field < 0 || field > 8 || !dptr) { set_error("bad field id"); return FDMB_ERR_INVALID; }
-    *dptr = h->f[field].p;
+    *dptr = h->owned_ptr(field);
     return FDMB_OK;
 }
 

@@ -437,6 +437,15 @@ __global__ void __launch_bounds__(PipeCfg<N>::THREADS) k_rows_pipe(RowsPipeArgs 
 }
 
 // ---- host-side launchers ----------------------------------------------------------------------
+// Preload mode: the launchers set up their kernel (which loads it on this device) and return without launching.
+// The sharded handles run their whole launch sequence once in this mode at creation: with lazy module loading the
+// first launch of a kernel may need a context synchronisation, which deadlocks behind a cross-GPU barrier kernel
+// that spins until a peer driven by the same host thread arrives.
+inline bool& preload_only()
+{
+    static thread_local bool v = false;
+    return v;
+}
 int device_sm_count();
 int current_device_slot();   // cudaGetDevice() clamped to [0, 63]
 
@@ -457,6 +466,7 @@ inline cudaError_t launch_cols_pipe_t(const CUtensorMap& tm, const CUtensorMap& 
         if (e != cudaSuccess) return e;
         if (per_sm < 1) per_sm = 1;
     }
+    if (preload_only()) return cudaSuccess;
     const long long ntiles = (long long)((a.nb + C::B - 1) / C::B) * a.no;
     long long grid = (long long)device_sm_count() * per_sm;
     if (grid > ntiles) grid = ntiles;
@@ -481,6 +491,7 @@ inline cudaError_t launch_rows_pipe_t(const RowsPipeArgs& a, cudaStream_t st)
         if (e != cudaSuccess) return e;
         if (per_sm < 1) per_sm = 1;
     }
+    if (preload_only()) return cudaSuccess;
     const long long ntiles = (a.nrows + C::BR - 1) / C::BR;
     long long grid = (long long)device_sm_count() * per_sm;
     if (grid > ntiles) grid = ntiles;

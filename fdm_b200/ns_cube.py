@@ -38,7 +38,26 @@ def _bind(L):
     L.fdmb_ns_cube_time_index.argtypes = [C.c_void_p]
     L.fdmb_ns_cube_time_index.restype = C.c_longlong
     L.fdmb_ns_cube_destroy.argtypes = [C.c_void_p]
+    L.fdmb_ns_cube_create_sharded.argtypes = [C.POINTER(C.c_void_p), P, C.c_int, C.c_int]
+    ip = C.POINTER(C.c_int)
+    L.fdmb_ns_cube_owned_planes.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, ip, ip]
+    L.fdmb_ns_cube_local_planes.argtypes = [C.c_void_p, C.c_int, ip, ip]
+    L.fdmb_ns_cube_export_ipc.argtypes = [C.c_void_p, C.c_void_p]
+    L.fdmb_ns_cube_attach_ipc.argtypes = [C.c_void_p, C.c_void_p]
+    L.fdmb_ns_cube_attach_local.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    L.fdmb_ns_cube_synchronize.argtypes = [C.c_void_p]
     L._ns_cube_bound = True
+
+
+def owned_planes(nz, field, rank, nranks):
+    """(first global z index, number of planes) of ``field`` that ``rank`` reports through ``field()``; the ranks'
+    ranges tile the reference array's z range (pure function, no device needed)."""
+    L = capi.lib()
+    _bind(L)
+    a, b = C.c_int(), C.c_int()
+    capi.check(L.fdmb_ns_cube_owned_planes(int(nz), FIELD_IDS[field], int(rank), int(nranks), C.byref(a), C.byref(b)),
+               "owned_planes")
+    return a.value, b.value
 
 
 class NSCube:
@@ -46,15 +65,51 @@ class NSCube:
     (src/ns_cube.h:58).  Defaults are the reference's (src/ns_cube.h:47-61)."""
 
     def __init__(self, nx=32, nz=32, Re=1.0, dt=0.001, u0=1.0,
-                 x1=-math.pi, y1=-math.pi, z1=-math.pi, x2=math.pi, y2=math.pi, z2=math.pi, verbose=0):
+                 x1=-math.pi, y1=-math.pi, z1=-math.pi, x2=math.pi, y2=math.pi, z2=math.pi, verbose=0,
+                 rank=0, nranks=1):
         L = capi.lib()
         _bind(L)
         self.params = NSCubeParams(x1, y1, z1, x2, y2, z2, u0, Re, dt, int(nx), int(nz), int(verbose))
         self.nx, self.ny, self.nz = int(nx), int(nx), int(nz)
         self.dt = float(dt)
+        self.rank, self.nranks = int(rank), int(nranks)
         self._h = C.c_void_p()
-        capi.check(L.fdmb_ns_cube_create(C.byref(self._h), C.byref(self.params)), "NSCube create")
+        if self.nranks > 1:
+            capi.check(L.fdmb_ns_cube_create_sharded(C.byref(self._h), C.byref(self.params), self.rank, self.nranks),
+                       "NSCube create_sharded")
+        else:
+            capi.check(L.fdmb_ns_cube_create(C.byref(self._h), C.byref(self.params)), "NSCube create")
         self._pinned = None
+
+    # ---- several GPUs: z-slabs, every rank holds and reports its own planes ----------------------
+    def local_planes(self, name):
+        a, b = C.c_int(), C.c_int()
+        capi.check(capi.lib().fdmb_ns_cube_local_planes(self._h, FIELD_IDS[name], C.byref(a), C.byref(b)), "local_planes")
+        return a.value, b.value
+
+    def connect(self, group=None):
+        """One process per GPU: exchange the IPC handles over ``torch.distributed`` and attach the peers."""
+        if self.nranks == 1:
+            return
+        import torch.distributed as dist
+        from .lapl_cube import IPC_HANDLE_BYTES
+        buf = C.create_string_buffer(2 * IPC_HANDLE_BYTES)
+        capi.check(capi.lib().fdmb_ns_cube_export_ipc(self._h, buf), "export_ipc")
+        gathered = [None] * self.nranks
+        dist.all_gather_object(gathered, buf.raw, group=group)
+        blob = b"".join(gathered)
+        capi.check(capi.lib().fdmb_ns_cube_attach_ipc(self._h, C.create_string_buffer(blob, len(blob))), "attach_ipc")
+        dist.barrier(group=group)
+
+    @staticmethod
+    def connect_local(parts):
+        """All ranks live in this process (one handle per device)."""
+        arr = (C.c_void_p * len(parts))(*[s._h for s in parts])
+        for s in parts:
+            capi.check(capi.lib().fdmb_ns_cube_attach_local(s._h, arr), "attach_local")
+
+    def synchronize(self):
+        capi.check(capi.lib().fdmb_ns_cube_synchronize(self._h), "synchronize")
 
     # ---- reference API -----------------------------------------------------------------
     def step(self, nsteps=1):

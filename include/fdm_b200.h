@@ -171,6 +171,23 @@ int fdmb_ns_cube_field_device_ptr(fdmb_ns_cube* h, int field, void** dptr);
 long long fdmb_ns_cube_time_index(fdmb_ns_cube* h);
 int fdmb_ns_cube_destroy(fdmb_ns_cube* h);
 
+/* NSCube over several GPUs of one node: the z-slabs of the sharded LaplCube above (fdmb_slab_range); stencil halo
+ * planes are read from the neighbours' memory over NVLink after a device-side barrier, the pressure solve is the
+ * sharded LaplCube.  The reference runs on one host only (src/ns_cube.cpp:27-62); results are identical to it.
+ *   create_sharded   this rank's part; collective in the sense that every rank must create, attach and step
+ *   owned_planes     which z planes (global index, e.g. -1 for w's bottom ghost) of a field a rank reports:
+ *                    the ranks' ranges tile the reference array's z range (pure function, no device needed)
+ *   local_planes     the same for a handle
+ *   export/attach    like the sharded LaplCube; one record = 2 * FDMB_IPC_HANDLE_BYTES per rank
+ *   field_size / get_field / set_field / field_device_ptr act on the OWNED planes of a sharded handle       */
+int fdmb_ns_cube_create_sharded(fdmb_ns_cube** h, const fdmb_ns_cube_params* p, int rank, int nranks);
+int fdmb_ns_cube_owned_planes(int nz, int field, int rank, int nranks, int* z_first, int* nplanes);
+int fdmb_ns_cube_local_planes(fdmb_ns_cube* h, int field, int* z_first, int* nplanes);
+int fdmb_ns_cube_export_ipc(fdmb_ns_cube* h, void* handles);
+int fdmb_ns_cube_attach_ipc(fdmb_ns_cube* h, const void* handles);
+int fdmb_ns_cube_attach_local(fdmb_ns_cube* h, fdmb_ns_cube* const* all);
+int fdmb_ns_cube_synchronize(fdmb_ns_cube* h);
+
 /* ---- NSCyl ----------------------------------------------------------------------
  * Replaces fdm::NSCyl<double,check,zflag> (src/ns_cyl.h:17-132, src/ns_cyl.cpp:23-484): flow between
  * two coaxial cylinders, inner one rotating with speed u0, on a staggered grid in (phi, z, r).

@@ -47,3 +47,30 @@ def test_sharded_data_path_gloo(tmp_path, world):
     r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     assert float(out.read_text()) < 1e-13
+
+
+def test_ns_owned_planes_tile_the_fields():
+    import fdm_b200
+    nz = 63
+    for f, (lo, hi) in {"u": (0, nz + 1), "w": (-1, nz + 1), "x": (1, nz), "H": (0, nz)}.items():
+        for P in (1, 2, 4, 8):
+            pos = lo
+            for r in range(P):
+                z0, n = fdm_b200.owned_planes(nz, f, r, P)
+                assert z0 == pos and n > 0
+                pos += n
+            assert pos == hi + 1
+    with pytest.raises(fdm_b200.FdmB200Error):
+        fdm_b200.owned_planes(7, "u", 0, 4)          # fewer than 4 planes per rank
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_ns_halo_plan_gloo(tmp_path, world):
+    out = tmp_path / "plan.txt"
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(29660 + world),
+           os.path.join(ROOT, "tests", "mp", "ns_plan_worker.py"), "--out", str(out)]
+    r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    assert out.read_text() == "ok"
