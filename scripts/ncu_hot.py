@@ -1,8 +1,11 @@
 """Hot SASS instructions (by stall samples) of one captured launch.  Usage: ncu_hot.py file.ncu-rep launch_index [top]"""
 import csv, io, subprocess, sys
 rep, kid = sys.argv[1], int(sys.argv[2]); topn = int(sys.argv[3]) if len(sys.argv) > 3 else 12
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--launch-skip", str(kid), "--launch-count", "1"],
-                     capture_output=True, text=True).stdout
+if rep.endswith(".csv"):      # a source page exported on the GPU box (scripts/gpu_profile.sh); kid is ignored
+    out = open(rep, errors="ignore").read()
+else:
+    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--launch-skip", str(kid), "--launch-count", "1"],
+                         capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 hi = [i for i, r in enumerate(rows) if r and r[0] == 'Address'][0]
 hdr = rows[hi]; ci = {h: i for i, h in enumerate(hdr)}

@@ -2,8 +2,11 @@
 Usage: ncu_src.py file.ncu-rep kernel_index(0-based among captured)"""
 import csv, io, subprocess, sys, collections
 rep, kid = sys.argv[1], int(sys.argv[2])
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--launch-skip", str(kid), "--launch-count", "1"],
-                     capture_output=True, text=True).stdout
+if rep.endswith(".csv"):      # a source page exported on the GPU box (scripts/gpu_profile.sh); kid is ignored
+    out = open(rep, errors="ignore").read()
+else:
+    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--launch-skip", str(kid), "--launch-count", "1"],
+                         capture_output=True, text=True).stdout
 lines = out.split('"Kernel Name",')[1].splitlines()
 print(lines[0][:120])
 rows = list(csv.reader(io.StringIO("\n".join(lines[1:]))))

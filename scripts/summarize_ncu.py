@@ -98,9 +98,13 @@ def launches(tag, wl):
 
 def full(tag, wl, traffic):
     rep = os.path.join(ROOT, "gpurun_out", tag, f"full_{wl}.ncu-rep")
-    if not os.path.exists(rep):
+    rawcsv = os.path.join(ROOT, "gpurun_out", tag, f"full_{wl}.raw.csv")
+    if os.path.exists(rawcsv):
+        raw = open(rawcsv, errors="ignore").read()
+    elif os.path.exists(rep):
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    else:
         return
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
     out = [f"# ncu --set full: bench.py --workload {wl} ({tag})", "",
@@ -148,6 +152,11 @@ def full(tag, wl, traffic):
             if re.search(rx, k):
                 tr[t] = sum(v) / len(v)
                 break
+    if wl.startswith("cube") and len(cols) == 5:
+        # the capture window is one solve: x fwd, y fwd, z fwd/divide/inv, y inv, x inv (LaunchScope tags of lapl_cube.cu)
+        for c, t in zip(cols, ["cube_x_fwd", "cube_y_fwd", "cube_z_fwd_div_inv", "cube_y_inv", "cube_x_inv"]):
+            if "dram_rd" in c:
+                tr[t] = to_bytes(*c["dram_rd"]) + to_bytes(*c["dram_wr"])
 
 
 def main():
@@ -155,7 +164,7 @@ def main():
     os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     traffic = json.load(open(tpath)) if os.path.exists(tpath) else {}
-    for wl in ("cube127", "cube255", "nscube255", "cube511"):
+    for wl in ("cube127", "cube255", "nscube255", "cube511", "cube1023"):
         launches(tag, wl)
         full(tag, wl, traffic)
     traffic["_source"] = f"ncu --set full captures of {tag}; bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum)"
