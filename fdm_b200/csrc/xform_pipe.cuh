@@ -395,24 +395,27 @@ __global__ void __launch_bounds__(PipeCfg<N>::THREADS) k_rows_pipe(RowsPipeArgs 
             if (cnt & 1) __syncthreads();
         }
         // first touch: staging (dense, lanes along the row) -> compute tile; the DST fold happens here and
-        // writes the planar layout (even / odd slots de-interleaved)
-        for (int r = warp; r < BR; r += NW) {
+        // writes the planar layout (even / odd slots de-interleaved).  PARTS warps share a row when the CTA has
+        // more warps than rows, so that no warp idles.
+        constexpr int PARTS = NW > BR ? NW / BR : 1;
+        for (int q = warp; q < BR * PARTS; q += NW) {
+            const int r = q % BR, part = q / BR;
             const double* src = st + r * a.in_pitch;
             double* dst = tile + r * P;
             const bool ok = r < rows;
             if constexpr (KIND == XF_DST) {
-                for (int j = 1 + lane; j < M; j += 32) {
+                for (int j = 1 + lane + 32 * part; j < M; j += 32 * PARTS) {
                     double x1 = ok ? src[j - 1] : 0.0, x2 = ok ? src[N - j - 1] : 0.0;
                     double y1 = SF1[j] * (x1 + x2), y2 = h2 * (x1 - x2);
                     dst[prefold_row<N, RG, C::SWZ>(j)] = y1 + y2;
                     dst[prefold_row<N, RG, C::SWZ>(N - j)] = y1 - y2;
                 }
-                if (lane == 0) {
+                if (lane == 0 && part == 0) {
                     dst[prefold_row<N, RG, C::SWZ>(0)] = 0.0;
                     dst[prefold_row<N, RG, C::SWZ>(M)] = ok ? a.scale * src[M - 1] : 0.0;
                 }
             } else {
-                for (int j = lane; j < N; j += 32) dst[j] = ok ? src[j] : 0.0;
+                for (int j = lane + 32 * part; j < N; j += 32 * PARTS) dst[j] = ok ? src[j] : 0.0;
             }
         }
         fence_proxy_async();
@@ -426,11 +429,13 @@ __global__ void __launch_bounds__(PipeCfg<N>::THREADS) k_rows_pipe(RowsPipeArgs 
                                                    OutTile<N, RG>{tile + b * P, 1});
         else
             xform_tile<N, G, KIND, true>(tile + b * P, 1, g, a.scale, SNs, WMs, scr + b, BR);
-        for (int r = warp; r < rows; r += NW) {
+        for (int q = warp; q < BR * PARTS; q += NW) {
+            const int r = q % BR, part = q / BR;
+            if (r >= rows) continue;
             double* dst = a.out + out_row(row0 + r) * a.out_pitch;
             const double* src = tile + r * P;
 #pragma unroll 4
-            for (int x = lane; x < a.nvalid; x += 32) dst[x] = (KIND == XF_DST) ? src[PL::row(x + 1)] : src[x];
+            for (int x = lane + 32 * part; x < a.nvalid; x += 32 * PARTS) dst[x] = (KIND == XF_DST) ? src[PL::row(x + 1)] : src[x];
         }
         __syncthreads();   // the compute tile is rewritten by the next first touch
     }
