@@ -188,6 +188,25 @@ __global__ void k_mg_barrier(PeerFlags pf, int rank, int nranks, unsigned long l
     __threadfence_system();
 }
 
+int launch_mg_barrier(void* const* peer_blocks, size_t off_flags, int rank, int nranks, unsigned long long epoch,
+                      cudaStream_t st)
+{
+    PeerFlags pf{};
+    for (int q = 0; q < nranks; q++)
+        pf.f[q] = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(peer_blocks[q]) + off_flags);
+    LaunchScope scope("mg_barrier", st);
+    k_mg_barrier<<<1, 32, 0, st>>>(pf, rank, nranks, epoch);
+    FDMB_CHECK_LAUNCH();
+    return FDMB_OK;
+}
+
+int preload_mg_barrier()
+{
+    cudaFuncAttributes fa;
+    FDMB_CUDA(cudaFuncGetAttributes(&fa, k_mg_barrier));
+    return FDMB_OK;
+}
+
 }  // namespace fdmb
 
 using namespace fdmb;

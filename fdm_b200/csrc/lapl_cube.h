@@ -12,6 +12,11 @@ cudaError_t launch_cols_cube_divide(int N, bool periodic, const ColsArgs& a, con
 // persistent TMA-fed variants (transform lengths >= 32)
 inline bool pipe_supported_N(int N) { return supported_N(N) && N >= 32; }
 inline int pipe_B(int N) { return N <= 512 ? 16 : 8; }
+// cross-GPU barrier on a stream over the flag arrays at `off_flags` inside every rank's peer-mapped block
+// (FDMB_MAX_RANKS u64 epochs each, zero-initialised); epoch must increase by one per call on every rank
+int launch_mg_barrier(void* const* peer_blocks, size_t off_flags, int rank, int nranks, unsigned long long epoch,
+                      cudaStream_t st);
+int preload_mg_barrier();
 inline int pipe_B_sharded(int N) { return N <= 1024 ? 16 : 8; }     // PipeCfg<N, true>::B
 cudaError_t launch_rows_pipe(int N, int kind, const RowsPipeArgs& a, cudaStream_t st, const char* tag);
 cudaError_t launch_cols_pipe(int N, int kind, const ColsMaps& tm, ColsPipeArgs a, cudaStream_t st, const char* tag);

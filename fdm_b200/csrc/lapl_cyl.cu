@@ -11,6 +11,7 @@
 // diagonally dominant so LAPACK never pivots) is recomputed on the fly.
 #include <cmath>
 #include <cstdint>
+#include <cstring>
 #include <new>
 #include <vector>
 
@@ -47,7 +48,8 @@ __global__ void __launch_bounds__(128) k_tridiag_rows(TridiagArgs a)
     if (tid < TS && row0 + tid < a.nsys) {
         const long long row = row0 + tid;
         const int outer = (int)(row / a.nmid), mid = (int)(row % a.nmid);
-        const double lo = a.lm_outer[outer], lmz = a.lm_mid[mid + a.mid0];
+        const double lo = a.swap ? a.lm_outer[mid] : a.lm_outer[outer];
+        const double lmz = a.swap ? a.lm_mid[outer + a.mid0] : a.lm_mid[mid + a.mid0];
         double* b = tb + tid * P - 1;          // 1-based
         double* iv = ti + tid * P - 1;
         // D_j = -2/dr2 - lm_phi/r/r - lm_z   (lapl_cyl.cpp:153)
@@ -81,10 +83,10 @@ __global__ void __launch_bounds__(128) k_tridiag_rows(TridiagArgs a)
 
 size_t tridiag_rows_smem(int nr) { return sizeof(double) * (size_t)(2 * TS * (nr | 1) + 3 * (nr + 1)); }
 
-cudaError_t launch_tridiag_rows(const TridiagArgs& a, cudaStream_t st, const char* tag)
+// sets the kernel's shared-memory limit for systems of length nr on the current device (this also loads the kernel)
+cudaError_t prepare_tridiag_rows(int nr)
 {
-    LaunchScope scope(tag, st);
-    const size_t smem = tridiag_rows_smem(a.nr);
+    const size_t smem = tridiag_rows_smem(nr);
     static size_t set_smem_dev[64] = {0};     // function attributes are per device
     size_t& set_smem = set_smem_dev[current_device_slot()];
     if (smem > set_smem) {
@@ -92,8 +94,16 @@ cudaError_t launch_tridiag_rows(const TridiagArgs& a, cudaStream_t st, const cha
         if (e != cudaSuccess) return e;
         set_smem = smem;
     }
+    return cudaSuccess;
+}
+
+cudaError_t launch_tridiag_rows(const TridiagArgs& a, cudaStream_t st, const char* tag)
+{
+    LaunchScope scope(tag, st);
+    cudaError_t e = prepare_tridiag_rows(a.nr);
+    if (e != cudaSuccess) return e;
     const unsigned grid = (unsigned)((a.nsys + TS - 1) / TS);
-    k_tridiag_rows<<<grid, 128, smem, st>>>(a);
+    k_tridiag_rows<<<grid, 128, tridiag_rows_smem(a.nr), st>>>(a);
     return cudaGetLastError();
 }
 
@@ -140,6 +150,8 @@ int fdmb_lapl_cyl::init()
     if ((rc = up(&d_lmphi, lm_phi)) || (rc = up(&d_lmz, lm_z)) || (rc = up(&d_L, L)) || (rc = up(&d_U, U)) ||
         (rc = up(&d_ir2, ir2)))
         return rc;
+    FDMB_CUDA(cudaGetDevice(&device));
+    if (nranks > 1) return init_sharded();
     FDMB_CUDA(cudaMalloc(&d_work, sizeof(double) * (size_t)nphi * nz * pr));
     if (pipe_enabled()) {
         const unsigned long long s1 = 8ull * pr, s2 = 8ull * (unsigned long long)nz * pr;
@@ -155,15 +167,142 @@ int fdmb_lapl_cyl::init()
     return FDMB_OK;
 }
 
+static int ilog2i(int v) { int l = 0; while ((1 << l) < v) l++; return l; }
+
+int fdmb_lapl_cyl::init_sharded()
+{
+    const int J0 = zperiodic ? 0 : 1;
+    if (nranks != 2 && nranks != 4 && nranks != 8) {
+        set_error("LaplCyl3FFT2: nranks must be 1, 2, 4 or 8 (got %d)", nranks);
+        return FDMB_ERR_INVALID;
+    }
+    if (rank < 0 || rank >= nranks) { set_error("LaplCyl3FFT2: rank %d out of range", rank); return FDMB_ERR_INVALID; }
+    if (!pipe_supported_N(nphi) || !pipe_supported_N(Nz) || nphi / nranks < 2 || Nz / nranks < 2 || (nr & 1)) {
+        set_error("LaplCyl3FFT2: the sharded solve needs nphi and the z transform length >= 32 and >= 2*nranks, and an "
+                  "even nr (got nphi=%d, Nz=%d, nr=%d)", nphi, Nz, nr);
+        return FDMB_ERR_INVALID;
+    }
+    int rc;
+    if ((rc = preload_mg_barrier())) return rc;
+    FDMB_CUDA(prepare_tridiag_rows(nr));
+    Sphi = nphi / nranks; Sz = Nz / nranks;
+    phi_first = rank * Sphi;
+    slab_range(nz, zperiodic, nranks, rank, &z_first, &nzl);
+    const size_t a_bytes = (sizeof(double) * (size_t)Sphi * nz * pr + 255) & ~(size_t)255;
+    const size_t t_bytes = (sizeof(double) * (size_t)Sz * nphi * pr + 255) & ~(size_t)255;
+    off_T = a_bytes; off_flags = a_bytes + t_bytes;
+    mg_bytes = off_flags + 256;
+    FDMB_CUDA(cudaMalloc(&mg_block, mg_bytes));
+    FDMB_CUDA(cudaMemset(mg_block, 0, mg_bytes));
+    d_A = reinterpret_cast<double*>(mg_block);
+    d_T = reinterpret_cast<double*>(static_cast<char*>(mg_block) + off_T);
+    peer_block[rank] = mg_block;
+    d_work = d_A;
+    // local pencils: the uniform allocation keeps the slot-0 row block on rank 0 of a Dirichlet z axis
+    double* t_loc = d_T + (size_t)(z_first + J0 - rank * Sz) * nphi * pr;
+    if ((rc = make_cols_maps(&tm_tphi, t_loc, nphi, 1, nr, nphi, nzl, 8ull * pr, 8ull * (unsigned long long)nphi * pr,
+                             pipe_B_sharded(nphi))))
+        return rc;
+    if ((rc = make_cols_maps(&tm_tphi_l, t_loc, nphi, 1, nr, nphi, nzl, 8ull * pr, 8ull * (unsigned long long)nphi * pr,
+                             pipe_B(nphi))))
+        return rc;
+    if ((rc = make_cols_maps(&tm_za, d_A, Nz, 1, nr, nz, Sphi, 8ull * pr, 8ull * (unsigned long long)nz * pr, pipe_B(Nz))))
+        return rc;
+    pipe_z = pipe_phi = true;
+    // load every kernel of the sharded solve on this device now (preload_only(), xform_pipe.cuh)
+    preload_only() = true;
+    attached = true;
+    rc = solve_device_sharded(d_A, d_A, stream);
+    attached = false;
+    preload_only() = false;
+    tm_in_ptr = nullptr;
+    return rc;
+}
+
+int fdmb_lapl_cyl::barrier(cudaStream_t st)
+{
+    if (preload_only()) return FDMB_OK;
+    epoch++;
+    return launch_mg_barrier(peer_block, off_flags, rank, nranks, epoch, st);
+}
+
+// d_in / d_out: this rank's phi-slab [Sphi][nz][nr] of the caller's arrays
+int fdmb_lapl_cyl::solve_device_sharded(double* d_out, const double* d_in, cudaStream_t st)
+{
+    if (!attached) { set_error("LaplCyl3FFT2: sharded handle used before attach_ipc/attach_local"); return FDMB_ERR_COMM; }
+    if ((reinterpret_cast<uintptr_t>(d_in) & 15) != 0) {
+        set_error("LaplCyl3FFT2: the sharded solve needs a 16-byte aligned rhs slab");
+        return FDMB_ERR_INVALID;
+    }
+    const double SQRT_M_1_PI = 0.56418958354775629;   // lapl_cyl.h:175
+    const int J0 = zperiodic ? 0 : 1;
+    const int kzf = zperiodic ? XF_PFWD : XF_DST, kzi = zperiodic ? XF_PINV : XF_DST;
+    const long long wplane = (long long)nz * pr, uplane = (long long)nz * nr, tplane = (long long)nphi * pr;
+    int rc;
+    if (tm_in_ptr != d_in) {
+        if ((rc = make_cols_maps(&tm_in, d_in, Nz, 1, nr, nz, Sphi, 8ull * nr, 8ull * uplane, pipe_B_sharded(Nz)))) return rc;
+        tm_in_ptr = d_in;
+    }
+    {   // z forward straight from the caller's slab, transposing into the pencil buffers T_q[z slot & (Sz-1)][phi][r]
+        ColsPipeArgs p{};
+        p.out = nullptr; p.nvalid = nz; p.nb = nr; p.no = Sphi; p.taxis = 1; p.reverse = 0; p.scale = dz * slz;
+        p.SN = tz.SN; p.WM = tz.WM;
+        OutShard om{};
+        for (int q = 0; q < nranks; q++) om.base[q] = reinterpret_cast<double*>(static_cast<char*>(peer_block[q]) + off_T);
+        om.logS = ilog2i(Sz); om.maskS = Sz - 1; om.sj = tplane; om.so = pr; om.o_off = phi_first;
+        FDMB_CUDA(launch_cols_pipe_shard(Nz, kzf, tm_in, p, om, st, "cyl_z_fwd_xpose"));
+    }
+    if ((rc = barrier(st))) return rc;
+    double* t_loc = d_T + (size_t)(z_first + J0 - rank * Sz) * nphi * pr;
+    {   // phi forward on the local pencils (in place)
+        ColsPipeArgs p{};
+        p.out = t_loc; p.out_sj = pr; p.out_so = tplane; p.nvalid = nphi; p.nb = nr; p.no = nzl; p.taxis = 1;
+        p.reverse = 0; p.scale = dphi * SQRT_M_1_PI; p.SN = tphi.SN; p.WM = tphi.WM;
+        FDMB_CUDA(launch_cols_pipe(nphi, XF_PFWD, tm_tphi_l, p, st, "cyl_phi_fwd"));
+    }
+    if (!preload_only()) {   // tridiagonal solves along r; rows are (z slot, phi mode) pairs here
+        TridiagArgs t{};
+        t.data = t_loc; t.pitch = pr; t.nr = nr; t.nmid = nphi; t.nsys = (long long)nzl * nphi; t.swap = 1;
+        t.lm_outer = d_lmphi; t.lm_mid = d_lmz; t.mid0 = z_first + J0; t.c0 = -2 / (dr * dr);
+        t.L = d_L; t.U = d_U; t.ir2 = d_ir2;
+        FDMB_CUDA(launch_tridiag_rows(t, st, "cyl_r_tridiag"));
+    }
+    {   // phi inverse, stores scattered back into the peers' slabs A_q[phi & (Sphi-1)][z][r]
+        ColsPipeArgs p{};
+        p.out = nullptr; p.nvalid = nphi; p.nb = nr; p.no = nzl; p.taxis = 1; p.reverse = 0; p.scale = SQRT_M_1_PI;
+        p.SN = tphi.SN; p.WM = tphi.WM;
+        OutShard om{};
+        for (int q = 0; q < nranks; q++) om.base[q] = reinterpret_cast<double*>(peer_block[q]);
+        om.logS = ilog2i(Sphi); om.maskS = Sphi - 1; om.sj = wplane; om.so = pr; om.o_off = z_first;
+        FDMB_CUDA(launch_cols_pipe_shard(nphi, XF_PINV, tm_tphi, p, om, st, "cyl_phi_inv_xpose"));
+    }
+    if ((rc = barrier(st))) return rc;
+    {   // z inverse on the slab, written to the caller's array
+        ColsPipeArgs p{};
+        p.out = d_out; p.out_sj = nr; p.out_so = uplane; p.nvalid = nz; p.nb = nr; p.no = Sphi; p.taxis = 1;
+        p.reverse = 0; p.scale = slz; p.SN = tz.SN; p.WM = tz.WM;
+        FDMB_CUDA(launch_cols_pipe(Nz, kzi, tm_za, p, st, "cyl_z_inv"));
+    }
+    return FDMB_OK;
+}
+
 fdmb_lapl_cyl::~fdmb_lapl_cyl()
 {
     cudaFree(d_lmphi); cudaFree(d_lmz); cudaFree(d_L); cudaFree(d_U); cudaFree(d_ir2);
-    cudaFree(d_work); cudaFree(d_rhs); cudaFree(d_ans);
+    if (nranks > 1) {
+        for (int q = 0; q < nranks; q++)
+            if (q != rank && peer_ipc[q] && peer_block[q]) cudaIpcCloseMemHandle(peer_block[q]);
+        cudaFree(mg_block);
+    } else {
+        cudaFree(d_work);
+    }
+    cudaFree(d_rhs); cudaFree(d_ans);
     if (stream) cudaStreamDestroy(stream);
 }
 
 int fdmb_lapl_cyl::solve_device(double* d_out, const double* d_in, cudaStream_t st)
 {
+    if (nranks > 1) return solve_device_sharded(d_out, d_in, st);
     const double SQRT_M_1_PI = 0.56418958354775629;   // lapl_cyl.h:175
     const long long wplane = (long long)nz * pr;      // work-array stride between phi planes
     const long long uplane = (long long)nz * nr;      // caller-array stride between phi planes
@@ -229,7 +368,7 @@ int fdmb_lapl_cyl::solve_device(double* d_out, const double* d_in, cudaStream_t 
 
 int fdmb_lapl_cyl::solve_host(double* ans, const double* rhs)
 {
-    const size_t bytes = sizeof(double) * (size_t)nr * nz * nphi;
+    const size_t bytes = sizeof(double) * (size_t)nr * nz * (nranks > 1 ? Sphi : nphi);   // this rank's slab
     if (!d_rhs) FDMB_CUDA(cudaMalloc(&d_rhs, bytes));
     if (!d_ans) FDMB_CUDA(cudaMalloc(&d_ans, bytes));
     FDMB_CUDA(cudaMemcpyAsync(d_rhs, rhs, bytes, cudaMemcpyHostToDevice, stream));
@@ -238,6 +377,18 @@ int fdmb_lapl_cyl::solve_host(double* ans, const double* rhs)
     FDMB_CUDA(cudaMemcpyAsync(ans, d_ans, bytes, cudaMemcpyDeviceToHost, stream));
     FDMB_CUDA(cudaStreamSynchronize(stream));
     return FDMB_OK;
+}
+
+// runs `body` with the handle's device current (several ranks may share one process)
+template <typename Fn> static int cyl_on_device(fdmb_lapl_cyl* h, Fn body)
+{
+    if (h->nranks < 2) return body();
+    int cur = 0;
+    FDMB_CUDA(cudaGetDevice(&cur));
+    if (cur != h->device) FDMB_CUDA(cudaSetDevice(h->device));
+    int rc = body();
+    if (cur != h->device) cudaSetDevice(cur);
+    return rc;
 }
 
 extern "C" {
@@ -257,16 +408,96 @@ int fdmb_lapl_cyl_create(fdmb_lapl_cyl** out, double dr, double dz, double r0, d
     return FDMB_OK;
 }
 
+int fdmb_lapl_cyl_create_sharded(fdmb_lapl_cyl** out, double dr, double dz, double r0, double lr, double lz, int nr, int nz,
+                                 int nphi, int zperiodic, int rank, int nranks)
+{
+    if (!out) { set_error("null handle pointer"); return FDMB_ERR_INVALID; }
+    *out = nullptr;
+    auto* h = new (std::nothrow) fdmb_lapl_cyl();
+    if (!h) { set_error("out of host memory"); return FDMB_ERR_NOMEM; }
+    h->dr = dr; h->dz = dz; h->r0 = r0; h->lr = lr; h->lz = lz;
+    h->nr = nr; h->nz = nz; h->nphi = nphi; h->zperiodic = zperiodic ? 1 : 0;
+    h->rank = rank; h->nranks = nranks;
+    int rc = h->init();
+    if (rc) { delete h; return rc; }
+    *out = h;
+    return FDMB_OK;
+}
+
+int fdmb_lapl_cyl_local_slab(fdmb_lapl_cyl* h, int* phi_first, int* nphi_local)
+{
+    if (!h || !phi_first || !nphi_local) { set_error("null argument"); return FDMB_ERR_INVALID; }
+    *phi_first = h->nranks > 1 ? h->phi_first : 0;
+    *nphi_local = h->nranks > 1 ? h->Sphi : h->nphi;
+    return FDMB_OK;
+}
+
+int fdmb_lapl_cyl_export_ipc(fdmb_lapl_cyl* h, void* handle)
+{
+    if (!h || !handle || h->nranks < 2) { set_error("export_ipc needs a sharded handle"); return FDMB_ERR_INVALID; }
+    cudaIpcMemHandle_t ih;
+    FDMB_CUDA(cudaIpcGetMemHandle(&ih, h->mg_block));
+    memcpy(handle, &ih, sizeof(ih));
+    return FDMB_OK;
+}
+
+int fdmb_lapl_cyl_attach_ipc(fdmb_lapl_cyl* h, const void* handles)
+{
+    if (!h || !handles || h->nranks < 2) { set_error("attach_ipc needs a sharded handle"); return FDMB_ERR_INVALID; }
+    for (int q = 0; q < h->nranks; q++) {
+        if (q == h->rank) continue;
+        cudaIpcMemHandle_t ih;
+        memcpy(&ih, (const char*)handles + (size_t)q * FDMB_IPC_HANDLE_BYTES, sizeof(ih));
+        cudaError_t e = cudaIpcOpenMemHandle(&h->peer_block[q], ih, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            set_error("cudaIpcOpenMemHandle for rank %d failed: %s", q, cudaGetErrorString(e));
+            return FDMB_ERR_COMM;
+        }
+        h->peer_ipc[q] = true;
+    }
+    h->attached = true;
+    return FDMB_OK;
+}
+
+int fdmb_lapl_cyl_attach_local(fdmb_lapl_cyl* h, fdmb_lapl_cyl* const* all)
+{
+    if (!h || !all || h->nranks < 2) { set_error("attach_local needs a sharded handle"); return FDMB_ERR_INVALID; }
+    int cur = 0;
+    FDMB_CUDA(cudaGetDevice(&cur));
+    FDMB_CUDA(cudaSetDevice(h->device));
+    for (int q = 0; q < h->nranks; q++) {
+        if (q == h->rank) continue;
+        if (!all[q] || all[q]->nranks != h->nranks || all[q]->rank != q || all[q]->mg_bytes != h->mg_bytes) {
+            set_error("attach_local: handle %d does not belong to this sharded solve", q);
+            cudaSetDevice(cur);
+            return FDMB_ERR_INVALID;
+        }
+        if (all[q]->device != h->device) {
+            cudaError_t e = cudaDeviceEnablePeerAccess(all[q]->device, 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+            else if (e != cudaSuccess) {
+                set_error("cudaDeviceEnablePeerAccess(%d -> %d) failed: %s", h->device, all[q]->device, cudaGetErrorString(e));
+                cudaSetDevice(cur);
+                return FDMB_ERR_COMM;
+            }
+        }
+        h->peer_block[q] = all[q]->mg_block;
+    }
+    FDMB_CUDA(cudaSetDevice(cur));
+    h->attached = true;
+    return FDMB_OK;
+}
+
 int fdmb_lapl_cyl_solve(fdmb_lapl_cyl* h, double* ans, const double* rhs)
 {
     if (!h || !ans || !rhs) { set_error("null argument"); return FDMB_ERR_INVALID; }
-    return h->solve_host(ans, rhs);
+    return cyl_on_device(h, [&] { return h->solve_host(ans, rhs); });
 }
 
 int fdmb_lapl_cyl_solve_device(fdmb_lapl_cyl* h, double* d_ans, const double* d_rhs, void* stream)
 {
     if (!h || !d_ans || !d_rhs) { set_error("null argument"); return FDMB_ERR_INVALID; }
-    return h->solve_device(d_ans, d_rhs, stream ? (cudaStream_t)stream : h->stream);
+    return cyl_on_device(h, [&] { return h->solve_device(d_ans, d_rhs, stream ? (cudaStream_t)stream : h->stream); });
 }
 
 int fdmb_lapl_cyl_destroy(fdmb_lapl_cyl* h)

@@ -12,6 +12,8 @@ struct TridiagArgs {
     const double* lm_outer;   // eigenvalue by outer index (phi mode), scaled by ir2[j]
     const double* lm_mid;     // eigenvalue by mid index (z mode), offset by mid0
     int mid0;
+    int swap;                 // 1: rows are (z slot, phi mode) pairs instead: lm_outer is read with `mid`, lm_mid with
+                              //    `outer + mid0` (the pencil layout of the multi-GPU solve)
     double c0;                // -2/dr^2
     const double* L;          // L[j], U[j], ir2[j], j = 1..nr
     const double* U;
@@ -36,6 +38,25 @@ struct fdmb_lapl_cyl {
     bool pipe_z = false, pipe_phi = false;
     fdmb::ColsMaps tm_z{}, tm_phi{}, tm_in{};
     const void* tm_in_ptr = nullptr;
+
+    // ---- phi-slab sharding over `nranks` GPUs.  Rank r owns phi in [r*Sphi, (r+1)*Sphi) of the caller's
+    // arrays and, between the two transposes, the z slots [r*Sz, (r+1)*Sz) for ALL phi (pencil buffer T).  The sweep
+    // order is z forward -> (transpose) -> phi forward, r tridiagonals, phi inverse -> (transpose) -> z inverse; the
+    // axis transforms commute, so the result differs from the reference's phi,z,r,z,phi order by round-off only.
+    int rank = 0, nranks = 1, device = 0;
+    int Sphi = 0, Sz = 0, phi_first = 0, z_first = 0, nzl = 0;
+    void* mg_block = nullptr;                 // [slab A | pencils T | flags]
+    size_t off_T = 0, off_flags = 0, mg_bytes = 0;
+    double *d_A = nullptr, *d_T = nullptr;
+    void* peer_block[fdmb::FDMB_MAX_RANKS] = {};
+    bool peer_ipc[fdmb::FDMB_MAX_RANKS] = {};
+    bool attached = false;
+    unsigned long long epoch = 0;
+    fdmb::ColsMaps tm_tphi{}, tm_tphi_l{}, tm_za{};   // phi sweeps over the local pencils (wide tiles for the transposing
+                                                      // one, normal tiles for the local one), z inverse over the slab
+    int init_sharded();
+    int solve_device_sharded(double* d_out, const double* d_in, cudaStream_t st);
+    int barrier(cudaStream_t st);
 
     int init();
     int solve_device(double* d_out, const double* d_in, cudaStream_t st);

@@ -142,6 +142,16 @@ int fdmb_lapl_cyl_create(fdmb_lapl_cyl** h, double dr, double dz, double r0, dou
 int fdmb_lapl_cyl_solve(fdmb_lapl_cyl* h, double* ans, const double* rhs);
 int fdmb_lapl_cyl_solve_device(fdmb_lapl_cyl* h, double* d_ans, const double* d_rhs, void* stream);
 int fdmb_lapl_cyl_destroy(fdmb_lapl_cyl* h);
+/* LaplCyl3FFT2 over 2, 4 or 8 GPUs of one node: phi-slabs (rank r owns phi in [r*nphi/P, (r+1)*nphi/P) of the
+ * arrays); the commuting axis transforms are reordered to z, (transpose), phi, r, phi, (transpose), z so that only two
+ * NVLink transposes are needed; both are peer stores fused into the sweeps.  Needs nphi and the z
+ * transform length >= 32, an even nr and 16-byte aligned slabs.  create/attach/solve are collective.        */
+int fdmb_lapl_cyl_create_sharded(fdmb_lapl_cyl** h, double dr, double dz, double r0, double lr, double lz,
+                                 int nr, int nz, int nphi, int zperiodic, int rank, int nranks);
+int fdmb_lapl_cyl_local_slab(fdmb_lapl_cyl* h, int* phi_first, int* nphi_local);
+int fdmb_lapl_cyl_export_ipc(fdmb_lapl_cyl* h, void* handle);
+int fdmb_lapl_cyl_attach_ipc(fdmb_lapl_cyl* h, const void* handles);
+int fdmb_lapl_cyl_attach_local(fdmb_lapl_cyl* h, fdmb_lapl_cyl* const* all);
 
 /* ---- NSCube ---------------------------------------------------------------------
  * Replaces fdm::NSCube<double,check> (src/ns_cube.h:13-92, src/ns_cube.cpp:27-277).
