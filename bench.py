@@ -47,7 +47,20 @@ WORKLOADS = {
                                                 "(BASELINE configs[4]; z-slab decomposed over the ranks when N>1)"),
     "nscube31": dict(kind="ns", n=31, Re=250.0, dt=0.01, label="NSCube 31^3 Re=250 dt=0.01 step (configs[0])"),
     "nscube255": dict(kind="ns", n=255, Re=1000.0, dt=0.005, label="NSCube 255^3 Re=1000 dt=0.005 step (configs[2])"),
+    # cylindrical workloads (single GPU): nr x nz x nphi
+    "nscyl128": dict(kind="nscyl", n=128, nr=128, nz=127, nphi=128, Re=200.0, dt=0.01,
+                     label="NSCyl Taylor-Couette nr=128 nz=127 nphi=128 Re=200 dt=0.01 step (configs[3])"),
+    "cyl128": dict(kind="cyl", n=128, nr=128, nz=127, nphi=128,
+                   label="LaplCyl3FFT2 Dirichlet-z solve nr=128 nz=127 nphi=128 (the pressure solve of configs[3])"),
 }
+
+
+def cyl_geometry(wl):
+    import math
+    # the solver NSCyl builds for itself: src/ns_cyl.h:94-97 with the README box R = pi, r = pi/2, h = 10
+    R, r0, h = math.pi, math.pi / 2, 10.0
+    dr = (R - r0) / wl["nr"]; dz = h / wl["nz"]
+    return (dr, dz, r0 - dr / 2, R - r0 + dr, h + dz, wl["nr"], wl["nz"], wl["nphi"])
 
 
 def measured_peaks():
@@ -137,6 +150,20 @@ def run_reference(args, wl):
         units = nn ** 3 / 1e9
         metric, unit = "poisson_solve_gpts_per_s", "Gpts/s"
         sample = f"full {nn}^3 solve per step" + ("" if nn == n else f" (bounded sample of the {n}^3 workload; Gpts/s is size-normalised)")
+    elif wl["kind"] == "cyl":
+        S = ref.LaplCyl3FFT2(*cyl_geometry(wl))
+        shape = (wl["nphi"], wl["nz"], wl["nr"])
+        rhs = O.synthetic_rhs(shape, seed=1234)
+        step = lambda: S.solve(rhs)
+        units = shape[0] * shape[1] * shape[2] / 1e9
+        metric, unit = "poisson_solve_gpts_per_s", "Gpts/s"
+        sample = "full solve per step"
+    elif wl["kind"] == "nscyl":
+        ns = ref.NSCyl(nr=wl["nr"], nz=wl["nz"], nphi=wl["nphi"], Re=wl["Re"], dt=wl["dt"])
+        step = lambda: ns.step(1)
+        units = 1.0
+        metric, unit = "ns_steps_per_s", "steps/s"
+        sample = "full step per step"
     else:
         ns = ref.NSCube(nx=n, nz=n, Re=wl["Re"], dt=wl["dt"])
         step = lambda: ns.step(1)
@@ -181,6 +208,22 @@ def cpu_baseline(wl):
                 t0 = time.perf_counter(); S.solve(rhs); best = min(best, time.perf_counter() - t0)
             return {"value": nn ** 3 / 1e9 / best, "unit": "Gpts/s", "cores": cores, "kind": "reference",
                     "sample": f"best of {reps} full {nn}^3 solves, {best * 1e3:.1f} ms each"}
+        if wl["kind"] == "cyl":
+            S = ref.LaplCyl3FFT2(*cyl_geometry(wl))
+            shape = (wl["nphi"], wl["nz"], wl["nr"])
+            rhs = O.synthetic_rhs(shape, seed=1234)
+            S.solve(rhs)
+            best = 1e30
+            for _ in range(5):
+                t0 = time.perf_counter(); S.solve(rhs); best = min(best, time.perf_counter() - t0)
+            return {"value": rhs.size / 1e9 / best, "unit": "Gpts/s", "cores": cores, "kind": "reference",
+                    "sample": f"best of 5 full solves, {best * 1e3:.1f} ms each"}
+        if wl["kind"] == "nscyl":
+            ns = ref.NSCyl(nr=wl["nr"], nz=wl["nz"], nphi=wl["nphi"], Re=wl["Re"], dt=wl["dt"])
+            ns.step(1)
+            t0 = time.perf_counter(); ns.step(5); dt = (time.perf_counter() - t0) / 5
+            return {"value": 1.0 / dt, "unit": "steps/s", "cores": cores, "kind": "reference",
+                    "sample": f"5 full steps, {dt * 1e3:.1f} ms each"}
         nn = min(n, 127)
         ns = ref.NSCube(nx=nn, nz=nn, Re=wl["Re"], dt=wl["dt"])
         ns.step(1)
@@ -272,6 +315,46 @@ def main():
             capi.check(L.fdmb_lapl_cube_solve(S._h, C.cast(h_ans.data_ptr(), dp), C.cast(h_rhs.data_ptr(), dp)), "solve")
         h2d = d2h = 8 * lpts
         pts_kernel = lpts
+    elif wl["kind"] in ("cyl", "nscyl"):
+        if world > 1:
+            raise SystemExit("the cylindrical bench workloads are single-GPU (the sharded LaplCyl3FFT2 is covered by tests)")
+        pts = lpts = wl["nr"] * wl["nz"] * wl["nphi"]
+        if wl["kind"] == "cyl":
+            S = fdm_b200.LaplCyl3FFT2(*cyl_geometry(wl))
+            pair_bytes = 2 * 8 * pts
+            nbuf = max(2, int(np.ceil(2.2 * 126e6 / pair_bytes)))
+            rhs = [torch.rand(pts, dtype=torch.float64, device=dev) - 0.5 for _ in range(nbuf)]
+            ans = [torch.empty(pts, dtype=torch.float64, device=dev) for _ in range(nbuf)]
+            l2_policy = f"rotating {nbuf} rhs/ans pairs ({nbuf * pair_bytes / 1e6:.0f} MB > 126 MB L2)"
+
+            def step(i):
+                S.solve_device(ans[i % nbuf].data_ptr(), rhs[i % nbuf].data_ptr(), sptr)
+            units_per_step = pts / 1e9
+            metric, unit = "poisson_solve_gpts_per_s", "Gpts/s"
+            algo_bytes_step = SOLVE_BYTES_PER_PT * pts
+            h_rhs = torch.rand(pts, dtype=torch.float64).pin_memory()
+            h_ans = torch.empty(pts, dtype=torch.float64).pin_memory()
+            dp = C.POINTER(C.c_double)
+
+            def e2e_step():
+                capi.check(L.fdmb_lapl_cyl_solve(S._h, C.cast(h_ans.data_ptr(), dp), C.cast(h_rhs.data_ptr(), dp)), "solve")
+            h2d = d2h = 8 * pts
+        else:
+            kw = dict(nr=wl["nr"], nz=wl["nz"], nphi=wl["nphi"], Re=wl["Re"], dt=wl["dt"])
+            ns = fdm_b200.NSCyl(**kw)
+            l2_policy = f"state of 13 arrays = {13 * 8 * pts / 1e6:.0f} MB > 126 MB L2"
+
+            def step(i):
+                ns.step_device(1, sptr)
+            units_per_step = 1.0
+            metric, unit = "ns_steps_per_s", "steps/s"
+            algo_bytes_step = NS_BYTES_PER_PT * pts
+            ns2 = fdm_b200.NSCyl(**kw)
+
+            def e2e_step():
+                ns2.step_host_roundtrip()
+            h2d = d2h = ns2.state_bytes()
+        pts_kernel = pts
     else:
         if not hasattr(fdm_b200, "NSCube"):
             raise SystemExit("NSCube workload not built")
@@ -400,7 +483,8 @@ def main():
 
 def kernel_sweeps(tag):
     """How many read+write sweeps over the grid one launch of this kernel stands for."""
-    return {"ns_fgh": 3.0, "ns_rhs": 2.0, "ns_fgh_rhs": 3.5, "ns_update": 4.0}.get(tag, 1.0)
+    return {"ns_fgh": 3.0, "ns_rhs": 2.0, "ns_fgh_rhs": 3.5, "ns_update": 4.0,
+            "nscyl_fgh": 3.0, "nscyl_lfgh": 4.5, "nscyl_rhs": 2.0, "nscyl_update": 4.0}.get(tag, 1.0)
 
 
 def load_traffic(tag, workload):

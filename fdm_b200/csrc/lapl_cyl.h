@@ -18,8 +18,12 @@ struct TridiagArgs {
     const double* L;          // L[j], U[j], ir2[j], j = 1..nr
     const double* U;
     const double* ir2;
+    double* piv;              // optional [nr][nsys] reciprocal pivots (j-major: coalesced over systems), filled once by
+                              // launch_tridiag_pivots; takes the divisions out of the per-solve recurrence
 };
 cudaError_t launch_tridiag_rows(const TridiagArgs& a, cudaStream_t st, const char* tag);
+cudaError_t launch_tridiag_pivots(const TridiagArgs& a, cudaStream_t st);
+cudaError_t prepare_tridiag_rows(int nr);
 size_t tridiag_rows_smem(int nr);
 }  // namespace fdmb
 
@@ -34,6 +38,7 @@ struct fdmb_lapl_cyl {
     double *d_lmphi = nullptr, *d_lmz = nullptr;   // eigenvalues (lapl_cyl.cpp:132-141)
     double *d_L = nullptr, *d_U = nullptr, *d_ir2 = nullptr;   // r-dependent matrix entries (lapl_cyl.cpp:151-159)
     double* d_work = nullptr;
+    double* d_piv = nullptr;           // reciprocal pivots of every (phi mode, z mode) system, 8 B per grid point
     double *d_rhs = nullptr, *d_ans = nullptr;
     bool pipe_z = false, pipe_phi = false;
     fdmb::ColsMaps tm_z{}, tm_phi{}, tm_in{};

@@ -103,6 +103,19 @@ class NSCyl:
     def state_bytes(self):
         return 8 * self.size()
 
+    def step_host_roundtrip(self):
+        """One step the way a host-resident caller sees it: upload u,v,w,p from pinned host memory, step,
+        download u,v,w,p (what the reference keeps in ns.u.vec ...)."""
+        import torch
+        if getattr(self, "_pinned", None) is None:
+            self._pinned = {f: torch.from_numpy(self.field(f)).pin_memory() for f in "uvwp"}
+        L = capi.lib()
+        for f, t in self._pinned.items():
+            capi.check(L.fdmb_ns_cyl_set_field(self._h, FIELD_IDS[f], C.cast(t.data_ptr(), capi.dp)), "set_field")
+        self.step(1)
+        for f, t in self._pinned.items():
+            capi.check(L.fdmb_ns_cyl_get_field(self._h, FIELD_IDS[f], C.cast(t.data_ptr(), capi.dp)), "get_field")
+
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
             capi.lib().fdmb_ns_cyl_destroy(self._h)
