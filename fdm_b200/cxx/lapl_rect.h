@@ -13,6 +13,10 @@
 
 #include "lapl_cube.h"     // tensor / compat tensor, FDMB_VERIFY
 
+#if __has_include("asp_misc.h")
+#include "asp_misc.h"      // the reference header includes it; its callers use asp::sq, asp::format through it
+#endif
+
 namespace fdm {
 
 template <typename T, bool check, typename F = tensor_flags<>>

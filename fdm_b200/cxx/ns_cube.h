@@ -10,7 +10,9 @@
 // exactly what the reference's callers can observe.  Long runs switch it off and call
 // sync_to_host() before they look (plot interval), or sync_to_device() after they wrote a field.
 #pragma once
+#include <chrono>
 #include <cmath>
+#include <string>
 #include <vector>
 
 #if __has_include("config.h")
@@ -19,6 +21,7 @@
 #include "fdm_compat_config.h"
 #endif
 #include "lapl_cube.h"
+#include "lapl_rect.h"     // the reference's ns_cube.h includes it (src/ns_cube.h:9); velocity_plot.h users rely on that
 
 namespace fdm {
 

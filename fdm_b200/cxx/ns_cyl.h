@@ -9,8 +9,12 @@
 // vrandom = 1 seeds v exactly like the reference (default-seeded std::default_random_engine, loop order
 // of src/ns_cyl.h:99-108), on the host, and uploads it.
 #pragma once
+// (the system headers the reference's ns_cyl.h pulls in: its callers rely on them transitively)
+#include <chrono>
+#include <climits>
 #include <cmath>
 #include <random>
+#include <string>
 #include <vector>
 
 #if __has_include("config.h")
@@ -19,6 +23,10 @@
 #include "fdm_compat_config.h"
 #endif
 #include "lapl_cyl.h"
+
+#if __has_include("asp_misc.h")
+#include "asp_misc.h"      // the reference header includes it; its callers use asp::sq, asp::format through it
+#endif
 
 namespace fdm {
 

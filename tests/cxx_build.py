@@ -22,3 +22,54 @@ def build(out, with_reference_headers=False):
         cmd += ["-L" + LIBDIR, "-lfdm_b200", "-Wl,-rpath," + LIBDIR]
     subprocess.run(cmd, check=True)
     return out
+
+
+REPLACED = ("lapl_cube.h", "lapl_rect.h", "lapl_cyl.h", "ns_cube.h", "ns_cyl.h")
+
+
+def make_overlay(dst):
+    """The reference's src/ with the five class headers REPLACED by the drop-in ones (what a maintainer does; an extra
+    include directory is not enough, because a quoted #include from a reference header looks in its own directory
+    first).  Everything else, and test/*.cpp, are symlinks to the untouched reference files."""
+    ref = "/root/reference"
+    os.makedirs(os.path.join(dst, "src"), exist_ok=True)
+    os.makedirs(os.path.join(dst, "test"), exist_ok=True)
+    for name in os.listdir(os.path.join(ref, "src")):
+        tgt = os.path.join(dst, "src", name)
+        if name in REPLACED:
+            src = os.path.join(ROOT, "fdm_b200", "cxx", name)
+        else:
+            src = os.path.join(ref, "src", name)
+        if not os.path.lexists(tgt):
+            os.symlink(src, tgt)
+    for name in os.listdir(os.path.join(ref, "test")):
+        tgt = os.path.join(dst, "test", name)
+        if not os.path.lexists(tgt):
+            os.symlink(os.path.join(ref, "test", name), tgt)
+    return dst
+
+
+def compile_in_overlay(overlay, rel, out):
+    """Compile an UNMODIFIED reference translation unit (path relative to the overlay) against the drop-in headers."""
+    cmd = ["/usr/bin/g++", "-std=c++20", "-O1", "-c", "-I" + os.path.join(ROOT, "include"),
+           "-I" + os.path.join(overlay, "src"), "-I" + os.path.join(ROOT, "oracle", "stub"), "-include", "cmath",
+           os.path.join(overlay, rel), "-o", out]
+    subprocess.run(cmd, check=True, capture_output=True, text=True)
+    return out
+
+
+DRIVER = os.path.join(ROOT, "tests", "cxx", "_build", "fdm_ns_cube")
+
+
+def build_reference_driver(overlay, out=DRIVER):
+    """The reference's OWN driver executable fdm_ns_cube (test/test_ns_cube.cpp + src/velocity_plot.cpp + src/config.cpp
+    + src/asp_misc.cpp, all unmodified) built against the replaced class headers and linked with libfdm_b200.so.
+    plot() needs plplot, which is absent: its symbols stay unresolved and the driver is run with --plot:png=0."""
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    srcs = [os.path.join(overlay, p) for p in ("test/test_ns_cube.cpp", "src/velocity_plot.cpp", "src/config.cpp",
+                                               "src/asp_misc.cpp")]
+    cmd = ["/usr/bin/g++", "-std=c++20", "-O2", "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(overlay, "src"),
+           "-I" + os.path.join(ROOT, "oracle", "stub"), "-include", "cmath", *srcs, "-o", out,
+           "-L" + LIBDIR, "-lfdm_b200", "-Wl,-rpath,$ORIGIN/../../../fdm_b200", "-Wl,--unresolved-symbols=ignore-all"]
+    subprocess.run(cmd, check=True, capture_output=True, text=True)
+    return out

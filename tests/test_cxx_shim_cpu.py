@@ -31,3 +31,20 @@ def test_shim_aborts_without_device(tmp_path):
     r = subprocess.run([exe, "cube", "15", str(rhs), str(tmp_path / "ans.bin")], capture_output=True, text=True)
     assert r.returncode == -signal.SIGABRT
     assert "verify(" in r.stderr
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="reference tree not present")
+@pytest.mark.parametrize("unit", ["src/velocity_plot.cpp", "test/test_ns_cube.cpp", "test/test_ns_cyl_spectral.cpp",
+                                  "test/nbody.cpp"])
+def test_reference_callers_compile_unchanged(tmp_path, unit):
+    """the callers either side of the path -- the slice plotter / VTK writer, the two drivers and the PM
+    N-body step -- compile UNMODIFIED once the five class headers in src/ are replaced by the drop-in ones."""
+    ov = cxx_build.make_overlay(str(tmp_path / "overlay"))
+    cxx_build.compile_in_overlay(ov, unit, str(tmp_path / "unit.o"))
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="reference tree not present")
+def test_reference_driver_links_against_the_library(tmp_path):
+    ov = cxx_build.make_overlay(str(tmp_path / "overlay"))
+    exe = cxx_build.build_reference_driver(ov, str(tmp_path / "fdm_ns_cube"))
+    assert os.access(exe, os.X_OK)

@@ -103,3 +103,37 @@ def test_cxx_ns_cyl(exe, tmp_path, ref, lsteps):
     got = np.concatenate([np.fromfile(tmp_path / f"nc_{f}.bin") for f in "uvwp"])
     want = np.concatenate([po.field(f).ravel() for f in "uvwp"])
     assert O.rel_l2(got, want) < 1e-12
+
+
+def test_reference_driver_fdm_ns_cube_on_the_gpu_path(tmp_path, ref):
+    """The reference's own driver (test/test_ns_cube.cpp, unmodified; built by __graft_entry__.build() where the
+    reference tree exists) runs the README cavity case on the B200 path and writes its VTK files through the
+    unmodified velocity_plotter::vtk_out; the cell-centred velocities must equal the compiled reference's."""
+    import os
+    exe = cxx_build.DRIVER
+    if not os.path.exists(exe):
+        if not os.path.isdir("/root/reference/src"):
+            pytest.skip("tests/cxx/_build/fdm_ns_cube not built (needs /root/reference at build time)")
+        cxx_build.build_reference_driver(cxx_build.make_overlay(str(tmp_path / "overlay")))
+    n, steps = 31, 20
+    r = subprocess.run([exe, f"--ns:nx={n}", f"--ns:nz={n}", "--ns:Re=250", "--ns:dt=0.01", f"--ns:steps={steps}",
+                        "--plot:png=0", "--plot:vtk=1", "--plot:interval=10"], cwd=tmp_path, capture_output=True,
+                       text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-1000:] + r.stderr[-1000:]
+    assert "It took me" in r.stdout
+    R = ref.NSCube(nx=n, nz=n, Re=250.0, dt=0.01)
+    for step in (0, 10, 20):
+        if step:
+            R.step(10)
+        lines = (tmp_path / f"step_{step:07d}.vtk").read_text().splitlines()
+        assert lines[1] == f"step {step}" and lines[3] == "DATASET STRUCTURED_POINTS"
+        k = lines.index("VECTORS u double")
+        got = np.array([[float(x) for x in ln.split()] for ln in lines[k + 1:k + 1 + n ** 3]])
+        u = R.field("u").reshape(n + 2, n + 2, n + 3); v = R.field("v").reshape(n + 2, n + 3, n + 2)
+        w = R.field("w").reshape(n + 3, n + 2, n + 2)
+        # src/velocity_plot.cpp:205-215: i,k,j = 1..n; u index j -> j+1, v index k -> k+1, w index i -> i+1
+        uc = 0.5 * (u[1:n + 1, 1:n + 1, 2:n + 2] + u[1:n + 1, 1:n + 1, 1:n + 1])
+        vc = 0.5 * (v[1:n + 1, 2:n + 2, 1:n + 1] + v[1:n + 1, 1:n + 1, 1:n + 1])
+        wc = 0.5 * (w[2:n + 2, 1:n + 1, 1:n + 1] + w[1:n + 1, 1:n + 1, 1:n + 1])
+        want = np.stack([uc.ravel(), vc.ravel(), wc.ravel()], axis=1)
+        assert np.max(np.abs(got - want)) < 1.5e-6        # "%f": six decimals
