@@ -396,11 +396,21 @@ def main():
     barrier()
     launches = L.fdmb_launch_count() - launches0
     ms = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
+    # nvidia-smi samples every 100 ms: a timed region shorter than ~0.5 s is followed by an UNTIMED tail of the same
+    # steps (every rank runs it: the sharded steps are collective) so that the clocks are sampled under this load
+    tail = 0
+    if ms < 500.0:
+        tail = int(500.0 / max(ms / K, 1e-3)) + 1
+        for i in range(tail):
+            step(W + K + i)
+        barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    if clocks is not None:
+        clocks["window"] = "timed region" if tail == 0 else f"timed region + {tail} identical untimed steps"
     value = units_per_step * K * world / (ms * 1e-3)
 
     # ---- per-kernel live timing for the roofline (separate pass, same steps) -----

@@ -17,6 +17,8 @@
 #include <random>
 #include <vector>
 
+#include <cstring>
+
 #include "common.h"
 #include "lapl_cyl.h"
 
@@ -25,16 +27,18 @@ namespace fdmb {
 // offset-indexed 3-D view [phi][z][r], row-major, last index fastest (src/tensor.h:207-219)
 struct CFld {
     double* p;
-    int lz, lr;           // lowest z / r index
+    int li, lz, lr;       // lowest phi / z / r index (li != 0: a rank's window of a sharded run, indexed globally;
+                          // phi = -1 and phi = nphi are the wrap-around halo planes there)
     long long sp, sz;     // strides (doubles) of the phi and z axes
     __host__ __device__ __forceinline__ double& at(int i, int k, int j) const
     {
-        return p[(long long)i * sp + (long long)(k - lz) * sz + (j - lr)];
+        return p[(long long)(i - li) * sp + (long long)(k - lz) * sz + (j - lr)];
     }
 };
 
 struct CylGeom {
     int nr, nz, nphi;
+    int wrap;                       // 1: phi neighbours wrap inside the array (one GPU); 0: halo planes hold them
     int zper;                       // z periodic?
     int z_, z0, z1, zn, znn;        // ns_cyl.h:71-75
     double U0, dt;
@@ -54,10 +58,10 @@ struct CylGeom {
 
 // ---- init_bound (ns_cyl.cpp:81-172) --------------------------------------------------------------
 // r-direction ghosts of w, v, u (ns_cyl.cpp:83-104): one thread per (phi, z row)
-__global__ void k_cyl_bound_r(CFld u, CFld v, CFld w, CylGeom g)
+__global__ void k_cyl_bound_r(CFld u, CFld v, CFld w, CylGeom g, int i0)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x + g.z_;
-    const int i = blockIdx.y;
+    const int i = blockIdx.y + i0;
     if (k > g.znn) return;
     const int nr = g.nr;
     if (k >= g.z0) {
@@ -74,10 +78,10 @@ __global__ void k_cyl_bound_r(CFld u, CFld v, CFld w, CylGeom g)
 
 // z-direction ghosts, Dirichlet z only (ns_cyl.cpp:106-128).  The v mirror loops its r index over
 // z0..znn (ns_cyl.cpp:108) -- reproduced, clamped to the allocated r range.
-__global__ void k_cyl_bound_z(CFld u, CFld v, CFld w, CylGeom g, int jmax_v)
+__global__ void k_cyl_bound_z(CFld u, CFld v, CFld w, CylGeom g, int jmax_v, int i0)
 {
     const int j = blockIdx.x * blockDim.x + threadIdx.x - 1;   // -1 .. nr+1
-    const int i = blockIdx.y;
+    const int i = blockIdx.y + i0;
     const int nr = g.nr, nz = g.nz;
     if (j > nr + 1) return;
     if (j >= g.z0 && j <= jmax_v) {
@@ -93,10 +97,10 @@ __global__ void k_cyl_bound_z(CFld u, CFld v, CFld w, CylGeom g, int jmax_v)
 }
 
 // pressure ghosts (ns_cyl.cpp:132-171); blockIdx.z = 0: r faces, 1: z faces (Dirichlet z)
-__global__ void k_cyl_bound_p(CFld u, CFld v, CFld p, CylGeom g)
+__global__ void k_cyl_bound_p(CFld u, CFld v, CFld p, CylGeom g, int i0)
 {
     const int a = blockIdx.x * blockDim.x + threadIdx.x;
-    const int i = blockIdx.y;
+    const int i = blockIdx.y + i0;
     const int nr = g.nr, nz = g.nz;
     if (blockIdx.z == 0) {
         const int k = a + g.z1;
@@ -127,13 +131,13 @@ __device__ __forceinline__ double sq(double x) { return x * x; }
 //   G where j >= 1, H where k >= z1 and j >= 1.
 template <bool LIN>
 __global__ void __launch_bounds__(256)
-k_cyl_fgh(CFld u, CFld v, CFld w, CFld u0, CFld v0, CFld w0, CFld F, CFld G, CFld H, CylGeom g)
+k_cyl_fgh(CFld u, CFld v, CFld w, CFld u0, CFld v0, CFld w0, CFld F, CFld G, CFld H, CylGeom g, int i0)
 {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int k = blockIdx.y * blockDim.y + threadIdx.y + g.z0;
-    const int i = blockIdx.z;
+    const int i = blockIdx.z + i0;
     if (j > g.nr || k > g.zn) return;
-    const int ip = (i + 1 == g.nphi) ? 0 : i + 1, im = (i == 0) ? g.nphi - 1 : i - 1;
+    const int ip = (g.wrap && i + 1 == g.nphi) ? 0 : i + 1, im = (g.wrap && i == 0) ? g.nphi - 1 : i - 1;
     int kp = k + 1, km = k - 1;
     if (g.zper) { if (kp == g.nz) kp = 0; if (km < 0) km = g.nz - 1; }
 #define U(a, b, c) u.at(a, b, c)
@@ -251,13 +255,13 @@ k_cyl_fgh(CFld u, CFld v, CFld w, CFld u0, CFld v0, CFld w0, CFld F, CFld G, CFl
 }
 
 // ---- poisson RHS (ns_cyl.cpp:408-439) --------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_cyl_rhs(CFld F, CFld G, CFld H, CFld p, CFld R, CylGeom g)
+__global__ void __launch_bounds__(256) k_cyl_rhs(CFld F, CFld G, CFld H, CFld p, CFld R, CylGeom g, int i0)
 {
     const int j = blockIdx.x * blockDim.x + threadIdx.x + 1;
     const int k = blockIdx.y * blockDim.y + threadIdx.y + g.z1;
-    const int i = blockIdx.z;
+    const int i = blockIdx.z + i0;
     if (j > g.nr || k > g.zn) return;
-    const int im = (i == 0) ? g.nphi - 1 : i - 1;
+    const int im = (g.wrap && i == 0) ? g.nphi - 1 : i - 1;
     int km = k - 1;
     if (g.zper && km < 0) km = g.nz - 1;
     const double ir = g.cir[j];
@@ -273,13 +277,13 @@ __global__ void __launch_bounds__(256) k_cyl_rhs(CFld F, CFld G, CFld H, CFld p,
 
 // ---- update_uvwp (ns_cyl.cpp:445-484) --------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-k_cyl_update(CFld u, CFld v, CFld w, CFld p, CFld x, CFld F, CFld G, CFld H, CylGeom g)
+k_cyl_update(CFld u, CFld v, CFld w, CFld p, CFld x, CFld F, CFld G, CFld H, CylGeom g, int i0)
 {
     const int j = blockIdx.x * blockDim.x + threadIdx.x + 1;
     const int k = blockIdx.y * blockDim.y + threadIdx.y + g.z1;
-    const int i = blockIdx.z;
+    const int i = blockIdx.z + i0;
     if (j > g.nr || k > g.zn) return;
-    const int ip = (i + 1 == g.nphi) ? 0 : i + 1;
+    const int ip = (g.wrap && i + 1 == g.nphi) ? 0 : i + 1;
     const double xc = x.at(i, k, j);
     if (j < g.nr) u.at(i, k, j) = F.at(i, k, j) - g.dtdr * (x.at(i, k, j + 1) - xc);
     if (k < g.nz) {                                  // k = z1 .. nz-1 (ns_cyl.cpp:462)
@@ -291,65 +295,142 @@ k_cyl_update(CFld u, CFld v, CFld w, CFld p, CFld x, CFld F, CFld G, CFld H, Cyl
     p.at(i, k, j) = xc;                              // p = x over the index-range intersection (tensor.h:103-111)
 }
 
+// ---- halo pull: whole phi planes copied from the neighbours' windows (peer loads over NVLink) ---------
+constexpr int CYL_MAX_PULLS = 8;
+struct CylPullList {
+    const double* src[CYL_MAX_PULLS];
+    double* dst[CYL_MAX_PULLS];
+    long long n[CYL_MAX_PULLS];
+    int count;
+};
+__global__ void __launch_bounds__(256) k_cyl_pull(CylPullList pl)
+{
+    const int s = blockIdx.y;
+    if (s >= pl.count) return;
+    const double* __restrict__ src = pl.src[s];
+    double* __restrict__ dst = pl.dst[s];
+    const long long n = pl.n[s];
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x)
+        dst[e] = src[e];
+}
+
 }  // namespace fdmb
 
 using namespace fdmb;
+
+// phi planes of field `fld` (u v w p x F G H RHS u0 v0 w0) that rank `rank` of `nranks` HOLDS: its own planes
+// [rank*S, (rank+1)*S) plus the wrap-around halo planes its stencils read (phi = -1 and phi = nphi exist there)
+static void cyl_window(int fld, int nphi, int rank, int nranks, int* wlo, int* whi)
+{
+    if (nranks == 1) { *wlo = 0; *whi = nphi - 1; return; }
+    const int S = nphi / nranks, lo = rank * S, hi = lo + S - 1;
+    switch (fld) {
+    case 0: case 1: case 2: case 9: case 10: case 11: *wlo = lo - 1; *whi = hi + 1; break;   // u v w (u0 v0 w0): +-1
+    case 4: *wlo = lo; *whi = hi + 1; break;                                                  // x: update reads x[i+1]
+    case 7: *wlo = lo - 1; *whi = hi; break;                                                  // H: divergence reads H[i-1]
+    default: *wlo = lo; *whi = hi; break;                                                     // p F G RHS
+    }
+}
+
+struct CylLayout {
+    int wlo[12], whi[12];
+    int lz[12], lr[12];
+    long long sz[12], sp[12], count[12];
+    size_t off[12], bytes;
+};
+static void cyl_layout(int nr, int nz, int nphi, int zper, int rank, int nranks, CylLayout* L)
+{
+    const int z_ = zper ? 0 : -1, z0 = 0, z1 = zper ? 0 : 1, zn = zper ? nz - 1 : nz, znn = zper ? nz - 1 : nz + 1;
+    // extents: ns_cyl.h:80-93
+    const int Z0[12] = {z0, z_, z0, z0, z1, z1, z0, z1, z1, z0, z_, z0};
+    const int Z1[12] = {znn, znn, znn, znn, zn, zn, zn, zn, zn, znn, znn, znn};
+    const int R0[12] = {-1, 0, 0, 0, 1, 0, 1, 1, 1, -1, 0, 0};
+    const int R1[12] = {nr + 1, nr + 1, nr + 1, nr + 1, nr, nr, nr, nr, nr, nr + 1, nr + 1, nr + 1};
+    size_t o = 0;
+    for (int f = 0; f < 12; f++) {
+        cyl_window(f, nphi, rank, nranks, &L->wlo[f], &L->whi[f]);
+        L->lz[f] = Z0[f]; L->lr[f] = R0[f];
+        L->sz[f] = R1[f] - R0[f] + 1;
+        L->sp[f] = (long long)(Z1[f] - Z0[f] + 1) * L->sz[f];
+        L->count[f] = (long long)(L->whi[f] - L->wlo[f] + 1) * L->sp[f];
+        L->off[f] = o;
+        o += (sizeof(double) * (size_t)L->count[f] + 255) & ~(size_t)255;
+    }
+    L->bytes = o;
+}
 
 struct fdmb_ns_cyl {
     fdmb_ns_cyl_params prm{};
     int nr = 0, nz = 0, nphi = 0, zper = 0;
     double dr = 0, dz = 0, dphi = 0;
     CylGeom g{};
-    CFld f[12]{};               // u v w p x F G H RHS u0 v0 w0
-    long long count[12]{};
+    CFld f[12]{};               // u v w p x F G H RHS u0 v0 w0 (windows over the global arrays when sharded)
+    CylLayout lay{};
     double* d_tab = nullptr;    // r-dependent factor tables
     fdmb_lapl_cyl* lapl = nullptr;
     cudaStream_t stream = nullptr;
     long long time_index = 0;
+    // phi-slab sharding (nranks == 1: the windows are the whole arrays and phi wraps inside them)
+    int rank = 0, nranks = 1, plo = 0, phi = 0, device = 0;     // plo..phi: this rank's own phi planes
+    void* block = nullptr;                                        // all twelve windows in one allocation
+    void* peer_block[FDMB_MAX_RANKS] = {};
+    bool peer_ipc[FDMB_MAX_RANKS] = {};
+    bool attached = false;
 
     int init();
     int step(int nsteps, int linear, cudaStream_t st);
+    int pull(const int* flds, const int* planes, const int* from, int n, cudaStream_t st);
+    double* owned_ptr(int fld) const { return f[fld].p + (long long)(plo - lay.wlo[fld]) * lay.sp[fld]; }
+    long long owned_count(int fld) const { return (long long)(phi - plo + 1) * lay.sp[fld]; }
     ~fdmb_ns_cyl();
 };
-
-static int make_cfield(CFld& f, long long& count, int nphi, int z0, int z1, int r0, int r1)
-{
-    f.lz = z0; f.lr = r0;
-    f.sz = r1 - r0 + 1;
-    f.sp = (long long)(z1 - z0 + 1) * f.sz;
-    count = (long long)nphi * f.sp;
-    FDMB_CUDA(cudaMalloc(&f.p, sizeof(double) * count));
-    FDMB_CUDA(cudaMemset(f.p, 0, sizeof(double) * count));
-    return FDMB_OK;
-}
 
 int fdmb_ns_cyl::init()
 {
     nr = prm.nr; nz = prm.nz; nphi = prm.nphi; zper = prm.zperiodic ? 1 : 0;
     if (nr < 3 || nz < 3 || nphi < 4) { set_error("NSCyl: nr, nz >= 3 and nphi >= 4 required"); return FDMB_ERR_INVALID; }
+    if (nranks > 1 && nphi / nranks < 2) {
+        set_error("NSCyl: the sharded step needs at least 2 phi planes per rank (nphi=%d, %d ranks)", nphi, nranks);
+        return FDMB_ERR_INVALID;
+    }
     const double R = prm.R, r0 = prm.r, h1 = prm.h1, h2 = prm.h2;
     dr = (R - r0) / nr; dz = (h2 - h1) / nz; dphi = 2 * M_PI / nphi;          // ns_cyl.h:77
     const double dr2 = dr * dr, dz2 = dz * dz, dphi2 = dphi * dphi;
     // ns_cyl.h:95-97
-    int rc = fdmb_lapl_cyl_create(&lapl, dr, dz, r0 - dr / 2, R - r0 + dr, zper ? h2 - h1 : h2 - h1 + dz, nr, nz, nphi, zper);
+    int rc;
+    if (nranks > 1)
+        rc = fdmb_lapl_cyl_create_sharded(&lapl, dr, dz, r0 - dr / 2, R - r0 + dr, zper ? h2 - h1 : h2 - h1 + dz, nr, nz, nphi,
+                                          zper, rank, nranks);
+    else
+        rc = fdmb_lapl_cyl_create(&lapl, dr, dz, r0 - dr / 2, R - r0 + dr, zper ? h2 - h1 : h2 - h1 + dz, nr, nz, nphi, zper);
     if (rc) return rc;
+    FDMB_CUDA(cudaGetDevice(&device));
     FDMB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-    g.nr = nr; g.nz = nz; g.nphi = nphi; g.zper = zper;
+    {   // load this translation unit's kernels now (see the note in ns_cube.cu: lazy loading behind a spinning barrier)
+        cudaFuncAttributes fa;
+        FDMB_CUDA(cudaFuncGetAttributes(&fa, k_cyl_pull));
+        FDMB_CUDA(cudaFuncGetAttributes(&fa, k_cyl_bound_r));
+        FDMB_CUDA(cudaFuncGetAttributes(&fa, k_cyl_bound_z));
+        FDMB_CUDA(cudaFuncGetAttributes(&fa, k_cyl_bound_p));
+        FDMB_CUDA(cudaFuncGetAttributes(&fa, k_cyl_fgh<false>));
+        FDMB_CUDA(cudaFuncGetAttributes(&fa, k_cyl_fgh<true>));
+        FDMB_CUDA(cudaFuncGetAttributes(&fa, k_cyl_rhs));
+        FDMB_CUDA(cudaFuncGetAttributes(&fa, k_cyl_update));
+    }
+    g.nr = nr; g.nz = nz; g.nphi = nphi; g.zper = zper; g.wrap = nranks == 1 ? 1 : 0;
     g.z_ = zper ? 0 : -1; g.z0 = 0; g.z1 = zper ? 0 : 1; g.zn = zper ? nz - 1 : nz; g.znn = zper ? nz - 1 : nz + 1;
-    const int z_ = g.z_, z0 = g.z0, z1 = g.z1, zn = g.zn, znn = g.znn;
-    // extents: ns_cyl.h:80-93
-    if ((rc = make_cfield(f[0], count[0], nphi, z0, znn, -1, nr + 1))) return rc;   // u
-    if ((rc = make_cfield(f[1], count[1], nphi, z_, znn, 0, nr + 1))) return rc;    // v
-    if ((rc = make_cfield(f[2], count[2], nphi, z0, znn, 0, nr + 1))) return rc;    // w
-    if ((rc = make_cfield(f[3], count[3], nphi, z0, znn, 0, nr + 1))) return rc;    // p
-    if ((rc = make_cfield(f[4], count[4], nphi, z1, zn, 1, nr))) return rc;         // x
-    if ((rc = make_cfield(f[5], count[5], nphi, z1, zn, 0, nr))) return rc;         // F
-    if ((rc = make_cfield(f[6], count[6], nphi, z0, zn, 1, nr))) return rc;         // G
-    if ((rc = make_cfield(f[7], count[7], nphi, z1, zn, 1, nr))) return rc;         // H
-    if ((rc = make_cfield(f[8], count[8], nphi, z1, zn, 1, nr))) return rc;         // RHS
-    if ((rc = make_cfield(f[9], count[9], nphi, z0, znn, -1, nr + 1))) return rc;   // u0
-    if ((rc = make_cfield(f[10], count[10], nphi, z_, znn, 0, nr + 1))) return rc;  // v0
-    if ((rc = make_cfield(f[11], count[11], nphi, z0, znn, 0, nr + 1))) return rc;  // w0
+    const int z1 = g.z1, zn = g.zn;
+    plo = nranks > 1 ? rank * (nphi / nranks) : 0;
+    phi = nranks > 1 ? plo + nphi / nranks - 1 : nphi - 1;
+    cyl_layout(nr, nz, nphi, zper, rank, nranks, &lay);
+    FDMB_CUDA(cudaMalloc(&block, lay.bytes));
+    FDMB_CUDA(cudaMemset(block, 0, lay.bytes));
+    for (int k = 0; k < 12; k++) {
+        f[k].p = reinterpret_cast<double*>(static_cast<char*>(block) + lay.off[k]);
+        f[k].li = lay.wlo[k]; f[k].lz = lay.lz[k]; f[k].lr = lay.lr[k];
+        f[k].sz = lay.sz[k]; f[k].sp = lay.sp[k];
+    }
+    peer_block[rank] = block;
     g.U0 = prm.u0; g.dt = prm.dt;
     const double Re = prm.Re;
     g.cRr = 1.0 / Re / dr2; g.cRz = 1.0 / Re / dz2; g.cRp = 1.0 / Re / dphi2;
@@ -378,25 +459,58 @@ int fdmb_ns_cyl::init()
     g.crp = d_tab + 8 * T; g.crm = d_tab + 9 * T;
     if (prm.vrandom == 1) {
         // ns_cyl.h:99-108: default-seeded std::default_random_engine, uniform(-1e-3, 1e-3), drawn in
-        // (phi, z, r) order -- the same standard-library sequence as the reference build
-        std::vector<double> hv(count[1], 0.0);
+        // (phi, z, r) order -- the same standard-library sequence as the reference build; a sharded rank draws the
+        // whole sequence and keeps its own planes
+        std::vector<double> hv((size_t)owned_count(1), 0.0);
         std::default_random_engine generator;
         std::uniform_real_distribution<double> distribution(-1e-3, 1e-3);
         for (int i = 0; i < nphi; i++)
             for (int k = z1; k <= zn; k++)
-                for (int j = 1; j <= nr; j++)
-                    hv[(size_t)i * f[1].sp + (size_t)(k - f[1].lz) * f[1].sz + (j - f[1].lr)] = distribution(generator);
-        FDMB_CUDA(cudaMemcpy(f[1].p, hv.data(), sizeof(double) * hv.size(), cudaMemcpyHostToDevice));
+                for (int j = 1; j <= nr; j++) {
+                    const double val = distribution(generator);
+                    if (i >= plo && i <= phi)
+                        hv[(size_t)(i - plo) * f[1].sp + (size_t)(k - f[1].lz) * f[1].sz + (j - f[1].lr)] = val;
+                }
+        FDMB_CUDA(cudaMemcpy(owned_ptr(1), hv.data(), sizeof(double) * hv.size(), cudaMemcpyHostToDevice));
     }
     return FDMB_OK;
 }
 
 fdmb_ns_cyl::~fdmb_ns_cyl()
 {
-    for (auto& a : f) cudaFree(a.p);
+    for (int q = 0; q < nranks; q++)
+        if (q != rank && peer_ipc[q] && peer_block[q]) cudaIpcCloseMemHandle(peer_block[q]);
+    cudaFree(block);
     cudaFree(d_tab);
     if (lapl) fdmb_lapl_cyl_destroy(lapl);
     if (stream) cudaStreamDestroy(stream);
+}
+
+// copy phi plane planes[s] (this rank's numbering: -1 and nphi are the wrap-around halos) of field flds[s] from the
+// window of rank from[s], which owns it
+int fdmb_ns_cyl::pull(const int* flds, const int* planes, const int* from, int n, cudaStream_t st)
+{
+    CylPullList pl{};
+    long long nmax = 0;
+    for (int s = 0; s < n; s++) {
+        const int k = flds[s];
+        CylLayout q;
+        cyl_layout(nr, nz, nphi, zper, from[s], nranks, &q);
+        const int gsrc = (planes[s] + nphi) % nphi;                   // the plane's index on its owner
+        pl.src[s] = reinterpret_cast<const double*>(static_cast<const char*>(peer_block[from[s]]) + q.off[k]) +
+                    (long long)(gsrc - q.wlo[k]) * q.sp[k];
+        pl.dst[s] = f[k].p + (long long)(planes[s] - lay.wlo[k]) * lay.sp[k];
+        pl.n[s] = lay.sp[k];
+        if (pl.n[s] > nmax) nmax = pl.n[s];
+    }
+    pl.count = n;
+    LaunchScope sc("nscyl_halo_pull", st);
+    long long bx = (nmax + 256 * 4 - 1) / (256 * 4);
+    if (bx > 512) bx = 512;
+    if (bx < 1) bx = 1;
+    k_cyl_pull<<<dim3((unsigned)bx, n), 256, 0, st>>>(pl);
+    FDMB_CHECK_LAUNCH();
+    return FDMB_OK;
 }
 
 int fdmb_ns_cyl::step(int nsteps, int linear, cudaStream_t st)
@@ -404,50 +518,97 @@ int fdmb_ns_cyl::step(int nsteps, int linear, cudaStream_t st)
     const CFld &u = f[0], &v = f[1], &w = f[2], &p = f[3], &x = f[4], &F = f[5], &G = f[6], &H = f[7], &R = f[8];
     const CFld &u0 = f[9], &v0 = f[10], &w0 = f[11];
     const int nzrows = g.znn - g.z_ + 1;
+    const int nown = phi - plo + 1;
+    const int wlo = lay.wlo[0], nwin = lay.whi[0] - lay.wlo[0] + 1;     // planes of u, v, w held here (own + halos)
+    const int prev = (rank + nranks - 1) % nranks, next = (rank + 1) % nranks;
+    if (nranks > 1 && !attached) { set_error("NSCyl: sharded handle used before attach_ipc/attach_local"); return FDMB_ERR_COMM; }
+    int rc;
     for (int s = 0; s < nsteps; s++) {
+        if (nranks > 1) {
+            // every rank has finished the previous update (or set_field): fetch the wrap-around halo planes
+            if ((rc = lapl->barrier(st))) return rc;
+            int flds[12], planes[12], from[12], n = 0;
+            for (int k = 0; k < 3; k++) {
+                flds[n] = k; planes[n] = plo - 1; from[n++] = prev;
+                flds[n] = k; planes[n] = phi + 1; from[n++] = next;
+            }
+            if ((rc = pull(flds, planes, from, 6, st))) return rc;
+            if (linear) {
+                n = 0;
+                for (int k = 9; k < 12; k++) {
+                    flds[n] = k; planes[n] = plo - 1; from[n++] = prev;
+                    flds[n] = k; planes[n] = phi + 1; from[n++] = next;
+                }
+                if ((rc = pull(flds, planes, from, 6, st))) return rc;
+            }
+        }
         {
             LaunchScope sc("nscyl_bound_r", st);
-            dim3 grid((nzrows + 127) / 128, nphi);
-            k_cyl_bound_r<<<grid, 128, 0, st>>>(u, v, w, g);
+            dim3 grid((nzrows + 127) / 128, nwin);
+            k_cyl_bound_r<<<grid, 128, 0, st>>>(u, v, w, g, wlo);
         }
         if (!zper) {
             LaunchScope sc("nscyl_bound_z", st);
             const int jmax_v = g.znn < nr + 1 ? g.znn : nr + 1;
-            dim3 grid((nr + 3 + 127) / 128, nphi);
-            k_cyl_bound_z<<<grid, 128, 0, st>>>(u, v, w, g, jmax_v);
+            dim3 grid((nr + 3 + 127) / 128, nwin);
+            k_cyl_bound_z<<<grid, 128, 0, st>>>(u, v, w, g, jmax_v, wlo);
         }
         {
             LaunchScope sc("nscyl_bound_p", st);
             const int na = (g.zn - g.z1 + 1) > nr ? (g.zn - g.z1 + 1) : nr;
-            dim3 grid((na + 127) / 128, nphi, zper ? 1 : 2);
-            k_cyl_bound_p<<<grid, 128, 0, st>>>(u, v, p, g);
+            dim3 grid((na + 127) / 128, nown, zper ? 1 : 2);
+            k_cyl_bound_p<<<grid, 128, 0, st>>>(u, v, p, g, plo);
         }
         {
             LaunchScope sc(linear ? "nscyl_lfgh" : "nscyl_fgh", st);
             dim3 block(64, 4);
-            dim3 grid((nr + 1 + 63) / 64, (g.zn - g.z0 + 1 + 3) / 4, nphi);
-            if (linear) k_cyl_fgh<true><<<grid, block, 0, st>>>(u, v, w, u0, v0, w0, F, G, H, g);
-            else k_cyl_fgh<false><<<grid, block, 0, st>>>(u, v, w, u0, v0, w0, F, G, H, g);
+            dim3 grid((nr + 1 + 63) / 64, (g.zn - g.z0 + 1 + 3) / 4, nown);
+            if (linear) k_cyl_fgh<true><<<grid, block, 0, st>>>(u, v, w, u0, v0, w0, F, G, H, g, plo);
+            else k_cyl_fgh<false><<<grid, block, 0, st>>>(u, v, w, u0, v0, w0, F, G, H, g, plo);
+        }
+        if (nranks > 1) {
+            // the divergence reads H on the plane below the slab: fetch it from its owner
+            if ((rc = lapl->barrier(st))) return rc;
+            int fld = 7, plane = plo - 1;
+            if ((rc = pull(&fld, &plane, &prev, 1, st))) return rc;
         }
         {
             LaunchScope sc("nscyl_rhs", st);
             dim3 block(64, 4);
-            dim3 grid((nr + 63) / 64, (g.zn - g.z1 + 1 + 3) / 4, nphi);
-            k_cyl_rhs<<<grid, block, 0, st>>>(F, G, H, p, R, g);
+            dim3 grid((nr + 63) / 64, (g.zn - g.z1 + 1 + 3) / 4, nown);
+            k_cyl_rhs<<<grid, block, 0, st>>>(F, G, H, p, R, g, plo);
         }
         FDMB_CHECK_LAUNCH();
-        int rc = lapl->solve_device(x.p, R.p, st);      // ns_cyl.cpp:441
+        rc = lapl->solve_device(x.p, R.p, st);      // ns_cyl.cpp:441
         if (rc) return rc;
+        if (nranks > 1) {
+            // the neighbour above has written its x slab: fetch the plane the w update reads
+            if ((rc = lapl->barrier(st))) return rc;
+            int fld = 4, plane = phi + 1;
+            if ((rc = pull(&fld, &plane, &next, 1, st))) return rc;
+        }
         {
             LaunchScope sc("nscyl_update", st);
             dim3 block(64, 4);
-            dim3 grid((nr + 63) / 64, (g.zn - g.z1 + 1 + 3) / 4, nphi);
-            k_cyl_update<<<grid, block, 0, st>>>(u, v, w, p, x, F, G, H, g);
+            dim3 grid((nr + 63) / 64, (g.zn - g.z1 + 1 + 3) / 4, nown);
+            k_cyl_update<<<grid, block, 0, st>>>(u, v, w, p, x, F, G, H, g, plo);
         }
         FDMB_CHECK_LAUNCH();
         time_index++;
     }
     return FDMB_OK;
+}
+
+// runs `body` with the handle's device current (several ranks may share one process)
+template <typename Fn> static int cyl_ns_on_device(fdmb_ns_cyl* h, Fn body)
+{
+    if (h->nranks < 2) return body();
+    int cur = 0;
+    FDMB_CUDA(cudaGetDevice(&cur));
+    if (cur != h->device) FDMB_CUDA(cudaSetDevice(h->device));
+    int rc = body();
+    if (cur != h->device) cudaSetDevice(cur);
+    return rc;
 }
 
 extern "C" {
@@ -461,70 +622,162 @@ int fdmb_ns_cyl_default_params(fdmb_ns_cyl_params* p)
     return FDMB_OK;
 }
 
-int fdmb_ns_cyl_create(fdmb_ns_cyl** out, const fdmb_ns_cyl_params* p)
+static int ns_cyl_create(fdmb_ns_cyl** out, const fdmb_ns_cyl_params* p, int rank, int nranks)
 {
     if (!out || !p) { set_error("null argument"); return FDMB_ERR_INVALID; }
     *out = nullptr;
+    if (nranks != 1 && nranks != 2 && nranks != 4 && nranks != 8) {
+        set_error("NSCyl: nranks must be 1, 2, 4 or 8 (got %d)", nranks);
+        return FDMB_ERR_INVALID;
+    }
+    if (rank < 0 || rank >= nranks) { set_error("NSCyl: rank %d out of range", rank); return FDMB_ERR_INVALID; }
     auto* h = new (std::nothrow) fdmb_ns_cyl();
     if (!h) { set_error("out of host memory"); return FDMB_ERR_NOMEM; }
-    h->prm = *p;
+    h->prm = *p; h->rank = rank; h->nranks = nranks;
     int rc = h->init();
     if (rc) { delete h; return rc; }
     *out = h;
     return FDMB_OK;
 }
 
+int fdmb_ns_cyl_create(fdmb_ns_cyl** out, const fdmb_ns_cyl_params* p) { return ns_cyl_create(out, p, 0, 1); }
+
+int fdmb_ns_cyl_create_sharded(fdmb_ns_cyl** out, const fdmb_ns_cyl_params* p, int rank, int nranks)
+{
+    return ns_cyl_create(out, p, rank, nranks);
+}
+
+int fdmb_ns_cyl_local_slab(fdmb_ns_cyl* h, int* phi_first, int* nphi_local)
+{
+    if (!h || !phi_first || !nphi_local) { set_error("null argument"); return FDMB_ERR_INVALID; }
+    *phi_first = h->plo; *nphi_local = h->phi - h->plo + 1;
+    return FDMB_OK;
+}
+
+int fdmb_ns_cyl_export_ipc(fdmb_ns_cyl* h, void* handles)
+{
+    if (!h || !handles || h->nranks < 2) { set_error("export_ipc needs a sharded handle"); return FDMB_ERR_INVALID; }
+    int rc = fdmb_lapl_cyl_export_ipc(h->lapl, handles);
+    if (rc) return rc;
+    cudaIpcMemHandle_t ih;
+    FDMB_CUDA(cudaIpcGetMemHandle(&ih, h->block));
+    memcpy(static_cast<char*>(handles) + FDMB_IPC_HANDLE_BYTES, &ih, sizeof(ih));
+    return FDMB_OK;
+}
+
+// handles: nranks records of 2 * FDMB_IPC_HANDLE_BYTES (solver block, field block), indexed by rank
+int fdmb_ns_cyl_attach_ipc(fdmb_ns_cyl* h, const void* handles)
+{
+    if (!h || !handles || h->nranks < 2) { set_error("attach_ipc needs a sharded handle"); return FDMB_ERR_INVALID; }
+    char solver[FDMB_MAX_RANKS * FDMB_IPC_HANDLE_BYTES];
+    for (int q = 0; q < h->nranks; q++)
+        memcpy(solver + (size_t)q * FDMB_IPC_HANDLE_BYTES, static_cast<const char*>(handles) + (size_t)q * 2 * FDMB_IPC_HANDLE_BYTES,
+               FDMB_IPC_HANDLE_BYTES);
+    int rc = fdmb_lapl_cyl_attach_ipc(h->lapl, solver);
+    if (rc) return rc;
+    for (int q = 0; q < h->nranks; q++) {
+        if (q == h->rank) continue;
+        cudaIpcMemHandle_t ih;
+        memcpy(&ih, static_cast<const char*>(handles) + (size_t)q * 2 * FDMB_IPC_HANDLE_BYTES + FDMB_IPC_HANDLE_BYTES, sizeof(ih));
+        cudaError_t e = cudaIpcOpenMemHandle(&h->peer_block[q], ih, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            set_error("cudaIpcOpenMemHandle for rank %d failed: %s", q, cudaGetErrorString(e));
+            return FDMB_ERR_COMM;
+        }
+        h->peer_ipc[q] = true;
+    }
+    h->attached = true;
+    return FDMB_OK;
+}
+
+int fdmb_ns_cyl_attach_local(fdmb_ns_cyl* h, fdmb_ns_cyl* const* all)
+{
+    if (!h || !all || h->nranks < 2) { set_error("attach_local needs a sharded handle"); return FDMB_ERR_INVALID; }
+    fdmb_lapl_cyl* solvers[FDMB_MAX_RANKS] = {};
+    for (int q = 0; q < h->nranks; q++) {
+        if (!all[q] || all[q]->nranks != h->nranks || all[q]->rank != q || all[q]->nphi != h->nphi || all[q]->nr != h->nr) {
+            set_error("attach_local: handle %d does not belong to this sharded run", q);
+            return FDMB_ERR_INVALID;
+        }
+        solvers[q] = all[q]->lapl;
+    }
+    int rc = fdmb_lapl_cyl_attach_local(h->lapl, solvers);      // also enables peer access between the devices
+    if (rc) return rc;
+    for (int q = 0; q < h->nranks; q++) h->peer_block[q] = all[q]->block;
+    h->attached = true;
+    return FDMB_OK;
+}
+
+int fdmb_ns_cyl_synchronize(fdmb_ns_cyl* h)
+{
+    if (!h) { set_error("null argument"); return FDMB_ERR_INVALID; }
+    return cyl_ns_on_device(h, [&] {
+        FDMB_CUDA(cudaStreamSynchronize(h->stream));
+        return (int)FDMB_OK;
+    });
+}
+
 int fdmb_ns_cyl_step(fdmb_ns_cyl* h, int nsteps)
 {
     if (!h || nsteps < 0) { set_error("bad argument"); return FDMB_ERR_INVALID; }
-    int rc = h->step(nsteps, 0, h->stream);
-    if (rc) return rc;
-    FDMB_CUDA(cudaStreamSynchronize(h->stream));
-    return FDMB_OK;
+    return cyl_ns_on_device(h, [&] {
+        int rc = h->step(nsteps, 0, h->stream);
+        if (rc) return rc;
+        FDMB_CUDA(cudaStreamSynchronize(h->stream));
+        return (int)FDMB_OK;
+    });
 }
 
 int fdmb_ns_cyl_lstep(fdmb_ns_cyl* h, int nsteps)
 {
     if (!h || nsteps < 0) { set_error("bad argument"); return FDMB_ERR_INVALID; }
-    int rc = h->step(nsteps, 1, h->stream);
-    if (rc) return rc;
-    FDMB_CUDA(cudaStreamSynchronize(h->stream));
-    return FDMB_OK;
+    return cyl_ns_on_device(h, [&] {
+        int rc = h->step(nsteps, 1, h->stream);
+        if (rc) return rc;
+        FDMB_CUDA(cudaStreamSynchronize(h->stream));
+        return (int)FDMB_OK;
+    });
 }
 
 int fdmb_ns_cyl_step_async(fdmb_ns_cyl* h, int nsteps, int linear, void* stream)
 {
     if (!h || nsteps < 0) { set_error("bad argument"); return FDMB_ERR_INVALID; }
-    return h->step(nsteps, linear ? 1 : 0, stream ? (cudaStream_t)stream : h->stream);
+    return cyl_ns_on_device(h, [&] { return h->step(nsteps, linear ? 1 : 0, stream ? (cudaStream_t)stream : h->stream); });
 }
 
 int fdmb_ns_cyl_field_size(fdmb_ns_cyl* h, int field, long long* count)
 {
     if (!h || field < 0 || field > 11 || !count) { set_error("bad field id"); return FDMB_ERR_INVALID; }
-    *count = h->count[field];
+    *count = h->owned_count(field);
     return FDMB_OK;
 }
 
 int fdmb_ns_cyl_get_field(fdmb_ns_cyl* h, int field, double* host)
 {
     if (!h || field < 0 || field > 11 || !host) { set_error("bad field id"); return FDMB_ERR_INVALID; }
-    FDMB_CUDA(cudaMemcpyAsync(host, h->f[field].p, sizeof(double) * h->count[field], cudaMemcpyDeviceToHost, h->stream));
-    FDMB_CUDA(cudaStreamSynchronize(h->stream));
-    return FDMB_OK;
+    return cyl_ns_on_device(h, [&] {
+        FDMB_CUDA(cudaMemcpyAsync(host, h->owned_ptr(field), sizeof(double) * h->owned_count(field), cudaMemcpyDeviceToHost,
+                                  h->stream));
+        FDMB_CUDA(cudaStreamSynchronize(h->stream));
+        return (int)FDMB_OK;
+    });
 }
 
 int fdmb_ns_cyl_set_field(fdmb_ns_cyl* h, int field, const double* host)
 {
     if (!h || field < 0 || field > 11 || !host) { set_error("bad field id"); return FDMB_ERR_INVALID; }
-    FDMB_CUDA(cudaMemcpyAsync(h->f[field].p, host, sizeof(double) * h->count[field], cudaMemcpyHostToDevice, h->stream));
-    FDMB_CUDA(cudaStreamSynchronize(h->stream));
-    return FDMB_OK;
+    return cyl_ns_on_device(h, [&] {
+        FDMB_CUDA(cudaMemcpyAsync(h->owned_ptr(field), host, sizeof(double) * h->owned_count(field), cudaMemcpyHostToDevice,
+                                  h->stream));
+        FDMB_CUDA(cudaStreamSynchronize(h->stream));
+        return (int)FDMB_OK;
+    });
 }
 
 int fdmb_ns_cyl_field_device_ptr(fdmb_ns_cyl* h, int field, void** dptr)
 {
     if (!h || field < 0 || field > 11 || !dptr) { set_error("bad field id"); return FDMB_ERR_INVALID; }
-    *dptr = h->f[field].p;
+    *dptr = h->owned_ptr(field);
     return FDMB_OK;
 }
 

@@ -40,6 +40,12 @@ def _bind(L):
     L.fdmb_ns_cyl_time_index.argtypes = [C.c_void_p]
     L.fdmb_ns_cyl_time_index.restype = C.c_longlong
     L.fdmb_ns_cyl_destroy.argtypes = [C.c_void_p]
+    L.fdmb_ns_cyl_create_sharded.argtypes = [C.POINTER(C.c_void_p), P, C.c_int, C.c_int]
+    L.fdmb_ns_cyl_local_slab.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.fdmb_ns_cyl_export_ipc.argtypes = [C.c_void_p, C.c_void_p]
+    L.fdmb_ns_cyl_attach_ipc.argtypes = [C.c_void_p, C.c_void_p]
+    L.fdmb_ns_cyl_attach_local.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    L.fdmb_ns_cyl_synchronize.argtypes = [C.c_void_p]
     L._ns_cyl_bound = True
 
 
@@ -47,7 +53,7 @@ class NSCyl:
     """Taylor-Couette flow; defaults are the reference's (src/ns_cyl.h:57-68)."""
 
     def __init__(self, nr=32, nz=31, nphi=32, Re=1.0, dt=0.001, u0=1.0, R=math.pi, r=math.pi / 2,
-                 h1=0.0, h2=10.0, verbose=0, vrandom=0, zperiodic=False):
+                 h1=0.0, h2=10.0, verbose=0, vrandom=0, zperiodic=False, rank=0, nranks=1):
         L = capi.lib()
         _bind(L)
         self.params = NSCylParams(R, r, h1, h2, u0, Re, dt, int(nr), int(nz), int(nphi), int(verbose),
@@ -55,8 +61,41 @@ class NSCyl:
         self.nr, self.nz, self.nphi = int(nr), int(nz), int(nphi)
         self.zperiodic = bool(zperiodic)
         self.dt = float(dt)
+        self.rank, self.nranks = int(rank), int(nranks)
         self._h = C.c_void_p()
-        capi.check(L.fdmb_ns_cyl_create(C.byref(self._h), C.byref(self.params)), "NSCyl create")
+        if self.nranks > 1:
+            capi.check(L.fdmb_ns_cyl_create_sharded(C.byref(self._h), C.byref(self.params), self.rank, self.nranks),
+                       "NSCyl create_sharded")
+        else:
+            capi.check(L.fdmb_ns_cyl_create(C.byref(self._h), C.byref(self.params)), "NSCyl create")
+        a, b = C.c_int(), C.c_int()
+        capi.check(L.fdmb_ns_cyl_local_slab(self._h, C.byref(a), C.byref(b)), "local_slab")
+        self.phi_first, self.nphi_local = a.value, b.value      # this rank's phi planes (all of them on one GPU)
+
+    # ---- several GPUs: phi-slabs; field()/set_field() act on this rank's planes ------------------------
+    def connect(self, group=None):
+        """One process per GPU: exchange the IPC handles over ``torch.distributed`` and attach the peers."""
+        if self.nranks == 1:
+            return
+        import torch.distributed as dist
+        from .lapl_cube import IPC_HANDLE_BYTES
+        buf = C.create_string_buffer(2 * IPC_HANDLE_BYTES)
+        capi.check(capi.lib().fdmb_ns_cyl_export_ipc(self._h, buf), "export_ipc")
+        gathered = [None] * self.nranks
+        dist.all_gather_object(gathered, buf.raw, group=group)
+        blob = b"".join(gathered)
+        capi.check(capi.lib().fdmb_ns_cyl_attach_ipc(self._h, C.create_string_buffer(blob, len(blob))), "attach_ipc")
+        dist.barrier(group=group)
+
+    @staticmethod
+    def connect_local(parts):
+        """All ranks live in this process (one handle per device)."""
+        arr = (C.c_void_p * len(parts))(*[s._h for s in parts])
+        for s in parts:
+            capi.check(capi.lib().fdmb_ns_cyl_attach_local(s._h, arr), "attach_local")
+
+    def synchronize(self):
+        capi.check(capi.lib().fdmb_ns_cyl_synchronize(self._h), "synchronize")
 
     # ---- reference API -----------------------------------------------------------------
     def step(self, nsteps=1):

@@ -229,6 +229,16 @@ int fdmb_ns_cyl_set_field(fdmb_ns_cyl* h, int field, const double* host);
 int fdmb_ns_cyl_field_device_ptr(fdmb_ns_cyl* h, int field, void** dptr);
 long long fdmb_ns_cyl_time_index(fdmb_ns_cyl* h);
 int fdmb_ns_cyl_destroy(fdmb_ns_cyl* h);
+/* NSCyl over 2, 4 or 8 GPUs of one node: the phi-slabs of the sharded LaplCyl3FFT2; u, v, w (and u0, v0, w0 for the
+ * linearised step) keep one wrap-around halo plane each side, H one below and x one above, pulled from the
+ * neighbours' memory over NVLink after device-side barriers.  field_size / get_field / set_field / field_device_ptr
+ * act on this rank's own phi planes [phi_first, phi_first + nphi_local).  export/attach as for NSCube.            */
+int fdmb_ns_cyl_create_sharded(fdmb_ns_cyl** h, const fdmb_ns_cyl_params* p, int rank, int nranks);
+int fdmb_ns_cyl_local_slab(fdmb_ns_cyl* h, int* phi_first, int* nphi_local);
+int fdmb_ns_cyl_export_ipc(fdmb_ns_cyl* h, void* handles);
+int fdmb_ns_cyl_attach_ipc(fdmb_ns_cyl* h, const void* handles);
+int fdmb_ns_cyl_attach_local(fdmb_ns_cyl* h, fdmb_ns_cyl* const* all);
+int fdmb_ns_cyl_synchronize(fdmb_ns_cyl* h);
 
 #ifdef __cplusplus
 }
