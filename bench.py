@@ -47,7 +47,7 @@ WORKLOADS = {
                                                 "(BASELINE configs[4]; z-slab decomposed over the ranks when N>1)"),
     "nscube31": dict(kind="ns", n=31, Re=250.0, dt=0.01, label="NSCube 31^3 Re=250 dt=0.01 step (configs[0])"),
     "nscube255": dict(kind="ns", n=255, Re=1000.0, dt=0.005, label="NSCube 255^3 Re=1000 dt=0.005 step (configs[2])"),
-    # cylindrical workloads (single GPU): nr x nz x nphi
+    # cylindrical workloads: nr x nz x nphi (phi-slabs when N > 1)
     "nscyl128": dict(kind="nscyl", n=128, nr=128, nz=127, nphi=128, Re=200.0, dt=0.01,
                      label="NSCyl Taylor-Couette nr=128 nz=127 nphi=128 Re=200 dt=0.01 step (configs[3])"),
     "cyl128": dict(kind="cyl", n=128, nr=128, nz=127, nphi=128,
@@ -316,45 +316,49 @@ def main():
         h2d = d2h = 8 * lpts
         pts_kernel = lpts
     elif wl["kind"] in ("cyl", "nscyl"):
-        if world > 1:
-            raise SystemExit("the cylindrical bench workloads are single-GPU (the sharded LaplCyl3FFT2 is covered by tests)")
-        pts = lpts = wl["nr"] * wl["nz"] * wl["nphi"]
+        sharded = world > 1
+        shard_kw = dict(rank=rank, nranks=world) if sharded else {}
+        pts = wl["nr"] * wl["nz"] * wl["nphi"]
+        lpts = pts // world if sharded else pts                 # phi-slabs
         if wl["kind"] == "cyl":
-            S = fdm_b200.LaplCyl3FFT2(*cyl_geometry(wl))
-            pair_bytes = 2 * 8 * pts
+            S = fdm_b200.LaplCyl3FFT2(*cyl_geometry(wl), **shard_kw)
+            S.connect()
+            pair_bytes = 2 * 8 * lpts
             nbuf = max(2, int(np.ceil(2.2 * 126e6 / pair_bytes)))
-            rhs = [torch.rand(pts, dtype=torch.float64, device=dev) - 0.5 for _ in range(nbuf)]
-            ans = [torch.empty(pts, dtype=torch.float64, device=dev) for _ in range(nbuf)]
+            rhs = [torch.rand(lpts, dtype=torch.float64, device=dev) - 0.5 for _ in range(nbuf)]
+            ans = [torch.empty(lpts, dtype=torch.float64, device=dev) for _ in range(nbuf)]
             l2_policy = f"rotating {nbuf} rhs/ans pairs ({nbuf * pair_bytes / 1e6:.0f} MB > 126 MB L2)"
 
             def step(i):
                 S.solve_device(ans[i % nbuf].data_ptr(), rhs[i % nbuf].data_ptr(), sptr)
-            units_per_step = pts / 1e9
+            units_per_step = pts / 1e9 / (world if sharded else 1)
             metric, unit = "poisson_solve_gpts_per_s", "Gpts/s"
-            algo_bytes_step = SOLVE_BYTES_PER_PT * pts
-            h_rhs = torch.rand(pts, dtype=torch.float64).pin_memory()
-            h_ans = torch.empty(pts, dtype=torch.float64).pin_memory()
+            algo_bytes_step = SOLVE_BYTES_PER_PT * lpts
+            h_rhs = torch.rand(lpts, dtype=torch.float64).pin_memory()
+            h_ans = torch.empty(lpts, dtype=torch.float64).pin_memory()
             dp = C.POINTER(C.c_double)
 
             def e2e_step():
                 capi.check(L.fdmb_lapl_cyl_solve(S._h, C.cast(h_ans.data_ptr(), dp), C.cast(h_rhs.data_ptr(), dp)), "solve")
-            h2d = d2h = 8 * pts
+            h2d = d2h = 8 * lpts
         else:
             kw = dict(nr=wl["nr"], nz=wl["nz"], nphi=wl["nphi"], Re=wl["Re"], dt=wl["dt"])
-            ns = fdm_b200.NSCyl(**kw)
-            l2_policy = f"state of 13 arrays = {13 * 8 * pts / 1e6:.0f} MB > 126 MB L2"
+            ns = fdm_b200.NSCyl(**kw, **shard_kw)
+            ns.connect()
+            l2_policy = f"state of 13 arrays = {13 * 8 * lpts / 1e6:.0f} MB per GPU" + (" > 126 MB L2" if 13 * 8 * lpts > 126e6 else " (fits L2)")
 
             def step(i):
                 ns.step_device(1, sptr)
-            units_per_step = 1.0
+            units_per_step = 1.0 / (world if sharded else 1)
             metric, unit = "ns_steps_per_s", "steps/s"
-            algo_bytes_step = NS_BYTES_PER_PT * pts
-            ns2 = fdm_b200.NSCyl(**kw)
+            algo_bytes_step = NS_BYTES_PER_PT * lpts
+            ns2 = fdm_b200.NSCyl(**kw, **shard_kw)
+            ns2.connect()
 
             def e2e_step():
                 ns2.step_host_roundtrip()
             h2d = d2h = ns2.state_bytes()
-        pts_kernel = pts
+        pts_kernel = lpts
     else:
         if not hasattr(fdm_b200, "NSCube"):
             raise SystemExit("NSCube workload not built")
@@ -442,7 +446,7 @@ def main():
         # per GPU 48 n^3 / P bytes of HBM traffic plus two slab<->pencil transposes, each sending (and
         # receiving) 8 (n^3 / P) (P - 1) / P bytes over NVLink (900 GB/s per direction per GPU, nominal)
         nvl = 900.0
-        t_hbm = (SOLVE_BYTES_PER_PT if wl["kind"] == "cube" else NS_BYTES_PER_PT) * pts / world / (peak * 1e9) * 1e3
+        t_hbm = (SOLVE_BYTES_PER_PT if wl["kind"] in ("cube", "cyl") else NS_BYTES_PER_PT) * pts / world / (peak * 1e9) * 1e3
         xpose_bytes = 8.0 * pts / world * (world - 1) / world
         t_nvl = 2 * xpose_bytes / (nvl * 1e9) * 1e3
         t_step = ms / K
@@ -479,8 +483,8 @@ def main():
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": wl["label"], "l2_policy": l2_policy,
                        "parallelism": ("single GPU" if world == 1 else
-                                       f"z-slabs over {world} GPUs, slab<->pencil transposes as peer stores over NVLink"
-                                       + ("" if wl["kind"] == "cube" else ", stencil halo planes pulled from the neighbours")
+                                       f"{'phi' if 'cyl' in wl['kind'] else 'z'}-slabs over {world} GPUs, slab<->pencil transposes as peer stores over NVLink"
+                                       + ("" if wl["kind"] in ("cube", "cyl") else ", stencil halo planes pulled from the neighbours")
                                        if sharded else "independent replicas per rank")},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
         }
