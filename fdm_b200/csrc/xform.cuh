@@ -123,7 +123,7 @@ FDMB_PLAN(32, 4, 4, 1, 4)
 FDMB_PLAN(64, 8, 4, 1, 4)
 FDMB_PLAN(128, 8, 8, 1, 8)
 // radix <= 8 keeps the butterflies near 64 registers, so 24+ warps per SM stay resident
-FDMB_PLAN(256, 8, 4, 4, 16)
+FDMB_PLAN(256, 16, 8, 1, 8)
 FDMB_PLAN(512, 8, 8, 4, 32)
 FDMB_PLAN(1024, 8, 8, 8, 64)
 FDMB_PLAN(2048, 16, 8, 8, 64)

@@ -31,8 +31,8 @@ template <int N, bool WIDE = false> struct PipeCfg {
     static constexpr int GC = (N == 1024) ? 32 : G;
     static constexpr int THREADS_COLS = B * GC;
     // resident CTAs the register allocation must leave room for (plain sweep / fused forward-multiply-inverse sweep)
-    static constexpr int COLS_MIN_CTAS = (N == 1024 && !WIDE) ? 2 : (N == 256 ? 3 : 1);
-    static constexpr int COLS_MIN_CTAS_MID = (N == 1024 && !WIDE) ? 2 : (N == 256 ? 2 : 1);
+    static constexpr int COLS_MIN_CTAS = (N == 1024 && !WIDE) ? 2 : (N == 256 ? 4 : 1);
+    static constexpr int COLS_MIN_CTAS_MID = (N == 1024 && !WIDE) ? 2 : (N == 256 ? 4 : 1);
     static constexpr int SCR = (G + G / 8 + 1) * B;
     static constexpr bool SWZ = (B == 8);              // 64-byte tile rows: keep half-warps on rows of different parity
     // SN + WM + two fold tables SF (doubles)
