@@ -240,6 +240,51 @@ int fdmb_ns_cyl_attach_ipc(fdmb_ns_cyl* h, const void* handles);
 int fdmb_ns_cyl_attach_local(fdmb_ns_cyl* h, fdmb_ns_cyl* const* all);
 int fdmb_ns_cyl_synchronize(fdmb_ns_cyl* h);
 
+/* ---- velocity_plotter -------------------------------------------------------------
+ * Replaces fdm::velocity_plotter<double,check,F> (src/velocity_plot.h:11-143, src/velocity_plot.cpp:10-222),
+ * the step AFTER the path in both reference drivers (test/test_ns_cube.cpp:24-50, test/test_ns_cyl.cpp:53-92):
+ * mid-plane slices of the staggered velocity, their stream functions through LaplRectFFT2 / LaplRect
+ * (cylindrical column scales, src/velocity_plot.h:113-127) and the ASCII VTK writer.  The slices, right-hand
+ * sides, the three 2-D solves and the cell-centred velocities of the VTK file are computed on the device from
+ * the NS state where it lives; only 2-D slices (and, for vtk_out, 3 doubles per cell) cross PCIe.
+ * params     <-> the constructor (dx,dy,dz, nx,ny,nz, xx1,xx2, yy1,yy2, zz1,zz2, cyl); zperiodic / yperiodic
+ *                <-> F = tensor_flags<>, <periodic>, <periodic,periodic> (src/velocity_plot.cpp:222-235).
+ *                Axis names are the reference's: z slowest, x fastest (phi, z, r for cylinders).
+ * use_*      <-> void use(T* u, T* v, T* w): arrays with the reference's extents
+ *                u[z0..znn][y0..ynn][-1..nx+1], v[z0..znn][y_..ynn][0..nx+1], w[z_..znn][y0..ynn][0..nx+1]
+ *                (src/velocity_plot.h:97-99).  use_host re-uploads the host arrays at every update(), like the
+ *                reference re-reads them; use_device / use_ns_cube / use_ns_cyl read device memory in place
+ *                (the NS handle's stream is synchronised first; single-GPU NS handles only).
+ * update     <-> void update()  (src/velocity_plot.cpp:17-67)
+ * get_slice  <-> the members vx,wx,uy,wy,uz,vz,RHS_x,RHS_y,RHS_z,psi_x,psi_y,psi_z (src/velocity_plot.h:32-44),
+ *                row-major with the reference's extents; slice_dims gives rows x cols
+ * cell_velocity  the "VECTORS u" block of vtk_out before formatting: for i=z1..zn, k=y1..yn, j=1..nx the three
+ *                face averages (src/velocity_plot.cpp:180-182,209-213), 3 doubles per cell
+ * vtk_out    <-> void vtk_out(const std::string& name, int step) (src/velocity_plot.cpp:117-220), same bytes */
+typedef struct fdmb_vplot fdmb_vplot;
+typedef struct fdmb_vplot_params {
+    double dx, dy, dz;
+    int nx, ny, nz;
+    double xx1, xx2, yy1, yy2, zz1, zz2;
+    int cyl;
+    int zperiodic, yperiodic;
+} fdmb_vplot_params;
+enum { FDMB_SLICE_VX = 0, FDMB_SLICE_WX, FDMB_SLICE_UY, FDMB_SLICE_WY, FDMB_SLICE_UZ, FDMB_SLICE_VZ,
+       FDMB_SLICE_RHS_X, FDMB_SLICE_RHS_Y, FDMB_SLICE_RHS_Z, FDMB_SLICE_PSI_X, FDMB_SLICE_PSI_Y, FDMB_SLICE_PSI_Z,
+       FDMB_SLICE_COUNT };
+int fdmb_vplot_create(fdmb_vplot** h, const fdmb_vplot_params* p);
+int fdmb_vplot_field_size(fdmb_vplot* h, int field, long long* count);   /* field: FDMB_FIELD_U / _V / _W */
+int fdmb_vplot_use_host(fdmb_vplot* h, const double* u, const double* v, const double* w);
+int fdmb_vplot_use_device(fdmb_vplot* h, const double* d_u, const double* d_v, const double* d_w);
+int fdmb_vplot_use_ns_cube(fdmb_vplot* h, fdmb_ns_cube* ns);
+int fdmb_vplot_use_ns_cyl(fdmb_vplot* h, fdmb_ns_cyl* ns);
+int fdmb_vplot_update(fdmb_vplot* h);
+int fdmb_vplot_slice_dims(fdmb_vplot* h, int slice, int* rows, int* cols);
+int fdmb_vplot_get_slice(fdmb_vplot* h, int slice, double* host);
+int fdmb_vplot_cell_velocity(fdmb_vplot* h, double* host);
+int fdmb_vplot_vtk_out(fdmb_vplot* h, const char* name, int time_index);
+int fdmb_vplot_destroy(fdmb_vplot* h);
+
 #ifdef __cplusplus
 }
 #endif

@@ -472,6 +472,95 @@ class NSCube:
 # --------------------------------------------------------------------------------------
 
 
+# --------------------------------------------------------------------------------------
+# velocity_plotter (reference: src/velocity_plot.h:59-129, src/velocity_plot.cpp:17-67,117-220)
+# --------------------------------------------------------------------------------------
+class VelocityPlotter:
+    """update() and the VECTORS block of vtk_out, restated with numpy index arithmetic.
+    Axes as in the reference: z slowest, x fastest; zperiodic / yperiodic <-> F."""
+
+    def __init__(self, dx, dy, dz, nx, ny, nz, xx1, xx2, yy1, yy2, zz1, zz2, cyl=False, zperiodic=False,
+                 yperiodic=False):
+        self.dx, self.dy, self.dz, self.nx, self.ny, self.nz = dx, dy, dz, nx, ny, nz
+        self.zp, self.yp, self.cyl = bool(zperiodic), bool(yperiodic), bool(cyl)
+        yp, zp = self.yp, self.zp
+        # velocity_plot.h:67-83
+        ly = yy2 - yy1 if yp else yy2 - yy1 + dy
+        lz = zz2 - zz1 if zp else zz2 - zz1 + dz
+        self.y_, self.y1, self.yn, self.ynn = (0, 0, ny - 1, ny - 1) if yp else (-1, 1, ny, ny + 1)
+        self.z_, self.z1, self.zn, self.znn = (0, 0, nz - 1, nz - 1) if zp else (-1, 1, nz, nz + 1)
+        # velocity_plot.h:101-105
+        self.lapl_x = LaplRectFFT2(dy, dz, ly, lz, ny, nz, yperiodic=zp, xperiodic=yp)
+        self.lapl_y = LaplRect(dx, dz, xx2 - xx1 + dx, lz, nx, nz, yperiodic=zp)
+        self.lapl_z = LaplRect(dx, dy, xx2 - xx1 + dx, ly, nx, ny, yperiodic=yp)
+        if cyl:  # velocity_plot.h:113-127
+            j = np.arange(nx + 1, dtype=np.float64)
+            r = xx1 + j * dx - dx / 2
+            one = np.ones(1)
+            self.lapl_y.lm_y_scale = np.concatenate([one, (1. / r / r)[1:]])
+            self.lapl_y.U_scale = np.concatenate([one, ((r + dx / 2) / r)[1:]])
+            self.lapl_y.L_scale = np.concatenate([one, ((r - dx / 2) / r)[1:]])
+            self.lapl_z.U_scale = self.lapl_y.U_scale.copy()
+            self.lapl_z.L_scale = self.lapl_y.L_scale.copy()
+
+    def shapes(self):
+        """Extents of u, v, w (velocity_plot.h:97-99)."""
+        Zc, Yc = self.znn + 1, self.ynn + 1
+        return ((Zc, Yc, self.nx + 3), (Zc, self.ynn - self.y_ + 1, self.nx + 2),
+                (self.znn - self.z_ + 1, Yc, self.nx + 2))
+
+    def _views(self, u, v, w):
+        su, sv, sw = self.shapes()
+        u, v, w = np.reshape(u, su), np.reshape(v, sv), np.reshape(w, sw)
+        nz, ny = self.nz, self.ny
+        wz = (lambda i: (i + nz) % nz) if self.zp else (lambda i: i)
+        wy = (lambda k: (k + ny) % ny) if self.yp else (lambda k: k)
+        U = lambda i, k, j: u[i, k, j + 1]                   # noqa: E731
+        V = lambda i, k, j: v[i, wy(k) - self.y_, j]         # noqa: E731
+        W = lambda i, k, j: w[wz(i) - self.z_, k, j]         # noqa: E731
+        return U, V, W, wz, wy
+
+    def update(self, u, v, w):
+        U, V, W, wz, wy = self._views(u, v, w)
+        nx, ny, nz, dx, dy, dz = self.nx, self.ny, self.nz, self.dx, self.dy, self.dz
+        I = np.arange(0, self.znn + 1)[:, None]
+        K = np.arange(0, self.ynn + 1)
+        J = np.arange(0, nx + 2)
+        out = {}
+        out["vx"] = 0.5 * (V(I, K[None, :] - 1, nx // 2) + V(I, K[None, :], nx // 2))        # :19-24
+        out["wx"] = 0.5 * (W(I - 1, K[None, :], nx // 2) + W(I, K[None, :], nx // 2))
+        out["uy"] = 0.5 * (U(I, ny // 2, J[None, :] - 1) + U(I, ny // 2, J[None, :]))        # :26-31
+        out["wy"] = 0.5 * (W(I - 1, ny // 2, J[None, :]) + W(I, ny // 2, J[None, :]))
+        Kc = K[:, None]
+        out["uz"] = 0.5 * (U(nz // 2, Kc, J[None, :] - 1) + U(nz // 2, Kc, J[None, :]))      # :33-38
+        out["vz"] = 0.5 * (V(nz // 2, Kc - 1, J[None, :]) + V(nz // 2, Kc, J[None, :]))
+        Ii = np.arange(self.z1, self.zn + 1)[:, None]
+        Ki = np.arange(self.y1, self.yn + 1)
+        Ji = np.arange(1, nx + 1)[None, :]
+        vx, wx, uy, wy_, uz, vz = (out[k] for k in ("vx", "wx", "uy", "wy", "uz", "vz"))
+        out["RHS_x"] = ((wx[Ii, wy(Ki + 1)[None, :]] - wx[Ii, wy(Ki - 1)[None, :]]) / 2 / dy
+                        - (vx[wz(Ii + 1), Ki[None, :]] - vx[wz(Ii - 1), Ki[None, :]]) / 2 / dz)   # :40-44
+        out["RHS_y"] = ((wy_[Ii, Ji + 1] - wy_[Ii, Ji - 1]) / 2 / dx
+                        - (uy[wz(Ii + 1), Ji] - uy[wz(Ii - 1), Ji]) / 2 / dz)                     # :48-52
+        Kic = Ki[:, None]
+        out["RHS_z"] = ((vz[Kic, Ji + 1] - vz[Kic, Ji - 1]) / 2 / dx
+                        - (uz[wy(Kic + 1), Ji] - uz[wy(Kic - 1), Ji]) / 2 / dy)                   # :56-60
+        out["psi_x"] = self.lapl_x.solve(out["RHS_x"])
+        out["psi_y"] = self.lapl_y.solve(out["RHS_y"])
+        out["psi_z"] = self.lapl_z.solve(out["RHS_z"])
+        return out
+
+    def cell_velocity(self, u, v, w):
+        """(cells, 3): the face averages vtk_out prints (or rotates, for cylinders) -- :180-182, :209-213."""
+        U, V, W, wz, wy = self._views(u, v, w)
+        I = np.arange(self.z1, self.zn + 1)[:, None, None]
+        K = np.arange(self.y1, self.yn + 1)[None, :, None]
+        J = np.arange(1, self.nx + 1)[None, None, :]
+        c = np.stack([0.5 * (U(I, K, J) + U(I, K, J - 1)), 0.5 * (V(I, K, J) + V(I, K - 1, J)),
+                      0.5 * (W(I, K, J) + W(I - 1, K, J))], axis=-1)
+        return c.reshape(-1, 3)
+
+
 def rel_l2(a, b):
     """||a-b||_2 / ||b||_2 with a 0/0 guard (both exactly zero -> 0)."""
     a = np.asarray(a, dtype=np.float64).ravel()

@@ -67,6 +67,12 @@ def lib():
         L.ref_ns_cyl_get_field.argtypes = [C.c_void_p, C.c_int, _dp]
         L.ref_ns_cyl_set_field.argtypes = [C.c_void_p, C.c_int, _dp]
         L.ref_ns_cyl_destroy.argtypes = [C.c_void_p]
+        L.ref_vplot_create.restype = C.c_void_p
+        L.ref_vplot_create.argtypes = [C.c_int] + [C.c_double] * 3 + [C.c_int] * 3 + [C.c_double] * 6 + [C.c_int]
+        L.ref_vplot_update.argtypes = [C.c_void_p, _dp, _dp, _dp]
+        L.ref_vplot_get_slice.argtypes = [C.c_void_p, C.c_int, _dp]
+        L.ref_vplot_vtk_out.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+        L.ref_vplot_destroy.argtypes = [C.c_void_p]
         _lib = L
     return _lib
 
@@ -217,4 +223,38 @@ class NSCyl:
     def __del__(self):
         if getattr(self, "h", None):
             lib().ref_ns_cyl_destroy(self.h)
+            self.h = None
+
+
+SLICE_IDS = {"vx": 0, "wx": 1, "uy": 2, "wy": 3, "uz": 4, "vz": 5, "RHS_x": 6, "RHS_y": 7, "RHS_z": 8,
+             "psi_x": 9, "psi_y": 10, "psi_z": 11}
+
+
+class VelocityPlotter:
+    """The unmodified fdm::velocity_plotter<double,false,F> (src/velocity_plot.h, src/velocity_plot.cpp)."""
+
+    def __init__(self, dx, dy, dz, nx, ny, nz, xx1, xx2, yy1, yy2, zz1, zz2, cyl=False, zperiodic=False,
+                 yperiodic=False):
+        flags = 3 if (zperiodic and yperiodic) else (1 if zperiodic else 0)
+        assert not (yperiodic and not zperiodic)
+        self.h = lib().ref_vplot_create(flags, dx, dy, dz, nx, ny, nz, xx1, xx2, yy1, yy2, zz1, zz2, int(bool(cyl)))
+        self._keep = None
+
+    def update(self, u, v, w):
+        """use(u, v, w); update()"""
+        self._keep = [np.ascontiguousarray(a, dtype=np.float64).ravel() for a in (u, v, w)]
+        lib().ref_vplot_update(self.h, *[_p(a) for a in self._keep])
+
+    def slice(self, name):
+        n = lib().ref_vplot_get_slice(self.h, SLICE_IDS[name], None)
+        out = np.empty(n)
+        lib().ref_vplot_get_slice(self.h, SLICE_IDS[name], _p(out))
+        return out
+
+    def vtk_out(self, name, time_index):
+        lib().ref_vplot_vtk_out(self.h, str(name).encode(), int(time_index))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().ref_vplot_destroy(self.h)
             self.h = None

@@ -8,6 +8,10 @@
 //                                                 column scales written through the public vectors
 //   shim_check cyl <nr> <nz> <nphi> <rhs.bin> <ans.bin>      LaplCyl3FFT2<double,true>
 //   shim_check nscyl <steps> <lsteps> <prefix> [--ns:...]    NSCyl<double,true>, dumps <prefix>_{u,v,w,p}.bin
+//   shim_check vplot <n> <steps> <prefix> [--ns:...]         NSCube + velocity_plotter as in test/test_ns_cube.cpp:24-50:
+//                                                 host use(u,v,w), device use(ns), float instantiation; dumps
+//                                                 <prefix>_{host,dev,flt}_psi_{x,y,z}.bin, <prefix>_{host,dev}.vtk, .ppm
+//   shim_check vplotcyl <steps> <zero> <prefix> [--ns:...]   NSCyl + velocity_plotter as in test/test_ns_cyl.cpp:53-92
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -18,6 +22,7 @@
 #include "ns_cube.h"
 #include "ns_cyl.h"
 #include "lapl_rect.h"
+#include "velocity_plot.h"
 
 using namespace fdm;
 
@@ -120,6 +125,69 @@ int main(int argc, char** argv)
         spit(prefix + "_u.bin", ns.u.vec, ns.u.size); spit(prefix + "_v.bin", ns.v.vec, ns.v.size);
         spit(prefix + "_w.bin", ns.w.vec, ns.w.size); spit(prefix + "_p.bin", ns.p.vec, ns.p.size);
         printf("time_index %d size %d\n", ns.time_index, ns.size());
+        return 0;
+    }
+    if (mode == "vplot") {
+        int steps = atoi(argv[3]);
+        std::string prefix = argv[4];
+        std::string a1 = "--ns:nx=" + std::to_string(n), a2 = "--ns:nz=" + std::to_string(n);
+        std::vector<char*> args{argv[0], a1.data(), a2.data()};
+        for (int i = 5; i < argc; i++) args.push_back(argv[i]);
+        Config c;
+        c.rewrite((int)args.size(), args.data());
+        NSCube<double, true> ns(c);
+        velocity_plotter<double, true> plot(ns.dx, ns.dy, ns.dz, ns.nx, ns.ny, ns.nz, ns.x1, ns.x2, ns.y1, ns.y2, ns.z1, ns.z2);
+        plot.use(ns.u.vec, ns.v.vec, ns.w.vec);            // the reference's way: host mirrors
+        for (int i = 0; i < steps; i++) ns.step();
+        plot.update();
+        spit(prefix + "_host_psi_x.bin", plot.psi_x.vec, plot.psi_x.size);
+        spit(prefix + "_host_psi_y.bin", plot.psi_y.vec, plot.psi_y.size);
+        spit(prefix + "_host_psi_z.bin", plot.psi_z.vec, plot.psi_z.size);
+        plot.vtk_out(prefix + "_host.vtk", ns.time_index);
+        velocity_plotter<double, true> dplot(ns.dx, ns.dy, ns.dz, ns.nx, ns.ny, ns.nz, ns.x1, ns.x2, ns.y1, ns.y2, ns.z1, ns.z2);
+        dplot.use(ns);                                     // device state in place
+        dplot.update();
+        spit(prefix + "_dev_psi_x.bin", dplot.psi_x.vec, dplot.psi_x.size);
+        spit(prefix + "_dev_psi_y.bin", dplot.psi_y.vec, dplot.psi_y.size);
+        spit(prefix + "_dev_psi_z.bin", dplot.psi_z.vec, dplot.psi_z.size);
+        dplot.vtk_out(prefix + "_dev.vtk", ns.time_index);
+        dplot.plot(prefix + "_dev.png", ns.time_index * ns.dt);
+        // index like a reference caller: psi_y[i][j], i = z1..zn, j = 1..nx
+        if (!(std::abs(dplot.psi_y[ns.nz / 2][ns.nx / 2]) > 0)) { fprintf(stderr, "psi_y mirror empty\n"); return 3; }
+        std::vector<float> fu(ns.u.vec, ns.u.vec + ns.u.size), fv(ns.v.vec, ns.v.vec + ns.v.size),
+            fw(ns.w.vec, ns.w.vec + ns.w.size);
+        velocity_plotter<float, false> fplot(ns.dx, ns.dy, ns.dz, ns.nx, ns.ny, ns.nz, ns.x1, ns.x2, ns.y1, ns.y2, ns.z1, ns.z2);
+        fplot.use(fu.data(), fv.data(), fw.data());
+        fplot.update();
+        std::vector<double> t(fplot.psi_y.vec, fplot.psi_y.vec + fplot.psi_y.size);
+        spit(prefix + "_flt_psi_y.bin", t.data(), t.size());
+        spit(prefix + "_u.bin", ns.u.vec, ns.u.size); spit(prefix + "_v.bin", ns.v.vec, ns.v.size);
+        spit(prefix + "_w.bin", ns.w.vec, ns.w.size);
+        printf("time_index %d\n", ns.time_index);
+        return 0;
+    }
+    if (mode == "vplotcyl") {
+        int steps = atoi(argv[2]);
+        std::string prefix = argv[4];
+        std::vector<char*> args{argv[0]};
+        for (int i = 5; i < argc; i++) args.push_back(argv[i]);
+        Config c;
+        c.rewrite((int)args.size(), args.data());
+        using Task = NSCyl<double, true, tensor_flag::periodic>;
+        Task ns(c);
+        velocity_plotter<double, true, typename Task::tensor_flags> plot(ns.dr, ns.dz, ns.dphi, ns.nr, ns.nz, ns.nphi,
+                                                                         ns.r0, ns.R, ns.h1, ns.h2, 0, 2 * M_PI, true);
+        plot.set_labels("R", "Z", "PHI");
+        plot.use(ns);
+        for (int i = 0; i < steps; i++) ns.step();
+        plot.update();
+        spit(prefix + "_dev_psi_x.bin", plot.psi_x.vec, plot.psi_x.size);
+        spit(prefix + "_dev_psi_y.bin", plot.psi_y.vec, plot.psi_y.size);
+        spit(prefix + "_dev_psi_z.bin", plot.psi_z.vec, plot.psi_z.size);
+        plot.vtk_out(prefix + "_dev.vtk", ns.time_index);
+        spit(prefix + "_u.bin", ns.u.vec, ns.u.size); spit(prefix + "_v.bin", ns.v.vec, ns.v.size);
+        spit(prefix + "_w.bin", ns.w.vec, ns.w.size);
+        printf("time_index %d\n", ns.time_index);
         return 0;
     }
     if (mode == "ns") {

@@ -27,16 +27,18 @@ def build(out, with_reference_headers=False):
 REPLACED = ("lapl_cube.h", "lapl_rect.h", "lapl_cyl.h", "ns_cube.h", "ns_cyl.h")
 
 
-def make_overlay(dst):
+def make_overlay(dst, native_plotter=False):
     """The reference's src/ with the five class headers REPLACED by the drop-in ones (what a maintainer does; an extra
     include directory is not enough, because a quoted #include from a reference header looks in its own directory
-    first).  Everything else, and test/*.cpp, are symlinks to the untouched reference files."""
+    first).  Everything else, and test/*.cpp, are symlinks to the untouched reference files.
+    native_plotter: velocity_plot.h is replaced too (header-only device-side plotter; src/velocity_plot.cpp is then
+    dropped from the build)."""
     ref = "/root/reference"
     os.makedirs(os.path.join(dst, "src"), exist_ok=True)
     os.makedirs(os.path.join(dst, "test"), exist_ok=True)
     for name in os.listdir(os.path.join(ref, "src")):
         tgt = os.path.join(dst, "src", name)
-        if name in REPLACED:
+        if name in REPLACED or (native_plotter and name == "velocity_plot.h"):
             src = os.path.join(ROOT, "fdm_b200", "cxx", name)
         else:
             src = os.path.join(ref, "src", name)
@@ -59,6 +61,21 @@ def compile_in_overlay(overlay, rel, out):
 
 
 DRIVER = os.path.join(ROOT, "tests", "cxx", "_build", "fdm_ns_cube")
+
+
+DRIVER_NATIVE_PLOT = os.path.join(ROOT, "tests", "cxx", "_build", "fdm_ns_cube_native_plot")
+
+
+def build_reference_driver_native_plot(overlay, out=DRIVER_NATIVE_PLOT):
+    """The same unmodified driver source with velocity_plot.h replaced as well (overlay made with native_plotter=True):
+    no src/velocity_plot.cpp, no plplot symbols -- everything resolves."""
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    srcs = [os.path.join(overlay, p) for p in ("test/test_ns_cube.cpp", "src/config.cpp", "src/asp_misc.cpp")]
+    cmd = ["/usr/bin/g++", "-std=c++20", "-O2", "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(overlay, "src"),
+           "-I" + os.path.join(ROOT, "oracle", "stub"), "-include", "cmath", *srcs, "-o", out,
+           "-L" + LIBDIR, "-lfdm_b200", "-Wl,-rpath,$ORIGIN/../../../fdm_b200"]
+    subprocess.run(cmd, check=True, capture_output=True, text=True)
+    return out
 
 
 def build_reference_driver(overlay, out=DRIVER):

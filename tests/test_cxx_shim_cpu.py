@@ -48,3 +48,14 @@ def test_reference_driver_links_against_the_library(tmp_path):
     ov = cxx_build.make_overlay(str(tmp_path / "overlay"))
     exe = cxx_build.build_reference_driver(ov, str(tmp_path / "fdm_ns_cube"))
     assert os.access(exe, os.X_OK)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="reference tree not present")
+def test_reference_driver_builds_with_the_native_plotter(tmp_path):
+    """velocity_plot.h replaced too: the unmodified test/test_ns_cube.cpp links with no
+    src/velocity_plot.cpp and no unresolved plplot symbols."""
+    ov = cxx_build.make_overlay(str(tmp_path / "overlay"), native_plotter=True)
+    exe = cxx_build.build_reference_driver_native_plot(ov, str(tmp_path / "fdm_ns_cube_np"))
+    assert os.access(exe, os.X_OK)
+    r = subprocess.run(["nm", "-u", "-C", exe], capture_output=True, text=True)
+    assert "matrix_plotter" not in r.stdout and "pl" + "init" not in r.stdout

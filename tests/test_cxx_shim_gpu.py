@@ -137,3 +137,81 @@ def test_reference_driver_fdm_ns_cube_on_the_gpu_path(tmp_path, ref):
         wc = 0.5 * (w[2:n + 2, 1:n + 1, 1:n + 1] + w[1:n + 1, 1:n + 1, 1:n + 1])
         want = np.stack([uc.ravel(), vc.ravel(), wc.ravel()], axis=1)
         assert np.max(np.abs(got - want)) < 1.5e-6        # "%f": six decimals
+
+
+def test_cxx_velocity_plotter_on_ns_cube(exe, tmp_path, ref):
+    """The drop-in velocity_plotter used like test/test_ns_cube.cpp:24-50: host use(u,v,w), device use(ns) and the
+    float instantiation give the reference plotter's stream functions on the same fields; VTK files byte-identical."""
+    n, steps = 31, 12
+    r = subprocess.run([exe, "vplot", str(n), str(steps), str(tmp_path / "vp"), "--ns:Re=250", "--ns:dt=0.01"],
+                       check=True, capture_output=True, text=True)
+    assert f"time_index {steps}" in r.stdout
+    u, v, w = (np.fromfile(tmp_path / f"vp_{f}.bin") for f in "uvw")
+    d = 2 * math.pi / n
+    R = ref.VelocityPlotter(d, d, d, n, n, n, -math.pi, math.pi, -math.pi, math.pi, -math.pi, math.pi)
+    R.update(u, v, w)
+    for s in ("psi_x", "psi_y", "psi_z"):
+        want = R.slice(s)
+        assert np.abs(want).max() > 0 or s != "psi_y"
+        for kind in ("host", "dev"):
+            assert O.rel_l2(np.fromfile(tmp_path / f"vp_{kind}_{s}.bin"), want) < 1e-12, (s, kind)
+    assert O.rel_l2(np.fromfile(tmp_path / "vp_flt_psi_y.bin"), R.slice("psi_y")) < 1e-5
+    R.vtk_out(tmp_path / "ref.vtk", steps)
+    want = (tmp_path / "ref.vtk").read_bytes()
+    assert (tmp_path / "vp_host.vtk").read_bytes() == want
+    assert (tmp_path / "vp_dev.vtk").read_bytes() == want
+    ppm = (tmp_path / "vp_dev.ppm").read_bytes()
+    assert ppm.startswith(b"P6\n")
+
+
+def test_cxx_velocity_plotter_on_ns_cyl(exe, tmp_path, ref):
+    """test/test_ns_cyl.cpp:53-92 (periodic z): cylindrical column scales, hexahedral VTK."""
+    nr, nz, nphi, steps = 32, 32, 32, 10
+    r = subprocess.run([exe, "vplotcyl", str(steps), "0", str(tmp_path / "vc"), f"--ns:nr={nr}", f"--ns:nz={nz}",
+                        f"--ns:nphi={nphi}", "--ns:Re=200", "--ns:dt=0.01"], check=True, capture_output=True, text=True)
+    assert f"time_index {steps}" in r.stdout
+    u, v, w = (np.fromfile(tmp_path / f"vc_{f}.bin") for f in "uvw")
+    r0, R0, h1, h2 = math.pi / 2, math.pi, 0.0, 10.0
+    R = ref.VelocityPlotter((R0 - r0) / nr, (h2 - h1) / nz, 2 * math.pi / nphi, nr, nz, nphi, r0, R0, h1, h2, 0.0,
+                            2 * math.pi, cyl=True, zperiodic=True, yperiodic=True)
+    R.update(u, v, w)
+    for s in ("psi_x", "psi_y", "psi_z"):
+        assert O.rel_l2(np.fromfile(tmp_path / f"vc_dev_{s}.bin"), R.slice(s)) < 1e-12, s
+    R.vtk_out(tmp_path / "ref.vtk", steps)
+    la = (tmp_path / "ref.vtk").read_text().splitlines()
+    lb = (tmp_path / "vc_dev.vtk").read_text().splitlines()
+    k = la.index("VECTORS u double")
+    assert la[:k + 1] == lb[:k + 1] and len(la) == len(lb)
+
+
+def test_reference_driver_with_the_native_plotter(tmp_path, ref):
+    """The unmodified test/test_ns_cube.cpp built with velocity_plot.h replaced as well (no src/velocity_plot.cpp, no
+    plplot): its VTK files equal the compiled reference's byte for byte, and plot() leaves its panels as .ppm."""
+    import os
+    exe = cxx_build.DRIVER_NATIVE_PLOT
+    if not os.path.exists(exe):
+        if not os.path.isdir("/root/reference/src"):
+            pytest.skip("tests/cxx/_build/fdm_ns_cube_native_plot not built (needs /root/reference at build time)")
+        cxx_build.build_reference_driver_native_plot(
+            cxx_build.make_overlay(str(tmp_path / "overlay"), native_plotter=True))
+    n, steps = 31, 20
+    r = subprocess.run([exe, f"--ns:nx={n}", f"--ns:nz={n}", "--ns:Re=250", "--ns:dt=0.01", f"--ns:steps={steps}",
+                        "--plot:png=1", "--plot:vtk=1", "--plot:interval=10"], cwd=tmp_path, capture_output=True,
+                       text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-1000:] + r.stderr[-1000:]
+    Rn = ref.NSCube(nx=n, nz=n, Re=250.0, dt=0.01)
+    d = 2 * math.pi / n
+    P = ref.VelocityPlotter(d, d, d, n, n, n, -math.pi, math.pi, -math.pi, math.pi, -math.pi, math.pi)
+    for step in (0, 10, 20):
+        if step:
+            Rn.step(10)
+        P.update(*(Rn.field(f) for f in "uvw"))
+        P.vtk_out(tmp_path / "ref.vtk", step)
+        got = (tmp_path / f"step_{step:07d}.vtk").read_text().splitlines()
+        want = (tmp_path / "ref.vtk").read_text().splitlines()
+        k = want.index("VECTORS u double")
+        assert got[:k + 1] == want[:k + 1] and len(got) == len(want)
+        a = np.array([[float(x) for x in ln.split()] for ln in got[k + 1:]])
+        b = np.array([[float(x) for x in ln.split()] for ln in want[k + 1:]])
+        assert np.max(np.abs(a - b)) < 1.5e-6          # the two NS runs agree to 1e-12, "%f" prints six decimals
+        assert (tmp_path / f"step_{step:07d}.ppm").read_bytes().startswith(b"P6\n")
