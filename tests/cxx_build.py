@@ -90,3 +90,12 @@ def build_reference_driver(overlay, out=DRIVER):
            "-L" + LIBDIR, "-lfdm_b200", "-Wl,-rpath,$ORIGIN/../../../fdm_b200", "-Wl,--unresolved-symbols=ignore-all"]
     subprocess.run(cmd, check=True, capture_output=True, text=True)
     return out
+
+
+def build_example(name, out):
+    """examples/<name>.cpp: our own thin drivers with the reference drivers' command lines, against the compat headers."""
+    cmd = ["/usr/bin/g++", "-std=c++17", "-O1", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"),
+           "-I" + os.path.join(ROOT, "fdm_b200", "cxx"), os.path.join(ROOT, "examples", name + ".cpp"), "-o", out,
+           "-L" + LIBDIR, "-lfdm_b200", "-Wl,-rpath," + LIBDIR]
+    subprocess.run(cmd, check=True, capture_output=True, text=True)
+    return out

@@ -59,3 +59,14 @@ def test_reference_driver_builds_with_the_native_plotter(tmp_path):
     assert os.access(exe, os.X_OK)
     r = subprocess.run(["nm", "-u", "-C", exe], capture_output=True, text=True)
     assert "matrix_plotter" not in r.stdout and "pl" + "init" not in r.stdout
+
+
+@pytest.mark.parametrize("name", ["fdm_ns_cube", "fdm_ns_cyl"])
+def test_example_drivers_build_and_fail_loudly_without_device(tmp_path, name):
+    exe = cxx_build.build_example(name, str(tmp_path / name))
+    import fdm_b200
+    if fdm_b200.lib().fdmb_device_count() > 0:
+        pytest.skip("a GPU is present")
+    r = subprocess.run([exe, "--ns:nx=15", "--ns:nz=15", "--ns:nr=16", "--ns:nphi=16"], capture_output=True, text=True,
+                       cwd=tmp_path)
+    assert r.returncode == -signal.SIGABRT and "verify(" in r.stderr
