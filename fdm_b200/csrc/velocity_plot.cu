@@ -18,114 +18,39 @@
 #include <vector>
 
 #include "common.h"
+#include "vplot_math.h"
 
 namespace fdmb {
 
-// Index ranges of src/velocity_plot.h:73-83 and the array extents of :85-99.
-struct VGeom {
-    int nx, ny, nz;
-    int zper, yper;
-    int y_, y1, yn, ynn;    // y0 = z0 = 0
-    int z_, z1, zn, znn;
-    int Yc, Zc;             // points in y0..ynn, z0..znn
-    int Yv;                 // points in y_..ynn (v)
-    int Yi, Zi;             // points in y1..yn, z1..zn
-    double dx, dy, dz;
-};
+// The per-element arithmetic lives in vplot_math.h (shared with the host emulation test).
 
-__device__ __forceinline__ int wrap_z(const VGeom& g, int i) { return g.zper ? (i + g.nz) % g.nz : i; }
-__device__ __forceinline__ int wrap_y(const VGeom& g, int k) { return g.yper ? (k + g.ny) % g.ny : k; }
-// u[z0..znn][y0..ynn][-1..nx+1], v[z0..znn][y_..ynn][0..nx+1], w[z_..znn][y0..ynn][0..nx+1]
-__device__ __forceinline__ long long iu(const VGeom& g, int i, int k, int j)
-{
-    return ((long long)i * g.Yc + k) * (g.nx + 3) + (j + 1);
-}
-__device__ __forceinline__ long long iv(const VGeom& g, int i, int k, int j)
-{
-    return ((long long)i * g.Yv + (k - g.y_)) * (g.nx + 2) + j;
-}
-__device__ __forceinline__ long long iw(const VGeom& g, int i, int k, int j)
-{
-    return ((long long)(i - g.z_) * g.Yc + k) * (g.nx + 2) + j;
-}
-
-// src/velocity_plot.cpp:19-38: face averages on the planes x = nx/2, y = ny/2, z = nz/2
 __global__ void k_vplot_slices(VGeom g, const double* __restrict__ u, const double* __restrict__ v,
                                const double* __restrict__ w, double* __restrict__ vx, double* __restrict__ wx,
                                double* __restrict__ uy, double* __restrict__ wy, double* __restrict__ uz,
                                double* __restrict__ vz)
 {
-    const int X2 = g.nx + 2;
-    const long long n0 = (long long)g.Zc * g.Yc, n1 = (long long)g.Zc * X2, n2 = (long long)g.Yc * X2;
-    const int jm = g.nx / 2, km = g.ny / 2, im = g.nz / 2;
-    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n0 + n1 + n2;
-         t += (long long)gridDim.x * blockDim.x) {
-        if (t < n0) {
-            const int i = (int)(t / g.Yc), k = (int)(t % g.Yc);
-            vx[t] = 0.5 * (v[iv(g, i, wrap_y(g, k - 1), jm)] + v[iv(g, i, k, jm)]);
-            wx[t] = 0.5 * (w[iw(g, wrap_z(g, i - 1), k, jm)] + w[iw(g, i, k, jm)]);
-        } else if (t < n0 + n1) {
-            const long long s = t - n0;
-            const int i = (int)(s / X2), j = (int)(s % X2);
-            uy[s] = 0.5 * (u[iu(g, i, km, j - 1)] + u[iu(g, i, km, j)]);
-            wy[s] = 0.5 * (w[iw(g, wrap_z(g, i - 1), km, j)] + w[iw(g, i, km, j)]);
-        } else {
-            const long long s = t - n0 - n1;
-            const int k = (int)(s / X2), j = (int)(s % X2);
-            uz[s] = 0.5 * (u[iu(g, im, k, j - 1)] + u[iu(g, im, k, j)]);
-            vz[s] = 0.5 * (v[iv(g, im, wrap_y(g, k - 1), j)] + v[iv(g, im, k, j)]);
-        }
-    }
+    const long long n = vplot_slice_elems(g);
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x)
+        vplot_slice_elem(g, t, u, v, w, vx, wx, uy, wy, uz, vz);
 }
 
-// src/velocity_plot.cpp:40-64: centred differences of the slices (periodic axes wrap inside the slice)
 __global__ void k_vplot_rhs(VGeom g, const double* __restrict__ vx, const double* __restrict__ wx,
                             const double* __restrict__ uy, const double* __restrict__ wy,
                             const double* __restrict__ uz, const double* __restrict__ vz, double* __restrict__ rx,
                             double* __restrict__ ry, double* __restrict__ rz)
 {
-    const int X2 = g.nx + 2;
-    const long long n0 = (long long)g.Zi * g.Yi, n1 = (long long)g.Zi * g.nx, n2 = (long long)g.Yi * g.nx;
-    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n0 + n1 + n2;
-         t += (long long)gridDim.x * blockDim.x) {
-        if (t < n0) {
-            const int i = (int)(t / g.Yi) + g.z1, k = (int)(t % g.Yi) + g.y1;
-            const int kp = wrap_y(g, k + 1), kmn = wrap_y(g, k - 1), ip = wrap_z(g, i + 1), imn = wrap_z(g, i - 1);
-            const double a = wx[(long long)i * g.Yc + kp] - wx[(long long)i * g.Yc + kmn];
-            const double b = vx[(long long)ip * g.Yc + k] - vx[(long long)imn * g.Yc + k];
-            rx[t] = a / 2 / g.dy - b / 2 / g.dz;
-        } else if (t < n0 + n1) {
-            const long long s = t - n0;
-            const int i = (int)(s / g.nx) + g.z1, j = (int)(s % g.nx) + 1;
-            const int ip = wrap_z(g, i + 1), imn = wrap_z(g, i - 1);
-            const double a = wy[(long long)i * X2 + j + 1] - wy[(long long)i * X2 + j - 1];
-            const double b = uy[(long long)ip * X2 + j] - uy[(long long)imn * X2 + j];
-            ry[s] = a / 2 / g.dx - b / 2 / g.dz;
-        } else {
-            const long long s = t - n0 - n1;
-            const int k = (int)(s / g.nx) + g.y1, j = (int)(s % g.nx) + 1;
-            const int kp = wrap_y(g, k + 1), kmn = wrap_y(g, k - 1);
-            const double a = vz[(long long)k * X2 + j + 1] - vz[(long long)k * X2 + j - 1];
-            const double b = uz[(long long)kp * X2 + j] - uz[(long long)kmn * X2 + j];
-            rz[s] = a / 2 / g.dx - b / 2 / g.dy;
-        }
-    }
+    const long long n = vplot_rhs_elems(g);
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x)
+        vplot_rhs_elem(g, t, vx, wx, uy, wy, uz, vz, rx, ry, rz);
 }
 
-// src/velocity_plot.cpp:180-182,209-213: cell-centred velocity = average of the two faces, i=z1..zn, k=y1..yn, j=1..nx.
 // One thread per cell, lanes along x; the three components are interleaved as the VTK file wants them.
 __global__ void k_vplot_cells(VGeom g, const double* __restrict__ u, const double* __restrict__ v,
                               const double* __restrict__ w, double* __restrict__ out)
 {
-    const long long n = (long long)g.Zi * g.Yi * g.nx;
-    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
-        const int j = (int)(t % g.nx) + 1;
-        const long long r = t / g.nx;
-        const int k = (int)(r % g.Yi) + g.y1, i = (int)(r / g.Yi) + g.z1;
-        out[3 * t + 0] = 0.5 * (u[iu(g, i, k, j)] + u[iu(g, i, k, j - 1)]);
-        out[3 * t + 1] = 0.5 * (v[iv(g, i, k, j)] + v[iv(g, i, wrap_y(g, k - 1), j)]);
-        out[3 * t + 2] = 0.5 * (w[iw(g, i, k, j)] + w[iw(g, wrap_z(g, i - 1), k, j)]);
-    }
+    const long long n = vplot_cell_elems(g);
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x)
+        vplot_cell_elem(g, t, u, v, w, out);
 }
 
 }  // namespace fdmb
@@ -166,17 +91,10 @@ int fdmb_vplot::init()
         set_error("velocity_plotter: periodic y needs periodic z (tensor_flags<periodic,periodic>)");
         return FDMB_ERR_INVALID;
     }
-    g.nx = p.nx; g.ny = p.ny; g.nz = p.nz; g.zper = p.zperiodic ? 1 : 0; g.yper = p.yperiodic ? 1 : 0;
-    g.dx = p.dx; g.dy = p.dy; g.dz = p.dz;
-    g.y_ = g.yper ? 0 : -1; g.y1 = g.yper ? 0 : 1; g.yn = g.yper ? p.ny - 1 : p.ny; g.ynn = g.yper ? p.ny - 1 : p.ny + 1;
-    g.z_ = g.zper ? 0 : -1; g.z1 = g.zper ? 0 : 1; g.zn = g.zper ? p.nz - 1 : p.nz; g.znn = g.zper ? p.nz - 1 : p.nz + 1;
-    g.Yc = g.ynn + 1; g.Zc = g.znn + 1; g.Yv = g.ynn - g.y_ + 1;
-    g.Yi = g.yn - g.y1 + 1; g.Zi = g.zn - g.z1 + 1;
+    g = vplot_make_geom(p.nx, p.ny, p.nz, p.zperiodic, p.yperiodic, p.dx, p.dy, p.dz);
     ly = g.yper ? p.yy2 - p.yy1 : p.yy2 - p.yy1 + p.dy;      // src/velocity_plot.h:67-68
     lz = g.zper ? p.zz2 - p.zz1 : p.zz2 - p.zz1 + p.dz;
-    fsz[0] = (long long)g.Zc * g.Yc * (p.nx + 3);
-    fsz[1] = (long long)g.Zc * g.Yv * (p.nx + 2);
-    fsz[2] = (long long)(g.znn - g.z_ + 1) * g.Yc * (p.nx + 2);
+    for (int f = 0; f < 3; f++) fsz[f] = vplot_field_elems(g, f);
 
     // src/velocity_plot.h:101-105: lapl_x(dy,dz,ly,lz,ny,nz) on [z][y]; lapl_y(dx,dz,..,nx,nz) on [z][x];
     // lapl_z(dx,dy,..,nx,ny) on [y][x]
@@ -250,7 +168,7 @@ int fdmb_vplot::update()
     if (rc) return rc;
     const int threads = 256;
     {
-        const long long n = (long long)g.Zc * g.Yc + (long long)(g.Zc + g.Yc) * (p.nx + 2);
+        const long long n = vplot_slice_elems(g);
         LaunchScope scope("vplot_slices", stream);
         k_vplot_slices<<<(unsigned)((n + threads - 1) / threads), threads, 0, stream>>>(
             g, dfield[0], dfield[1], dfield[2], d_slice[FDMB_SLICE_VX], d_slice[FDMB_SLICE_WX], d_slice[FDMB_SLICE_UY],
@@ -258,7 +176,7 @@ int fdmb_vplot::update()
         FDMB_CHECK_LAUNCH();
     }
     {
-        const long long n = (long long)g.Zi * g.Yi + (long long)(g.Zi + g.Yi) * p.nx;
+        const long long n = vplot_rhs_elems(g);
         LaunchScope scope("vplot_rhs", stream);
         k_vplot_rhs<<<(unsigned)((n + threads - 1) / threads), threads, 0, stream>>>(
             g, d_slice[FDMB_SLICE_VX], d_slice[FDMB_SLICE_WX], d_slice[FDMB_SLICE_UY], d_slice[FDMB_SLICE_WY],

@@ -71,3 +71,53 @@ def test_restatement_vs_golden(name):
         assert np.array_equal(got[s].ravel(), g[f"{name}/{s}"]), s
     for s in PSI:
         assert O.rel_l2(got[s].ravel(), g[f"{name}/{s}"]) < 1e-12, s
+
+
+# ---- the device arithmetic itself, emulated on the host ---------------------------------------------------
+@pytest.fixture(scope="module")
+def emul():
+    import ctypes as C
+    import subprocess
+    here = os.path.join(ROOT, "tests", "host_emul")
+    src, lib = os.path.join(here, "vplot_host.cpp"), os.path.join(here, "libvplot_host.so")
+    hdr = os.path.join(ROOT, "fdm_b200", "csrc", "vplot_math.h")
+    if (not os.path.exists(lib)) or os.path.getmtime(lib) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        # -ffp-contract=off: what the device code does is irrelevant here, the arithmetic has no multiply-add pair
+        subprocess.run(["/usr/bin/g++", "-O1", "-std=c++17", "-shared", "-fPIC", src, "-o", lib], check=True)
+    L = C.CDLL(lib)
+    dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
+    L.emul_vplot_field_elems.restype = C.c_longlong
+    L.emul_vplot_field_elems.argtypes = [C.c_int] * 6
+    L.emul_vplot_dims.argtypes = [C.c_int] * 5 + [ip]
+    L.emul_vplot_update.argtypes = [C.c_int] * 5 + [C.c_double] * 3 + [dp] * 12
+    L.emul_vplot_cells.restype = C.c_longlong
+    L.emul_vplot_cells.argtypes = [C.c_int] * 5 + [dp] * 4
+    return L
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_device_arithmetic_emulated_on_the_host(emul, name):
+    """fdm_b200/csrc/vplot_math.h (the functions the CUDA kernels call) against the restatement, bit for bit."""
+    import ctypes as C
+    args, kw = CASES[name]
+    dx, dy, dz, nx, ny, nz = args[:6]
+    zp, yp = int(kw.get("zperiodic", False)), int(kw.get("yperiodic", False))
+    u, v, w = fields(name, seed=3)
+    Or = O.VelocityPlotter(*args, **kw)
+    assert [emul.emul_vplot_field_elems(nx, ny, nz, zp, yp, f) for f in range(3)] == [a.size for a in (u, v, w)]
+    dims = (C.c_int * 18)()
+    emul.emul_vplot_dims(nx, ny, nz, zp, yp, dims)
+    want = Or.update(u, v, w)
+    outs = []
+    for s, key in enumerate(SLICES):
+        assert (dims[2 * s], dims[2 * s + 1]) == want[key].shape, key
+        outs.append(np.full(want[key].shape, np.nan))
+    p = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))      # noqa: E731
+    emul.emul_vplot_update(nx, ny, nz, zp, yp, dx, dy, dz, p(u), p(v), p(w), *[p(a) for a in outs])
+    for key, a in zip(SLICES, outs):
+        assert np.array_equal(a, want[key]), key
+    cells = Or.cell_velocity(u, v, w)
+    assert emul.emul_vplot_cells(nx, ny, nz, zp, yp, p(u), p(v), p(w), None) == cells.shape[0]
+    got = np.full(cells.shape, np.nan)
+    emul.emul_vplot_cells(nx, ny, nz, zp, yp, p(u), p(v), p(w), p(got))
+    assert np.array_equal(got, cells)
