@@ -21,31 +21,33 @@
 namespace fdmb {
 
 // ---- batched tridiagonal solve along the contiguous axis -------------------------------------
-// A CTA stages TS systems (rows of nr doubles) in an odd-pitch shared-memory tile with coalesced
+// A CTA stages ts systems (rows of nr doubles) in an odd-pitch shared-memory tile with coalesced
 // loads; thread s then runs the Thomas recurrence of system s (conflict-free: consecutive lanes sit
 // one odd pitch apart), keeping the reciprocal pivots in a second tile; coalesced store.
+// ts = TS for systems that fit (nr <= ~430); longer systems get a lower tile (tridiag_tile_rows) so that
+// e.g. the reference's 511 x 511 LaplRect case (ut/ut_lapl_rect.cpp:384-455) still runs.
 constexpr int TS = 32;
 
-__global__ void __launch_bounds__(128) k_tridiag_rows(TridiagArgs a)
+__global__ void __launch_bounds__(128) k_tridiag_rows(TridiagArgs a, int ts)
 {
     extern __shared__ double smem[];
     const int P = a.nr | 1;                    // odd pitch
     double* tb = smem;                         // rhs / solution
-    double* ti = smem + TS * P;                // reciprocal pivots
-    double* cL = ti + TS * P;                  // coefficient tables, 1-based
+    double* ti = smem + ts * P;                // reciprocal pivots
+    double* cL = ti + ts * P;                  // coefficient tables, 1-based
     double* cU = cL + (a.nr + 1);
     double* cR = cU + (a.nr + 1);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     for (int j = tid + 1; j <= a.nr; j += blockDim.x) { cL[j] = a.L[j]; cU[j] = a.U[j]; cR[j] = a.ir2[j]; }
-    const long long row0 = (long long)blockIdx.x * TS;
-    for (int r = warp; r < TS; r += 4) {
+    const long long row0 = (long long)blockIdx.x * ts;
+    for (int r = warp; r < ts; r += 4) {
         const long long row = row0 + r;
         if (row >= a.nsys) break;
         const double* src = a.data + row * a.pitch;
         for (int x = lane; x < a.nr; x += 32) tb[r * P + x] = src[x];
     }
     __syncthreads();
-    if (tid < TS && row0 + tid < a.nsys) {
+    if (tid < ts && row0 + tid < a.nsys) {
         const long long row = row0 + tid;
         const int outer = (int)(row / a.nmid), mid = (int)(row % a.nmid);
         const double lo = a.swap ? a.lm_outer[mid] : a.lm_outer[outer];
@@ -73,7 +75,7 @@ __global__ void __launch_bounds__(128) k_tridiag_rows(TridiagArgs a)
         }
     }
     __syncthreads();
-    for (int r = warp; r < TS; r += 4) {
+    for (int r = warp; r < ts; r += 4) {
         const long long row = row0 + r;
         if (row >= a.nsys) break;
         double* dst = a.data + row * a.pitch;
@@ -107,24 +109,24 @@ __global__ void __launch_bounds__(128) k_tridiag_pivots(TridiagArgs a)
 
 constexpr int TSP = 64;       // systems per CTA of the pivot-table variant
 
-__global__ void __launch_bounds__(256) k_tridiag_rows_piv(TridiagArgs a)
+__global__ void __launch_bounds__(256) k_tridiag_rows_piv(TridiagArgs a, int ts)
 {
     extern __shared__ double smem[];
     const int P = a.nr | 1;                    // odd pitch
     double* tb = smem;                         // rhs / solution
-    double* cL = tb + TSP * P;                 // coefficient tables, 1-based
+    double* cL = tb + ts * P;                 // coefficient tables, 1-based
     double* cU = cL + (a.nr + 1);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     for (int j = tid + 1; j <= a.nr; j += blockDim.x) { cL[j] = a.L[j]; cU[j] = a.U[j]; }
-    const long long row0 = (long long)blockIdx.x * TSP;
-    for (int r = warp; r < TSP; r += 8) {
+    const long long row0 = (long long)blockIdx.x * ts;
+    for (int r = warp; r < ts; r += 8) {
         const long long row = row0 + r;
         if (row >= a.nsys) break;
         const double* src = a.data + row * a.pitch;
         for (int x = lane; x < a.nr; x += 32) tb[r * P + x] = src[x];
     }
     __syncthreads();
-    if (tid < TSP && row0 + tid < a.nsys) {
+    if (tid < ts && row0 + tid < a.nsys) {
         const double* __restrict__ iv = a.piv + row0 + tid;      // iv[(j-1) * nsys] = 1 / d_j
         double* b = tb + tid * P - 1;                            // 1-based
         constexpr int CH = 16;                                   // pivots fetched CH at a time: CH global loads in flight
@@ -172,7 +174,7 @@ __global__ void __launch_bounds__(256) k_tridiag_rows_piv(TridiagArgs a)
         }
     }
     __syncthreads();
-    for (int r = warp; r < TSP; r += 8) {
+    for (int r = warp; r < ts; r += 8) {
         const long long row = row0 + r;
         if (row >= a.nsys) break;
         double* dst = a.data + row * a.pitch;
@@ -180,26 +182,38 @@ __global__ void __launch_bounds__(256) k_tridiag_rows_piv(TridiagArgs a)
     }
 }
 
-static size_t tridiag_rows_piv_smem(int nr) { return sizeof(double) * (size_t)(TSP * (nr | 1) + 2 * (nr + 1)); }
+constexpr size_t TRIDIAG_SMEM_MAX = 220 * 1024;
+static size_t rows_smem(int nr, int ts) { return sizeof(double) * (size_t)(2 * ts * (nr | 1) + 3 * (nr + 1)); }
+static size_t rows_piv_smem(int nr, int ts) { return sizeof(double) * (size_t)(ts * (nr | 1) + 2 * (nr + 1)); }
 
-size_t tridiag_rows_smem(int nr) { return sizeof(double) * (size_t)(2 * TS * (nr | 1) + 3 * (nr + 1)); }
+// systems per CTA: the full tile (TS / TSP) when it fits in shared memory, else halved down to 4
+static int tridiag_tile_rows(int nr, bool piv)
+{
+    int ts = piv ? TSP : TS;
+    while (ts > 4 && (piv ? rows_piv_smem(nr, ts) : rows_smem(nr, ts)) > TRIDIAG_SMEM_MAX) ts >>= 1;
+    return ts;
+}
 
-// sets the kernel's shared-memory limit for systems of length nr on the current device (this also loads the kernel)
+// shared memory of the on-the-fly variant for systems of length nr; callers reject nr when it exceeds 220 KB
+// (nr > ~2500: not even four systems fit)
+size_t tridiag_rows_smem(int nr) { return rows_smem(nr, tridiag_tile_rows(nr, false)); }
+
+// raises both kernels' dynamic shared-memory limit on the current device (this also loads the kernels)
 cudaError_t prepare_tridiag_rows(int nr)
 {
-    const size_t smem = tridiag_rows_smem(nr);
-    static size_t set_smem_dev[64] = {0};     // function attributes are per device
-    size_t& set_smem = set_smem_dev[current_device_slot()];
-    if (smem > set_smem) {
-        cudaError_t e = cudaFuncSetAttribute(k_tridiag_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    (void)nr;
+    static bool done_dev[64] = {false};       // function attributes are per device
+    bool& done = done_dev[current_device_slot()];
+    if (!done) {
+        cudaError_t e = cudaFuncSetAttribute(k_tridiag_rows, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)TRIDIAG_SMEM_MAX);
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(k_tridiag_rows_piv, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)tridiag_rows_piv_smem(nr));
+        e = cudaFuncSetAttribute(k_tridiag_rows_piv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRIDIAG_SMEM_MAX);
         if (e != cudaSuccess) return e;
         cudaFuncAttributes fa;
         e = cudaFuncGetAttributes(&fa, k_tridiag_pivots);
         if (e != cudaSuccess) return e;
-        set_smem = smem;
+        done = true;
     }
     return cudaSuccess;
 }
@@ -217,11 +231,12 @@ cudaError_t launch_tridiag_rows(const TridiagArgs& a, cudaStream_t st, const cha
     cudaError_t e = prepare_tridiag_rows(a.nr);
     if (e != cudaSuccess) return e;
     if (a.piv) {
-        k_tridiag_rows_piv<<<(unsigned)((a.nsys + TSP - 1) / TSP), 256, tridiag_rows_piv_smem(a.nr), st>>>(a);
+        const int ts = tridiag_tile_rows(a.nr, true);
+        k_tridiag_rows_piv<<<(unsigned)((a.nsys + ts - 1) / ts), 256, rows_piv_smem(a.nr, ts), st>>>(a, ts);
         return cudaGetLastError();
     }
-    const unsigned grid = (unsigned)((a.nsys + TS - 1) / TS);
-    k_tridiag_rows<<<grid, 128, tridiag_rows_smem(a.nr), st>>>(a);
+    const int ts = tridiag_tile_rows(a.nr, false);
+    k_tridiag_rows<<<(unsigned)((a.nsys + ts - 1) / ts), 128, rows_smem(a.nr, ts), st>>>(a, ts);
     return cudaGetLastError();
 }
 

@@ -73,6 +73,14 @@ def test_cyl_residual_property(fb):
     assert O.rel_l2(lap, rhs) < 1e-10
 
 
+@pytest.mark.parametrize("nr,nz,nphi", [(431, 7, 8), (512, 7, 16), (1000, 3, 8)])
+def test_cyl_long_radial_systems(fb, nr, nz, nphi):
+    """nr beyond the full shared-memory tile of the r sweep: lower tiles, same arithmetic."""
+    args = geom(nr, nz, nphi, False)
+    rhs = O.synthetic_rhs((nphi, nz, nr), seed=nr)
+    assert O.rel_l2(fb.LaplCyl3FFT2(*args).solve(rhs), O.LaplCyl3FFT2(*args).solve(rhs)) < TOL
+
+
 def test_cyl_errors(fb):
     with pytest.raises(fb.FdmB200Error):
         fb.LaplCyl3FFT2(0.1, 0.1, 1.0, 3.3, 3.3, 32, 32, 32)         # Dirichlet z needs nz = 2^k - 1

@@ -37,6 +37,20 @@ def test_rect_vs_oracle(fb, nx, ny, yp):
     assert O.rel_l2(a, O.LaplRect(*g, yperiodic=yp).solve(rhs)) < TOL
 
 
+@pytest.mark.parametrize("nx,ny,yp", [(511, 31, False), (1023, 16, True), (860, 7, False), (2047, 7, False)])
+def test_rect_long_tridiagonals(fb, nx, ny, yp):
+    """Systems too long for the full 32-row shared-memory tile run with a lower tile (16, 8, 4 rows): the
+    reference's own 511 x 511 case (ut/ut_lapl_rect.cpp:384-455) and the plotter's LaplRect at 511^3 / 1023^3."""
+    g = geom(nx, ny, yp, dx=0.01)
+    rhs = O.synthetic_rhs((ny, nx), seed=nx)
+    assert O.rel_l2(fb.LaplRect(*g, yperiodic=yp).solve(rhs), O.LaplRect(*g, yperiodic=yp).solve(rhs)) < TOL
+
+
+def test_rect_tridiagonal_length_limit(fb):
+    with pytest.raises(fb.FdmB200Error):
+        fb.LaplRect(*geom(4000, 7))          # not even four systems fit in shared memory
+
+
 @pytest.mark.parametrize("nx,ny,yp,xp", [(31, 15, False, False), (127, 255, False, False), (63, 64, True, False),
                                          (64, 32, True, True), (1023, 7, False, False), (3, 3, False, False)])
 def test_rectfft2_vs_oracle(fb, nx, ny, yp, xp):
