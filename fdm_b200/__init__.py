@@ -12,6 +12,7 @@ from .lapl_cyl import LaplCyl3FFT2  # noqa: F401
 from .lapl_rect import LaplRect, LaplRectFFT2  # noqa: F401
 from .ns_cyl import NSCyl  # noqa: F401
 from .velocity_plot import VelocityPlotter  # noqa: F401
+from .nbody import NBodyPM  # noqa: F401
 
 
 def fft_batch(kind, N, data, dx=1.0):

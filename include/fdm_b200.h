@@ -285,6 +285,40 @@ int fdmb_vplot_cell_velocity(fdmb_vplot* h, double* host);
 int fdmb_vplot_vtk_out(fdmb_vplot* h, const char* name, int time_index);
 int fdmb_vplot_destroy(fdmb_vplot* h);
 
+/* ---- particle-mesh N-body step -------------------------------------------------------
+ * Replaces the step of NBody<double,check,CIC3<double>> in the reference's test/nbody.cpp (:24-596), the second
+ * in-tree consumer of the periodic LaplCube, with the program's default local = 0 (mesh forces
+ * only; the short-range pair correction of :344-388 is "need to check" in the reference and not built here).
+ * params      <-> the constructor (x0,y0,z0,l,n,...,dt,G) :104-131; cell size h = l / n, n = 2^k
+ *                 deposit_all = 0 reproduces distribute_masses (:257-272), which walks the cell lists with one
+ *                 offset for all three axes and so deposits only the bodies whose cell indices are all even or all
+ *                 odd; 1 deposits every body (the evident intent).  The mean density uses all bodies either way.
+ * set_bodies  <-> bodies[b].x, .v, .mass (:46-58); x, v are [N][3] like Body::x[3]; a and aprev start at 0.  The
+ *                 reference seeds them from std::default_random_engine (:541-587); a caller hands them over instead.
+ * calc_accel  <-> calc_a_pm() (:292-421): f = -mass/l^3 + cloud-in-cell deposit, rhs = 4 pi G f / h^3,
+ *                 psi = periodic LaplCube solve, E = 4-point difference of psi, a = cloud-in-cell gather of E
+ * step        <-> step() (:133-142) = calc_a_pm() + move() (:469-487, velocity Verlet, periodic wrap), nsteps times;
+ *                 everything stays on the device
+ * get_bodies  field FDMB_PM_X / _V / _A / _APREV ([N][3]) or FDMB_PM_MASS ([N])
+ * get_grid    FDMB_PM_F / _RHS / _PSI (n^3, [z][y][x]) or FDMB_PM_E (n^3 x 3) as after the last calc_accel   */
+typedef struct fdmb_pm fdmb_pm;
+typedef struct fdmb_pm_params {
+    double x0, y0, z0, l;
+    double dt, G;
+    int n;
+    int deposit_all;
+} fdmb_pm_params;
+enum { FDMB_PM_X = 0, FDMB_PM_V, FDMB_PM_A, FDMB_PM_APREV, FDMB_PM_MASS };
+enum { FDMB_PM_F = 0, FDMB_PM_RHS, FDMB_PM_PSI, FDMB_PM_E };
+int fdmb_pm_create(fdmb_pm** h, const fdmb_pm_params* p);
+int fdmb_pm_set_bodies(fdmb_pm* h, long long N, const double* x, const double* v, const double* mass);
+long long fdmb_pm_count(fdmb_pm* h);
+int fdmb_pm_calc_accel(fdmb_pm* h);
+int fdmb_pm_step(fdmb_pm* h, int nsteps);
+int fdmb_pm_get_bodies(fdmb_pm* h, int field, double* host);
+int fdmb_pm_get_grid(fdmb_pm* h, int grid, double* host);
+int fdmb_pm_destroy(fdmb_pm* h);
+
 #ifdef __cplusplus
 }
 #endif

@@ -561,6 +561,80 @@ class VelocityPlotter:
         return c.reshape(-1, 3)
 
 
+# --------------------------------------------------------------------------------------
+# Particle-mesh N-body step (reference: test/nbody.cpp:24-596 with local = 0, src/interpolate.h:66-100)
+# --------------------------------------------------------------------------------------
+class NBodyPM:
+    """One step = calc_a_pm() (:292-421: CIC deposit on a periodic n^3 grid, rhs = 4 pi G f / h^3, periodic LaplCube,
+    4-point field differencing, CIC gather) followed by move() (:469-503, velocity Verlet with periodic wrap).
+    Bodies are given by the caller (the reference seeds them from std::default_random_engine, :541-587)."""
+
+    def __init__(self, x0, y0, z0, l, n, dt, G, deposit_all=False):
+        self.origin = np.array([x0, y0, z0], dtype=np.float64)
+        self.l, self.n, self.h, self.dt, self.G = float(l), int(n), l / n, float(dt), float(G)
+        self.deposit_all = bool(deposit_all)      # False = the reference's behaviour
+        h = self.h
+        self.solver = LaplCube(h, h, h, l, l, l, n, n, n, periodic=True)
+
+    def set_bodies(self, x, v, mass):
+        self.x, self.v = np.array(x, dtype=np.float64), np.array(v, dtype=np.float64)
+        self.m = np.array(mass, dtype=np.float64)
+        self.a, self.aprev = np.zeros_like(self.x), np.zeros_like(self.x)
+        self.mass = 0.0
+        for mb in self.m:          # sequential like :583
+            self.mass += mb
+
+    def _cic(self):
+        """interpolate.h:66-100: base cell (j0,k0,i0) and the 2x2x2 weights M[i][k][j]; x[0] <-> j (fastest axis)."""
+        h = self.h
+        rel = self.x - self.origin
+        base = np.floor(rel / h).astype(np.int64)
+        fr = (rel - base * h) / h
+        fx, fy, fz = fr[:, 0], fr[:, 1], fr[:, 2]
+        wx, wy, wz = np.stack([1 - fx, fx], 1), np.stack([1 - fy, fy], 1), np.stack([1 - fz, fz], 1)
+        M = wz[:, :, None, None] * wy[:, None, :, None] * wx[:, None, None, :]      # [body][i][k][j]
+        d = np.arange(2)
+        n = self.n
+        I = (base[:, 2, None] + d)[:, :, None, None] % n
+        K = (base[:, 1, None] + d)[:, None, :, None] % n
+        J = (base[:, 0, None] + d)[:, None, None, :] % n
+        I, K, J = np.broadcast_arrays(I, K, J)
+        return I, K, J, M
+
+    def calc_a_pm(self):
+        n, h, l = self.n, self.h, self.l
+        I, K, J, M = self._cic()
+        self.f = np.full((n, n, n), -self.mass / l / l / l)
+        # distribute_masses (:257-272) walks the cell lists with ONE offset for all three axes
+        # (i = off, off+2, ...; k = off, ...; j = off, ...; off = 0, 1): only bodies whose cell indices are all even
+        # or all odd are deposited -- a quarter of them.  Reproduced, not fixed (the mean density still uses all).
+        i0, k0, j0 = I[:, 0, 0, 0], K[:, 0, 0, 0], J[:, 0, 0, 0]
+        dep = ((i0 % 2 == k0 % 2) & (k0 % 2 == j0 % 2)) | self.deposit_all
+        np.add.at(self.f, (I[dep], K[dep], J[dep]), self.m[dep, None, None, None] * M[dep])
+        self.rhs = 4 * self.G * math.pi * self.f / h / h / h
+        self.psi = self.solver.solve(self.rhs).reshape(n, n, n)
+        psi, beta = self.psi, 4. / 3.
+        E = np.empty((n, n, n, 3))
+        for m, ax in enumerate((2, 1, 0)):          # E[..][0] differences along x (last axis), :333-339
+            E[..., m] = (-beta * (np.roll(psi, -1, ax) - np.roll(psi, 1, ax)) / 2 / h
+                         - (1 - beta) * (np.roll(psi, -2, ax) - np.roll(psi, 2, ax)) / 4 / h)
+        self.E = E
+        self.a = np.einsum("bikjm,bikj->bm", E[I, K, J], M)       # :434-466 with F = 0
+
+    def move(self):
+        dt, l, o = self.dt, self.l, self.origin
+        self.x = self.x + (dt * self.v + 0.5 * dt * dt * self.aprev)
+        self.x = np.where(self.x < o, self.x + l, self.x)
+        self.x = np.where(self.x >= o + l, self.x - l, self.x)
+        self.v = self.v + 0.5 * dt * (self.a + self.aprev)
+        self.aprev = self.a.copy()
+
+    def step(self, nsteps=1):
+        for _ in range(nsteps):
+            self.calc_a_pm()
+            self.move()
+
+
 def rel_l2(a, b):
     """||a-b||_2 / ||b||_2 with a 0/0 guard (both exactly zero -> 0)."""
     a = np.asarray(a, dtype=np.float64).ravel()

@@ -67,6 +67,15 @@ def lib():
         L.ref_ns_cyl_get_field.argtypes = [C.c_void_p, C.c_int, _dp]
         L.ref_ns_cyl_set_field.argtypes = [C.c_void_p, C.c_int, _dp]
         L.ref_ns_cyl_destroy.argtypes = [C.c_void_p]
+        L.ref_nbody_create.restype = C.c_void_p
+        L.ref_nbody_create.argtypes = [C.c_double] * 4 + [C.c_int] * 3 + [C.c_double] * 3 + [C.c_int] * 2
+        L.ref_nbody_count.argtypes = [C.c_void_p]
+        L.ref_nbody_total_mass.argtypes = [C.c_void_p]
+        L.ref_nbody_total_mass.restype = C.c_double
+        L.ref_nbody_get.argtypes = [C.c_void_p, C.c_int, _dp]
+        L.ref_nbody_step.argtypes = [C.c_void_p, C.c_int]
+        L.ref_nbody_get_grid.argtypes = [C.c_void_p, C.c_int, _dp]
+        L.ref_nbody_destroy.argtypes = [C.c_void_p]
         L.ref_vplot_create.restype = C.c_void_p
         L.ref_vplot_create.argtypes = [C.c_int] + [C.c_double] * 3 + [C.c_int] * 3 + [C.c_double] * 6 + [C.c_int]
         L.ref_vplot_update.argtypes = [C.c_void_p, _dp, _dp, _dp]
@@ -257,4 +266,39 @@ class VelocityPlotter:
     def __del__(self):
         if getattr(self, "h", None):
             lib().ref_vplot_destroy(self.h)
+            self.h = None
+
+
+class NBody:
+    """The unmodified NBody<double,false,CIC3<double>> of test/nbody.cpp (local = 0: particle-mesh forces only)."""
+
+    _BODY = {"x": 0, "v": 1, "a": 2, "aprev": 3, "mass": 4}
+    _GRID = {"f": 0, "rhs": 1, "psi": 2, "E": 3}
+
+    def __init__(self, x0=-10.0, y0=-10.0, z0=-10.0, l=20.0, n=32, npp=64, N=1000, dt=0.001, G=1.0, vel=4.0, sgn=-1,
+                 solar=0):
+        self.n = n
+        self.h = lib().ref_nbody_create(x0, y0, z0, l, n, npp, N, dt, G, vel, sgn, solar)
+        self.N = lib().ref_nbody_count(self.h)
+
+    def bodies(self, name):
+        out = np.empty(self.N if name == "mass" else (self.N, 3))
+        lib().ref_nbody_get(self.h, self._BODY[name], _p(out))
+        return out
+
+    def total_mass(self):
+        return lib().ref_nbody_total_mass(self.h)
+
+    def step(self, nsteps=1):
+        lib().ref_nbody_step(self.h, nsteps)      # prints one line per step like the reference (:505-507)
+
+    def grid(self, name):
+        n = self.n
+        out = np.empty((n, n, n, 3) if name == "E" else (n, n, n))
+        lib().ref_nbody_get_grid(self.h, self._GRID[name], _p(out))
+        return out
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().ref_nbody_destroy(self.h)
             self.h = None
