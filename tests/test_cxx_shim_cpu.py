@@ -70,3 +70,18 @@ def test_example_drivers_build_and_fail_loudly_without_device(tmp_path, name):
     r = subprocess.run([exe, "--ns:nx=15", "--ns:nz=15", "--ns:nr=16", "--ns:nphi=16"], capture_output=True, text=True,
                        cwd=tmp_path)
     assert r.returncode == -signal.SIGABRT and "verify(" in r.stderr
+
+
+def test_nbody_example_seeds_the_reference_bodies(tmp_path, ref):
+    """examples/fdm_nbody.cpp repeats init_points (test/nbody.cpp:541-587) with the same std::default_random_engine:
+    the state it hands to the device equals the one the compiled reference program starts from."""
+    exe = cxx_build.build_example("fdm_nbody", str(tmp_path / "fdm_nbody"))
+    N = 400
+    subprocess.run([exe, "--nbody:n=16", f"--nbody:N={N}", "--nbody:steps=1", "--out:prefix=nb"], capture_output=True,
+                   text=True, cwd=tmp_path)       # aborts at create without a device, after the initial dump
+    R = ref.NBody(n=16, N=N)
+    # same random sequence; the reference build contracts l*u + origin into one FMA (-mfma), this one does not: 1 ulp
+    assert np.max(np.abs(np.fromfile(tmp_path / "nb_x0.bin").reshape(N, 3) - R.bodies("x"))) <= 4e-15
+    assert np.max(np.abs(np.fromfile(tmp_path / "nb_mass.bin") - R.bodies("mass"))) <= 5e-16
+    v = np.fromfile(tmp_path / "nb_v0.bin").reshape(N, 3)
+    assert np.max(np.abs(v - R.bodies("v"))) <= 1e-14 * np.max(np.abs(v))

@@ -75,3 +75,19 @@ def test_fdm_ns_cyl_refuses_stabilisation(tmp_path):
     exe = cxx_build.build_example("fdm_ns_cyl", str(tmp_path / "fdm_ns_cyl"))
     r = subprocess.run([exe, "--st:enable=1"], cwd=tmp_path, capture_output=True, text=True)
     assert r.returncode == 2 and "not supported" in r.stderr
+
+
+def test_fdm_nbody_example(tmp_path, ref, capfd):
+    exe = cxx_build.build_example("fdm_nbody", str(tmp_path / "fdm_nbody"))
+    n, N, steps = 32, 3000, 12
+    r = subprocess.run([exe, f"--nbody:n={n}", f"--nbody:N={N}", f"--nbody:steps={steps}", "--plot:interval=5",
+                        "--out:prefix=nb"], cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-1000:] + r.stderr[-1000:]
+    assert r.stdout.count("step=") == 3 and "total:" in r.stdout
+    R = ref.NBody(n=n, N=N)
+    R.step(steps)
+    capfd.readouterr()
+    for f in "xva":
+        assert O.rel_l2(np.fromfile(tmp_path / f"nb_{f}.bin").reshape(N, 3), R.bodies(f)) < 1e-12, f
+    r = subprocess.run([exe, "--nbody:local=1"], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 2 and "not supported" in r.stderr
