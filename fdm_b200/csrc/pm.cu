@@ -84,7 +84,7 @@ int fdmb_pm::init()
 {
     if (p.n < 4 || !(p.l > 0)) { set_error("NBody: n >= 4 and l > 0 required"); return FDMB_ERR_INVALID; }
     g.n = p.n; g.N = 0; g.l = p.l; g.h = p.l / p.n; g.ox = p.x0; g.oy = p.y0; g.oz = p.z0; g.dt = p.dt; g.G = p.G;
-    g.rho0 = 0; g.deposit_all = p.deposit_all ? 1 : 0;
+    g.rho0 = 0; g.deposit_all = p.deposit_all ? 1 : 0; g.lgn = pm_log2_or_neg(p.n);
     n3 = (long long)p.n * p.n * p.n;
     // solver3(h,h,h,l,l,l,n,n,n), periodic on every axis (:128, :29-31)
     int rc = fdmb_lapl_cube_create(&solver, g.h, g.h, g.h, p.l, p.l, p.l, p.n, p.n, p.n, 1);

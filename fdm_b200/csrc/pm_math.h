@@ -17,7 +17,16 @@ struct PMGeom {
     double dt, G;
     double rho0;            // -mass / l^3: the mean density subtracted before the deposit (:296-302)
     int deposit_all;        // 0: the reference's cell walk (see pm_deposits), 1: every body
+    int lgn;                // log2(n) when n is a power of two (cell index by shifts), else -1
 };
+
+inline int pm_log2_or_neg(int n)
+{
+    if (n <= 0 || (n & (n - 1))) return -1;
+    int lg = 0;
+    while ((1 << lg) < n) lg++;
+    return lg;
+}
 
 // Cloud-in-cell: base cell and per-axis weights; M[i][k][j] = (wz[i] * wy[k]) * wx[j] like interpolate.h:88-97.
 struct PMCic {
@@ -35,7 +44,14 @@ FDMB_HD PMCic pm_cic(const PMGeom& g, double x, double y, double z)
     return c;
 }
 
-FDMB_HD int pm_wrap(int i, int n) { i %= n; return i < 0 ? i + n : i; }   // fdm::tensor periodic wrap
+// fdm::tensor periodic wrap (src/tensor.h:119-123); n is a power of two wherever the periodic LaplCube accepts it,
+// then the wrap is a mask (two's complement: -1 & (n-1) = n-1)
+FDMB_HD int pm_wrap(int i, int n)
+{
+    if ((n & (n - 1)) == 0) return i & (n - 1);
+    i %= n;
+    return i < 0 ? i + n : i;
+}
 
 // distribute_masses (:257-272) walks the per-cell body lists with ONE offset for all three axes (i, k, j = off,
 // off + 2, ...; off = 0, 1), so only bodies whose cell indices are all even or all odd are ever deposited.
@@ -67,12 +83,18 @@ FDMB_HD double pm_rhs(const PMGeom& g, double f) { return 4 * g.G * M_PI * f / g
 FDMB_HD void pm_field_elem(const PMGeom& g, long long t, const double* psi, double* E)
 {
     const int n = g.n;
-    const int j = (int)(t % n), k = (int)((t / n) % n), i = (int)(t / ((long long)n * n));
+    int i, k, j;
+    if (g.lgn >= 0) { j = (int)(t & (n - 1)); k = (int)((t >> g.lgn) & (n - 1)); i = (int)(t >> (2 * g.lgn)); }
+    else { j = (int)(t % n); k = (int)((t / n) % n); i = (int)(t / ((long long)n * n)); }
     const double beta = 4. / 3., h = g.h;
-    auto P = [&](int ii, int kk, int jj) { return psi[((long long)pm_wrap(ii, n) * n + pm_wrap(kk, n)) * n + pm_wrap(jj, n)]; };
-    E[3 * t + 0] = -beta * (P(i, k, j + 1) - P(i, k, j - 1)) / 2 / h - (1 - beta) * (P(i, k, j + 2) - P(i, k, j - 2)) / 4 / h;
-    E[3 * t + 1] = -beta * (P(i, k + 1, j) - P(i, k - 1, j)) / 2 / h - (1 - beta) * (P(i, k + 2, j) - P(i, k - 2, j)) / 4 / h;
-    E[3 * t + 2] = -beta * (P(i + 1, k, j) - P(i - 1, k, j)) / 2 / h - (1 - beta) * (P(i + 2, k, j) - P(i - 2, k, j)) / 4 / h;
+    // the cell's own row / plane offsets once, then one wrapped index per tap
+    const long long plane = (long long)n * n, row = (long long)i * plane + (long long)k * n;
+    auto X = [&](int jj) { return psi[row + pm_wrap(jj, n)]; };
+    auto Y = [&](int kk) { return psi[(long long)i * plane + (long long)pm_wrap(kk, n) * n + j]; };
+    auto Z = [&](int ii) { return psi[(long long)pm_wrap(ii, n) * plane + (long long)k * n + j]; };
+    E[3 * t + 0] = -beta * (X(j + 1) - X(j - 1)) / 2 / h - (1 - beta) * (X(j + 2) - X(j - 2)) / 4 / h;
+    E[3 * t + 1] = -beta * (Y(k + 1) - Y(k - 1)) / 2 / h - (1 - beta) * (Y(k + 2) - Y(k - 2)) / 4 / h;
+    E[3 * t + 2] = -beta * (Z(i + 1) - Z(i - 1)) / 2 / h - (1 - beta) * (Z(i + 2) - Z(i - 2)) / 4 / h;
 }
 
 // calc_accelerations (:434-466, F = 0 without the local pair forces): a = sum E[cell] * M

@@ -14,7 +14,7 @@ void emul_pm_deposit(int n, long long N, double l, double ox, double oy, double 
                      int deposit_all, const double* x, const double* mass, double* f, double* rhs)
 {
     PMGeom g{};
-    g.n = n; g.N = N; g.l = l; g.h = l / n; g.ox = ox; g.oy = oy; g.oz = oz; g.G = G; g.deposit_all = deposit_all;
+    g.n = n; g.N = N; g.l = l; g.h = l / n; g.ox = ox; g.oy = oy; g.oz = oz; g.G = G; g.deposit_all = deposit_all; g.lgn = pm_log2_or_neg(n);
     g.rho0 = -total_mass / l / l / l;
     const long long n3 = (long long)n * n * n;
     for (long long t = 0; t < n3; t++) f[t] = g.rho0;
@@ -27,7 +27,7 @@ void emul_pm_gather_move(int n, long long N, double l, double ox, double oy, dou
                          double* E, double* x, double* v, double* a, double* aprev, int do_move)
 {
     PMGeom g{};
-    g.n = n; g.N = N; g.l = l; g.h = l / n; g.ox = ox; g.oy = oy; g.oz = oz; g.dt = dt;
+    g.n = n; g.N = N; g.l = l; g.h = l / n; g.ox = ox; g.oy = oy; g.oz = oz; g.dt = dt; g.lgn = pm_log2_or_neg(n);
     const long long n3 = (long long)n * n * n;
     for (long long t = 0; t < n3; t++) pm_field_elem(g, t, psi, E);
     for (long long b = 0; b < N; b++) {
