@@ -42,6 +42,7 @@ def lib():
     L.fdmb_lapl_cube_create.argtypes = [C.POINTER(C.c_void_p)] + [C.c_double] * 6 + [C.c_int] * 4
     L.fdmb_lapl_cube_solve.argtypes = [C.c_void_p, dp, dp]
     L.fdmb_lapl_cube_solve_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.fdmb_lapl_cube_solve_batch.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
     L.fdmb_lapl_cube_destroy.argtypes = [C.c_void_p]
     ip = C.POINTER(C.c_int)
     L.fdmb_slab_range.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, ip, ip]

@@ -377,7 +377,14 @@ fdmb_lapl_cube::~fdmb_lapl_cube()
     } else {
         cudaFree(d_work);
     }
-    cudaFree(d_rhs); cudaFree(d_ans);
+    cudaFree(d_rhs); cudaFree(d_ans); cudaFree(d_rhs1); cudaFree(d_ans1);
+    for (int b = 0; b < 2; b++) {
+        if (ev_up[b]) cudaEventDestroy(ev_up[b]);
+        if (ev_cmp[b]) cudaEventDestroy(ev_cmp[b]);
+        if (ev_dn[b]) cudaEventDestroy(ev_dn[b]);
+    }
+    if (s_up) cudaStreamDestroy(s_up);
+    if (s_dn) cudaStreamDestroy(s_dn);
     if (stream) cudaStreamDestroy(stream);
 }
 
@@ -537,6 +544,51 @@ int fdmb_lapl_cube::solve_host(double* ans, const double* rhs)
     return FDMB_OK;
 }
 
+// `count` independent solves with host arrays, software-pipelined over two staging pairs: the upload of solve i+1
+// and the download of solve i-1 run on their own streams while solve i computes (PCIe is full duplex, so a long
+// batch costs max(upload, download, compute) per solve instead of their sum).  Same kernels, same results as
+// `count` calls of solve_host.
+int fdmb_lapl_cube::solve_batch(int count, double* const* ans, const double* const* rhs)
+{
+    if (nranks > 1) { set_error("LaplCube: solve_batch is for single-GPU handles"); return FDMB_ERR_INVALID; }
+    const size_t bytes = sizeof(double) * (size_t)nx * ny * nz;
+    if (!d_rhs) FDMB_CUDA(cudaMalloc(&d_rhs, bytes));
+    if (!d_ans) FDMB_CUDA(cudaMalloc(&d_ans, bytes));
+    if (count > 1) {
+        if (!d_rhs1) FDMB_CUDA(cudaMalloc(&d_rhs1, bytes));
+        if (!d_ans1) FDMB_CUDA(cudaMalloc(&d_ans1, bytes));
+    }
+    if (!s_up) FDMB_CUDA(cudaStreamCreateWithFlags(&s_up, cudaStreamNonBlocking));
+    if (!s_dn) FDMB_CUDA(cudaStreamCreateWithFlags(&s_dn, cudaStreamNonBlocking));
+    for (int b = 0; b < 2; b++) {
+        if (!ev_up[b]) FDMB_CUDA(cudaEventCreateWithFlags(&ev_up[b], cudaEventDisableTiming));
+        if (!ev_cmp[b]) FDMB_CUDA(cudaEventCreateWithFlags(&ev_cmp[b], cudaEventDisableTiming));
+        if (!ev_dn[b]) FDMB_CUDA(cudaEventCreateWithFlags(&ev_dn[b], cudaEventDisableTiming));
+    }
+    double* dr[2] = {d_rhs, d_rhs1};
+    double* da[2] = {d_ans, d_ans1};
+    // earlier work on the handle's stream (a previous solve_host / solve_device) may still use the staging buffers
+    FDMB_CUDA(cudaStreamSynchronize(stream));
+    for (int i = 0; i < count; i++) {
+        const int b = i & 1;
+        if (i >= 2) FDMB_CUDA(cudaStreamWaitEvent(s_up, ev_cmp[b], 0));      // solve i-2 has consumed dr[b]
+        FDMB_CUDA(cudaMemcpyAsync(dr[b], rhs[i], bytes, cudaMemcpyHostToDevice, s_up));
+        FDMB_CUDA(cudaEventRecord(ev_up[b], s_up));
+        FDMB_CUDA(cudaStreamWaitEvent(stream, ev_up[b], 0));
+        if (i >= 2) FDMB_CUDA(cudaStreamWaitEvent(stream, ev_dn[b], 0));     // download i-2 has drained da[b]
+        int rc = solve_device(da[b], dr[b], stream);
+        if (rc) { cudaDeviceSynchronize(); return rc; }
+        FDMB_CUDA(cudaEventRecord(ev_cmp[b], stream));
+        FDMB_CUDA(cudaStreamWaitEvent(s_dn, ev_cmp[b], 0));
+        FDMB_CUDA(cudaMemcpyAsync(ans[i], da[b], bytes, cudaMemcpyDeviceToHost, s_dn));
+        FDMB_CUDA(cudaEventRecord(ev_dn[b], s_dn));
+    }
+    FDMB_CUDA(cudaStreamSynchronize(s_dn));
+    FDMB_CUDA(cudaStreamSynchronize(stream));
+    FDMB_CUDA(cudaStreamSynchronize(s_up));
+    return FDMB_OK;
+}
+
 extern "C" {
 
 int fdmb_lapl_cube_create(fdmb_lapl_cube** out, double dx, double dy, double dz, double lx, double ly, double lz,
@@ -651,6 +703,14 @@ int fdmb_lapl_cube_solve(fdmb_lapl_cube* h, double* ans, const double* rhs)
 {
     if (!h || !ans || !rhs) { set_error("null argument"); return FDMB_ERR_INVALID; }
     return h->solve_host(ans, rhs);
+}
+
+int fdmb_lapl_cube_solve_batch(fdmb_lapl_cube* h, int count, double* const* ans, const double* const* rhs)
+{
+    if (!h || count < 0 || (count > 0 && (!ans || !rhs))) { set_error("null argument"); return FDMB_ERR_INVALID; }
+    for (int i = 0; i < count; i++)
+        if (!ans[i] || !rhs[i]) { set_error("solve_batch: null array %d", i); return FDMB_ERR_INVALID; }
+    return h->solve_batch(count, ans, rhs);
 }
 
 int fdmb_lapl_cube_solve_device(fdmb_lapl_cube* h, double* d_ans, const double* d_rhs, void* stream)

@@ -54,6 +54,11 @@ struct fdmb_lapl_cube {
     double *d_lmx = nullptr, *d_lmy = nullptr, *d_lmz = nullptr;
     double* d_work = nullptr;
     double *d_rhs = nullptr, *d_ans = nullptr;   // staging for the host-pointer entry point
+    // second staging pair, copy streams and events of the pipelined multi-solve entry point (solve_batch)
+    double *d_rhs1 = nullptr, *d_ans1 = nullptr;
+    cudaStream_t s_up = nullptr, s_dn = nullptr;
+    cudaEvent_t ev_up[2] = {nullptr, nullptr}, ev_cmp[2] = {nullptr, nullptr}, ev_dn[2] = {nullptr, nullptr};
+    int solve_batch(int count, double* const* ans, const double* const* rhs);
     bool pipe_y = false, pipe_z = false;         // tensor maps over d_work are valid
     fdmb::ColsMaps tm_y{}, tm_z{}, tm_yw{};      // tm_yw: wide-tile maps of the sharded y forward sweep
     int blog = 0, nyb = 0;                       // blocked work array [yb][z][yi][x], 1 << blog rows per block (0: natural)

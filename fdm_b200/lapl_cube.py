@@ -53,6 +53,16 @@ class LaplCube:
         capi.check(capi.lib().fdmb_lapl_cube_solve(self._h, capi.as_dp(ans), capi.as_dp(rhs)), "LaplCube solve")
         return ans
 
+    def solve_batch(self, ans_ptrs, rhs_ptrs):
+        """Pipelined independent solves: raw HOST pointers (ints; page-locked memory lets the copies overlap the
+        solves).  Same results as one ``solve`` per pair."""
+        n = len(rhs_ptrs)
+        if len(ans_ptrs) != n:
+            raise ValueError("one ans per rhs")
+        a = (C.c_void_p * n)(*ans_ptrs)
+        r = (C.c_void_p * n)(*rhs_ptrs)
+        capi.check(capi.lib().fdmb_lapl_cube_solve_batch(self._h, n, a, r), "LaplCube solve_batch")
+
     def solve_device(self, d_ans, d_rhs, stream=0):
         """Device-resident solve: raw device pointers (ints), asynchronous on ``stream``."""
         capi.check(capi.lib().fdmb_lapl_cube_solve_device(self._h, C.c_void_p(d_ans), C.c_void_p(d_rhs),

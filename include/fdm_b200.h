@@ -78,6 +78,11 @@ int fdmb_lapl_cube_create(fdmb_lapl_cube** h, double dx, double dy, double dz,
                           double lx, double ly, double lz, int nx, int ny, int nz, int periodic);
 int fdmb_lapl_cube_solve(fdmb_lapl_cube* h, double* ans, const double* rhs);
 int fdmb_lapl_cube_solve_device(fdmb_lapl_cube* h, double* d_ans, const double* d_rhs, void* stream);
+/* B200 extension: `count` independent solves with HOST arrays (ans[i], rhs[i] as for solve), software-pipelined over
+ * two device staging pairs: the upload of solve i+1 and the download of solve i-1 overlap solve i, so a long batch
+ * costs max(upload, download, compute) per solve instead of their sum.  Page-locked host arrays are needed for the
+ * copies to overlap; results are bit-identical to `count` calls of solve.  Single-GPU handles only.              */
+int fdmb_lapl_cube_solve_batch(fdmb_lapl_cube* h, int count, double* const* ans, const double* const* rhs);
 int fdmb_lapl_cube_destroy(fdmb_lapl_cube* h);
 
 /* Multi-GPU LaplCube: the grid is cut into z-slabs, one rank (= one GPU, normally one process) per

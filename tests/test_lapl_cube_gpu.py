@@ -150,3 +150,27 @@ def test_cube_blocked_work_layout(fb, ref, monkeypatch, shape):
     got = S.solve(rhs)
     assert O.rel_l2(got, want) < TOL
     assert O.rel_l2(S.solve(rhs), want) < TOL        # a second solve: padding rows untouched
+
+
+@pytest.mark.parametrize("n,count", [(63, 1), (63, 2), (127, 5)])
+def test_cube_solve_batch_equals_single_solves(fb, n, count):
+    """fdmb_lapl_cube_solve_batch pipelines uploads, solves and downloads over two staging pairs; the answers are
+    bit-identical to one solve() per right-hand side (page-locked and pageable host memory)."""
+    import torch
+    dx = 1.0 / n; l = 1 + dx
+    S = fb.LaplCube(dx, dx, dx, l, l, l, n, n, n)
+    rhs = [O.synthetic_rhs((n, n, n), seed=100 + i) for i in range(count)]
+    want = [S.solve(r) for r in rhs]
+    # pageable numpy arrays
+    ans = [np.full((n, n, n), np.nan) for _ in range(count)]
+    S.solve_batch([a.ctypes.data for a in ans], [r.ctypes.data for r in rhs])
+    for a, w in zip(ans, want):
+        assert np.array_equal(a, w)
+    # page-locked buffers, answers rotating through two arrays like bench.py does
+    prhs = [torch.from_numpy(r).pin_memory() for r in rhs]
+    pans = [torch.empty(n ** 3, dtype=torch.float64).pin_memory() for _ in range(min(count, 2))]
+    S.solve_batch([pans[i % 2].data_ptr() for i in range(count)], [t.data_ptr() for t in prhs])
+    for i in range(max(0, count - 2), count):           # the last answers written to each rotating buffer survive
+        assert np.array_equal(pans[i % 2].numpy().reshape(n, n, n), want[i])
+    # a plain solve afterwards still works on the shared staging buffers
+    assert np.array_equal(S.solve(rhs[0]), want[0])
