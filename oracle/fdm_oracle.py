@@ -5,7 +5,10 @@ Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline /
 (``fdm_b200``) never does; it fails loudly when its CUDA library is missing.
 
 Parity status: PINNED.  Every function here is checked in
-``tests/test_oracle_cpu.py`` against (a) the unmodified reference compiled into
+``tests/test_oracle_cpu.py`` (transforms, LaplCube, LaplRect*, LaplCyl3FFT2, NSCube),
+``tests/test_oracle_nscyl_cpu.py`` (NSCyl step / L_step), ``tests/test_velocity_plot_cpu.py``
+(velocity_plotter), ``tests/test_nbody_cpu.py`` (particle-mesh N-body step) and
+``tests/test_reference_kat.py`` against (a) the unmodified reference compiled into
 ``oracle/_ref/libfdm_ref.so`` (when present), (b) the golden vectors under
 ``tests/golden`` that were generated from that library by
 ``tests/golden/make_golden.py``, and (c) the reference's own known-answer
@@ -465,6 +468,241 @@ class NSCube:
         v.v(I, Km, J)[...] = G.v(I, Km, J) - dt / dy * (x.v(I, (2, ny), J) - x.v(I, Km, J))
         w.v(Im, K, J)[...] = H.v(Im, K, J) - dt / dz * (x.v((2, nz), K, J) - x.v(Im, K, J))
         p.v(I, K, J)[...] = x.a  # tensor::operator= copies the index-range intersection
+
+
+# --------------------------------------------------------------------------------------
+# NSCyl (reference: src/ns_cyl.h:56-110, src/ns_cyl.cpp:23-484)
+# --------------------------------------------------------------------------------------
+
+
+class PT:
+    """[phi][z][r] array with inclusive z / r index ranges; phi always wraps, z wraps when ``zper``
+    (fdm::tensor with tensor_flags<periodic, zflag>, src/ns_cyl.h:21-22, src/tensor.h:119-123)."""
+
+    def __init__(self, nphi, zr, rr, zper):
+        self.nphi, self.lz, self.lr, self.zper = nphi, zr[0], rr[0], zper
+        self.a = np.zeros((nphi, zr[1] - zr[0] + 1, rr[1] - rr[0] + 1), dtype=np.float64)
+
+    def g(self, K, J, di=0, dk=0, dj=0):
+        """Values at (i + di, k + dk, j + dj) for all i, k in K = (k0, k1), j in J = (j0, j1)."""
+        I = (np.arange(self.nphi) + di) % self.nphi
+        Kk = np.arange(K[0], K[1] + 1) + dk - self.lz
+        if self.zper:
+            Kk %= self.a.shape[1]
+        Jj = np.arange(J[0], J[1] + 1) + dj - self.lr
+        return self.a[np.ix_(I, Kk, Jj)]
+
+    def put(self, K, J, val):
+        self.a[:, K[0] - self.lz:K[1] - self.lz + 1, J[0] - self.lr:J[1] - self.lr + 1] = val
+
+
+class NSCyl:
+    """Flow between two coaxial cylinders, inner one rotating; fields [phi][z][r] with the reference's extents.
+    The verify() wall invariants inside init_bound (ns_cyl.cpp:136-163) are not re-checked here."""
+
+    def __init__(self, nr=32, nz=31, nphi=32, Re=1.0, dt=0.001, u0=1.0, R=math.pi, r=math.pi / 2, h1=0.0, h2=10.0,
+                 zperiodic=False):
+        self.R, self.r0, self.h1, self.h2, self.U0, self.Re, self.dt = R, r, h1, h2, u0, Re, dt
+        self.nr, self.nz, self.nphi, self.zp = nr, nz, nphi, bool(zperiodic)
+        zp = self.zp
+        # ns_cyl.h:70-74
+        self.z_, self.z0, self.z1, self.zn, self.znn = (0, 0, 0, nz - 1, nz - 1) if zp else (-1, 0, 1, nz, nz + 1)
+        self.dr, self.dz, self.dphi = (R - r) / nr, (h2 - h1) / nz, 2 * math.pi / nphi
+        self.dr2, self.dz2, self.dphi2 = self.dr ** 2, self.dz ** 2, self.dphi ** 2
+        z_, z0, z1, zn, znn = self.z_, self.z0, self.z1, self.zn, self.znn
+        mk = lambda zr, rr: PT(nphi, zr, rr, zp)      # noqa: E731
+        # ns_cyl.h:80-93
+        self.u, self.v, self.w = mk((z0, znn), (-1, nr + 1)), mk((z_, znn), (0, nr + 1)), mk((z0, znn), (0, nr + 1))
+        self.p = mk((z0, znn), (0, nr + 1))
+        self.u0, self.v0, self.w0 = mk((z0, znn), (-1, nr + 1)), mk((z_, znn), (0, nr + 1)), mk((z0, znn), (0, nr + 1))
+        self.x, self.RHS = mk((z1, zn), (1, nr)), mk((z1, zn), (1, nr))
+        self.F, self.G, self.H = mk((z1, zn), (0, nr)), mk((z0, zn), (1, nr)), mk((z1, zn), (1, nr))
+        # ns_cyl.h:95-97
+        self.lapl = LaplCyl3FFT2(self.dr, self.dz, r - self.dr / 2, R - r + self.dr,
+                                 h2 - h1 if zp else h2 - h1 + self.dz, nr, nz, nphi, zperiodic=zp)
+        self.time_index = 0
+
+    def fields(self):
+        return {k: getattr(self, k).a for k in ("u", "v", "w", "p", "x", "F", "G", "H", "RHS", "u0", "v0", "w0")}
+
+    def field(self, name):
+        return self.fields()[name].ravel()
+
+    def set_field(self, name, a):
+        t = getattr(self, name).a
+        t[...] = np.asarray(a, dtype=np.float64).reshape(t.shape)
+
+    def step(self, nsteps=1, linear=False):
+        for _ in range(nsteps):                       # ns_cyl.cpp:23-63 / :66-78
+            self.init_bound()
+            self.L_FGH() if linear else self.FGH()
+            self.poisson()
+            self.update_uvwp()
+            self.time_index += 1
+
+    def init_bound(self):  # ns_cyl.cpp:81-172, statement order preserved
+        nr, nz, U0, Re, dr, dz, r0 = self.nr, self.nz, self.U0, self.Re, self.dr, self.dz, self.r0
+        u, v, w, p = self.u, self.v, self.w, self.p
+        z_, z0, z1, zn, znn = self.z_, self.z0, self.z1, self.zn, self.znn
+        Kw, Kv = (z0, znn), (z_, znn)
+        w.put(Kw, (0, 0), 2 * U0 - w.g(Kw, (1, 1)))                      # inner cylinder: 0.5 (w0 + w1) = U0
+        w.put(Kw, (nr + 1, nr + 1), -w.g(Kw, (nr, nr)))
+        v.put(Kv, (0, 0), -v.g(Kv, (1, 1)))
+        v.put(Kv, (nr + 1, nr + 1), -v.g(Kv, (nr, nr)))
+        u.put(Kw, (-1, -1), u.g(Kw, (1, 1)))
+        u.put(Kw, (nr + 1, nr + 1), u.g(Kw, (nr - 1, nr - 1)))
+        if not self.zp:
+            # :107-112 loops the r index over z0..znn (sic)
+            assert znn <= nr + 1, "the reference walks out of v's r range when nz > nr"
+            Jq = (z0, znn)
+            v.put((-1, -1), Jq, v.g((1, 1), Jq))
+            v.put((nz + 1, nz + 1), Jq, v.g((nz - 1, nz - 1), Jq))
+            Ju, Jw = (-1, nr + 1), (0, nr + 1)
+            u.put((0, 0), Ju, -u.g((1, 1), Ju))
+            u.put((nz + 1, nz + 1), Ju, -u.g((nz, nz), Ju))
+            w.put((0, 0), Jw, -w.g((1, 1), Jw))
+            w.put((nz + 1, nz + 1), Jw, -w.g((nz, nz), Jw))
+        K = (z1, zn)
+        r = r0 + 0 * dr - dr / 2
+        p.put(K, (0, 0), p.g(K, (1, 1)) - ((r + 0.5 * dr) * u.g(K, (1, 1)) / r - 2 * u.g(K, (0, 0))
+                                          + (r - 0.5 * dr) * u.g(K, (-1, -1)) / r) / Re / dr)
+        r = r0 + nr * dr - dr / 2
+        p.put(K, (nr + 1, nr + 1), p.g(K, (nr, nr)) + ((r + 0.5 * dr) * u.g(K, (nr + 1, nr + 1)) / r - 2 * u.g(K, (nr, nr))
+                                                      + (r - 0.5 * dr) * u.g(K, (nr - 1, nr - 1)) / r) / Re / dr)
+        if not self.zp:
+            J = (1, nr)
+            p.put((0, 0), J, p.g((1, 1), J) - (v.g((1, 1), J) - 2 * v.g((0, 0), J) + v.g((-1, -1), J)) / Re / dz)
+            p.put((nz + 1, nz + 1), J, p.g((nz, nz), J)
+                  + (v.g((nz + 1, nz + 1), J) - 2 * v.g((nz, nz), J) + v.g((nz - 1, nz - 1), J)) / Re / dz)
+
+    def _radii(self, J, staggered):
+        j = np.arange(J[0], J[1] + 1, dtype=np.float64)
+        r = self.r0 + self.dr * j - (self.dr / 2 if staggered else 0.0)      # :184 / :217
+        return r, (r + 0.5 * self.dr) / r, (r - 0.5 * self.dr) / r, r * r
+
+    def FGH(self):  # ns_cyl.cpp:175-277
+        nr, Re, dt, dr, dz, dphi = self.nr, self.Re, self.dt, self.dr, self.dz, self.dphi
+        dr2, dz2, dphi2 = self.dr2, self.dz2, self.dphi2
+        u, v, w = self.u, self.v, self.w
+        z0, z1, zn = self.z0, self.z1, self.zn
+        # F (r): i = 1..nphi with periodic wrap = every phi (:181), k = z1..zn, j = 0..nr
+        K, J = (z1, zn), (0, nr)
+        r, r2, r1, rr = self._radii(J, False)
+        U = lambda di=0, dk=0, dj=0: u.g(K, J, di, dk, dj)      # noqa: E731
+        V = lambda di=0, dk=0, dj=0: v.g(K, J, di, dk, dj)      # noqa: E731
+        W = lambda di=0, dk=0, dj=0: w.g(K, J, di, dk, dj)      # noqa: E731
+        self.F.put(K, J, U() + dt * (
+            (r2 * U(dj=1) - 2 * U() + r1 * U(dj=-1)) / Re / dr2 +
+            (U(dk=1) - 2 * U() + U(dk=-1)) / Re / dz2 +
+            (U(di=1) - 2 * U() + U(di=-1)) / Re / dphi2 / rr -
+            (r2 * _sq(0.5 * (U() + U(dj=1))) - r1 * _sq(0.5 * (U(dj=-1) + U()))) / dr -
+            0.25 * ((U() + U(dk=1)) * (V(dj=1) + V()) - (U(dk=-1) + U()) * (V(dk=-1, dj=1) + V(dk=-1))) / dz -
+            0.25 * ((U() + U(di=1)) * (W(dj=1) + W()) - (U(di=-1) + U()) * (W(di=-1, dj=1) + W(di=-1))) / dphi / r
+            + _sq(0.5 * (W(dj=1) + W())) / r - U() / rr / Re
+            - 2 * (0.5 * (W(dj=1) + W()) - 0.5 * (W(di=-1, dj=1) + W(di=-1))) / rr / dphi / Re))
+        # G (z): k = z0..zn, j = 1..nr
+        K, J = (z0, zn), (1, nr)
+        r, r2, r1, rr = self._radii(J, True)
+        self.G.put(K, J, V() + dt * (
+            (r2 * V(dj=1) - 2 * V() + r1 * V(dj=-1)) / Re / dr2 +
+            (V(dk=1) - 2 * V() + V(dk=-1)) / Re / dz2 +
+            (V(di=1) - 2 * V() + V(di=-1)) / Re / dphi2 / rr -
+            (_sq(0.5 * (V() + V(dk=1))) - _sq(0.5 * (V(dk=-1) + V()))) / dz -
+            0.25 * (r2 * (U() + U(dk=1)) * (V(dj=1) + V()) - r1 * (U(dj=-1) + U(dk=1, dj=-1)) * (V() + V(dj=-1))) / dr -
+            0.25 * ((W() + W(dk=1)) * (V() + V(di=1)) - (W(di=-1) + W(di=-1, dk=1)) * (V(di=-1) + V())) / dphi / r))
+        # H (phi): k = z1..zn, j = 1..nr
+        K, J = (z1, zn), (1, nr)
+        self.H.put(K, J, W() + dt * (
+            (r2 * W(dj=1) - 2 * W() + r1 * W(dj=-1)) / Re / dr2 +
+            (W(dk=1) - 2 * W() + W(dk=-1)) / Re / dz2 +
+            (W(di=1) - 2 * W() + W(di=-1)) / Re / dphi2 / rr -
+            (_sq(0.5 * (W(di=1) + W())) - _sq(0.5 * (W(di=-1) + W()))) / dphi / r -
+            0.25 * (r2 * (U(di=1) + U()) * (W(dj=1) + W()) - r1 * (U(di=1, dj=-1) + U(dj=-1)) * (W() + W(dj=-1))) / dr -
+            0.25 * ((W() + W(dk=1)) * (V() + V(di=1)) - (W(dk=-1) + W()) * (V(dk=-1) + V(di=1, dk=-1))) / dz
+            - W() * 0.5 * (U(di=1) + U()) / r - W() / rr / Re
+            + 2 * (0.5 * (U(di=1) + U()) - 0.5 * (U() + U(di=-1))) / rr / dphi / Re))
+
+    def L_FGH(self):  # ns_cyl.cpp:280-405: FGH linearised about u0, v0, w0
+        nr, Re, dt, dr, dz, dphi = self.nr, self.Re, self.dt, self.dr, self.dz, self.dphi
+        dr2, dz2, dphi2 = self.dr2, self.dz2, self.dphi2
+        u, v, w, u0, v0, w0 = self.u, self.v, self.w, self.u0, self.v0, self.w0
+        z0, z1, zn = self.z0, self.z1, self.zn
+        K, J = (z1, zn), (0, nr)
+        r, r2, r1, rr = self._radii(J, False)
+        U = lambda di=0, dk=0, dj=0: u.g(K, J, di, dk, dj)        # noqa: E731
+        V = lambda di=0, dk=0, dj=0: v.g(K, J, di, dk, dj)        # noqa: E731
+        W = lambda di=0, dk=0, dj=0: w.g(K, J, di, dk, dj)        # noqa: E731
+        U0 = lambda di=0, dk=0, dj=0: u0.g(K, J, di, dk, dj)      # noqa: E731
+        V0 = lambda di=0, dk=0, dj=0: v0.g(K, J, di, dk, dj)      # noqa: E731
+        W0 = lambda di=0, dk=0, dj=0: w0.g(K, J, di, dk, dj)      # noqa: E731
+        self.F.put(K, J, U() + dt * (
+            (r2 * U(dj=1) - 2 * U() + r1 * U(dj=-1)) / Re / dr2 +
+            (U(dk=1) - 2 * U() + U(dk=-1)) / Re / dz2 +
+            (U(di=1) - 2 * U() + U(di=-1)) / Re / dphi2 / rr -
+            (r2 * (0.5 * U() + U(dj=1)) * (U0() + U0(dj=1)) - r1 * (0.5 * U(dj=-1) + U()) * (U0(dj=-1) + U0())) / dr -
+            0.25 * ((U() + U(dk=1)) * (V0(dj=1) + V0()) - (U(dk=-1) + U()) * (V0(dk=-1, dj=1) + V0(dk=-1))) / dz -
+            0.25 * ((U0() + U0(dk=1)) * (V(dj=1) + V()) - (U0(dk=-1) + U0()) * (V(dk=-1, dj=1) + V(dk=-1))) / dz -
+            0.25 * ((U() + U(di=1)) * (W0(dj=1) + W0()) - (U(di=-1) + U()) * (W0(di=-1, dj=1) + W0(di=-1))) / dphi / r -
+            0.25 * ((U0() + U0(di=1)) * (W(dj=1) + W()) - (U0(di=-1) + U0()) * (W(di=-1, dj=1) + W(di=-1))) / dphi / r
+            + 0.5 * (W(dj=1) + W()) * (W0(dj=1) + W0()) / r
+            - U() / rr / Re
+            - 2 * (0.5 * (W(dj=1) + W()) - 0.5 * (W(di=-1, dj=1) + W(di=-1))) / rr / dphi / Re))
+        K, J = (z0, zn), (1, nr)
+        r, r2, r1, rr = self._radii(J, True)
+        self.G.put(K, J, V() + dt * (
+            (r2 * V(dj=1) - 2 * V() + r1 * V(dj=-1)) / Re / dr2 +
+            (V(dk=1) - 2 * V() + V(dk=-1)) / Re / dz2 +
+            (V(di=1) - 2 * V() + V(di=-1)) / Re / dphi2 / rr -
+            (0.5 * (V() + V(dk=1)) * (V0() + V0(dk=1)) - 0.5 * (V(dk=-1) + V()) * (V0(dk=-1) + V0())) / dz -
+            0.25 * (r2 * (U() + U(dk=1)) * (V0(dj=1) + V0()) - r1 * (U(dj=-1) + U(dk=1, dj=-1)) * (V0() + V0(dj=-1))) / dr -
+            0.25 * (r2 * (U0() + U0(dk=1)) * (V(dj=1) + V()) - r1 * (U0(dj=-1) + U0(dk=1, dj=-1)) * (V() + V(dj=-1))) / dr -
+            0.25 * ((W() + W(dk=1)) * (V0() + V0(di=1)) - (W(di=-1) + W(di=-1, dk=1)) * (V0(di=-1) + V0())) / dphi / r -
+            0.25 * ((W0() + W0(dk=1)) * (V() + V(di=1)) - (W0(di=-1) + W0(di=-1, dk=1)) * (V(di=-1) + V())) / dphi / r))
+        K, J = (z1, zn), (1, nr)
+        self.H.put(K, J, W() + dt * (
+            (r2 * W(dj=1) - 2 * W() + r1 * W(dj=-1)) / Re / dr2 +
+            (W(dk=1) - 2 * W() + W(dk=-1)) / Re / dz2 +
+            (W(di=1) - 2 * W() + W(di=-1)) / Re / dphi2 / rr -
+            (0.5 * (W(di=1) + W()) * (W0(di=1) + W0()) - 0.5 * (W(di=-1) + W()) * (W0(di=-1) + W0())) / dphi / r -
+            0.25 * (r2 * (U(di=1) + U()) * (W0(dj=1) + W0()) - r1 * (U(di=1, dj=-1) + U(dj=-1)) * (W0() + W0(dj=-1))) / dr -
+            0.25 * (r2 * (U0(di=1) + U0()) * (W(dj=1) + W()) - r1 * (U0(di=1, dj=-1) + U0(dj=-1)) * (W() + W(dj=-1))) / dr -
+            0.25 * ((W() + W(dk=1)) * (V0() + V0(di=1)) - (W(dk=-1) + W()) * (V0(dk=-1) + V0(di=1, dk=-1))) / dz -
+            0.25 * ((W0() + W0(dk=1)) * (V() + V(di=1)) - (W0(dk=-1) + W0()) * (V(dk=-1) + V(di=1, dk=-1))) / dz
+            - W0() * 0.5 * (U(di=1) + U()) / r
+            - W() * 0.5 * (U0(di=1) + U0()) / r
+            - W() / rr / Re
+            + 2 * (0.5 * (U(di=1) + U()) - 0.5 * (U() + U(di=-1))) / rr / dphi / Re))
+
+    def poisson(self):  # ns_cyl.cpp:408-442
+        nr, nz, dt, dr, dz, dphi, dr2, dz2 = self.nr, self.nz, self.dt, self.dr, self.dz, self.dphi, self.dr2, self.dz2
+        F, G, H, p, RHS = self.F, self.G, self.H, self.p, self.RHS
+        K, J = (self.z1, self.zn), (1, nr)
+        r, _, _, _ = self._radii(J, True)
+        R = (((r + 0.5 * dr) * F.g(K, J) - (r - 0.5 * dr) * F.g(K, J, dj=-1)) / r / dr
+             + (G.g(K, J) - G.g(K, J, dk=-1)) / dz
+             + (H.g(K, J) - H.g(K, J, di=-1)) / dphi / r) / dt
+        RHS.put(K, J, R)
+        a = RHS.a                                             # [phi][k - z1][j - 1]
+        if not self.zp:
+            a[:, 0, :] -= p.g((0, 0), J)[:, 0, :] / dz2
+        a[:, :, 0] -= (r[0] - dr / 2) / r[0] * p.g(K, (0, 0))[:, :, 0] / dr2
+        a[:, :, -1] -= (r[-1] + dr / 2) / r[-1] * p.g(K, (nr + 1, nr + 1))[:, :, 0] / dr2
+        if not self.zp:
+            a[:, -1, :] -= p.g((nz + 1, nz + 1), J)[:, 0, :] / dz2
+        self.x.a[...] = self.lapl.solve(a).reshape(a.shape)
+
+    def update_uvwp(self):  # ns_cyl.cpp:445-484
+        nr, nz, dt, dr, dz, dphi = self.nr, self.nz, self.dt, self.dr, self.dz, self.dphi
+        u, v, w, p, x, F, G, H = self.u, self.v, self.w, self.p, self.x, self.F, self.G, self.H
+        z1, zn = self.z1, self.zn
+        K, J = (z1, zn), (1, nr - 1)
+        u.put(K, J, F.g(K, J) - dt / dr * (x.g(K, J, dj=1) - x.g(K, J)))
+        K, J = (z1, nz - 1), (1, nr)                           # "k < nz /*ok*/": the periodic case wraps x[k+1]
+        v.put(K, J, G.g(K, J) - dt / dz * (x.g(K, J, dk=1) - x.g(K, J)))
+        K, J = (z1, zn), (1, nr)
+        r, _, _, _ = self._radii(J, True)
+        w.put(K, J, H.g(K, J) - dt / dphi / r * (x.g(K, J, di=1) - x.g(K, J)))
+        p.put(K, J, x.a)                                       # tensor::operator= copies the index-range intersection
 
 
 # --------------------------------------------------------------------------------------
