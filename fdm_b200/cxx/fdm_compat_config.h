@@ -37,15 +37,35 @@ public:
     {
         FILE* f = fopen(filename.c_str(), "r");
         if (!f) return;
+        // same line grammar as Config::load (src/config.cpp:78-120): "[section]" at the start of a line; lines that
+        // start with '#' or ';' are comments; otherwise "key = value" where an inline ";" starts a comment and key and
+        // value are the first two tokens separated by blanks, tabs or '='; lines before the first section are ignored
         char line[4096];
         std::string sec;
+        bool have_sec = false;
         while (fgets(line, sizeof(line), f)) {
-            std::string s = trim(line);
-            if (s.empty() || s[0] == ';' || s[0] == '#') continue;
-            if (s.front() == '[' && s.back() == ']') { sec = trim(s.substr(1, s.size() - 2)); continue; }
-            size_t eq = s.find('=');
-            if (eq == std::string::npos) continue;
-            data[sec][trim(s.substr(0, eq))] = trim(s.substr(eq + 1));
+            std::string s(line);
+            if (s[0] == '[') {
+                size_t e = s.find_first_of(" \t\r\n", 1);
+                std::string name = s.substr(1, (e == std::string::npos ? s.size() : e) - 1);
+                if (!name.empty()) {                       // sscanf("[%s]") + drop the last character
+                    name.pop_back();
+                    sec = name; have_sec = true; data[sec];
+                    continue;
+                }
+            }
+            if (s[0] == '#' || s[0] == ';' || !have_sec) continue;
+            size_t c = s.find(';');
+            if (c != std::string::npos) s.resize(c);
+            const char* sep = " =\t\r\n";
+            size_t k0 = s.find_first_not_of(sep);
+            if (k0 == std::string::npos) continue;
+            size_t k1 = s.find_first_of(sep, k0);
+            if (k1 == std::string::npos) continue;
+            size_t v0 = s.find_first_not_of(sep, k1);
+            if (v0 == std::string::npos) continue;
+            size_t v1 = s.find_first_of(sep, v0);
+            data[sec][s.substr(k0, k1 - k0)] = s.substr(v0, v1 == std::string::npos ? std::string::npos : v1 - v0);
         }
         fclose(f);
     }
