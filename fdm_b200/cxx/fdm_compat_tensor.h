@@ -73,15 +73,64 @@ public:
         if (!data) { storage.assign((size_t)size, T(0)); vec = storage.data(); } else vec = data;
     }
     tensor(const tensor&) = delete;
-    tensor& operator=(const tensor&) = delete;
+
+    // copies the index-range INTERSECTION of the two tensors, axis by axis (src/tensor.h:103-111,276-279); this is how
+    // the reference writes `p = x` (interior of p from x, src/ns_cube.cpp:275) and `u = ns.u` (test/test_ns_cyl.cpp:95)
+    tensor& operator=(const tensor& other)
+    {
+        int from[rank], to[rank];
+        for (int a = 0; a < rank; a++) {
+            const int olo = other.lo_[a], ohi = other.lo_[a] + other.len_[a] - 1, hi = lo_[a] + len_[a] - 1;
+            from[a] = lo_[a] > olo ? lo_[a] : olo;
+            to[a] = hi < ohi ? hi : ohi;
+            if (from[a] > to[a]) return *this;
+        }
+        int idx[rank];
+        for (int a = 0; a < rank; a++) idx[a] = from[a];
+        for (;;) {
+            long long d = 0, s = 0;
+            for (int a = 0; a < rank; a++) { d += (long long)(idx[a] - lo_[a]) * stride_[a]; s += (long long)(idx[a] - other.lo_[a]) * other.stride_[a]; }
+            vec[d] = other.vec[s];
+            int a = rank - 1;
+            while (a >= 0 && ++idx[a] > to[a]) { idx[a] = from[a]; a--; }
+            if (a < 0) break;
+        }
+        return *this;
+    }
 
     decltype(auto) operator[](int i) { return cursor<0, F>{vec, lo_, len_, stride_}[i]; }
+    // offset of element {z, y, x} from vec (src/tensor.h:258-260); periodic axes wrap, like operator[]
+    int index(const std::array<int, rank>& indices)
+    {
+        long long off = 0;
+        for (int a = 0; a < rank; a++) off += (long long)(wrap(a, indices[a]) - lo_[a]) * stride_[a];
+        return (int)off;
+    }
     void use(T* p) { vec = p; }
     T maxabs() const
     {
         T m = 0;
         for (long long i = 0; i < size; i++) { T a = std::abs(vec[i]); if (a > m) m = a; }
         return m;
+    }
+    // Euclidean norm (the reference calls BLAS nrm2, src/tensor.h:272-274)
+    T norm2() const
+    {
+        long double s = 0;
+        for (long long i = 0; i < size; i++) s += (long double)vec[i] * (long double)vec[i];
+        return (T)std::sqrt((double)s);
+    }
+
+private:
+    template <typename FF> static constexpr bool axis_periodic(int a)
+    {
+        if (a == 0) return has_tensor_flag(FF::head, tensor_flag::periodic);
+        else return axis_periodic<typename FF::tail>(a - 1);
+    }
+    int wrap(int a, int i) const
+    {
+        if (axis_periodic<F>(a)) { const int l = lo_[a], n = len_[a]; i = ((i - l) % n + n) % n + l; }
+        return i;
     }
 };
 
