@@ -239,6 +239,29 @@ def cpu_baseline(wl):
         return {"value": None, "unit": "", "cores": 0, "kind": "reference", "sample": f"failed: {e}"}
 
 
+def bind_to_gpu_numa_node(torch, local):
+    """One process per GPU: run (and therefore first-touch the pinned host buffers of the e2e leg) on the NUMA node
+    the GPU hangs off, so that the eight ranks' PCIe traffic does not cross the socket interconnect.  Pure host
+    placement; a no-op wherever the topology is not exposed (sysfs numa_node = -1, containers, VMs)."""
+    try:
+        pr = torch.cuda.get_device_properties(local)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
+        if node < 0:
+            return {"gpu": bdf, "node": node, "bound": False}
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return {"gpu": bdf, "node": node, "bound": False}
+        os.sched_setaffinity(0, cpus)
+        return {"gpu": bdf, "node": node, "bound": True, "cpus": len(cpus)}
+    except Exception as e:        # placement is an optimisation, never a reason to fail the run
+        return {"bound": False, "error": type(e).__name__}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -263,6 +286,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(torch, local) if world > 1 else None
     L = fdm_b200.lib()
     capi.check(L.fdmb_set_device(local), "set_device")
     if world > 1:
@@ -485,6 +509,8 @@ def main():
     e2e = {"value": units_per_step * Ke * world / te, "unit": unit, "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": d2h, "steps": Ke, "ms_per_step": 1e3 * te / Ke,
            "api": "one synchronous host-pointer call per step (the reference's solve(ans, rhs) / step())"}
+    if numa is not None:
+        e2e["host_placement"] = numa      # rank 0's NUMA binding (see bind_to_gpu_numa_node)
     if e2e_batch is not None and not args.no_e2e_batch:
         # same copies per solve, but neighbouring solves' transfers overlap (fdmb_lapl_cube_solve_batch)
         e2e_batch(2)

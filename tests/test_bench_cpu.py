@@ -46,3 +46,22 @@ def test_own_arm_needs_a_gpu():
     r = run("--workload", "cube127", "--steps", "1", "--warmup", "1")
     assert r.returncode != 0
     assert not [ln for ln in r.stdout.splitlines() if ln.startswith("{")]      # no number without the CUDA path
+
+
+def test_numa_binding_never_raises(tmp_path):
+    """bench.py's host-placement helper is an optimisation: whatever the box exposes, it returns a record."""
+    import importlib.util
+    import types
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    before = os.sched_getaffinity(0)
+
+    class Props:
+        pci_domain_id, pci_bus_id, pci_device_id = 0, 0x1b, 0
+    fake = types.SimpleNamespace(cuda=types.SimpleNamespace(get_device_properties=lambda i: Props()))
+    r = b.bind_to_gpu_numa_node(fake, 0)
+    assert isinstance(r, dict) and "bound" in r
+    broken = types.SimpleNamespace(cuda=types.SimpleNamespace(get_device_properties=lambda i: object()))
+    assert b.bind_to_gpu_numa_node(broken, 0)["bound"] is False
+    os.sched_setaffinity(0, before)
