@@ -52,3 +52,21 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 src = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "oracle" not in src.replace("test oracle", ""), os.path.join(dirpath, f)
+
+
+def test_argument_validation_precedes_cuda():
+    """Geometry errors are reported as such (FDMB_ERR_INVALID with the reference's rule in the message), before any
+    CUDA call -- so they read the same on a box without a device."""
+    import fdm_b200
+    cases = [
+        (lambda: fdm_b200.VelocityPlotter(0.1, 0.1, 0.1, 31, 32, 31, 0, 3.1, 0, 3.2, 0, 3.1, yperiodic=True), "periodic y needs periodic z"),
+        (lambda: fdm_b200.VelocityPlotter(0.1, 0.1, 0.1, 1, 31, 31, 0, 3.1, 0, 3.1, 0, 3.1), "must be >= 2"),
+        (lambda: fdm_b200.VelocityPlotter(0.1, 0.1, 0.1, 31, 30, 31, 0, 3.1, 0, 3.0, 0, 3.1), "powers of two"),
+        (lambda: fdm_b200.NBodyPM(n=2), "n >= 4"),
+        (lambda: fdm_b200.LaplRect(0.1, 0.1, 1.0, 1.0, 16, 16), "powers of two"),
+        (lambda: fdm_b200.LaplRect(0.01, 0.1, 40.0, 0.8, 4000, 7), "shared-memory tile"),
+    ]
+    for make, needle in cases:
+        with pytest.raises(fdm_b200.FdmB200Error) as e:
+            make()
+        assert "code -1" in str(e.value) and needle in str(e.value), str(e.value)
