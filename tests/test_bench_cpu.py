@@ -65,3 +65,19 @@ def test_numa_binding_never_raises(tmp_path):
     broken = types.SimpleNamespace(cuda=types.SimpleNamespace(get_device_properties=lambda i: object()))
     assert b.bind_to_gpu_numa_node(broken, 0)["bound"] is False
     os.sched_setaffinity(0, before)
+
+
+def test_cpu_baseline_sample(ref):
+    """cpu_baseline times the unmodified reference over a bounded sample and says what the sample was."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod2", os.path.join(ROOT, "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    b.CPU_SAMPLE_SECONDS = 0.3
+    for wl, unit in (("cube127", "Gpts/s"), ("nscube31", "steps/s")):
+        r = b.cpu_baseline(b.WORKLOADS[wl])
+        assert r["kind"] == "reference" and r["unit"] == unit and r["value"] > 0 and r["cores"] >= 1
+        assert "s of work" in r["sample"] and "mean" in r["sample"]
+    calls = []
+    reps, mean, best = b.timed_sample(lambda: calls.append(1), min_seconds=0.0)
+    assert reps == len(calls) == 3 and best <= mean
