@@ -123,7 +123,8 @@ int fdmb_lapl_cube_attach_local(fdmb_lapl_cube* h, fdmb_lapl_cube* const* all);
  *                doubles each, entry j for column j; NULL keeps the current values) that the
  *                cylindrical slice plotter overwrites (src/velocity_plot.h:113-127)
  * solve      <-> void solve(T* ans, T* rhs); arrays are [ny rows][nx], x fastest.
- * Dirichlet axes need n+1 = 2^k, periodic axes n = 2^k on every transformed axis.          */
+ * Dirichlet axes need n+1 = 2^k, periodic axes n = 2^k on every transformed axis (2^k <= 2048); the
+ * tridiagonal axis of kind 0 (x) takes any nx from 2 to about 2500 (shared-memory tile of the sweep).  */
 typedef struct fdmb_lapl_rect fdmb_lapl_rect;
 int fdmb_lapl_rect_create(fdmb_lapl_rect** h, int kind, int yperiodic, int xperiodic,
                           double dx, double dy, double lx, double ly, int nx, int ny);
@@ -140,7 +141,8 @@ int fdmb_lapl_rect_destroy(fdmb_lapl_rect* h);
  * create <-> constructor (dr,dz,r0,lr,lz,nr,nz,nphi)       src/lapl_cyl.h:212-245
  * solve  <-> void solve(T* ans, T* rhs)                    src/lapl_cyl.cpp:11-128
  * Arrays are [phi 0..nphi-1][z z1..zn][r 1..nr], r fastest (src/lapl_cyl.h:222).
- * nphi and the z transform length (nz+1 Dirichlet, nz periodic) must be powers of two. */
+ * nphi and the z transform length (nz+1 Dirichlet, nz periodic) must be powers of two (<= 2048);
+ * nr is free, from 2 to about 2500 (shared-memory tile of the r sweep). */
 typedef struct fdmb_lapl_cyl fdmb_lapl_cyl;
 int fdmb_lapl_cyl_create(fdmb_lapl_cyl** h, double dr, double dz, double r0, double lr, double lz,
                          int nr, int nz, int nphi, int zperiodic);
