@@ -92,6 +92,12 @@ public:
     {
         FDMB_VERIFY(fdmb_lapl_cube_solve_device(handle, d_ans, d_rhs, stream));
     }
+    // B200 extension: `count` independent solves with HOST arrays, transfers of neighbouring solves overlapped
+    // (fdmb_lapl_cube_solve_batch; page-locked arrays let the copies overlap; same answers as `count` solve() calls)
+    void solve_batch(int count, double* const* ans, const double* const* rhs)
+    {
+        FDMB_VERIFY(fdmb_lapl_cube_solve_batch(handle, count, ans, rhs));
+    }
     fdmb_lapl_cube* native_handle() const { return handle; }
 
 private:

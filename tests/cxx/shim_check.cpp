@@ -26,6 +26,10 @@
 
 using namespace fdm;
 
+// every member of the veneers compiles, also the ones no mode below calls (solve_device, solve_batch, ...)
+template class fdm::LaplCube<double, true>;
+template class fdm::LaplCube<float, false>;
+
 static std::vector<double> slurp(const char* fn, size_t n)
 {
     std::vector<double> v(n);
