@@ -130,6 +130,47 @@ def cube_geometry(n):
     return dict(dx=dx, l=1.0 + dx)
 
 
+def golden_full_size():
+    """The committed one-off run of the unmodified reference at the full 1023^3 size (tests/golden/make_golden_cube1023.py)."""
+    try:
+        g = np.load(os.path.join(ROOT, "tests", "golden", "golden_cube1023_v1.npz"))
+        sec, thr, n = float(g["ref_seconds"]), int(g["ref_threads"]), int(g["n"])
+        return {"n": n, "seconds": sec, "threads": thr, "gpts_per_s": n ** 3 / 1e9 / sec,
+                "where": "dev container, tests/golden/make_golden_cube1023.py (committed fixture golden_cube1023_v1.npz)"}
+    except Exception:
+        return None
+
+
+def reference_full_size(n, cores):
+    """ONE real solve of the full-size workload by the unmodified reference on this box (needs ~27 GB of host memory
+    and 10-30 s); skipped when the host is short of memory or FDMB_BENCH_FULLREF=0."""
+    if os.environ.get("FDMB_BENCH_FULLREF", "1") == "0":
+        return {"skipped": "FDMB_BENCH_FULLREF=0"}
+    try:
+        import psutil
+        need = 3.3 * 8 * n ** 3            # rhs, ans, the reference's internal copy + slack
+        avail = psutil.virtual_memory().available
+        if avail < need + 8e9:
+            return {"skipped": f"host has {avail / 1e9:.0f} GB available, the {n}^3 reference solve needs {need / 1e9:.0f} GB"}
+        from oracle import ref
+        g = cube_geometry(n)
+        rhs = np.empty((n, n, n))
+        rng = np.random.Generator(np.random.Philox(key=99))
+        plane = rng.random((n, n)) - 0.5
+        for z in range(n):                      # cheap synthetic field: one random plane, modulated along z
+            np.multiply(plane, np.cos(0.37 * z) + 0.1, out=rhs[z])
+        S = ref.LaplCube(g["dx"], g["dx"], g["dx"], g["l"], g["l"], g["l"], n, n, n)
+        t0 = time.perf_counter()
+        ans = S.solve(rhs)
+        dt = time.perf_counter() - t0
+        ok = bool(np.isfinite(ans[::97, ::89, ::83]).all())
+        del ans, rhs, S
+        return {"n": n, "seconds": dt, "threads": cores, "gpts_per_s": n ** 3 / 1e9 / dt, "finite": ok,
+                "where": "this run, this box: one full-size solve of the unmodified reference"}
+    except Exception as e:
+        return {"skipped": f"{type(e).__name__}: {e}"}
+
+
 def run_reference(args, wl):
     """--impl reference: the reference's own CPU implementation (oracle/_ref) on the host cores."""
     rank = int(os.environ.get("RANK", "0"))
@@ -140,9 +181,11 @@ def run_reference(args, wl):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libfdm_ref.so not built"}))
         return
     n = wl["n"]
-    cores = ref.num_threads()
+    cores = ref.use_all_cores()       # torch.distributed.run exports OMP_NUM_THREADS=1: use every core we may run on
+    extra_cfg = {}
+    full = None
     if wl["kind"] == "cube":
-        nn = min(n, 255)      # bounded sample: the reference needs ~26 GB and ~30 s per 1023^3 solve
+        nn = min(n, 255)      # bounded sample: the reference needs ~27 GB and 10-30 s per 1023^3 solve
         g = cube_geometry(nn)
         S = ref.LaplCube(g["dx"], g["dx"], g["dx"], g["l"], g["l"], g["l"], nn, nn, nn)
         rhs = O.synthetic_rhs((nn, nn, nn), seed=1234)
@@ -150,6 +193,9 @@ def run_reference(args, wl):
         units = nn ** 3 / 1e9
         metric, unit = "poisson_solve_gpts_per_s", "Gpts/s"
         sample = f"full {nn}^3 solve per step" + ("" if nn == n else f" (bounded sample of the {n}^3 workload; Gpts/s is size-normalised)")
+        if nn != n:
+            extra_cfg["reference_sample"] = (f"each step is one full {nn}^3 LaplCube solve of the unmodified reference; Gpts/s is "
+                                             f"size-normalised; cpu_baseline.full_size holds real {n}^3 solves")
     elif wl["kind"] == "cyl":
         S = ref.LaplCyl3FFT2(*cyl_geometry(wl))
         shape = (wl["nphi"], wl["nz"], wl["nr"])
@@ -177,13 +223,18 @@ def run_reference(args, wl):
         step()
     dt = time.perf_counter() - t0
     value = units * args.steps / dt
+    cb = {"value": value, "unit": unit, "cores": cores, "kind": "reference", "sample": sample}
+    if wl["kind"] == "cube" and n > 255:
+        cb["full_size_committed"] = golden_full_size()
+        if args.gpus == 1:
+            cb["full_size"] = reference_full_size(n, cores)
     print(json.dumps({
         "impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "strong" if wl["kind"] == "cube" else "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wl["label"]},
-        "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": "reference", "sample": sample},
+        "config": {"workload": wl["label"], **extra_cfg},
+        "cpu_baseline": cb,
         "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -212,7 +263,7 @@ def cpu_baseline(wl):
         if not ref.available():
             return {"value": None, "unit": "", "cores": 0, "kind": "reference", "sample": "oracle/_ref not built"}
         n = wl["n"]
-        cores = ref.num_threads()
+        cores = ref.use_all_cores()
         if wl["kind"] == "cube":
             nn = min(n, 255)
             g = cube_geometry(nn)
@@ -220,9 +271,12 @@ def cpu_baseline(wl):
             rhs = O.synthetic_rhs((nn, nn, nn), seed=1234)
             S.solve(rhs)
             reps, mean, best = timed_sample(lambda: S.solve(rhs))
-            return {"value": nn ** 3 / 1e9 / mean, "unit": "Gpts/s", "cores": cores, "kind": "reference",
-                    "sample": f"{reps} full {nn}^3 solves, {reps * mean:.1f} s of work: mean {mean * 1e3:.1f} ms, best "
-                              f"{best * 1e3:.1f} ms" + ("" if nn == n else f" (Gpts/s is size-normalised; the {n}^3 solve needs 26 GB on the host)")}
+            out = {"value": nn ** 3 / 1e9 / mean, "unit": "Gpts/s", "cores": cores, "kind": "reference",
+                   "sample": f"{reps} full {nn}^3 solves, {reps * mean:.1f} s of work: mean {mean * 1e3:.1f} ms, best "
+                             f"{best * 1e3:.1f} ms" + ("" if nn == n else f" (Gpts/s is size-normalised; the {n}^3 solve needs 27 GB on the host)")}
+            if nn != n:
+                out["full_size_committed"] = golden_full_size()
+            return out
         if wl["kind"] == "cyl":
             S = ref.LaplCyl3FFT2(*cyl_geometry(wl))
             shape = (wl["nphi"], wl["nz"], wl["nr"])
@@ -283,6 +337,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e-batch", action="store_true", help="skip the pipelined multi-solve e2e measurement")
+    ap.add_argument("--no-extra", action="store_true", help="skip the NS steps/s lines added to the default workload")
+    ap.add_argument("--no-check", action="store_true", help="skip the closed-form known-answer check of the cube solve")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
@@ -298,6 +354,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    affinity0 = os.sched_getaffinity(0)
     numa = bind_to_gpu_numa_node(torch, local) if world > 1 else None
     L = fdm_b200.lib()
     capi.check(L.fdmb_set_device(local), "set_device")
@@ -534,6 +591,38 @@ def main():
                             "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                             "api": "fdmb_lapl_cube_solve_batch: independent solves, transfers overlapped"}
 
+    # ---- correctness of what was just timed: closed-form eigenvector known answer (fdm_b200/selfcheck.py) ----
+    check = None
+    if wl["kind"] == "cube" and not args.no_check:
+        from fdm_b200 import selfcheck
+        g = cube_geometry(n)
+        z0 = S.z_first if sharded else 0
+        k_rhs, k_want = selfcheck.kat_device(torch, n, g["dx"], z0, nz_local, dev)
+        k_ans = ans[0].view(nz_local, n, n)
+        k_ans.fill_(float("nan"))
+        torch.cuda.synchronize()
+        S.solve_device(k_ans.data_ptr(), k_rhs.data_ptr(), sptr)
+        torch.cuda.synchronize()
+        nd = torch.stack([((k_ans - k_want) ** 2).sum(), (k_want ** 2).sum()])
+        if world > 1:
+            dist.all_reduce(nd)
+        check = {"kind": "eigenvector known answer: rhs = 5 discrete sine products (modes 1 .. n), ans = rhs / -(lx+ly+lz) "
+                         "in closed form; whole grid, all ranks (fdm_b200/selfcheck.py)",
+                 "rel_l2": float((nd[0] / nd[1]).sqrt().item()), "tolerance": 1e-12,
+                 "modes": selfcheck.kat_modes(n)}
+        check["ok"] = bool(check["rel_l2"] <= check["tolerance"])
+        del k_rhs, k_want
+
+    # ---- the other half of the metric: NS steps/s on the same GPUs (default workload only) -------------------
+    extra = None
+    if args.workload == "cube1023" and not args.no_extra:
+        extra = {}
+        for name in ("nscube255", "nscyl128"):
+            try:
+                extra[name] = measure_ns(name, torch, dist, fdm_b200, world, rank, dev, stream, peak)
+            except Exception as e:          # never let an extra kill the headline line
+                extra[name] = {"error": f"{type(e).__name__}: {e}"}
+
     if rank == 0:
         out = {
             "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": K, "warmup": W,
@@ -547,11 +636,61 @@ def main():
                                        if sharded else "independent replicas per rank")},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
         }
-        if world == 1 and not args.no_cpu_baseline:
+        if check is not None:
+            out["check"] = check
+        if extra is not None:
+            out["extra"] = extra
+        if not args.no_cpu_baseline:
+            try:
+                os.sched_setaffinity(0, affinity0)      # undo the NUMA binding of the e2e leg: the baseline gets every core
+            except Exception:
+                pass
             out["cpu_baseline"] = cpu_baseline(wl)
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
+
+
+def measure_ns(name, torch, dist, fdm_b200, world, rank, dev, stream, peak, K=100, W=5):
+    """Device-resident NS steps/s of one of the NS workloads (sharded over the ranks when they are several)."""
+    wl = WORKLOADS[name]
+    sptr = stream.cuda_stream
+    if wl["kind"] == "nscyl":
+        sharded = world > 1
+        kw = dict(rank=rank, nranks=world) if sharded else {}
+        ns = fdm_b200.NSCyl(nr=wl["nr"], nz=wl["nz"], nphi=wl["nphi"], Re=wl["Re"], dt=wl["dt"], **kw)
+        pts = wl["nr"] * wl["nz"] * wl["nphi"]
+    else:
+        n = wl["n"]
+        sharded = world > 1 and (n + 1) // world >= 4
+        kw = dict(rank=rank, nranks=world) if sharded else {}
+        ns = fdm_b200.NSCube(nx=n, nz=n, Re=wl["Re"], dt=wl["dt"], **kw)
+        pts = n ** 3
+    ns.connect()
+    for _ in range(W):
+        ns.step_device(1, sptr)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(K):
+        ns.step_device(1, sptr)
+    e1.record(stream)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / K
+    ns.close()
+    lpts = pts / world if sharded else pts
+    return {"workload": wl["label"], "metric": "ns_steps_per_s", "value": 1e3 / ms, "unit": "steps/s", "ms_per_step": ms,
+            "steps": K, "warmup": W, "sharded_over": world if sharded else 1,
+            "step_frac": NS_BYTES_PER_PT * lpts / (ms * 1e-3) / 1e9 / peak,
+            "note": "fraction of the 168 B/pt HBM roofline per GPU (SURVEY 8d); device-resident, CUDA events, max over ranks"}
 
 
 def kernel_sweeps(tag):

@@ -15,18 +15,20 @@ from .velocity_plot import VelocityPlotter  # noqa: F401
 from .nbody import NBodyPM  # noqa: F401
 
 
-def fft_batch(kind, N, data, dx=1.0):
-    """Batched fdm::FFT<double> transforms.  kind: 'sFFT' | 'pFFT_1' | 'pFFT'."""
+def fft_batch(kind, N, data, dx=1.0, impl="auto"):
+    """Batched fdm::FFT<double> transforms.  kind: 'sFFT' | 'pFFT_1' | 'pFFT' | 'cFFT' (rows of N-1, N, N, N+1
+    values).  impl: 'auto' (the kernel the solvers use for this length), 'plain' or 'pipe'."""
     import numpy as np
     from . import capi
-    k = {"sFFT": 0, "pFFT_1": 1, "pFFT": 2}[kind]
+    k = {"sFFT": 0, "pFFT_1": 1, "pFFT": 2, "cFFT": 3}[kind]
     a = np.ascontiguousarray(data, dtype=np.float64)
-    nvalid = N - 1 if k == 0 else N
+    nvalid = {0: N - 1, 3: N + 1}.get(k, N)
     if a.ndim == 1:
         a = a[None, :]
     if a.shape[-1] != nvalid:
         raise ValueError(f"rows must hold {nvalid} entries for {kind} with N={N}")
     out = np.empty_like(a)
     batch = a.size // nvalid if nvalid else 0
-    capi.check(capi.lib().fdmb_fft_batch(k, int(N), batch, float(dx), capi.as_dp(a), capi.as_dp(out)), "fft_batch")
+    capi.check(capi.lib().fdmb_fft_batch_impl(k, int(N), batch, float(dx), capi.as_dp(a), capi.as_dp(out),
+                                              {"auto": 0, "plain": 1, "pipe": 2}[impl]), "fft_batch")
     return out.reshape(np.shape(data))

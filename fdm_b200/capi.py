@@ -39,6 +39,7 @@ def lib():
     L.fdmb_memcpy_h2d.argtypes = [C.c_void_p, C.c_void_p, C.c_ulonglong]
     L.fdmb_memcpy_d2h.argtypes = [C.c_void_p, C.c_void_p, C.c_ulonglong]
     L.fdmb_fft_batch.argtypes = [C.c_int, C.c_int, C.c_longlong, C.c_double, dp, dp]
+    L.fdmb_fft_batch_impl.argtypes = [C.c_int, C.c_int, C.c_longlong, C.c_double, dp, dp, C.c_int]
     L.fdmb_lapl_cube_create.argtypes = [C.POINTER(C.c_void_p)] + [C.c_double] * 6 + [C.c_int] * 4
     L.fdmb_lapl_cube_solve.argtypes = [C.c_void_p, dp, dp]
     L.fdmb_lapl_cube_solve_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]

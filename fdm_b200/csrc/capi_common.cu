@@ -1,5 +1,6 @@
 // Library-wide pieces of the C ABI: error string, device tables, raw memory helpers,
 // batched 1-D transforms (fdm::FFT<double>::{sFFT,pFFT_1,pFFT}).
+#include <atomic>
 #include <cmath>
 #include <cstdlib>
 #include <map>
@@ -13,7 +14,7 @@
 namespace fdmb {
 
 static thread_local std::string g_error;
-unsigned long long g_launch_count = 0;
+std::atomic<unsigned long long> g_launch_count{0};
 
 void set_error(const char* fmt, ...)
 {
@@ -26,24 +27,36 @@ void set_error(const char* fmt, ...)
 }
 const char* get_error() { return g_error.c_str(); }
 
-struct ProfRec { const char* tag; cudaEvent_t e0, e1; };
-static bool g_prof_on = false;
+// Per-launch profile records.  Several host threads may drive handles (one per device) at the same time: the
+// record list is guarded by a mutex, and every record remembers the device its events were created on.
+struct ProfRec { const char* tag; cudaEvent_t e0, e1; int dev; };
+static std::atomic<bool> g_prof_on{false};
+static std::mutex g_prof_mutex;
 static std::vector<ProfRec> g_prof;
 
 LaunchScope::LaunchScope(const char* tag_, cudaStream_t st_) : tag(tag_), st(st_), slot(-1)
 {
-    g_launch_count++;
-    if (g_prof_on) {
-        ProfRec r{tag, nullptr, nullptr};
-        cudaEventCreate(&r.e0); cudaEventCreate(&r.e1);
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    if (g_prof_on.load(std::memory_order_relaxed)) {
+        ProfRec r{tag, nullptr, nullptr, 0};
+        cudaGetDevice(&r.dev);
+        if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) { cudaGetLastError(); return; }
         cudaEventRecord(r.e0, st);
+        std::lock_guard<std::mutex> lock(g_prof_mutex);
         slot = (int)g_prof.size();
         g_prof.push_back(r);
     }
 }
 LaunchScope::~LaunchScope()
 {
-    if (slot >= 0) cudaEventRecord(g_prof[slot].e1, st);
+    if (slot < 0) return;
+    cudaEvent_t e1;
+    {
+        std::lock_guard<std::mutex> lock(g_prof_mutex);
+        if (slot >= (int)g_prof.size()) return;      // profile_end() ran in between
+        e1 = g_prof[slot].e1;
+    }
+    cudaEventRecord(e1, st);
 }
 
 static std::mutex g_tab_mutex;
@@ -263,7 +276,7 @@ int fdmb_set_device(int device)
     return FDMB_OK;
 }
 
-unsigned long long fdmb_launch_count(void) { return g_launch_count; }
+unsigned long long fdmb_launch_count(void) { return g_launch_count.load(); }
 
 int fdmb_malloc(void** dptr, unsigned long long bytes)
 {
@@ -293,6 +306,7 @@ int fdmb_device_synchronize(void)
 
 int fdmb_profile_begin(void)
 {
+    std::lock_guard<std::mutex> lock(g_prof_mutex);
     for (auto& r : g_prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
     g_prof.clear();
     g_prof_on = true;
@@ -302,18 +316,31 @@ int fdmb_profile_begin(void)
 int fdmb_profile_end(char* buf, int buflen)
 {
     g_prof_on = false;
-    FDMB_CUDA(cudaDeviceSynchronize());
+    int cur = 0;
+    FDMB_CUDA(cudaGetDevice(&cur));
+    std::lock_guard<std::mutex> lock(g_prof_mutex);
     std::map<std::string, std::pair<int, double>> agg;
     std::vector<std::string> order;
+    int failed = 0;
     for (auto& r : g_prof) {
         float ms = 0;
-        cudaEventElapsedTime(&ms, r.e0, r.e1);
-        if (!agg.count(r.tag)) order.push_back(r.tag);
-        agg[r.tag].first++;
-        agg[r.tag].second += ms;
+        // events belong to the device they were created on: measure there, skip (and count) what cannot be read
+        cudaError_t e = cudaSetDevice(r.dev);
+        if (e == cudaSuccess) e = cudaEventSynchronize(r.e1);
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, r.e0, r.e1);
+        if (e == cudaSuccess) {
+            if (!agg.count(r.tag)) order.push_back(r.tag);
+            agg[r.tag].first++;
+            agg[r.tag].second += ms;
+        } else {
+            cudaGetLastError();
+            failed++;
+        }
         cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);
     }
+    cudaSetDevice(cur);
     g_prof.clear();
+    if (failed) set_error("fdmb_profile_end: %d launch records could not be timed and were skipped", failed);
     std::string out;
     for (auto& t : order) {
         char line[256];
@@ -326,30 +353,52 @@ int fdmb_profile_end(char* buf, int buflen)
     return FDMB_OK;
 }
 
-int fdmb_fft_batch(int kind, int N, long long batch, double dx, const double* in, double* out)
+// impl: 0 = what the solvers use for this length (the persistent bulk-copy-fed sweep for N >= 32, the plain kernel below
+// that), 1 = plain kernel, 2 = persistent sweep (error if N < 32)
+int fdmb_fft_batch_impl(int kind, int N, long long batch, double dx, const double* in, double* out, int impl)
 {
-    if (kind < 0 || kind > 2 || !supported_N(N) || batch < 0 || !in || !out) {
-        set_error("fdmb_fft_batch: kind must be 0..2 and N a power of two in [4,2048] (got kind=%d N=%d)", kind, N);
+    if (kind < 0 || kind > 3 || !supported_N(N) || batch < 0 || !in || !out || impl < 0 || impl > 2) {
+        set_error("fdmb_fft_batch: kind must be 0..3 and N a power of two in [4,2048] (got kind=%d N=%d impl=%d)", kind, N, impl);
+        return FDMB_ERR_INVALID;
+    }
+    const bool can_pipe = kind != XF_DCT && pipe_supported_N(N);
+    if (impl == 2 && !can_pipe) {
+        set_error("fdmb_fft_batch: the persistent sweep needs N >= 32 and kind 0..2 (got kind=%d N=%d)", kind, N);
         return FDMB_ERR_INVALID;
     }
     if (batch == 0) return FDMB_OK;
-    const int nvalid = kind == XF_DST ? N - 1 : N;
+    const int nvalid = kind == XF_DST ? N - 1 : (kind == XF_DCT ? N + 1 : N);
     const size_t bytes = sizeof(double) * (size_t)batch * nvalid;
     Tables t;
     int rc = get_tables(N, &t);
     if (rc) return rc;
     double *d_in = nullptr, *d_out = nullptr;
     FDMB_CUDA(cudaMalloc(&d_in, bytes));
-    FDMB_CUDA(cudaMalloc(&d_out, bytes));
-    FDMB_CUDA(cudaMemcpy(d_in, in, bytes, cudaMemcpyHostToDevice));
-    RowsArgs r{};
-    r.in = d_in; r.out = d_out; r.nrows = batch; r.nvalid = nvalid;
-    r.in_pitch = r.out_pitch = nvalid; r.scale = dx; r.SN = t.SN; r.WM = t.WM;
-    cudaError_t e = launch_rows(N, kind, r, 0, "fft_batch");
+    if (cudaMalloc(&d_out, bytes) != cudaSuccess) { cudaFree(d_in); set_error("fdmb_fft_batch: out of device memory"); return FDMB_ERR_NOMEM; }
+    cudaError_t e = cudaMemcpy(d_in, in, bytes, cudaMemcpyHostToDevice);
+    const bool use_pipe = can_pipe && (impl == 2 || (impl == 0 && pipe_enabled()));
+    if (e == cudaSuccess) {
+        if (use_pipe) {
+            RowsPipeArgs p{};
+            p.in = d_in; p.out = d_out; p.nrows = batch; p.nvalid = nvalid; p.in_pitch = p.out_pitch = nvalid;
+            p.scale = dx; p.SN = t.SN; p.WM = t.WM;
+            e = launch_rows_pipe(N, kind, p, 0, "fft_batch");
+        } else {
+            RowsArgs r{};
+            r.in = d_in; r.out = d_out; r.nrows = batch; r.nvalid = nvalid;
+            r.in_pitch = r.out_pitch = nvalid; r.scale = dx; r.SN = t.SN; r.WM = t.WM;
+            e = launch_rows(N, kind, r, 0, "fft_batch");
+        }
+    }
     if (e == cudaSuccess) e = cudaMemcpy(out, d_out, bytes, cudaMemcpyDeviceToHost);
     cudaFree(d_in); cudaFree(d_out);
     if (e != cudaSuccess) { set_error("fdmb_fft_batch: %s", cudaGetErrorString(e)); return FDMB_ERR_CUDA; }
     return FDMB_OK;
+}
+
+int fdmb_fft_batch(int kind, int N, long long batch, double dx, const double* in, double* out)
+{
+    return fdmb_fft_batch_impl(kind, N, batch, dx, in, out, 0);
 }
 
 }  // extern "C"

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdio>
+#include <atomic>
 #include <cstdarg>
 #include <string>
 
@@ -51,7 +52,7 @@ int device_sm_count();
 int current_device_slot();   // cudaGetDevice() clamped to [0, 63]
 
 // counts kernel launches issued by this library (bench.py reports it as gpu_launches)
-extern unsigned long long g_launch_count;
+extern std::atomic<unsigned long long> g_launch_count;
 
 // Optional per-launch CUDA-event timing (fdmb_profile_begin/end).  Every launch site
 // wraps its kernel in a LaunchScope; outside profiling it only bumps the counter.

@@ -28,6 +28,7 @@ cudaError_t launch_rows(int N, int kind, const RowsArgs& a, cudaStream_t st, con
     case NN:                                                                   \
         if (kind == XF_DST) return launch_rows_t<NN, XF_DST>(a, st);           \
         if (kind == XF_PFWD) return launch_rows_t<NN, XF_PFWD>(a, st);         \
+        if (kind == XF_DCT) return launch_rows_t<NN, XF_DCT>(a, st);           \
         return launch_rows_t<NN, XF_PINV>(a, st);
     switch (N) { FDMB_FOR_EACH_N(X) }
 #undef X
@@ -272,6 +273,9 @@ int fdmb_lapl_cube::init()
         const size_t welems = (size_t)nyb * nz * YB * px;
         FDMB_CUDA(cudaMalloc(&d_work, sizeof(double) * welems));
         FDMB_CUDA(cudaMemset(d_work, 0, sizeof(double) * welems));      // the padding rows of the last block stay zero
+        // cudaMemset on device memory is asynchronous to the host and runs on the legacy default stream, which the
+        // handle's non-blocking streams do not order against: finish it before the handle is handed out
+        FDMB_CUDA(cudaDeviceSynchronize());
         const unsigned long long s_lo = 8ull * px, s_mid = s_lo * YB, s_hi = s_mid * (unsigned long long)nz;
         if ((rc = make_cols_maps_blocked(&tm_y, d_work, Ny, true, blog, nx, ny, nz, s_lo, s_mid, s_hi, pipe_B(Ny)))) return rc;
         if ((rc = make_cols_maps_blocked(&tm_z, d_work, Nz, false, blog, nx, ny, nz, s_lo, s_mid, s_hi, pipe_B(Nz)))) return rc;
@@ -318,6 +322,9 @@ int fdmb_lapl_cube::init_sharded()
     mg_bytes = off_flags + 256;
     FDMB_CUDA(cudaMalloc(&mg_block, mg_bytes));
     FDMB_CUDA(cudaMemset(mg_block, 0, mg_bytes));
+    // cudaMemset on device memory is asynchronous to the host and runs on the legacy default stream, which the
+    // handle's non-blocking streams do not order against: finish it before the handle is handed out
+    FDMB_CUDA(cudaDeviceSynchronize());
     d_A = reinterpret_cast<double*>(mg_block);
     d_T = reinterpret_cast<double*>(reinterpret_cast<char*>(mg_block) + off_T);
     d_flags = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(mg_block) + off_flags);
@@ -567,25 +574,39 @@ int fdmb_lapl_cube::solve_batch(int count, double* const* ans, const double* con
     }
     double* dr[2] = {d_rhs, d_rhs1};
     double* da[2] = {d_ans, d_ans1};
-    // earlier work on the handle's stream (a previous solve_host / solve_device) may still use the staging buffers
-    FDMB_CUDA(cudaStreamSynchronize(stream));
+    // Every exit, the failing ones included, first waits for the three streams: the copies read and write the
+    // CALLER's host arrays, which must not be in flight once this function has returned.
+    auto drain = [&]() { cudaStreamSynchronize(s_dn); cudaStreamSynchronize(stream); cudaStreamSynchronize(s_up); };
+#define FDMB_BATCH(call)                                                                                       \
+    do {                                                                                                       \
+        cudaError_t e__ = (call);                                                                              \
+        if (e__ != cudaSuccess) {                                                                              \
+            drain();                                                                                           \
+            set_error("%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e__));           \
+            return FDMB_ERR_CUDA;                                                                              \
+        }                                                                                                      \
+    } while (0)
+    // earlier work on the handle's stream (a previous solve_host / solve_device) may still use the staging buffers;
+    // a previous fdmb_lapl_cube_solve_device on a CALLER's stream uses d_work and is the caller's to order
+    FDMB_BATCH(cudaStreamSynchronize(stream));
     for (int i = 0; i < count; i++) {
         const int b = i & 1;
-        if (i >= 2) FDMB_CUDA(cudaStreamWaitEvent(s_up, ev_cmp[b], 0));      // solve i-2 has consumed dr[b]
-        FDMB_CUDA(cudaMemcpyAsync(dr[b], rhs[i], bytes, cudaMemcpyHostToDevice, s_up));
-        FDMB_CUDA(cudaEventRecord(ev_up[b], s_up));
-        FDMB_CUDA(cudaStreamWaitEvent(stream, ev_up[b], 0));
-        if (i >= 2) FDMB_CUDA(cudaStreamWaitEvent(stream, ev_dn[b], 0));     // download i-2 has drained da[b]
+        if (i >= 2) FDMB_BATCH(cudaStreamWaitEvent(s_up, ev_cmp[b], 0));      // solve i-2 has consumed dr[b]
+        FDMB_BATCH(cudaMemcpyAsync(dr[b], rhs[i], bytes, cudaMemcpyHostToDevice, s_up));
+        FDMB_BATCH(cudaEventRecord(ev_up[b], s_up));
+        FDMB_BATCH(cudaStreamWaitEvent(stream, ev_up[b], 0));
+        if (i >= 2) FDMB_BATCH(cudaStreamWaitEvent(stream, ev_dn[b], 0));     // download i-2 has drained da[b]
         int rc = solve_device(da[b], dr[b], stream);
-        if (rc) { cudaDeviceSynchronize(); return rc; }
-        FDMB_CUDA(cudaEventRecord(ev_cmp[b], stream));
-        FDMB_CUDA(cudaStreamWaitEvent(s_dn, ev_cmp[b], 0));
-        FDMB_CUDA(cudaMemcpyAsync(ans[i], da[b], bytes, cudaMemcpyDeviceToHost, s_dn));
-        FDMB_CUDA(cudaEventRecord(ev_dn[b], s_dn));
+        if (rc) { drain(); return rc; }
+        FDMB_BATCH(cudaEventRecord(ev_cmp[b], stream));
+        FDMB_BATCH(cudaStreamWaitEvent(s_dn, ev_cmp[b], 0));
+        FDMB_BATCH(cudaMemcpyAsync(ans[i], da[b], bytes, cudaMemcpyDeviceToHost, s_dn));
+        FDMB_BATCH(cudaEventRecord(ev_dn[b], s_dn));
     }
-    FDMB_CUDA(cudaStreamSynchronize(s_dn));
-    FDMB_CUDA(cudaStreamSynchronize(stream));
-    FDMB_CUDA(cudaStreamSynchronize(s_up));
+    FDMB_BATCH(cudaStreamSynchronize(s_dn));
+    FDMB_BATCH(cudaStreamSynchronize(stream));
+    FDMB_BATCH(cudaStreamSynchronize(s_up));
+#undef FDMB_BATCH
     return FDMB_OK;
 }
 

@@ -336,6 +336,9 @@ int fdmb_lapl_cyl::init_sharded()
     mg_bytes = off_flags + 256;
     FDMB_CUDA(cudaMalloc(&mg_block, mg_bytes));
     FDMB_CUDA(cudaMemset(mg_block, 0, mg_bytes));
+    // cudaMemset on device memory is asynchronous to the host and runs on the legacy default stream, which the
+    // handle's non-blocking streams do not order against: finish it before the handle is handed out
+    FDMB_CUDA(cudaDeviceSynchronize());
     d_A = reinterpret_cast<double*>(mg_block);
     d_T = reinterpret_cast<double*>(static_cast<char*>(mg_block) + off_T);
     peer_block[rank] = mg_block;

@@ -3,10 +3,14 @@
 // :44-60, constructor src/lapl_rect.h:40-68) and fdm::LaplRectFFT2<double,check,F>::solve
 // (src/lapl_rect.cpp:113-207, constructor src/lapl_rect.h:89-105).
 //
-//   LaplRect     : y transform (strided axis) -> one tridiagonal system along x per y mode
-//                  (the no-pivot recurrence of LAPACK gtsv, which the reference calls at
-//                  src/lapl_rect.cpp:90; the matrices are diagonally dominant for the column
-//                  scales the reference uses) -> y inverse.  x is always Dirichlet (:47).
+//   LaplRect     : y transform (strided axis) -> one tridiagonal system along x per y mode -> y inverse.
+//                  x is always Dirichlet (:47).  The reference solves the systems with LAPACK gtsv
+//                  (src/lapl_rect.cpp:90: Gaussian elimination with PARTIAL PIVOTING, info checked); here
+//                  they are solved by the Thomas recurrence without pivoting, which gives the same
+//                  answer (to round-off) exactly when gtsv never swaps rows, i.e. for row-wise diagonally
+//                  dominant matrices.  That holds for the default scales and for the cylindrical column
+//                  scales of src/velocity_plot.h:113-127 (|L| + |U| = 2 <= |D|); set_scales REJECTS scales
+//                  for which it does not (FDMB_ERR_INVALID) instead of returning a silently different answer.
 //   LaplRectFFT2 : y transform -> x transform -> divide by -(lm_y[k]*lm_y_scale[j] + lm_x[j])
 //                  -> x inverse -> y inverse; the doubly periodic null mode is set to 1 (:169-172).
 // The per-column scales lm_y_scale / L_scale / U_scale (src/lapl_rect.h:57-59) are public members
@@ -32,6 +36,7 @@ struct fdmb_lapl_rect {
     double *d_lmy = nullptr, *d_lmx = nullptr;           // by array row / column (0-based)
     double *d_ysc = nullptr, *d_Lc = nullptr, *d_Uc = nullptr;   // lm_y_scale, L_scale/dx2, U_scale/dx2; nx+1 each
     double* d_zero = nullptr;
+    std::vector<double> h_ysc, h_L, h_U;                 // host copies of the public scales (validation)
     double* d_work = nullptr;
     double *d_rhs = nullptr, *d_ans = nullptr;
 
@@ -103,6 +108,9 @@ int fdmb_lapl_rect::init()
     FDMB_CUDA(cudaMalloc(&d_Uc, sizeof(double) * (nx + 1)));
     FDMB_CUDA(cudaMalloc(&d_zero, sizeof(double)));
     FDMB_CUDA(cudaMemset(d_zero, 0, sizeof(double)));
+    // cudaMemset on device memory is asynchronous to the host and runs on the legacy default stream, which the
+    // handle's non-blocking streams do not order against: finish it before the handle is handed out
+    FDMB_CUDA(cudaDeviceSynchronize());
     FDMB_CUDA(cudaMalloc(&d_work, sizeof(double) * (size_t)ny * px));
     std::vector<double> ones(nx + 1, 1.0);   // lapl_rect.h:57-59
     return set_scales(ones.data(), ones.data(), ones.data());
@@ -112,6 +120,25 @@ int fdmb_lapl_rect::set_scales(const double* lm_y_scale, const double* L_scale, 
 {
     const double dx2 = dx * dx;
     std::vector<double> t(nx + 1);
+    if (h_ysc.empty()) { h_ysc.assign(nx + 1, 1.0); h_L.assign(nx + 1, 1.0); h_U.assign(nx + 1, 1.0); }
+    {   // validate before anything is changed: the no-pivot recurrence needs row-wise diagonal dominance,
+        // |D_j| = 2/dx2 + lm_y[k] lm_y_scale[j] >= |L_j| + |U_j| for every mode k (lm_y >= 0, src/lapl_rect.cpp:44-60)
+        const double* ys = lm_y_scale ? lm_y_scale : h_ysc.data();
+        const double* Ls = L_scale ? L_scale : h_L.data();
+        const double* Us = U_scale ? U_scale : h_U.data();
+        for (int j = 1; j <= nx && kind == 0; j++) {
+            const double off = (j > 1 ? std::fabs(Ls[j]) : 0.0) + (j < nx ? std::fabs(Us[j]) : 0.0);
+            if (!(ys[j] >= 0.0) || !(off <= 2.0 * (1.0 + 1e-12))) {
+                set_error("LaplRect: column scales at j=%d (lm_y_scale=%g, L_scale=%g, U_scale=%g) make the tridiagonal "
+                          "systems non-dominant; the reference's gtsv would pivot (src/lapl_rect.cpp:90), the device "
+                          "recurrence does not", j, ys[j], Ls[j], Us[j]);
+                return FDMB_ERR_INVALID;
+            }
+        }
+        if (lm_y_scale) h_ysc.assign(lm_y_scale, lm_y_scale + nx + 1);
+        if (L_scale) h_L.assign(L_scale, L_scale + nx + 1);
+        if (U_scale) h_U.assign(U_scale, U_scale + nx + 1);
+    }
     if (lm_y_scale) FDMB_CUDA(cudaMemcpy(d_ysc, lm_y_scale, sizeof(double) * (nx + 1), cudaMemcpyHostToDevice));
     if (L_scale) {
         for (int j = 0; j <= nx; j++) t[j] = L_scale[j] / dx2;   // init_Mat: L_scale[j]/dx2

@@ -411,6 +411,9 @@ int fdmb_ns_cube::init()
     ns_layout(nx, ny, nz, rank, nranks, &lay);
     FDMB_CUDA(cudaMalloc(&block, lay.bytes));
     FDMB_CUDA(cudaMemset(block, 0, lay.bytes));
+    // cudaMemset on device memory is asynchronous to the host and runs on the legacy default stream, which the
+    // handle's non-blocking streams do not order against: finish it before the handle is handed out
+    FDMB_CUDA(cudaDeviceSynchronize());
     static const int Y0[9] = {0, -1, 0, 0, 1, 1, 0, 1, 1}, X0[9] = {-1, 0, 0, 0, 1, 0, 1, 1, 1};
     for (int k = 0; k < 9; k++) {
         f[k].p = reinterpret_cast<double*>(static_cast<char*>(block) + lay.off[k]);

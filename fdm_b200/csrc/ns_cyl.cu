@@ -425,6 +425,9 @@ int fdmb_ns_cyl::init()
     cyl_layout(nr, nz, nphi, zper, rank, nranks, &lay);
     FDMB_CUDA(cudaMalloc(&block, lay.bytes));
     FDMB_CUDA(cudaMemset(block, 0, lay.bytes));
+    // cudaMemset on device memory is asynchronous to the host and runs on the legacy default stream, which the
+    // handle's non-blocking streams do not order against: finish it before the handle is handed out
+    FDMB_CUDA(cudaDeviceSynchronize());
     for (int k = 0; k < 12; k++) {
         f[k].p = reinterpret_cast<double*>(static_cast<char*>(block) + lay.off[k]);
         f[k].li = lay.wlo[k]; f[k].lz = lay.lz[k]; f[k].lr = lay.lr[k];
@@ -782,6 +785,16 @@ int fdmb_ns_cyl_field_device_ptr(fdmb_ns_cyl* h, int field, void** dptr)
 }
 
 long long fdmb_ns_cyl_time_index(fdmb_ns_cyl* h) { return h ? h->time_index : -1; }
+
+// NSCyl::U0 is a public, non-const member of the reference class (src/ns_cyl.h:23) that callers change between
+// steps (test/test_ns_cyl_spectral.cpp sets ns.U0 = 0 before its L_step loop); takes effect at the next step
+int fdmb_ns_cyl_set_u0(fdmb_ns_cyl* h, double u0)
+{
+    if (!h) { set_error("null handle"); return FDMB_ERR_INVALID; }
+    h->prm.u0 = u0;
+    h->g.U0 = u0;
+    return FDMB_OK;
+}
 
 int fdmb_ns_cyl_destroy(fdmb_ns_cyl* h)
 {

@@ -98,6 +98,9 @@ int fdmb_pm::init()
     FDMB_CUDA(cudaMemset(d_rhs, 0, sizeof(double) * n3));
     FDMB_CUDA(cudaMemset(d_psi, 0, sizeof(double) * n3));
     FDMB_CUDA(cudaMemset(d_E, 0, sizeof(double) * 3 * n3));
+    // cudaMemset on device memory is asynchronous to the host and runs on the legacy default stream, which the
+    // handle's non-blocking streams do not order against: finish it before the handle is handed out
+    FDMB_CUDA(cudaDeviceSynchronize());
     return FDMB_OK;
 }
 
@@ -146,6 +149,9 @@ int fdmb_pm::set_bodies(long long N, const double* x, const double* v, const dou
     FDMB_CUDA(cudaMemcpy(d_v, t.data(), bytes, cudaMemcpyHostToDevice));
     FDMB_CUDA(cudaMemset(d_a, 0, bytes));
     FDMB_CUDA(cudaMemset(d_aprev, 0, bytes));
+    // cudaMemset on device memory is asynchronous to the host and runs on the legacy default stream, which the
+    // handle's non-blocking streams do not order against: finish it before the handle is handed out
+    FDMB_CUDA(cudaDeviceSynchronize());
     FDMB_CUDA(cudaMemcpy(d_mass, mass, sizeof(double) * (size_t)N, cudaMemcpyHostToDevice));
     g.N = N;
     g.rho0 = -total / p.l / p.l / p.l;

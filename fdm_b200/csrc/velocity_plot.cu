@@ -123,6 +123,9 @@ int fdmb_vplot::init()
     FDMB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     FDMB_CUDA(cudaMalloc(&d_slices, sizeof(double) * total));
     FDMB_CUDA(cudaMemset(d_slices, 0, sizeof(double) * total));
+    // cudaMemset on device memory is asynchronous to the host and runs on the legacy default stream, which the
+    // handle's non-blocking streams do not order against: finish it before the handle is handed out
+    FDMB_CUDA(cudaDeviceSynchronize());
     long long off = 0;
     for (int s = 0; s < FDMB_SLICE_COUNT; s++) { d_slice[s] = d_slices + off; off += ((long long)rows[s] * cols[s] + 15) / 16 * 16; }
     return FDMB_OK;

@@ -7,6 +7,8 @@
 //                             S[N-k] = scale * sum s[j] sin(2 pi k j/N) (k=1..N/2-1)
 //   PINV  -- FFT<T>::pFFT   : S[j] = scale * (s[0]/2 + sum_{k=1}^{N/2-1}(s[k] cos + s[N-k] sin)
 //                                             + (-1)^j s[N/2]/2)
+//   DCT   -- FFT<T>::cFFT   : S[k] = scale * (s[0]/2 + sum_{j=1}^{N-1} s[j] cos(pi k j / N) + (-1)^k s[N]/2),
+//                             k = 0..N (src/fft.cpp:368-445, definition src/asp_fft.cpp:404-418)
 //
 // This is NOT the reference's Samarskii-Nikolaev recursion.  Every transform is
 // mapped onto one complex FFT of length M = N/2 held in shared memory:
@@ -35,7 +37,7 @@
 
 namespace fdmb {
 
-enum XformKind { XF_DST = 0, XF_PFWD = 1, XF_PINV = 2 };
+enum XformKind { XF_DST = 0, XF_PFWD = 1, XF_PINV = 2, XF_DCT = 3 };
 
 struct cd { double x, y; };
 __device__ __forceinline__ cd operator+(cd a, cd b) { return {a.x + b.x, a.y + b.y}; }
@@ -434,6 +436,110 @@ __device__ __forceinline__ void pinv_tile(double* col, int sj, int g, double sca
     __syncthreads();
 }
 
+// ---------------------------------------------------------------------------------
+// DCT-I with halved end points (cFFT) over slots 0..N of every column (N + 1 values).
+// y[j] = (x[j]+x[N-j])/2 - sin(pi j/N)(x[j]-x[N-j]) -> real FFT(N): S[2k] = Re Y[k],
+// S[2k+1] = S[2k-1] - Im Y[k], seeded with S[1] = (x[0]-x[N])/2 + sum x[j] cos(pi j/N),
+// which the fold accumulates on the way.  Ends with __syncthreads().
+// ---------------------------------------------------------------------------------
+template <int N, int G>
+__device__ __forceinline__ void dct_tile(double* col, int sj, int g, double scale,
+                                         const double* __restrict__ SN, const cd* __restrict__ WM,
+                                         double* scr, int scr_s)
+{
+    constexpr int M = N / 2;
+    static_assert(G <= M / 2 || M == 2, "too many threads per column");
+    double part = 0.0;
+#pragma unroll
+    for (int j = g + 1; j < M; j += G) {
+        double a = col[j * sj], c = col[(N - j) * sj];
+        double y1 = 0.5 * (a + c), y2 = SN[j] * (a - c);
+        col[j * sj] = y1 - y2;
+        col[(N - j) * sj] = y1 + y2;
+        part += SN[M - j] * (a - c);              // cos(pi j/N) x[j] + cos(pi (N-j)/N) x[N-j]
+    }
+    if (g == 0) {
+        double x0 = col[0], xn = col[N * sj];
+        col[0] = 0.5 * (x0 + xn);
+        part += 0.5 * (x0 - xn);
+    }
+    // S[1] / scale, parked in scratch slot G until the untangle (keeps a register free across the FFT passes)
+    if constexpr (G > 1) {
+        scr[g * scr_s] = part;
+        __syncthreads();
+        if (g == 0) {
+            double c1 = 0.0;
+#pragma unroll 8
+            for (int q = 0; q < G; q++) c1 += scr[q * scr_s];
+            scr[G * scr_s] = c1;
+        }
+    } else {
+        scr[G * scr_s] = part;
+    }
+    __syncthreads();
+
+    fft_inplace<N, G>(col, sj, g, WM);
+
+    constexpr int HP = (M / 2 >= G) ? (M / 2) / G : 1;
+    double r[HP][4];
+#pragma unroll
+    for (int i = 0; i < HP; i++) {
+        int k = g + i * G;
+        if (k < M / 2)
+            untangle<N>(col, sj, k, SN, scale, r[i][0], r[i][1], r[i][2], r[i][3]);
+    }
+    double zh_x = 0, zh_y = 0;
+    if (g == 0) {
+        int ph = fft_pos<N>(M / 2);
+        zh_x = scale * col[(2 * ph) * sj];
+        zh_y = scale * col[(2 * ph + 1) * sj];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < HP; i++) {
+        int k = g + i * G;
+        if (k == 0) {
+            col[0] = r[i][0];                         // S[0] = Re Y[0]
+            col[N * sj] = r[i][2];                    // S[N] = Re Y[M]
+            col[sj] = scale * scr[G * scr_s];         // S[1] seeds the running sum
+        } else if (k < M / 2) {
+            col[(2 * k) * sj] = r[i][0];
+            col[(2 * k + 1) * sj] = r[i][1];
+            col[(2 * (M - k)) * sj] = r[i][2];
+            col[(2 * (M - k) + 1) * sj] = r[i][3];
+        }
+    }
+    if (g == 0 && M >= 2) {
+        col[M * sj] = zh_x;                           // S[M]            = Re Y[M/2]
+        col[(M + 1) * sj] = zh_y;                     // S[M+1] - S[M-1] = -Im Y[M/2]
+    }
+    __syncthreads();
+
+    // inclusive prefix sum over the odd slots
+    constexpr int CS = M / G;
+    double a[CS];
+    double run = 0.0;
+#pragma unroll
+    for (int i = 0; i < CS; i++) {
+        int k = g * CS + i;
+        run += col[(2 * k + 1) * sj];
+        a[i] = run;
+    }
+    double off = 0.0;
+    if constexpr (G > 1) {
+        scr[g * scr_s] = run;
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < G; q++) if (q < g) off += scr[q * scr_s];
+    }
+#pragma unroll
+    for (int i = 0; i < CS; i++) {
+        int k = g * CS + i;
+        col[(2 * k + 1) * sj] = a[i] + off;
+    }
+    __syncthreads();
+}
+
 template <int N, int G, int KIND, bool PREFOLD = false>
 __device__ __forceinline__ void xform_tile(double* col, int sj, int g, double scale,
                                            const double* __restrict__ SN, const cd* __restrict__ WM,
@@ -441,6 +547,7 @@ __device__ __forceinline__ void xform_tile(double* col, int sj, int g, double sc
 {
     if constexpr (KIND == XF_DST) dst_tile<N, G, PREFOLD>(col, sj, g, scale, SN, WM, scr, scr_s);
     else if constexpr (KIND == XF_PFWD) pfwd_tile<N, G>(col, sj, g, scale, SN, WM);
+    else if constexpr (KIND == XF_DCT) dct_tile<N, G>(col, sj, g, scale, SN, WM, scr, scr_s);
     else pinv_tile<N, G>(col, sj, g, scale, SN, WM);
 }
 

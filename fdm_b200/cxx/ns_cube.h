@@ -6,7 +6,8 @@
 // reference's extents (src/ns_cube.h:66-75) so callers that read ns.u.vec or index
 // ns.u[i][k][j] (test/test_ns_cube.cpp:39, src/velocity_plot.cpp:12-15) keep working.
 //
-// Mirror policy: with auto_sync (default) every step() ends with a download of u,v,w,p, which is
+// Mirror policy: with auto_sync (default) every step() first uploads the mirrors the caller changed on the
+// host since they last agreed with the device (digest comparison) and ends with a download of u,v,w,p, which is
 // exactly what the reference's callers can observe.  Long runs switch it off and call
 // sync_to_host() before they look (plot interval), or sync_to_device() after they wrote a field.
 #pragma once
@@ -64,20 +65,21 @@ public:
         prm.x1 = x1; prm.y1 = y1; prm.z1 = z1; prm.x2 = x2; prm.y2 = y2; prm.z2 = z2;
         prm.u0 = U0; prm.Re = Re; prm.dt = dt; prm.nx = nx; prm.nz = nz; prm.verbose = verbose;
         FDMB_VERIFY(fdmb_ns_cube_create(&handle, &prm));
+        tensor* all[9] = {&u, &v, &w, &p, &x, &F, &G, &H, &RHS};
+        for (int id = 0; id < 9; id++) dig[id] = digest(all[id]->vec, (long long)all[id]->size);
     }
     ~NSCube() { if (handle) fdmb_ns_cube_destroy(handle); }
     NSCube(const NSCube&) = delete;
     NSCube& operator=(const NSCube&) = delete;
 
-    void step()
-    {
-        FDMB_VERIFY(fdmb_ns_cube_step(handle, 1));
-        time_index++;
-        if (auto_sync) sync_to_host(false);
-    }
+    void step() { steps(1); }
     // B200 extension: n steps back to back on the device, one host synchronisation at the end
     void steps(int n)
     {
+        if (auto_sync) {      // upload what the caller changed on the host since the mirrors last agreed with the device
+            push_if_changed(FDMB_FIELD_U, u); push_if_changed(FDMB_FIELD_V, v); push_if_changed(FDMB_FIELD_W, w);
+            push_if_changed(FDMB_FIELD_P, p);
+        }
         FDMB_VERIFY(fdmb_ns_cube_step(handle, n));
         time_index += n;
         if (auto_sync) sync_to_host(false);
@@ -99,6 +101,28 @@ public:
 private:
     fdmb_ns_cube* handle = nullptr;
     std::vector<double> cvt;
+    unsigned long long dig[9] = {};          // digest of each mirror when it last agreed with the device (by field id)
+
+    // ---- host-mirror coherence ------------------------------------------------------------------------------
+    // The reference's callers write the public tensors between steps (initial conditions, restarts: ns.u[i][k][j] = ...).  With auto_sync every step therefore starts by comparing a
+    // 64-bit digest of each mirror with the digest taken when the mirror last agreed with the device, and uploads
+    // the mirrors the caller changed; it ends with the download of u,v,w,p.  With auto_sync off the caller owns
+    // coherence (sync_to_host / sync_to_device).
+    static unsigned long long digest(const T* p, long long n)
+    {
+        unsigned long long h = 0x9E3779B97F4A7C15ull;
+        const unsigned char* b = reinterpret_cast<const unsigned char*>(p);
+        const long long bytes = n * (long long)sizeof(T), words = bytes / 8;
+        const unsigned long long* q = reinterpret_cast<const unsigned long long*>(b);
+        for (long long i = 0; i < words; i++) { h ^= q[i]; h *= 0x100000001B3ull; h ^= h >> 29; }
+        for (long long i = words * 8; i < bytes; i++) { h ^= b[i]; h *= 0x100000001B3ull; }
+        return h;
+    }
+
+    void push_if_changed(int id, tensor& t)
+    {
+        if (digest(t.vec, (long long)t.size) != dig[id]) push(id, t);
+    }
 
     void pull(int id, tensor& t)
     {
@@ -109,6 +133,7 @@ private:
             FDMB_VERIFY(fdmb_ns_cube_get_field(handle, id, cvt.data()));
             for (long long i = 0; i < (long long)t.size; i++) t.vec[i] = (T)cvt[i];
         }
+        if (auto_sync) dig[id] = digest(t.vec, (long long)t.size);
     }
     void push(int id, tensor& t)
     {
@@ -118,6 +143,7 @@ private:
             cvt.assign(t.vec, t.vec + t.size);
             FDMB_VERIFY(fdmb_ns_cube_set_field(handle, id, cvt.data()));
         }
+        dig[id] = digest(t.vec, (long long)t.size);
     }
 };
 

@@ -4,8 +4,10 @@
 // and size() as fdm::NSCyl<T,check,zflag> (reference src/ns_cyl.h:17-132, src/ns_cyl.cpp:23-78).  The
 // state lives on the device; the public tensors are HOST mirrors with the reference's extents
 // (src/ns_cyl.h:80-93), so callers that alias ns.u.vec (test/test_ns_cyl_spectral.cpp:60-94 packs
-// u,v,w,p into the ARPACK vector) keep working.  Mirror policy as in ns_cube.h: auto_sync downloads
-// u,v,w,p after every step; callers that write fields on the host call sync_to_device().
+// u,v,w,p into the ARPACK vector) keep working.  Mirror policy as in ns_cube.h: with auto_sync (default) a step
+// first uploads the mirrors the caller changed on the host (and a changed U0) and ends with the download of
+// u,v,w,p, so unmodified callers that write ns.u / ns.w0 / ns.U0 between steps behave like the reference; with
+// auto_sync off the caller calls sync_to_host() / sync_to_device() itself.
 // vrandom = 1 seeds v exactly like the reference (default-seeded std::default_random_engine, loop order
 // of src/ns_cyl.h:99-108), on the host, and uploads it.
 #pragma once
@@ -83,6 +85,9 @@ public:
                     for (int j = 1; j <= nr; j++) v[i][k][j] = distribution(generator);
             push(FDMB_FIELD_V, v);
         }
+        U0_dev = U0;
+        tensor* all[12] = {&u, &v, &w, &p, &x, &F, &G, &H, &RHS, &u0, &v0, &w0};
+        for (int id = 0; id < 12; id++) dig[id] = digest(all[id]->vec, (long long)all[id]->size);
     }
     ~NSCyl() { if (handle) fdmb_ns_cyl_destroy(handle); }
     NSCyl(const NSCyl&) = delete;
@@ -90,21 +95,12 @@ public:
 
     int size() const { return (int)(u.size + v.size + w.size + p.size); }
 
-    void step()
-    {
-        FDMB_VERIFY(fdmb_ns_cyl_step(handle, 1));
-        time_index++;
-        if (auto_sync) sync_to_host(false);
-    }
-    void L_step()
-    {
-        FDMB_VERIFY(fdmb_ns_cyl_lstep(handle, 1));
-        time_index++;
-        if (auto_sync) sync_to_host(false);
-    }
+    void step() { steps(1, false); }
+    void L_step() { steps(1, true); }
     // B200 extension: n steps back to back on the device
     void steps(int n, bool linear = false)
     {
+        before_step(linear);
         FDMB_VERIFY(linear ? fdmb_ns_cyl_lstep(handle, n) : fdmb_ns_cyl_step(handle, n));
         time_index += n;
         if (auto_sync) sync_to_host(false);
@@ -114,17 +110,51 @@ public:
         pull(FDMB_FIELD_U, u); pull(FDMB_FIELD_V, v); pull(FDMB_FIELD_W, w); pull(FDMB_FIELD_P, p);
         if (all) { pull(FDMB_FIELD_X, x); pull(FDMB_FIELD_F, F); pull(FDMB_FIELD_G, G); pull(FDMB_FIELD_H, H); pull(FDMB_FIELD_RHS, RHS); }
     }
-    // host mirrors -> device: the state u,v,w,p and the linearisation point u0,v0,w0
+    // host mirrors -> device: the state u,v,w,p, the linearisation point u0,v0,w0 and the wall speed U0
     void sync_to_device()
     {
         push(FDMB_FIELD_U, u); push(FDMB_FIELD_V, v); push(FDMB_FIELD_W, w); push(FDMB_FIELD_P, p);
         push(FDMB_FIELD_U0, u0); push(FDMB_FIELD_V0, v0); push(FDMB_FIELD_W0, w0);
+        FDMB_VERIFY(fdmb_ns_cyl_set_u0(handle, U0));
+        U0_dev = U0;
     }
     fdmb_ns_cyl* native_handle() const { return handle; }
 
 private:
     fdmb_ns_cyl* handle = nullptr;
     std::vector<double> cvt;
+    double U0_dev = 0;                       // the wall speed the device was last given
+    unsigned long long dig[12] = {};         // digest of each mirror when it last agreed with the device (by field id)
+
+    // ---- host-mirror coherence ------------------------------------------------------------------------------
+    // The reference's callers write the public tensors between steps (test/test_ns_cyl_spectral.cpp assigns
+    // ns.u = u; ... and ns.w0[...] before L_step()).  With auto_sync every step therefore starts by comparing a
+    // 64-bit digest of each mirror with the digest taken when the mirror last agreed with the device, and uploads
+    // the mirrors the caller changed; it ends with the download of u,v,w,p.  With auto_sync off the caller owns
+    // coherence (sync_to_host / sync_to_device).
+    static unsigned long long digest(const T* p, long long n)
+    {
+        unsigned long long h = 0x9E3779B97F4A7C15ull;
+        const unsigned char* b = reinterpret_cast<const unsigned char*>(p);
+        const long long bytes = n * (long long)sizeof(T), words = bytes / 8;
+        const unsigned long long* q = reinterpret_cast<const unsigned long long*>(b);
+        for (long long i = 0; i < words; i++) { h ^= q[i]; h *= 0x100000001B3ull; h ^= h >> 29; }
+        for (long long i = words * 8; i < bytes; i++) { h ^= b[i]; h *= 0x100000001B3ull; }
+        return h;
+    }
+
+    void push_if_changed(int id, tensor& t)
+    {
+        if (digest(t.vec, (long long)t.size) != dig[id]) push(id, t);
+    }
+    void before_step(bool linear)
+    {
+        if (U0 != U0_dev) { FDMB_VERIFY(fdmb_ns_cyl_set_u0(handle, U0)); U0_dev = U0; }
+        if (!auto_sync) return;
+        push_if_changed(FDMB_FIELD_U, u); push_if_changed(FDMB_FIELD_V, v); push_if_changed(FDMB_FIELD_W, w);
+        push_if_changed(FDMB_FIELD_P, p);
+        if (linear) { push_if_changed(FDMB_FIELD_U0, u0); push_if_changed(FDMB_FIELD_V0, v0); push_if_changed(FDMB_FIELD_W0, w0); }
+    }
 
     void pull(int id, tensor& t)
     {
@@ -135,6 +165,7 @@ private:
             FDMB_VERIFY(fdmb_ns_cyl_get_field(handle, id, cvt.data()));
             for (long long i = 0; i < (long long)t.size; i++) t.vec[i] = (T)cvt[i];
         }
+        if (auto_sync) dig[id] = digest(t.vec, (long long)t.size);
     }
     void push(int id, tensor& t)
     {
@@ -144,6 +175,7 @@ private:
             cvt.assign(t.vec, t.vec + t.size);
             FDMB_VERIFY(fdmb_ns_cyl_set_field(handle, id, cvt.data()));
         }
+        dig[id] = digest(t.vec, (long long)t.size);
     }
 };
 

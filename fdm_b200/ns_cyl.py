@@ -40,6 +40,7 @@ def _bind(L):
     L.fdmb_ns_cyl_time_index.argtypes = [C.c_void_p]
     L.fdmb_ns_cyl_time_index.restype = C.c_longlong
     L.fdmb_ns_cyl_destroy.argtypes = [C.c_void_p]
+    L.fdmb_ns_cyl_set_u0.argtypes = [C.c_void_p, C.c_double]
     L.fdmb_ns_cyl_create_sharded.argtypes = [C.POINTER(C.c_void_p), P, C.c_int, C.c_int]
     L.fdmb_ns_cyl_local_slab.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.fdmb_ns_cyl_export_ipc.argtypes = [C.c_void_p, C.c_void_p]
@@ -103,6 +104,11 @@ class NSCyl:
 
     def L_step(self, nsteps=1):
         capi.check(capi.lib().fdmb_ns_cyl_lstep(self._h, int(nsteps)), "NSCyl L_step")
+
+    def set_u0(self, u0):
+        """The public, non-const member ``U0`` of the reference class (src/ns_cyl.h:23): wall speed used from the
+        next step on (test/test_ns_cyl_spectral.cpp sets it to 0 for the perturbation problem)."""
+        capi.check(capi.lib().fdmb_ns_cyl_set_u0(self._h, float(u0)), "NSCyl set_u0")
 
     def size(self):
         """u.size + v.size + w.size + p.size (src/ns_cyl.h:114-116)."""

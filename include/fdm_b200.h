@@ -59,12 +59,15 @@ int fdmb_memcpy_d2h(void* dst, const void* src, unsigned long long bytes);
 int fdmb_device_synchronize(void);
 
 /* ---- 1-D transforms ------------------------------------------------------------
- * Batched fdm::FFT<double>::{sFFT,pFFT_1,pFFT}  (src/fft.h:82-90, src/fft.cpp:109-212,294-365).
+ * Batched fdm::FFT<double>::{sFFT,pFFT_1,pFFT,cFFT}  (src/fft.h:82-90, src/fft.cpp:109-212,294-365,368-445).
  * kind: 0 sFFT (DST-I over indices 1..N-1), 1 pFFT_1 (periodic, values->coefficients),
- *       2 pFFT (periodic, coefficients->values).
- * in/out: HOST arrays of `batch` rows; a row holds the N-1 (kind 0) or N (kind 1,2)
- * meaningful entries, contiguous.  out[k] = dx * (...) exactly as the reference.     */
+ *       2 pFFT (periodic, coefficients->values), 3 cFFT (DCT-I with halved end points over indices 0..N).
+ * in/out: HOST arrays of `batch` rows; a row holds the N-1 (kind 0), N (kind 1,2) or N+1 (kind 3)
+ * meaningful entries, contiguous.  out[k] = dx * (...) exactly as the reference.
+ * fdmb_fft_batch_impl selects the kernel: 0 = the one the solvers use for this length (the persistent
+ * bulk-copy-fed sweep for N >= 32, kinds 0..2), 1 = the plain tile kernel, 2 = the persistent sweep.        */
 int fdmb_fft_batch(int kind, int N, long long batch, double dx, const double* in, double* out);
+int fdmb_fft_batch_impl(int kind, int N, long long batch, double dx, const double* in, double* out, int impl);
 
 /* ---- LaplCube -------------------------------------------------------------------
  * Replaces fdm::LaplCube<double,check,F> (src/lapl_cube.h:9-106, src/lapl_cube.cpp:9-172).
@@ -235,6 +238,9 @@ int fdmb_ns_cyl_get_field(fdmb_ns_cyl* h, int field, double* host);
 int fdmb_ns_cyl_set_field(fdmb_ns_cyl* h, int field, const double* host);
 int fdmb_ns_cyl_field_device_ptr(fdmb_ns_cyl* h, int field, void** dptr);
 long long fdmb_ns_cyl_time_index(fdmb_ns_cyl* h);
+/* the public, non-const member U0 (src/ns_cyl.h:23; test/test_ns_cyl_spectral.cpp sets it to 0): wall speed used by
+ * init_bound from the next step on                                                                               */
+int fdmb_ns_cyl_set_u0(fdmb_ns_cyl* h, double u0);
 int fdmb_ns_cyl_destroy(fdmb_ns_cyl* h);
 /* NSCyl over 2, 4 or 8 GPUs of one node: the phi-slabs of the sharded LaplCyl3FFT2; u, v, w (and u0, v0, w0 for the
  * linearised step) keep one wrap-around halo plane each side, H one below and x one above, pulled from the

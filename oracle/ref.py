@@ -67,6 +67,7 @@ def lib():
         L.ref_ns_cyl_get_field.argtypes = [C.c_void_p, C.c_int, _dp]
         L.ref_ns_cyl_set_field.argtypes = [C.c_void_p, C.c_int, _dp]
         L.ref_ns_cyl_destroy.argtypes = [C.c_void_p]
+        L.ref_ns_cyl_set_u0.argtypes = [C.c_void_p, C.c_double]
         L.ref_nbody_create.restype = C.c_void_p
         L.ref_nbody_create.argtypes = [C.c_double] * 4 + [C.c_int] * 3 + [C.c_double] * 3 + [C.c_int] * 2
         L.ref_nbody_count.argtypes = [C.c_void_p]
@@ -92,6 +93,19 @@ def _p(a):
 
 def num_threads():
     return lib().ref_num_threads()
+
+
+def use_all_cores():
+    """OpenMP threads = the cores this process may run on, whatever OMP_NUM_THREADS says (torch.distributed.run sets
+    it to 1 for its workers).  Call BEFORE constructing a solver; returns the thread count now in force."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    L = lib()
+    L.ref_set_num_threads.argtypes = [C.c_int]
+    L.ref_set_num_threads.restype = C.c_int
+    return L.ref_set_num_threads(int(n))
 
 
 FFT_KINDS = {"sFFT": 0, "cFFT": 1, "pFFT_1": 2, "pFFT": 3}
@@ -228,6 +242,10 @@ class NSCyl:
         fid = FIELD_IDS[name]
         assert a.size == lib().ref_ns_cyl_field_size(self.h, fid)
         lib().ref_ns_cyl_set_field(self.h, fid, _p(a))
+
+    def set_u0(self, u0):
+        """The public member U0 (src/ns_cyl.h:23)."""
+        lib().ref_ns_cyl_set_u0(self.h, float(u0))
 
     def __del__(self):
         if getattr(self, "h", None):

@@ -124,6 +124,19 @@ int ref_num_threads()
 #endif
 }
 
+// torch.distributed.run exports OMP_NUM_THREADS=1 to its workers; bench.py's reference arm calls this before it
+// constructs a solver (FFTOmpSafe sizes its pool from omp_get_max_threads() at construction, src/fft.h:382-385)
+int ref_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n;
+    return 1;
+#endif
+}
+
 // ---- 1-D transforms: kind 0 sFFT, 1 cFFT, 2 pFFT_1, 3 pFFT ------------------
 // in: N+1 doubles (copied, the reference destroys its input), out: N+1 doubles.
 void ref_fft1d(int kind, int N, const double* in, double* out, double dx)
@@ -292,6 +305,12 @@ int ref_ns_cyl_set_field(void* vh, int id, const double* in)
     int n = h->zperiodic ? nscyl_field(h->p, id, &p) : nscyl_field(h->d, id, &p);
     if (n > 0) std::memcpy(p, in, sizeof(double) * n);
     return n;
+}
+// the public member U0 (src/ns_cyl.h:23), changed by test/test_ns_cyl_spectral.cpp between construction and L_step
+void ref_ns_cyl_set_u0(void* vh, double u0)
+{
+    auto* h = (NSCylH*)vh;
+    if (h->zperiodic) h->p->U0 = u0; else h->d->U0 = u0;
 }
 void ref_ns_cyl_destroy(void* vh)
 {

@@ -8,6 +8,7 @@
 //                                                 column scales written through the public vectors
 //   shim_check cyl <nr> <nz> <nphi> <rhs.bin> <ans.bin>      LaplCyl3FFT2<double,true>
 //   shim_check nscyl <steps> <lsteps> <prefix> [--ns:...]    NSCyl<double,true>, dumps <prefix>_{u,v,w,p}.bin
+//   shim_check nscylspec <lsteps> <prefix> <x.bin> [--ns:...]  the host-write pattern of test/test_ns_cyl_spectral.cpp
 //   shim_check vplot <n> <steps> <prefix> [--ns:...]         NSCube + velocity_plotter as in test/test_ns_cube.cpp:24-50:
 //                                                 host use(u,v,w), device use(ns), float instantiation; dumps
 //                                                 <prefix>_{host,dev,flt}_psi_{x,y,z}.bin, <prefix>_{host,dev}.vtk, .ppm
@@ -129,6 +130,52 @@ int main(int argc, char** argv)
         spit(prefix + "_u.bin", ns.u.vec, ns.u.size); spit(prefix + "_v.bin", ns.v.vec, ns.v.size);
         spit(prefix + "_w.bin", ns.w.vec, ns.w.size); spit(prefix + "_p.bin", ns.p.vec, ns.p.size);
         printf("time_index %d size %d\n", ns.time_index, ns.size());
+        return 0;
+    }
+    if (mode == "nscylspec") {
+        // The access pattern of test/test_ns_cyl_spectral.cpp:16,72-104 with NO B200-specific call: write the Couette
+        // profile into ns.w0 through the public tensor, set the public member U0 to 0, assign the state tensors from
+        // caller-owned storage (range intersection, tensor.h:103-111), run L_step(), read the state back -- twice,
+        // like two ARPACK iterations.  Arguments: <lsteps> <prefix> <x.bin> [--ns:...]; x.bin holds u|v|w|p.
+        int lsteps = atoi(argv[2]);
+        std::string prefix = argv[3];
+        std::vector<char*> args{argv[0]};
+        for (int i = 5; i < argc; i++) args.push_back(argv[i]);
+        Config c;
+        c.rewrite((int)args.size(), args.data());
+        using Task = NSCyl<double, true, tensor_flag::periodic>;
+        using tensor = typename Task::tensor;
+        Task ns(c);
+        const int nphi = ns.nphi, nz = ns.nz, nr = ns.nr;
+        tensor u{{0, nphi - 1, 0, nz - 1, 1, nr - 1}};
+        tensor v{{0, nphi - 1, 0, nz - 1, 1, nr}};
+        tensor w{{0, nphi - 1, 0, nz - 1, 1, nr}};
+        tensor p({0, nphi - 1, 0, nz - 1, 1, nr});
+        const size_t n = u.size + v.size + w.size + p.size;
+        auto xin = slurp(argv[4], n);
+        std::vector<double> y(n);
+        for (int i = 0; i < nphi; i++)
+            for (int k = 0; k < nz; k++)
+                for (int j = 0; j <= nr; j++) {
+                    double r = ns.r0 + ns.dr * j + ns.dr / 2;
+                    ns.w0[i][k][j] = -ns.U0 * ns.r0 * ns.r0 / (ns.R * ns.R - ns.r0 * ns.r0)
+                                     + ns.U0 * ns.r0 * ns.r0 * ns.R * ns.R / (ns.R * ns.R - ns.r0 * ns.r0) / r / r;
+                }
+        ns.U0 = 0;
+        for (int iter = 0; iter < 2; iter++) {
+            std::memcpy(y.data(), xin.data(), n * sizeof(double));
+            size_t off = 0;
+            u.use(y.data() + off); off += u.size;
+            v.use(y.data() + off); off += v.size;
+            w.use(y.data() + off); off += w.size;
+            p.use(y.data() + off); off += p.size;
+            ns.u = u; ns.v = v; ns.w = w; ns.p = p;
+            for (int i = 0; i < lsteps; i++) ns.L_step();
+            u = ns.u; v = ns.v; w = ns.w; p = ns.p;
+            spit(prefix + "_y" + std::to_string(iter) + ".bin", y.data(), n);
+            for (size_t i = 0; i < n; i++) xin[i] = y[i];          // next "ARPACK vector"
+        }
+        printf("time_index %d n %zu\n", ns.time_index, n);
         return 0;
     }
     if (mode == "vplot") {

@@ -121,13 +121,14 @@ extern "C" int emul_dst_fused(int N, double* data, int sj, double scale, int mod
     return -1;
 }
 
-// data: N slots with stride sj (slot 0 unused for kind 0)
+// data: N slots with stride sj (slot 0 unused for kind 0; N + 1 slots for kind 3 = cFFT)
 extern "C" int emul_xform(int kind, int N, double* data, int sj, double scale)
 {
 #define X(NN)                                                      \
     case NN:                                                       \
         if (kind == 0) run_one<NN, XF_DST>(data, sj, scale);       \
         else if (kind == 1) run_one<NN, XF_PFWD>(data, sj, scale); \
+        else if (kind == 3) run_one<NN, XF_DCT>(data, sj, scale);  \
         else run_one<NN, XF_PINV>(data, sj, scale);                \
         return 0;
     switch (N) { X(4) X(8) X(16) X(32) X(64) X(128) X(256) X(512) X(1024) X(2048) }

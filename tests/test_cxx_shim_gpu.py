@@ -105,6 +105,77 @@ def test_cxx_ns_cyl(exe, tmp_path, ref, lsteps):
     assert O.rel_l2(got, want) < 1e-12
 
 
+def test_cxx_ns_cyl_spectral_driver_pattern(exe, tmp_path, ref):
+    """test/test_ns_cyl_spectral.cpp:72-104 against the drop-in NSCyl with NO B200-specific call: the caller writes
+    ns.w0 through the public tensor, sets the public member U0 = 0, assigns ns.u/v/w/p from its own storage, runs
+    L_step() and copies the state out.  The header notices the host writes (mirror digests) and the changed U0."""
+    nr, nz, nphi, lsteps = 16, 16, 16, 3
+    kv = dict(nr=nr, nz=nz, nphi=nphi, Re=150.0, dt=0.01)
+    # extents of the driver's interior tensors: u [nphi][nz][1..nr-1], v, w, p [nphi][nz][1..nr]
+    sizes = [nphi * nz * (nr - 1)] + [nphi * nz * nr] * 3
+    x = O.synthetic_rhs((sum(sizes),), seed=31) * 1e-2
+    x.tofile(tmp_path / "x.bin")
+    subprocess.run([exe, "nscylspec", str(lsteps), str(tmp_path / "sp"), str(tmp_path / "x.bin")]
+                   + [f"--ns:{k}={v}" for k, v in kv.items()], check=True, capture_output=True, text=True)
+    # the same sequence on the compiled reference through its public members
+    R = ref.NSCyl(zperiodic=True, **kv)
+    R0, Rr = math.pi, math.pi / 2
+    dr = (R0 - Rr) / nr
+
+    def embed(name, block, jlo, jhi):
+        """Range-intersection assignment ns.f = f (tensor.h:103-111): interior block into the full field."""
+        full = R.field(name)
+        n_r = {"u": nr + 3}.get(name, nr + 2); r_lo = {"u": -1}.get(name, 0)
+        nzf = full.size // (nphi * n_r)
+        z_lo = -1 if (name == "v" and nzf == nz + 1) else 0
+        f = full.reshape(nphi, nzf, n_r)
+        f[:, 0 - z_lo:nz - z_lo, jlo - r_lo:jhi - r_lo + 1] = block
+        R.set_field(name, f)
+
+    def extract(name, jlo, jhi):
+        full = R.field(name)
+        n_r = {"u": nr + 3}.get(name, nr + 2); r_lo = {"u": -1}.get(name, 0)
+        nzf = full.size // (nphi * n_r)
+        z_lo = -1 if (name == "v" and nzf == nz + 1) else 0
+        return full.reshape(nphi, nzf, n_r)[:, 0 - z_lo:nz - z_lo, jlo - r_lo:jhi - r_lo + 1].copy()
+
+    w0 = R.field("w0").reshape(nphi, -1, nr + 2)
+    j = np.arange(nr + 1)
+    r = Rr + dr * j + dr / 2
+    w0[:, :nz, :nr + 1] = (-1.0 * Rr ** 2 / (R0 ** 2 - Rr ** 2) + 1.0 * Rr ** 2 * R0 ** 2 / (R0 ** 2 - Rr ** 2) / r / r)[None, None, :]
+    R.set_field("w0", w0)
+    R.set_u0(0.0)
+    xin = x.copy()
+    for it in range(2):
+        off = 0
+        for name, sz, (jlo, jhi) in zip("uvwp", sizes, [(1, nr - 1)] + [(1, nr)] * 3):
+            embed(name, xin[off:off + sz].reshape(nphi, nz, jhi - jlo + 1), jlo, jhi); off += sz
+        R.step(lsteps, linear=True)
+        want = np.concatenate([extract(name, jlo, jhi).ravel() for name, (jlo, jhi) in zip("uvwp", [(1, nr - 1)] + [(1, nr)] * 3)])
+        got = np.fromfile(tmp_path / f"sp_y{it}.bin")
+        assert O.rel_l2(got, want) < 1e-12, f"iteration {it}"
+        xin = want
+
+
+def test_lapl_rect_rejects_non_dominant_scales():
+    """LaplRect's device recurrence does not pivot; scales for which LAPACK gtsv (src/lapl_rect.cpp:90) would are
+    refused instead of answered differently."""
+    import fdm_b200
+    nx, ny = 31, 15
+    S = fdm_b200.LaplRect(0.1, 0.1, 3.2, 1.6, nx, ny)
+    ok = np.ones(nx + 1)
+    S.set_scales(ok, ok, ok)
+    bad = ok.copy(); bad[5] = 1.5
+    with pytest.raises(fdm_b200.FdmB200Error):
+        S.set_scales(ok, bad, ok)                    # |L| + |U| = 2.5 > 2
+    neg = ok.copy(); neg[7] = -0.5
+    with pytest.raises(fdm_b200.FdmB200Error):
+        S.set_scales(neg, None, None)
+    rhs = O.synthetic_rhs((ny, nx), seed=3)
+    a = S.solve(rhs)                                  # the rejected calls left the handle's scales untouched
+    assert O.rel_l2(a, O.LaplRect(0.1, 0.1, 3.2, 1.6, nx, ny).solve(rhs)) < 1e-12
+
+
 def test_reference_driver_fdm_ns_cube_on_the_gpu_path(tmp_path, ref):
     """The reference's own driver (test/test_ns_cube.cpp, unmodified; built by __graft_entry__.build() where the
     reference tree exists) runs the README cavity case on the B200 path and writes its VTK files through the

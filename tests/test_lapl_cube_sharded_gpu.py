@@ -100,6 +100,55 @@ def test_sharded_matches_single_gpu_255(fb):
         assert O.rel_l2(solve_in_process(fb, args, rhs, P), single) < 1e-13, f"P={P}"
 
 
+@pytest.mark.parametrize("shape", [(1023, 63, 31), (63, 1023, 31), (127, 1023, 63), (1023, 127, 15), (511, 63, 31), (63, 511, 127)],
+                         ids=lambda s: "x".join(map(str, s)))
+def test_sharded_long_axis_vs_oracle(fb, shape):
+    """Ny or Nz = 1024 / 512: the wide-tile transposing sweeps of the 1023^3 sharded solve (PipeCfg<1024, WIDE>:
+    16 columns, 512 threads) and their <512> siblings, ragged in the other axes."""
+    nz, ny, nx = shape
+    rhs = O.synthetic_rhs(shape, seed=sum(shape))
+    args = (0.1, 0.2, 0.3, 0.1 * (nx + 1), 0.2 * (ny + 1), 0.3 * (nz + 1), nx, ny, nz)
+    want = O.LaplCube(*args).solve(rhs)
+    for P in ranks_available(fb):
+        assert O.rel_l2(solve_in_process(fb, args, rhs, P, repeats=2), want) < TOL, f"P={P}"
+
+
+@pytest.mark.parametrize("n", [255, 1023])
+def test_sharded_eigenvector_kat_device(fb, n):
+    """The benchmarked sharded configuration (1023^3, z-slabs) against the closed-form eigenvector answer, built slab
+    by slab on each device (tests/golden/cube1023.py); no CPU solve needed."""
+    import torch
+    from tests.golden import cube1023 as G
+    L = fb.lib()
+    d, l = G.geometry(n)
+    for P in ranks_available(fb):
+        solvers, bufs = [], []
+        for r in range(P):
+            fb.capi.check(L.fdmb_set_device(r), "set_device")
+            s = fb.LaplCubeSharded(d, d, d, l, l, l, n, n, n, rank=r, nranks=P)
+            solvers.append(s)
+            with torch.cuda.device(r):
+                rhs, want = G.kat_device(torch, n, d, s.z_first, s.nz_local, torch.device("cuda", r))
+                bufs.append((rhs, want, torch.full_like(rhs, float("nan"))))
+                torch.cuda.synchronize()
+        fb.LaplCubeSharded.connect_local(solvers)
+        for _ in range(2):
+            for s, (rhs, want, ans) in zip(solvers, bufs):
+                s.solve_device(ans.data_ptr(), rhs.data_ptr())
+        num = den = 0.0
+        for r in range(P):
+            fb.capi.check(L.fdmb_set_device(r), "set_device")
+            fb.capi.check(L.fdmb_device_synchronize(), "sync")
+            rhs, want, ans = bufs[r]
+            with torch.cuda.device(r):
+                num += float(((ans - want) ** 2).sum()); den += float((want ** 2).sum())
+        for s in solvers:
+            s.close()
+        del bufs
+        fb.capi.check(L.fdmb_set_device(0), "set_device")
+        assert (num / den) ** 0.5 < TOL, f"P={P}"
+
+
 def test_sharded_rejects_bad_split(fb):
     with pytest.raises(fb.FdmB200Error):
         fb.LaplCubeSharded(1, 1, 1, 16, 16, 16, 15, 15, 15, rank=0, nranks=2)     # transform length 16 < 32

@@ -45,6 +45,10 @@ def test_tile_transforms(emul, N, sj):
     d = np.zeros(N * sj); d[::sj] = x
     assert emul.emul_xform(2, N, p(d), sj, 0.37) == 0
     assert O.rel_l2(d[::sj], O.pFFT(x, 0.37)) < 2e-15
+    x = rng.uniform(-1, 1, N + 1)                                 # cFFT: N + 1 values (src/fft.cpp:368-445)
+    d = np.zeros((N + 1) * sj); d[::sj] = x
+    assert emul.emul_xform(3, N, p(d), sj, 0.37) == 0
+    assert O.rel_l2(d[::sj], O.cFFT(x, 0.37)) < 2e-14
 
 
 def test_roundtrip_identity(emul):
