@@ -125,6 +125,16 @@ bool pipe_enabled()
     return v != 0;
 }
 
+bool ring_enabled()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("FDMB_RING");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v != 0;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -361,9 +371,9 @@ int fdmb_fft_batch_impl(int kind, int N, long long batch, double dx, const doubl
         set_error("fdmb_fft_batch: kind must be 0..3 and N a power of two in [4,2048] (got kind=%d N=%d impl=%d)", kind, N, impl);
         return FDMB_ERR_INVALID;
     }
-    const bool can_pipe = kind != XF_DCT && pipe_supported_N(N);
+    const bool can_pipe = kind != XF_DCT && rows_pipe_supported_N(N);
     if (impl == 2 && !can_pipe) {
-        set_error("fdmb_fft_batch: the persistent sweep needs N >= 32 and kind 0..2 (got kind=%d N=%d)", kind, N);
+        set_error("fdmb_fft_batch: the persistent sweep needs 32 <= N <= 1024 and kind 0..2 (got kind=%d N=%d)", kind, N);
         return FDMB_ERR_INVALID;
     }
     if (batch == 0) return FDMB_OK;

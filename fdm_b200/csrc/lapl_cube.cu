@@ -74,16 +74,18 @@ cudaError_t launch_cols_cube_divide(int N, bool periodic, const ColsArgs& a, con
     if (tm.taxis) { a.taxis = tm.taxis; a.boxhi = use_p ? tm.boxhi_p : tm.boxhi; a.blog = tm.blog; }
 
 #define FDMB_FOR_EACH_PIPE_N(X) X(32) X(64) X(128) X(256) X(512) X(1024) X(2048)
+#define FDMB_FOR_EACH_ROWS_PIPE_N(X) X(32) X(64) X(128) X(256) X(512) X(1024)
 
 cudaError_t launch_rows_pipe(int N, int kind, const RowsPipeArgs& a, cudaStream_t st, const char* tag)
 {
     LaunchScope scope(tag, st);
+    if (N == 1024 && kind == XF_DST && ring_enabled() && rows_ring_fits<1024>(a)) return launch_rows_ring_t<1024>(a, st);
 #define X(NN)                                                                       \
     case NN:                                                                        \
         if (kind == XF_DST) return launch_rows_pipe_t<NN, XF_DST>(a, st);           \
         if (kind == XF_PFWD) return launch_rows_pipe_t<NN, XF_PFWD>(a, st);         \
         return launch_rows_pipe_t<NN, XF_PINV>(a, st);
-    switch (N) { FDMB_FOR_EACH_PIPE_N(X) }
+    switch (N) { FDMB_FOR_EACH_ROWS_PIPE_N(X) }
 #undef X
     return cudaErrorInvalidValue;
 }
@@ -93,6 +95,7 @@ cudaError_t launch_cols_pipe(int N, int kind, const ColsMaps& tm, ColsPipeArgs a
     LaunchScope scope(tag, st);
     MidNone mid;
     FDMB_PICK_MAPS(kind == XF_DST)
+    if (N == 1024 && kind == XF_DST && ring_enabled()) return launch_cols_ring_t<1024, MidNone>(m1, m2, a, mid, st);
 #define X(NN)                                                                                          \
     case NN:                                                                                           \
         if (kind == XF_DST) return launch_cols_pipe_t<NN, XF_DST, MidNone, XF_DST>(m1, m2, a, mid, st);    \
@@ -110,6 +113,7 @@ cudaError_t launch_cols_pipe_blocked(int N, const ColsMaps& tm, ColsPipeArgs a, 
     LaunchScope scope(tag, st);
     MidNone mid;
     FDMB_PICK_MAPS(true)
+    if (N == 1024 && ring_enabled()) return launch_cols_ring_t<1024, MidNone, OutBlocked>(m1, m2, a, mid, st, ob);
 #define X(NN) case NN: return launch_cols_pipe_t<NN, XF_DST, MidNone, XF_DST, OutBlocked>(m1, m2, a, mid, st, ob);
     switch (N) { FDMB_FOR_EACH_PIPE_N(X) }
 #undef X
@@ -121,6 +125,7 @@ cudaError_t launch_cols_pipe_cube_divide(int N, bool periodic, const ColsMaps& t
 {
     LaunchScope scope(tag, st);
     FDMB_PICK_MAPS(!periodic)
+    if (N == 1024 && !periodic && ring_enabled()) return launch_cols_ring_t<1024, MidCubeDivide>(m1, m2, a, mid, st);
 #define X(NN)                                                                                              \
     case NN:                                                                                               \
         if (periodic) return launch_cols_pipe_t<NN, XF_PFWD, MidCubeDivide, XF_PINV>(m1, m2, a, mid, st);  \
@@ -262,7 +267,7 @@ int fdmb_lapl_cube::init()
     // by default until the sweeps' compute side is faster.
     {
         const char* e = getenv("FDMB_BLOCKED");
-        const bool can = pipe_enabled() && !periodic && pipe_supported_N(Nx) && pipe_supported_N(Ny) && pipe_supported_N(Nz);
+        const bool can = pipe_enabled() && !periodic && rows_pipe_supported_N(Nx) && pipe_supported_N(Ny) && pipe_supported_N(Nz);
         blog = (can && e && e[0] == '1') ? 6 : 0;
         if (blog && (1 << blog) > Ny / 2) blog = 4;      // small grids (tests): keep at least two blocks
         if (const char* b = getenv("FDMB_BLOG")) if (blog) blog = atoi(b);
@@ -407,7 +412,7 @@ int fdmb_lapl_cube::solve_device_sharded(double* d_out, const double* d_in, cuda
     int rc;
     auto rows = [&](const double* in, double* out, int in_pitch, int out_pitch, double scale, int kind, const char* tag,
                     int reverse) -> cudaError_t {
-        if (pipe_supported_N(Nx) && (reinterpret_cast<uintptr_t>(in) & 15) == 0) {
+        if (rows_pipe_supported_N(Nx) && (reinterpret_cast<uintptr_t>(in) & 15) == 0) {
             RowsPipeArgs p{};
             p.in = in; p.out = out; p.nrows = (long long)nzl * ny; p.nvalid = nx; p.in_pitch = in_pitch;
             p.out_pitch = out_pitch; p.reverse = reverse; p.scale = scale; p.SN = tx.SN; p.WM = tx.WM;
@@ -461,7 +466,7 @@ int fdmb_lapl_cube::solve_device(double* d_out, const double* d_in, cudaStream_t
     RowsArgs r{};
     r.in = d_in; r.out = d_work; r.nrows = (long long)nz * ny; r.nvalid = nx;
     r.in_pitch = nx; r.out_pitch = px; r.scale = dx * slx; r.SN = tx.SN; r.WM = tx.WM;
-    const bool pipe_x = pipe_enabled() && pipe_supported_N(Nx);
+    const bool pipe_x = pipe_enabled() && rows_pipe_supported_N(Nx);
     if (blog) {
         // blocked work array W[yb][z][yi][x]
         if ((reinterpret_cast<uintptr_t>(d_in) & 15) != 0) {

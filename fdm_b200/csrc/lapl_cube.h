@@ -3,6 +3,7 @@
 #include "common.h"
 #include "xform_kernels.cuh"
 #include "xform_pipe.cuh"
+#include "xform_ring.cuh"
 
 namespace fdmb {
 cudaError_t launch_rows(int N, int kind, const RowsArgs& a, cudaStream_t st, const char* tag);
@@ -11,7 +12,10 @@ cudaError_t launch_cols_cube_divide(int N, bool periodic, const ColsArgs& a, con
                                     cudaStream_t st, const char* tag);
 // persistent TMA-fed variants (transform lengths >= 32)
 inline bool pipe_supported_N(int N) { return supported_N(N) && N >= 32; }
+// the contiguous-axis sweep keeps a staging buffer AND a compute tile of 8 rows: N = 2048 (260 KB) does not fit one SM
+inline bool rows_pipe_supported_N(int N) { return pipe_supported_N(N) && N <= 1024; }
 inline int pipe_B(int N) { return N <= 512 ? 16 : 8; }
+bool ring_enabled();     // FDMB_RING=0 selects the one-tile-per-CTA sweeps at N = 1024 (A/B measurements)
 // cross-GPU barrier on a stream over the flag arrays at `off_flags` inside every rank's peer-mapped block
 // (FDMB_MAX_RANKS u64 epochs each, zero-initialised); epoch must increase by one per call on every rank
 int launch_mg_barrier(void* const* peer_blocks, size_t off_flags, int rank, int nranks, unsigned long long epoch,

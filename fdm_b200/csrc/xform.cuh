@@ -691,11 +691,32 @@ __device__ __forceinline__ int prefold_row(int j)
 // spectral values) are written to a second tile `ocol` that nobody reads during stage C, so the stage-C
 // results leave the registers at once (no barrier between the last loads and the first stores, half the
 // live registers).  ocol is this thread's column base in that tile (same sj); ignored when !SEP.
-template <int N, int G, int GAP, bool PREFOLD, bool SWZ, bool SEP = false, typename OUT>
-__device__ __forceinline__ void dst_tile_fused(double* col, int sj, int g, double hs,
-                                               const double* __restrict__ SN, const double* __restrict__ SF,
-                                               const cd* __restrict__ WM, double* scr, int scr_s, const OUT& out,
-                                               double* ocol = nullptr)
+// Barrier policy of the fused DST: the whole CTA (__syncthreads) or one consumer group of a CTA that runs several
+// tiles at once (a named barrier over the group's threads, xform_ring.cuh).
+struct CtaSync {
+    __device__ __forceinline__ void sync() const { __syncthreads(); }
+};
+// Input policy of stage A: where slot j of the sequence is read from.
+//   InPlanar : the planar tile itself (the strided-axis sweeps land their tiles in this layout)
+//   InDense  : a dense row in natural order, slot j at row[j - 1] (the contiguous-axis sweep lands its rows with a
+//              bulk copy); the planar tile may overlap the dense rows, because stage A reads every input into
+//              registers before the barrier that precedes its first store
+template <int N, int GAP> struct InPlanar {
+    const double* col; int sj;
+    __device__ __forceinline__ double e(int m) const { return col[Planar<N, GAP>::E(m) * sj]; }   // slot 2m
+    __device__ __forceinline__ double o(int m) const { return col[Planar<N, GAP>::O(m) * sj]; }   // slot 2m + 1
+};
+struct InDense {
+    const double* row; bool ok;
+    __device__ __forceinline__ double e(int m) const { return ok ? row[2 * m - 1] : 0.0; }
+    __device__ __forceinline__ double o(int m) const { return ok ? row[2 * m] : 0.0; }
+};
+
+template <int N, int G, int GAP, bool PREFOLD, bool SWZ, bool SEP = false, typename OUT, typename SYNC, typename IN>
+__device__ __forceinline__ void dst_tile_fused_x(double* col, int sj, int g, double hs,
+                                                 const double* __restrict__ SN, const double* __restrict__ SF,
+                                                 const cd* __restrict__ WM, double* scr, int scr_s, const OUT& out,
+                                                 double* ocol, const SYNC& sy, const IN& in)
 {
     using P = Plan<N>;
     using I = PlanInfo<N>;
@@ -718,15 +739,15 @@ __device__ __forceinline__ void dst_tile_fused(double* col, int sj, int g, doubl
                 const int m = q + n1 * S0;
                 // y[j] = hs * (sin(pi j/N)(x[j]+x[N-j]) + (x[j]-x[N-j])/2) for every j in 1..N-1, y[0] = 0;
                 // x[2m] = E[m], x[N-2m] = E[M-m], x[2m+1] = O[m], x[N-2m-1] = O[M-m-1]
-                double a0 = (m == 0) ? 0.0 : col[PL::E(m) * sj], c0 = (m == 0) ? 0.0 : col[PL::E(M - m) * sj];
-                double a1 = col[PL::O(m) * sj], c1 = col[PL::O(M - m - 1) * sj];
+                double a0 = (m == 0) ? 0.0 : in.e(m), c0 = (m == 0) ? 0.0 : in.e(M - m);
+                double a1 = in.o(m), c1 = in.o(M - m - 1);
                 double s0 = (n1 < R0 / 2) ? SF[2 * m] : SF[N - 2 * m];
                 double s1 = (n1 < R0 / 2) ? SF[2 * m + 1] : SF[N - 2 * m - 1];
                 v[it][n1].x = s0 * (a0 + c0) + h2 * (a0 - c0);
                 v[it][n1].y = s1 * (a1 + c1) + h2 * (a1 - c1);
             }
         }
-        __syncthreads();     // every mirrored read is done before anyone overwrites the inputs
+        sy.sync();     // every mirrored read is done before anyone overwrites the inputs
 #pragma unroll
         for (int it = 0; it < NA; it++) {
             const int q = g + it * G;
@@ -744,17 +765,17 @@ __device__ __forceinline__ void dst_tile_fused(double* col, int sj, int g, doubl
                 col[PL::O(s) * sj] = o.y;
             }
         }
-        __syncthreads();
+        sy.sync();
     } else {
         // the caller stored the folded sequence at prefold_row<N,GAP,SWZ>(j): already block-swizzled, so the
         // first pass stays in place (every thread rewrites exactly the rows it read)
         fft_pass_planar<N, GAP, M, R0, G, SWZ, SWZ>(col, sj, g, WM);
-        __syncthreads();
+        sy.sync();
     }
     // ---- stage B -------------------------------------------------------------------------
     if constexpr (I::NP == 3) {
         fft_pass_planar<N, GAP, M / R0, P::R1, G, SWZ, SWZ>(col, sj, g, WM);
-        __syncthreads();
+        sy.sync();
     }
     // ---- stage C: last pass on a block and its mirror block, untangle in registers -------------
     constexpr int RL = I::RL, LB = I::LB;
@@ -797,7 +818,7 @@ __device__ __forceinline__ void dst_tile_fused(double* col, int sj, int g, doubl
             }
         }
     }
-    if constexpr (!SEP) __syncthreads();
+    if constexpr (!SEP) sy.sync();
     double* scol = SEP ? ocol : col;      // where the seeds live
     if (active) {
         // seed k lives at O[k ^ ((k / CS) & 1)] when swizzled: (k / CS) & 1 is a per-thread constant
@@ -815,7 +836,7 @@ __device__ __forceinline__ void dst_tile_fused(double* col, int sj, int g, doubl
             scol[PL::O((hi ^ zb) + LB * d) * sj] = vb[d].x;
         }
     }
-    __syncthreads();
+    sy.sync();
     // ---- stage D: inclusive prefix sum over the odd slots: S[2k+1] = sum_{m<=k} A'_m ------------
     double a[CS];
     double run = 0.0;
@@ -830,7 +851,7 @@ __device__ __forceinline__ void dst_tile_fused(double* col, int sj, int g, doubl
     double off = 0.0;
     if constexpr (G > 1) {
         scr[g * scr_s] = run;
-        __syncthreads();
+        sy.sync();
         if constexpr (G <= 8) {
 #pragma unroll
             for (int q = 0; q < G; q++) if (q < g) off += scr[q * scr_s];
@@ -842,7 +863,7 @@ __device__ __forceinline__ void dst_tile_fused(double* col, int sj, int g, doubl
                 for (int q = 0; q < 8; q++) t += scr[(g + q) * scr_s];
                 scr2[(g >> 3) * scr_s] = t;
             }
-            __syncthreads();
+            sy.sync();
 #pragma unroll
             for (int q = 0; q < G / 8; q++) if (q < (g >> 3)) off += scr2[q * scr_s];
 #pragma unroll
@@ -854,7 +875,18 @@ __device__ __forceinline__ void dst_tile_fused(double* col, int sj, int g, doubl
         int k = g * CS + i;
         out.emit(2 * k + 1, a[i] + off);
     }
-    __syncthreads();
+    sy.sync();
+}
+
+// the whole CTA works on one tile, inputs in the planar tile (the sweeps of xform_pipe.cuh)
+template <int N, int G, int GAP, bool PREFOLD, bool SWZ, bool SEP = false, typename OUT>
+__device__ __forceinline__ void dst_tile_fused(double* col, int sj, int g, double hs,
+                                               const double* __restrict__ SN, const double* __restrict__ SF,
+                                               const cd* __restrict__ WM, double* scr, int scr_s, const OUT& out,
+                                               double* ocol = nullptr)
+{
+    dst_tile_fused_x<N, G, GAP, PREFOLD, SWZ, SEP>(col, sj, g, hs, SN, SF, WM, scr, scr_s, out, ocol, CtaSync{},
+                                                   InPlanar<N, GAP>{col, sj});
 }
 
 }  // namespace fdmb

@@ -12,6 +12,8 @@ for path in sys.argv[1:]:
     r = d.get("roofline", {})
     print(f"{d.get('value'):.4g} {d.get('unit')} n_gpus={d.get('n_gpus')} ms/step={d.get('ms_per_step'):.4g} "
           f"step_frac={r.get('step_frac', 0):.3f} e2e={d.get('e2e', {}).get('value', 0):.4g} clocks={d.get('clocks')}")
+    if "check" in d:
+        print(f"    check rel_l2 = {d['check']['rel_l2']:.3e} ok={d['check']['ok']}")
     if "sharded" in r:
         sh = r["sharded"]
         print(f"    aggregate HBM+NVLink roofline: {sh['t_roof_ms_no_overlap']:.3f} ms no-overlap -> frac {sh['frac_no_overlap']:.3f}")
