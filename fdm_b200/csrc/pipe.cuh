@@ -22,6 +22,11 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// plain arrival (release, CTA scope): counts towards the barrier's pending arrivals, no transaction bytes
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity)
 {
     asm volatile(

@@ -35,6 +35,15 @@
                           // (-5 % at 1023^3; at N <= 512 the extra registers cost a resident CTA)
 #endif
 
+#ifndef FDMB_TAB_ROT
+#define FDMB_TAB_ROT 0    // fused DST, N >= 1024: the 16 fold sines of a first-pass butterfly and the 16 untangle
+                          // cos / sin of a last-pass unit are rotations by multiples of pi/8 of ONE table pair, so they
+                          // cost 4 + 2 shared-memory loads and a few FMAs instead of 32 loads (every 64-bit load is two
+                          // wavefronts of the shared-memory pipe, even when it is a broadcast).  Measured at 1023^3
+                          // (r02e): 23.61 vs 23.44 ms -- the solve runs into the board's power cap (SM clock 1.79 of
+                          // 1.97 GHz) and the extra fp64 work costs what the saved loads gain.  Off.
+#endif
+
 namespace fdmb {
 
 enum XformKind { XF_DST = 0, XF_PFWD = 1, XF_PINV = 2, XF_DCT = 3 };
@@ -44,6 +53,13 @@ __device__ __forceinline__ cd operator+(cd a, cd b) { return {a.x + b.x, a.y + b
 __device__ __forceinline__ cd operator-(cd a, cd b) { return {a.x - b.x, a.y - b.y}; }
 __device__ __forceinline__ cd cmul(cd a, cd w) { return {a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x}; }
 __device__ __forceinline__ cd mul_mi(cd a) { return {a.y, -a.x}; }  // a * (-i)
+
+// compile-time loop: f(std::integral_constant<int, i>) for i = 0..n-1
+template <int I_> struct IntC { static constexpr int value = I_; };
+template <int n, int i = 0, typename F> __device__ __forceinline__ void static_for(F&& f)
+{
+    if constexpr (i < n) { f(IntC<i>{}); static_for<n, i + 1>(f); }
+}
 
 // ---- register butterflies, forward (e^{-2 pi i jk/R}), natural in / natural out ----
 template <int R> struct Dft;
@@ -661,6 +677,40 @@ __device__ __forceinline__ void fft_pass_planar(double* col, int sj, int g, cons
     }
 }
 
+// cos / sin of n pi/8, n = 0..8
+template <int n> struct Oct {
+    static constexpr double c = (n == 0) ? 1.0 : (n == 1) ? 0.92387953251128675613 : (n == 2) ? 0.70710678118654752440
+                              : (n == 3) ? 0.38268343236508977173 : (n == 4) ? 0.0 : (n == 5) ? -0.38268343236508977173
+                              : (n == 6) ? -0.70710678118654752440 : (n == 7) ? -0.92387953251128675613 : -1.0;
+    static constexpr double s = (n == 0 || n == 8) ? 0.0 : (n == 1 || n == 7) ? 0.38268343236508977173
+                              : (n == 2 || n == 6) ? 0.70710678118654752440 : (n == 3 || n == 5) ? 0.92387953251128675613 : 1.0;
+};
+// sin(a + n pi/8) and cos(a + n pi/8) from sa = sin a, ca = cos a (any common scale factor carries through)
+template <int n> __device__ __forceinline__ double rot_sin(double sa, double ca)
+{
+    if constexpr (n == 0) return sa;
+    else if constexpr (n == 4) return ca;
+    else if constexpr (n == 8) return -sa;
+    else return sa * Oct<n>::c + ca * Oct<n>::s;
+}
+template <int n> __device__ __forceinline__ double rot_cos(double sa, double ca)
+{
+    if constexpr (n == 0) return ca;
+    else if constexpr (n == 4) return -sa;
+    else if constexpr (n == 8) return -ca;
+    else return ca * Oct<n>::c - sa * Oct<n>::s;
+}
+
+// untangle with the pair's cos / sin of 2 pi k / N given
+__device__ __forceinline__ void untangle_cs(cd& zk, cd& zm, double c, double s)
+{
+    const double ex = zk.x + zm.x, ey = zk.y - zm.y;
+    const double ox = zk.y + zm.y, oy = zm.x - zk.x;
+    const double wx = c * ox + s * oy, wy = c * oy - s * ox;
+    zk.x = ex + wx; zk.y = -(ey + wy);
+    zm.x = ex - wx; zm.y = ey - wy;
+}
+
 // Untangle one (k, M-k) pair of the (pre-scaled) half-length FFT in place:
 // zk = Z[k], zm = Z[M-k], 0 < k < M/2  ->  zk = (A_k, B_k), zm = (A_{M-k}, B_{M-k}).
 template <int N>
@@ -728,24 +778,33 @@ __device__ __forceinline__ void dst_tile_fused_x(double* col, int sj, int g, dou
     constexpr int NA = S0 / G;            // first-pass butterflies per thread
 
     // ---- stage A -------------------------------------------------------------------------
+    constexpr bool TABROT = FDMB_TAB_ROT && N >= 1024 && R0 == 8 && I::RL == 8;
     if constexpr (!PREFOLD) {
         cd v[NA][R0];
         const double h2 = 0.5 * hs;
 #pragma unroll
         for (int it = 0; it < NA; it++) {
             const int q = g + it * G;
-#pragma unroll
-            for (int n1 = 0; n1 < R0; n1++) {
+            // TABROT: slot 2m = 2q + n1 N/8 sits at the angle pi 2q/N + n1 pi/8 (SF[j] = hs sin(pi j/N), cos = SF[N/2 - j])
+            double sa = 0, ca = 0, sb = 0, cb = 0;
+            if constexpr (TABROT) { sa = SF[2 * q]; ca = SF[N / 2 - 2 * q]; sb = SF[2 * q + 1]; cb = SF[N / 2 - 2 * q - 1]; }
+            auto leg = [&](auto n1c) {
+                constexpr int n1 = decltype(n1c)::value;
                 const int m = q + n1 * S0;
                 // y[j] = hs * (sin(pi j/N)(x[j]+x[N-j]) + (x[j]-x[N-j])/2) for every j in 1..N-1, y[0] = 0;
                 // x[2m] = E[m], x[N-2m] = E[M-m], x[2m+1] = O[m], x[N-2m-1] = O[M-m-1]
                 double a0 = (m == 0) ? 0.0 : in.e(m), c0 = (m == 0) ? 0.0 : in.e(M - m);
                 double a1 = in.o(m), c1 = in.o(M - m - 1);
-                double s0 = (n1 < R0 / 2) ? SF[2 * m] : SF[N - 2 * m];
-                double s1 = (n1 < R0 / 2) ? SF[2 * m + 1] : SF[N - 2 * m - 1];
+                double s0, s1;
+                if constexpr (TABROT) { s0 = rot_sin<n1>(sa, ca); s1 = rot_sin<n1>(sb, cb); }
+                else {
+                    s0 = (n1 < R0 / 2) ? SF[2 * m] : SF[N - 2 * m];
+                    s1 = (n1 < R0 / 2) ? SF[2 * m + 1] : SF[N - 2 * m - 1];
+                }
                 v[it][n1].x = s0 * (a0 + c0) + h2 * (a0 - c0);
                 v[it][n1].y = s1 * (a1 + c1) + h2 * (a1 - c1);
-            }
+            };
+            static_for<R0>(leg);
         }
         sy.sync();     // every mirrored read is done before anyone overwrites the inputs
 #pragma unroll
@@ -811,10 +870,21 @@ __device__ __forceinline__ void dst_tile_fused_x(double* col, int sj, int g, dou
             for (int d = 0; d < RL / 2; d++) untangle_inplace<N>(vb[d], vb[RL - 1 - d], LB / 2 + LB * d, SN);
         } else {
             // block lo: k = lo + LB*d; its partner M-k sits in block hi at d' = RL-1-d
+            if constexpr (TABROT) {
+                // 2 pi k/N = b + d pi/8 for k = lo + LB d, and (8 - d) pi/8 - b for k = hi + LB (RL-1-d), b = 2 pi lo/N
+                const double sb_ = SN[2 * lo], cb_ = SN[M - 2 * lo];
+                auto unit = [&](auto dc) {
+                    constexpr int d = decltype(dc)::value;
+                    if constexpr (d < RL / 2) untangle_cs(va[d], vb[RL - 1 - d], rot_cos<d>(sb_, cb_), rot_sin<d>(sb_, cb_));
+                    else untangle_cs(vb[RL - 1 - d], va[d], rot_cos<8 - d>(-sb_, cb_), rot_sin<8 - d>(-sb_, cb_));
+                };
+                static_for<RL>(unit);
+            } else {
 #pragma unroll
-            for (int d = 0; d < RL; d++) {
-                if (d < RL / 2) untangle_inplace<N>(va[d], vb[RL - 1 - d], lo + LB * d, SN);           // k < M/2
-                else untangle_inplace<N>(vb[RL - 1 - d], va[d], hi + LB * (RL - 1 - d), SN);
+                for (int d = 0; d < RL; d++) {
+                    if (d < RL / 2) untangle_inplace<N>(va[d], vb[RL - 1 - d], lo + LB * d, SN);           // k < M/2
+                    else untangle_inplace<N>(vb[RL - 1 - d], va[d], hi + LB * (RL - 1 - d), SN);
+                }
             }
         }
     }

@@ -13,6 +13,14 @@
 // Groups synchronise with named barriers (bar.sync id, 256); the three `full` mbarriers are shared.  The transform
 // itself is dst_tile_fused_x (xform.cuh), unchanged arithmetic: parity is that of the pipe kernels.
 //
+// Hand-off protocol.  A parity wait on an mbarrier is only meaningful while the waiter is at most ONE phase ahead of
+// the barrier.  The consumer of use j of a buffer can, however, arrive before the OTHER group has finished use j-1 and
+// re-armed the buffer -- and if use j-1 has not even landed yet (a slow load, e.g. a concurrent kernel hogging DRAM),
+// full[s] is still two phases back and the parity test passes on the stale phase.  Therefore every arming also
+// arrives on a second barrier armed[s]: the consumer of use j first waits for armed[s] (the previous arming of this
+// buffer, use j-1, was done by the consumer's own group, so it is never more than one phase ahead there) and only then
+// for full[s], which by then is in phase j or j+1.
+//
 //   k_cols_ring : strided-axis DST sweep, optionally forward -> spectral multiply -> inverse (the z sweep).
 //                 Tiles land in the planar layout through two tensor maps exactly as in k_cols_pipe.
 //   k_rows_ring : contiguous-axis DST sweep.  The 8 rows of a tile land DENSE (one bulk copy for the caller's
@@ -72,6 +80,7 @@ k_cols_ring(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUte
     double* SF1 = reinterpret_cast<double*>(WMs + N / 2);
     double* SF2 = SF1 + (N / 2 + 2);
     uint64_t* full = reinterpret_cast<uint64_t*>(SF2 + (N / 2 + 2));
+    uint64_t* armed = full + NBUF;
 
     const int tid = threadIdx.x;
     const int grp = tid / GT, t = tid % GT;
@@ -110,12 +119,13 @@ k_cols_ring(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUte
                 break;
             }
         }
+        mbar_arrive(&armed[s]);
     };
 
     if (tid == 0) {
         tma_prefetch_desc(&tm);
         tma_prefetch_desc(&tm2);
-        for (int s = 0; s < NBUF; s++) mbar_init(&full[s], 1);
+        for (int s = 0; s < NBUF; s++) { mbar_init(&full[s], 1); mbar_init(&armed[s], 1); }
         mbar_init_fence();
     }
     load_tables<N>(SNs, WMs, a.SN, a.WM);
@@ -141,6 +151,7 @@ k_cols_ring(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUte
                                    ? (long long)(o >> a.blog) * a.out_so_hi + (long long)(o & ((1 << a.blog) - 1)) * a.out_so
                                    : (long long)o * a.out_so;
         double* tile = bufs + s * BUF;
+        mbar_wait(&armed[s], parity);
         mbar_wait(&full[s], parity);
 
         const auto og = omap.emitter(a.out, a.out_sj, ooff, J0, o, b0 + b, bok);
@@ -179,6 +190,7 @@ __global__ void __launch_bounds__(RingCfg<N>::THREADS, 1) k_rows_ring(RowsPipeAr
     cd* WMs = reinterpret_cast<cd*>(SNs + (N / 2 + 2));
     double* SF1 = reinterpret_cast<double*>(WMs + N / 2);
     uint64_t* full = reinterpret_cast<uint64_t*>(SF1 + (N / 2 + 2));
+    uint64_t* armed = full + NBUF;
 
     const int tid = threadIdx.x;
     const int grp = tid / GT, t = tid % GT;
@@ -234,10 +246,11 @@ __global__ void __launch_bounds__(RingCfg<N>::THREADS, 1) k_rows_ring(RowsPipeAr
             mbar_expect_tx(&full[s], bytes);
             if (bytes) bulk_load_1d(buf, src, bytes, &full[s]);
         }
+        mbar_arrive(&armed[s]);
     };
 
     if (tid == 0) {
-        for (int s = 0; s < NBUF; s++) mbar_init(&full[s], 1);
+        for (int s = 0; s < NBUF; s++) { mbar_init(&full[s], 1); mbar_init(&armed[s], 1); }
         mbar_init_fence();
     }
     load_tables<N>(SNs, WMs, a.SN, a.WM);
@@ -258,6 +271,7 @@ __global__ void __launch_bounds__(RingCfg<N>::THREADS, 1) k_rows_ring(RowsPipeAr
         long long in_row0, row0; int rows;
         locate(tl, in_row0, row0, rows);
         double* buf = bufs + s * BUF;
+        mbar_wait(&armed[s], parity);
         mbar_wait(&full[s], parity);
         if (!per_row) {   // an odd tail (rows * pitch odd) leaves one double outside the 16-byte granularity of the bulk copy
             const long long cnt = (long long)rows * a.in_pitch;

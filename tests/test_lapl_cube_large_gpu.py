@@ -121,6 +121,34 @@ def test_cube_eigenvector_kat_device(fb, n):
     S.close()
 
 
+def test_cube1023_with_concurrent_memory_traffic(fb):
+    """Solves on the handle's stream while another stream saturates DRAM (tile loads arrive late and out of order): the
+    answer must stay bit-identical.  Regression test for the tile-ring hand-off (a consumer group two barrier phases
+    ahead of a buffer whose previous tile had not landed yet passed its parity wait on the stale phase)."""
+    import torch
+    n = 1023
+    d, l = G.geometry(n)
+    dev = torch.device("cuda", 0)
+    rhs = torch.rand(n ** 3, dtype=torch.float64, device=dev) - 0.5
+    quiet = torch.empty_like(rhs)
+    S = fb.LaplCube(d, d, d, l, l, l, n, n, n)
+    torch.cuda.synchronize()
+    S.solve_device(quiet.data_ptr(), rhs.data_ptr())
+    fb.capi.check(fb.lib().fdmb_device_synchronize(), "sync")
+    noise_a = torch.empty(1 << 29, dtype=torch.float64, device=dev)      # 4 GB each way
+    noise_b = torch.zeros(1 << 29, dtype=torch.float64, device=dev)
+    side = torch.cuda.Stream(device=dev)
+    for rep in range(3):
+        busy = torch.full_like(rhs, float("nan"))
+        with torch.cuda.stream(side):
+            for _ in range(6):
+                noise_a.copy_(noise_b)
+        S.solve_device(busy.data_ptr(), rhs.data_ptr())                 # no synchronisation in between
+        fb.capi.check(fb.lib().fdmb_device_synchronize(), "sync")
+        assert torch.equal(busy, quiet), f"repetition {rep}"
+    S.close()
+
+
 def test_cube1023_vs_reference_sample(fb):
     """The benchmarked configuration against the unmodified reference's own 1023^3 answer (sample, row, norm, sum),
     through the host-pointer entry point the reference's callers use."""
