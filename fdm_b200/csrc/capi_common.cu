@@ -125,6 +125,18 @@ bool pipe_enabled()
     return v != 0;
 }
 
+bool profiling_on() { return g_prof_on.load(std::memory_order_relaxed); }
+
+bool graphs_enabled()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("FDMB_GRAPH");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v != 0;
+}
+
 bool ring_enabled()
 {
     static int v = -1;

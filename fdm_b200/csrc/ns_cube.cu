@@ -234,6 +234,151 @@ __global__ void __launch_bounds__(256) k_fgh(Fld u, Fld v, Fld w, Fld F, Fld G, 
     if (k >= 1 && j >= 1) fgh_generic<false, false, true>(u, v, w, F, G, H, g, i, k, j);
 }
 
+// ---- FGH + divergence in one sweep (ns_cube.cpp:126-200 and 204-235) -------------------------------------------
+// z-marching, shared-memory staged.  A block owns a (TK-1) x (TJ-1) core of (k, j) points and marches over a chunk of
+// z planes; its TK x TJ threads cover the core plus one row below and one column to the left, where only the G / F
+// values the core's divergence needs are produced.  Per plane:
+//   * the (TK+2) x (TJ+2) halo tiles of u, v, w of planes i-1, i, i+1 sit in a ring of FOUR shared-memory planes per
+//     field: every value is fetched from global memory once per block, and plane i+2 streams into the fourth slot with
+//     asynchronous copies (cp.async, zero-filled outside the field) while plane i is computed;
+//   * every thread evaluates F, G, H at its point from the staged taps and publishes F, G in shared memory;
+//   * the core threads form RHS = ((F - F[j-1])/dx + (G - G[k-1])/dy + (H - H[i-1])/dz)/dt - ghost pressures, with H[i-1]
+//     carried in a register from the previous plane (the chunk's first plane i = ia - 1 only produces it).
+// Traffic: u, v, w read once, F, G, H, RHS written once = 56 B per point, against 80 B for k_fgh + k_rhs.
+// The same kernel serves a z-slab of the sharded step: it starts one plane below the slab like k_fgh did.
+template <int TJ, int TK>
+__global__ void __launch_bounds__(TJ * TK, 2)
+k_fgh_rhs(Fld u, Fld v, Fld w, Fld p, Fld F, Fld G, Fld H, Fld R, NSGeom g, int ia0, int ib0, int zchunk)
+{
+    constexpr int NT = TJ * TK;
+    constexpr int PW = TJ + 2 + 1;                 // tile pitch (odd: rows start in different banks)
+    constexpr int PLANE = (TK + 2) * PW;
+    extern __shared__ double fgh_smem[];
+    double (*su)[PLANE] = reinterpret_cast<double (*)[PLANE]>(fgh_smem);
+    double (*sv)[PLANE] = su + 4;
+    double (*sw)[PLANE] = sv + 4;
+    double (*sF)[TJ + 1] = reinterpret_cast<double (*)[TJ + 1]>(fgh_smem + 12 * PLANE);
+    double (*sG)[TJ + 1] = sF + TK;
+    const int tj = threadIdx.x, tk = threadIdx.y, tid = tk * TJ + tj;
+    const int j0 = 1 + blockIdx.x * (TJ - 1), k0 = 1 + blockIdx.y * (TK - 1);
+    const int ia = ia0 + blockIdx.z * zchunk;
+    const int ib = (ia + zchunk - 1 < ib0) ? ia + zchunk - 1 : ib0;
+    const int j = j0 - 1 + tj, k = k0 - 1 + tk;
+    const int nx = g.nx, ny = g.ny, nz = g.nz;
+    // global extents of the three fields (ns_cube.h:66-68); z: the planes this rank holds start at f.lz
+    // one element of a halo tile: asynchronous 8-byte copy, zero-filled outside the field (z: the planes this rank
+    // holds start at f.lz)
+    auto stage = [&](double* dst, const Fld& f, int i, int kk, int jj) {
+        const bool in = i >= f.lz && i <= nz + 1 && kk >= f.ly && kk <= ny + 1 && jj >= f.lx && jj <= nx + 1;
+        const double* src = in ? &f.at(i, kk, jj) : f.p;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src),
+                     "r"(in ? 8 : 0)
+                     : "memory");
+    };
+    auto load_plane = [&](int i) {
+        const int s = (i + 4) & 3;
+        for (int e = tid; e < (TK + 2) * (TJ + 2); e += NT) {
+            const int r = e / (TJ + 2), c = e - r * (TJ + 2);
+            const int kk = k0 - 2 + r, jj = j0 - 2 + c, off = r * PW + c;
+            stage(&su[s][off], u, i, kk, jj);
+            stage(&sv[s][off], v, i, kk, jj);
+            stage(&sw[s][off], w, i, kk, jj);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    load_plane(ia - 2); load_plane(ia - 1); load_plane(ia);
+    const bool core = tk >= 1 && tj >= 1 && k <= ny && j <= nx;
+    const bool doF = k >= 1 && k <= ny && j <= nx;            // j >= 0 always
+    const bool doG = j >= 1 && j <= nx && k <= ny;            // k >= 0 always
+    double hprev = 0.0;
+    for (int i = ia - 1; i <= ib; i++) {
+        // planes up to i + 1 have landed for everybody; plane i + 2 (needed from the next iteration on) streams into the
+        // slot plane i - 2 left, which nobody reads any more (the barrier at the end of the previous iteration)
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        if (i + 1 <= ib) load_plane(i + 2);
+        double fv = 0.0, gv = 0.0, hv = 0.0;
+        const bool fg = i >= ia;
+        {
+            // the 27 distinct taps of the three stencils, read once (every thread's 3 x 3 x 3 neighbourhood lies inside
+            // the staged tiles), named by (di,dk,dj) with m = -1, p = +1 like k_fgh
+            const int c0 = (tk + 1) * PW + (tj + 1);
+            const double* __restrict__ uc_ = su[(i + 4) & 3] + c0;
+            const double* __restrict__ uip = su[(i + 5) & 3] + c0;
+            const double* __restrict__ uim = su[(i + 3) & 3] + c0;
+            const double* __restrict__ vc_ = sv[(i + 4) & 3] + c0;
+            const double* __restrict__ vip = sv[(i + 5) & 3] + c0;
+            const double* __restrict__ vim = sv[(i + 3) & 3] + c0;
+            const double* __restrict__ wc_ = sw[(i + 4) & 3] + c0;
+            const double* __restrict__ wip = sw[(i + 5) & 3] + c0;
+            const double* __restrict__ wim = sw[(i + 3) & 3] + c0;
+            const double u000 = uc_[0], u00p = uc_[1], u00m = uc_[-1], u0p0 = uc_[PW], u0pm = uc_[PW - 1], u0m0 = uc_[-PW];
+            const double up00 = uip[0], up0m = uip[-1], um00 = uim[0];
+            const double v000 = vc_[0], v00p = vc_[1], v00m = vc_[-1], v0p0 = vc_[PW], v0m0 = vc_[-PW], v0mp = vc_[-PW + 1];
+            const double vp00 = vip[0], vpm0 = vip[-PW], vm00 = vim[0];
+            const double w000 = wc_[0], w00p = wc_[1], w00m = wc_[-1], w0p0 = wc_[PW], w0m0 = wc_[-PW];
+            const double wp00 = wip[0], wm00 = wim[0], wm0p = wim[1], wmp0 = wim[PW];
+            if (fg && doF)
+                fv = u000 + g.dt * (
+                    (u00p - 2 * u000 + u00m) * g.cRx +
+                    (u0p0 - 2 * u000 + u0m0) * g.cRy +
+                    (up00 - 2 * u000 + um00) * g.cRz -
+                    (sq(0.5 * (u000 + u00p)) - sq(0.5 * (u00m + u000))) * g.idx -
+                    0.25 * ((u000 + u0p0) * (v00p + v000) -
+                            (u0m0 + u000) * (v0mp + v0m0)) * g.idy -
+                    0.25 * ((u000 + up00) * (w00p + w000) -
+                            (um00 + u000) * (wm0p + wm00)) * g.idz);
+            if (fg && doG)
+                gv = v000 + g.dt * (
+                    (v00p - 2 * v000 + v00m) * g.cRx +
+                    (v0p0 - 2 * v000 + v0m0) * g.cRy +
+                    (vp00 - 2 * v000 + vm00) * g.cRz -
+                    (sq(0.5 * (v000 + v0p0)) - sq(0.5 * (v0m0 + v000))) * g.idy -
+                    0.25 * ((u000 + u0p0) * (v00p + v000) -
+                            (u00m + u0pm) * (v000 + v00m)) * g.idx -
+                    0.25 * ((w000 + w0p0) * (v000 + vp00) -
+                            (wm00 + wmp0) * (vm00 + v000)) * g.idz);
+            if (core)
+                hv = w000 + g.dt * (
+                    (w00p - 2 * w000 + w00m) * g.cRx +
+                    (w0p0 - 2 * w000 + w0m0) * g.cRy +
+                    (wp00 - 2 * w000 + wm00) * g.cRz -
+                    (sq(0.5 * (wp00 + w000)) - sq(0.5 * (wm00 + w000))) * g.idz -
+                    0.25 * ((up00 + u000) * (w00p + w000) -
+                            (up0m + u00m) * (w000 + w00m)) * g.idx -
+                    0.25 * ((w000 + w0p0) * (v000 + vp00) -
+                            (w0m0 + w000) * (v0m0 + vpm0)) * g.idy);
+        }
+        sF[tk][tj] = fv; sG[tk][tj] = gv;
+        __syncthreads();
+        if (fg) {
+            if (doF && (tj >= 1 || j == 0)) F.p[lin(F, i, k, j)] = fv;
+            if (doG && (tk >= 1 || k == 0)) G.p[lin(G, i, k, j)] = gv;
+        }
+        if (core) {
+            if (fg || i == 0) H.p[lin(H, i, k, j)] = hv;         // (plane ia - 1 belongs to the chunk below, except H[0])
+            if (fg) {
+                double r = ((fv - sF[tk][tj - 1]) * g.idx + (gv - sG[tk - 1][tj]) * g.idy + (hv - hprev) * g.idz) * g.idt;
+                if (i <= 1 || k <= 1 || j <= 1 || j >= nx || k >= ny || i >= nz) {
+                    if (i <= 1) r -= p.at(i - 1, k, j) * g.idz2;
+                    if (k <= 1) r -= p.at(i, k - 1, j) * g.idy2;
+                    if (j <= 1) r -= p.at(i, k, j - 1) * g.idx2;
+                    if (j >= nx) r -= p.at(i, k, j + 1) * g.idx2;
+                    if (k >= ny) r -= p.at(i, k + 1, j) * g.idy2;
+                    if (i >= nz) r -= p.at(i + 1, k, j) * g.idz2;
+                }
+                R.p[lin(R, i, k, j)] = r;
+            }
+            hprev = hv;
+        }
+    }
+}
+
+template <int TJ, int TK> constexpr size_t fgh_rhs_smem()
+{
+    return sizeof(double) * (size_t)(12 * (TK + 2) * (TJ + 3) + 2 * TK * (TJ + 1));
+}
+
 // ---- poisson RHS (ns_cube.cpp:205-235) ---------------------------------------------------
 __global__ void __launch_bounds__(256) k_rhs(Fld F, Fld G, Fld H, Fld p, Fld R, NSGeom g, int ilo)
 {
@@ -293,6 +438,17 @@ __global__ void __launch_bounds__(256) k_pull(PullList pl)
 }  // namespace fdmb
 
 using namespace fdmb;
+
+// FDMB_FGH_FUSED=1 selects the fused, shared-memory staged FGH + divergence sweep (k_fgh_rhs) for handles created
+// afterwards.  Measured at 255^3 (r02j/k): 625 us against 279 + 109 us for k_fgh + k_rhs -- both variants are bound by
+// instruction issue, not by DRAM (k_fgh: 34 % of peak DRAM throughput), so the 80 -> 56 B/pt of traffic the fusion
+// saves buys nothing while the per-element staging and the two barriers per plane cost issue slots.  Off by default;
+// parity-tested (tests/test_ns_cube_gpu.py::test_fused_fgh_rhs_matches).
+static bool fused_fgh_rhs_requested()
+{
+    const char* e = getenv("FDMB_FGH_FUSED");
+    return e && e[0] == '1';
+}
 
 // global z range of field `fld` (u v w p x F G H RHS), ns_cube.h:66-75
 static inline void field_zrange(int fld, int nz, int* lo, int* hi)
@@ -363,8 +519,12 @@ struct fdmb_ns_cube {
     bool peer_ipc[FDMB_MAX_RANKS] = {};
     bool attached = false;
 
+    StepGraph graph;            // one time step as a replayed CUDA graph (single-GPU handles)
+    bool fused = false;         // FGH + divergence in one sweep (k_fgh_rhs)
+
     int init();
     int step(int nsteps, cudaStream_t st);
+    int step_once(cudaStream_t st);
     int pull(const int* flds, const int* lo, const int* hi, const int* from, int n, cudaStream_t st);
     double* owned_ptr(int fld) const { return f[fld].p + (long long)(lay.olo[fld] - lay.wlo[fld]) * lay.sz[fld]; }
     long long owned_count(int fld) const { return (long long)(lay.ohi[fld] - lay.olo[fld] + 1) * lay.sz[fld]; }
@@ -374,6 +534,7 @@ struct fdmb_ns_cube {
 int fdmb_ns_cube::init()
 {
     nx = prm.nx; ny = prm.nx /* ns_cube.h:58: ny is read from key "nx" */; nz = prm.nz;
+    fused = fused_fgh_rhs_requested();
     if (nx < 3 || nz < 3) { set_error("NSCube: nx, nz must be >= 3"); return FDMB_ERR_INVALID; }
     if (nranks > 1 && (nz + 1) / nranks < 4) {
         set_error("NSCube: the sharded step needs at least 4 z planes per rank (nz=%d, %d ranks)", nz, nranks);
@@ -403,6 +564,8 @@ int fdmb_ns_cube::init()
         FDMB_CUDA(cudaFuncGetAttributes(&fa, k_pull));
         FDMB_CUDA(cudaFuncGetAttributes(&fa, k_fgh));
         FDMB_CUDA(cudaFuncGetAttributes(&fa, k_rhs));
+        FDMB_CUDA(cudaFuncSetAttribute(k_fgh_rhs<64, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fgh_rhs_smem<64, 8>()));
+        FDMB_CUDA(cudaFuncGetAttributes(&fa, k_fgh_rhs<64, 8>));
         FDMB_CUDA(cudaFuncGetAttributes(&fa, k_update));
         FDMB_CUDA(cudaFuncGetAttributes(&fa, k_bound_lid));
         FDMB_CUDA(cudaFuncGetAttributes(&fa, k_bound_mirror));
@@ -468,13 +631,24 @@ int fdmb_ns_cube::pull(const int* flds, const int* lo, const int* hi, const int*
 
 int fdmb_ns_cube::step(int nsteps, cudaStream_t st)
 {
+    if (nranks > 1 && !attached) { set_error("NSCube: sharded handle used before attach_ipc/attach_local"); return FDMB_ERR_COMM; }
+    for (int s = 0; s < nsteps; s++) {
+        // sharded steps carry the barrier epoch as a kernel argument: they are launched kernel by kernel
+        const int rc = nranks > 1 ? step_once(st) : graph.run(st, this, nullptr, [&]() { return step_once(st); });
+        if (rc) return rc;
+        time_index++;
+    }
+    return FDMB_OK;
+}
+
+int fdmb_ns_cube::step_once(cudaStream_t st)
+{
     const Fld &u = f[0], &v = f[1], &w = f[2], &p = f[3], &x = f[4], &F = f[5], &G = f[6], &H = f[7], &R = f[8];
     const int nmax = nx > ny ? (nx > nz ? nx : nz) : (ny > nz ? ny : nz);
     const bool bot = rank == 0, top = rank == nranks - 1;
     const int nzl = ihi - ilo + 1;
-    if (nranks > 1 && !attached) { set_error("NSCube: sharded handle used before attach_ipc/attach_local"); return FDMB_ERR_COMM; }
     int rc;
-    for (int s = 0; s < nsteps; s++) {
+    {
         if (nranks > 1) {
             // every rank has finished the previous update (or set_field): fetch the halo planes of u, v, w
             if ((rc = lapl->barrier(st))) return rc;
@@ -508,18 +682,33 @@ int fdmb_ns_cube::step(int nsteps, cudaStream_t st)
             dim3 grid((nmax + 127) / 128, rows, 3);
             k_bound_p<<<grid, 128, 0, st>>>(u, v, w, p, g, ilo, ihi, bot ? 1 : 0, top ? 1 : 0);
         }
-        {
-            LaunchScope sc("ns_fgh", st);
-            dim3 block(64, 4);
-            const int i0 = lay.wlo[7];                 // first plane of H
-            dim3 grid((nx + 1 + 63) / 64, (ny + 1 + 3) / 4, ihi - i0 + 1);
-            k_fgh<<<grid, block, 0, st>>>(u, v, w, F, G, H, g, i0, ilo);
-        }
-        {
-            LaunchScope sc("ns_rhs", st);
-            dim3 block(64, 4);
-            dim3 grid((nx + 63) / 64, (ny + 3) / 4, nzl);
-            k_rhs<<<grid, block, 0, st>>>(F, G, H, p, R, g, ilo);
+        if (fused) {
+            LaunchScope sc("ns_fgh_rhs", st);
+            constexpr int TJ = 64, TK = 8;
+            // z chunks: enough blocks for two waves of two resident blocks per SM, not more (each chunk recomputes one
+            // plane of H and reloads two planes)
+            const int tiles = ((nx + TJ - 2) / (TJ - 1)) * ((ny + TK - 2) / (TK - 1));
+            int nch = (4 * device_sm_count() + tiles - 1) / tiles;
+            if (nch < 1) nch = 1;
+            if (nch > nzl) nch = nzl;
+            const int zchunk = (nzl + nch - 1) / nch;
+            dim3 block(TJ, TK);
+            dim3 grid((nx + TJ - 2) / (TJ - 1), (ny + TK - 2) / (TK - 1), (nzl + zchunk - 1) / zchunk);
+            k_fgh_rhs<TJ, TK><<<grid, block, fgh_rhs_smem<TJ, TK>(), st>>>(u, v, w, p, F, G, H, R, g, ilo, ihi, zchunk);
+        } else {
+            {
+                LaunchScope sc("ns_fgh", st);
+                dim3 block(64, 4);
+                const int i0 = lay.wlo[7];                 // first plane of H
+                dim3 grid((nx + 1 + 63) / 64, (ny + 1 + 3) / 4, ihi - i0 + 1);
+                k_fgh<<<grid, block, 0, st>>>(u, v, w, F, G, H, g, i0, ilo);
+            }
+            {
+                LaunchScope sc("ns_rhs", st);
+                dim3 block(64, 4);
+                dim3 grid((nx + 63) / 64, (ny + 3) / 4, nzl);
+                k_rhs<<<grid, block, 0, st>>>(F, G, H, p, R, g, ilo);
+            }
         }
         FDMB_CHECK_LAUNCH();
         rc = lapl->solve_device(x.p, R.p, st);
@@ -539,7 +728,6 @@ int fdmb_ns_cube::step(int nsteps, cudaStream_t st)
             k_update<<<grid, block, 0, st>>>(u, v, w, p, x, F, G, H, g, ilo);
         }
         FDMB_CHECK_LAUNCH();
-        time_index++;
     }
     return FDMB_OK;
 }

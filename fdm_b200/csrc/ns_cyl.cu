@@ -377,8 +377,11 @@ struct fdmb_ns_cyl {
     bool peer_ipc[FDMB_MAX_RANKS] = {};
     bool attached = false;
 
+    StepGraph graph[2];         // one step() / L_step() as a replayed CUDA graph (single-GPU handles)
+
     int init();
     int step(int nsteps, int linear, cudaStream_t st);
+    int step_once(int linear, cudaStream_t st);
     int pull(const int* flds, const int* planes, const int* from, int n, cudaStream_t st);
     double* owned_ptr(int fld) const { return f[fld].p + (long long)(plo - lay.wlo[fld]) * lay.sp[fld]; }
     long long owned_count(int fld) const { return (long long)(phi - plo + 1) * lay.sp[fld]; }
@@ -518,15 +521,27 @@ int fdmb_ns_cyl::pull(const int* flds, const int* planes, const int* from, int n
 
 int fdmb_ns_cyl::step(int nsteps, int linear, cudaStream_t st)
 {
+    if (nranks > 1 && !attached) { set_error("NSCyl: sharded handle used before attach_ipc/attach_local"); return FDMB_ERR_COMM; }
+    for (int s = 0; s < nsteps; s++) {
+        // sharded steps carry the barrier epoch as a kernel argument: they are launched kernel by kernel
+        const int rc = nranks > 1 ? step_once(linear, st)
+                                  : graph[linear ? 1 : 0].run(st, this, nullptr, [&]() { return step_once(linear, st); });
+        if (rc) return rc;
+        time_index++;
+    }
+    return FDMB_OK;
+}
+
+int fdmb_ns_cyl::step_once(int linear, cudaStream_t st)
+{
     const CFld &u = f[0], &v = f[1], &w = f[2], &p = f[3], &x = f[4], &F = f[5], &G = f[6], &H = f[7], &R = f[8];
     const CFld &u0 = f[9], &v0 = f[10], &w0 = f[11];
     const int nzrows = g.znn - g.z_ + 1;
     const int nown = phi - plo + 1;
     const int wlo = lay.wlo[0], nwin = lay.whi[0] - lay.wlo[0] + 1;     // planes of u, v, w held here (own + halos)
     const int prev = (rank + nranks - 1) % nranks, next = (rank + 1) % nranks;
-    if (nranks > 1 && !attached) { set_error("NSCyl: sharded handle used before attach_ipc/attach_local"); return FDMB_ERR_COMM; }
     int rc;
-    for (int s = 0; s < nsteps; s++) {
+    {
         if (nranks > 1) {
             // every rank has finished the previous update (or set_field): fetch the wrap-around halo planes
             if ((rc = lapl->barrier(st))) return rc;
@@ -597,7 +612,6 @@ int fdmb_ns_cyl::step(int nsteps, int linear, cudaStream_t st)
             k_cyl_update<<<grid, block, 0, st>>>(u, v, w, p, x, F, G, H, g, plo);
         }
         FDMB_CHECK_LAUNCH();
-        time_index++;
     }
     return FDMB_OK;
 }
@@ -793,6 +807,7 @@ int fdmb_ns_cyl_set_u0(fdmb_ns_cyl* h, double u0)
     if (!h) { set_error("null handle"); return FDMB_ERR_INVALID; }
     h->prm.u0 = u0;
     h->g.U0 = u0;
+    h->graph[0].reset(); h->graph[1].reset();      // the captured launches carry the old wall speed as an argument
     return FDMB_OK;
 }
 

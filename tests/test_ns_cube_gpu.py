@@ -120,3 +120,29 @@ def test_ns255_one_step_properties(fb):
 def test_ns_errors(fb):
     with pytest.raises(fb.FdmB200Error):
         fb.NSCube(nx=32, nz=32)    # the README size: reference aborts in FFTTable (fft.cpp:67)
+
+
+@pytest.mark.parametrize("n,steps", [(15, 5), (31, 20), (63, 6), (127, 3)])
+def test_fused_fgh_rhs_matches(fb, ref, monkeypatch, n, steps):
+    """FDMB_FGH_FUSED=1: the z-marching, shared-memory staged FGH + divergence sweep (k_fgh_rhs; off by default, see
+    ns_cube.cu) against the compiled reference, all nine public fields (F, G, H, RHS included)."""
+    monkeypatch.setenv("FDMB_FGH_FUSED", "1")
+    ns = fb.NSCube(nx=n, nz=n, Re=400.0, dt=0.005)
+    R = ref.NSCube(nx=n, nz=n, Re=400.0, dt=0.005)
+    ns.step(steps); R.step(steps)
+    names = ("u", "v", "w", "p", "x", "F", "G", "H", "RHS")
+    compare(ns, {f: R.field(f) for f in names}, names)
+
+
+@pytest.mark.parametrize("steps", [1, 10])
+def test_ns255_multi_step_vs_compiled_reference(fb, ref, steps):
+    """BASELINE configs[2] (NSCube 255^3, Re = 1000, dt = 0.005) after 1 and 10 steps against the unmodified reference
+    (SURVEY 8d C3); per field and on the concatenated state, guarded against the exactly-zero fields of step 1."""
+    n = 255
+    ns = fb.NSCube(nx=n, nz=n, Re=1000.0, dt=0.005)
+    R = ref.NSCube(nx=n, nz=n, Re=1000.0, dt=0.005)
+    ns.step(steps); R.step(steps)
+    compare(ns, {f: R.field(f) for f in "uvwp"})
+    if steps == 1:      # uniform lid, zero divergence: v, w, p stay exactly zero (SURVEY 8d)
+        for f in "vwp":
+            assert not np.any(R.field(f)) and not np.any(ns.field(f)), f

@@ -154,6 +154,18 @@ def test_ns_cyl_config4_two_steps(fb, ref):
     compare(ns, {f: r.field(f) for f in "uvwp"})
 
 
+def test_ns_cyl_config4_1_10_100_steps(fb, ref):
+    """BASELINE configs[3] (nr=128, nz=127, nphi=128, Re=200, dt=0.01, vrandom=0: SURVEY 8d C4) from the reference's own
+    initial state, compared after 1, 10 and 100 steps with the unmodified reference (per field where the field is not
+    negligible, and on the concatenated state)."""
+    kw = dict(nr=128, nz=127, nphi=128, Re=200.0, dt=0.01)
+    ns = fb.NSCyl(**kw); r = ref.NSCyl(False, **kw)
+    done = 0
+    for steps in (1, 10, 100):
+        ns.step(steps - done); r.step(steps - done); done = steps
+        compare(ns, {f: r.field(f) for f in "uvwp"})
+
+
 def test_ns_cyl_errors(fb):
     with pytest.raises(fb.FdmB200Error):
         fb.NSCyl(nr=32, nz=32, nphi=32)      # Dirichlet z needs nz+1 = 2^k (reference aborts, src/fft.cpp:67)
