@@ -11,6 +11,7 @@
 // diagonally dominant so LAPACK never pivots) is recomputed on the fly.
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -89,7 +90,7 @@ __global__ void __launch_bounds__(128) k_tridiag_rows(TridiagArgs a, int ts)
 // thread-per-system recurrence reads them coalesced, no staging).  The per-solve recurrence is then one dependent
 // FMA per element forward and an FMA + multiply backward instead of a division chain: 43 -> ~12 us at 128 x 127 x 128.
 // The reference keeps its LU factors too (`matrices`, `ipivs`, src/lapl_cyl.h:235-236, 36 B per point; here 8 B).
-__global__ void __launch_bounds__(128) k_tridiag_pivots(TridiagArgs a)
+__global__ void __launch_bounds__(128) k_tridiag_pivots(TridiagArgs a, int rowmajor)
 {
     const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= a.nsys) return;
@@ -98,12 +99,68 @@ __global__ void __launch_bounds__(128) k_tridiag_pivots(TridiagArgs a)
     const double lmz = a.swap ? a.lm_mid[outer + a.mid0] : a.lm_mid[mid + a.mid0];
     double d = a.c0 - lo * a.ir2[1] - lmz;
     double inv = 1.0 / d;
-    a.piv[row] = inv;
+    a.piv[rowmajor ? row * a.nr : row] = inv;
     for (int j = 2; j <= a.nr; j++) {
         const double fact = a.L[j] * inv;
         d = (a.c0 - lo * a.ir2[j] - lmz) - fact * a.U[j - 1];
         inv = 1.0 / d;
-        a.piv[(long long)(j - 1) * a.nsys + row] = inv;
+        a.piv[rowmajor ? row * a.nr + (j - 1) : (long long)(j - 1) * a.nsys + row] = inv;
+    }
+}
+
+// ---- pivot table staged in shared memory ---------------------------------------------------------------------
+// ncu (profiles/r02m_full_nscyl128.md): k_tridiag_rows_piv spends its time waiting -- 16 round trips to L2 for the
+// pivots of each system, issued by a quarter of the CTA while the rest sits on the barrier (54 % of the stall samples).
+// Here a tile of TSS systems AND its pivots (row-major table, same shape as the data) are fetched with coalesced loads
+// by the whole CTA, the recurrence of a system then touches shared memory only (one dependent FMA per element forward,
+// FMA + multiply backward), and the solution leaves with coalesced stores.
+constexpr int TSS = 32;
+
+__global__ void __launch_bounds__(128) k_tridiag_rows_pivs(TridiagArgs a)
+{
+    extern __shared__ double smem[];
+    const int P = a.nr | 1;                    // odd pitch: lane s walks row s without bank conflicts
+    double* tb = smem;                         // rhs / solution
+    double* tp = tb + TSS * P;                 // reciprocal pivots
+    double* cL = tp + TSS * P;                 // coefficient tables, 1-based
+    double* cU = cL + (a.nr + 1);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarp = blockDim.x >> 5;
+    for (int j = tid + 1; j <= a.nr; j += blockDim.x) { cL[j] = a.L[j]; cU[j] = a.U[j]; }
+    const long long row0 = (long long)blockIdx.x * TSS;
+    for (int r = warp; r < TSS; r += nwarp) {
+        const long long row = row0 + r;
+        if (row >= a.nsys) break;
+        const double* src = a.data + row * a.pitch;
+        const double* pv = a.piv + row * a.nr;
+#pragma unroll 4
+        for (int x = lane; x < a.nr; x += 32) { tb[r * P + x] = src[x]; tp[r * P + x] = pv[x]; }
+    }
+    __syncthreads();
+    if (tid < TSS && row0 + tid < a.nsys) {
+        double* b = tb + tid * P - 1;          // 1-based
+        const double* iv = tp + tid * P - 1;   // iv[j] = 1 / d_j
+        double bp = b[1];
+#pragma unroll 4
+        for (int j = 2; j <= a.nr; j++) {
+            const double fact = cL[j] * iv[j - 1];              // dl_j / d_{j-1}: off the dependent chain
+            bp = b[j] - fact * bp;
+            b[j] = bp;
+        }
+        double x = bp * iv[a.nr];
+        b[a.nr] = x;
+#pragma unroll 4
+        for (int j = a.nr - 1; j >= 1; j--) {
+            x = (b[j] - cU[j] * x) * iv[j];
+            b[j] = x;
+        }
+    }
+    __syncthreads();
+    for (int r = warp; r < TSS; r += nwarp) {
+        const long long row = row0 + r;
+        if (row >= a.nsys) break;
+        double* dst = a.data + row * a.pitch;
+#pragma unroll 4
+        for (int x = lane; x < a.nr; x += 32) dst[x] = tb[r * P + x];
     }
 }
 
@@ -116,10 +173,10 @@ __global__ void __launch_bounds__(256) k_tridiag_rows_piv(TridiagArgs a, int ts)
     double* tb = smem;                         // rhs / solution
     double* cL = tb + ts * P;                 // coefficient tables, 1-based
     double* cU = cL + (a.nr + 1);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarp = blockDim.x >> 5;
     for (int j = tid + 1; j <= a.nr; j += blockDim.x) { cL[j] = a.L[j]; cU[j] = a.U[j]; }
     const long long row0 = (long long)blockIdx.x * ts;
-    for (int r = warp; r < ts; r += 8) {
+    for (int r = warp; r < ts; r += nwarp) {
         const long long row = row0 + r;
         if (row >= a.nsys) break;
         const double* src = a.data + row * a.pitch;
@@ -174,7 +231,7 @@ __global__ void __launch_bounds__(256) k_tridiag_rows_piv(TridiagArgs a, int ts)
         }
     }
     __syncthreads();
-    for (int r = warp; r < ts; r += 8) {
+    for (int r = warp; r < ts; r += nwarp) {
         const long long row = row0 + r;
         if (row >= a.nsys) break;
         double* dst = a.data + row * a.pitch;
@@ -185,6 +242,15 @@ __global__ void __launch_bounds__(256) k_tridiag_rows_piv(TridiagArgs a, int ts)
 constexpr size_t TRIDIAG_SMEM_MAX = 220 * 1024;
 static size_t rows_smem(int nr, int ts) { return sizeof(double) * (size_t)(2 * ts * (nr | 1) + 3 * (nr + 1)); }
 static size_t rows_piv_smem(int nr, int ts) { return sizeof(double) * (size_t)(ts * (nr | 1) + 2 * (nr + 1)); }
+static size_t rows_pivs_smem(int nr) { return sizeof(double) * (size_t)(2 * TSS * (nr | 1) + 2 * (nr + 1)); }
+// row-major pivots + the shared-memory staged recurrence while three CTAs still fit on an SM (nr <= ~140)
+static int tridiag_variant()
+{
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("FDMB_TRIDIAG"); v = e ? atoi(e) : 0; }
+    return v;
+}
+bool tridiag_piv_rowmajor(int nr) { return tridiag_variant() >= 2 && rows_pivs_smem(nr) <= 74 * 1024; }
 
 // systems per CTA: the full tile (TS / TSP) when it fits in shared memory, else halved down to 4
 static int tridiag_tile_rows(int nr, bool piv)
@@ -210,6 +276,8 @@ cudaError_t prepare_tridiag_rows(int nr)
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(k_tridiag_rows_piv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRIDIAG_SMEM_MAX);
         if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(k_tridiag_rows_pivs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRIDIAG_SMEM_MAX);
+        if (e != cudaSuccess) return e;
         cudaFuncAttributes fa;
         e = cudaFuncGetAttributes(&fa, k_tridiag_pivots);
         if (e != cudaSuccess) return e;
@@ -221,7 +289,7 @@ cudaError_t prepare_tridiag_rows(int nr)
 cudaError_t launch_tridiag_pivots(const TridiagArgs& a, cudaStream_t st)
 {
     LaunchScope scope("tridiag_pivots", st);
-    k_tridiag_pivots<<<(unsigned)((a.nsys + 127) / 128), 128, 0, st>>>(a);
+    k_tridiag_pivots<<<(unsigned)((a.nsys + 127) / 128), 128, 0, st>>>(a, tridiag_piv_rowmajor(a.nr) ? 1 : 0);
     return cudaGetLastError();
 }
 
@@ -230,9 +298,14 @@ cudaError_t launch_tridiag_rows(const TridiagArgs& a, cudaStream_t st, const cha
     LaunchScope scope(tag, st);
     cudaError_t e = prepare_tridiag_rows(a.nr);
     if (e != cudaSuccess) return e;
+    if (a.piv && tridiag_piv_rowmajor(a.nr)) {
+        k_tridiag_rows_pivs<<<(unsigned)((a.nsys + TSS - 1) / TSS), tridiag_variant() == 3 ? 32 : 128, rows_pivs_smem(a.nr), st>>>(a);
+        return cudaGetLastError();
+    }
     if (a.piv) {
         const int ts = tridiag_tile_rows(a.nr, true);
-        k_tridiag_rows_piv<<<(unsigned)((a.nsys + ts - 1) / ts), 256, rows_piv_smem(a.nr, ts), st>>>(a, ts);
+        const int nt = (tridiag_variant() == 1 && ts >= 32) ? ts : 256;      // 1: every thread of the CTA owns a system
+        k_tridiag_rows_piv<<<(unsigned)((a.nsys + ts - 1) / ts), nt, rows_piv_smem(a.nr, ts), st>>>(a, ts);
         return cudaGetLastError();
     }
     const int ts = tridiag_tile_rows(a.nr, false);

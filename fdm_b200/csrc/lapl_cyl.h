@@ -18,13 +18,16 @@ struct TridiagArgs {
     const double* L;          // L[j], U[j], ir2[j], j = 1..nr
     const double* U;
     const double* ir2;
-    double* piv;              // optional [nr][nsys] reciprocal pivots (j-major: coalesced over systems), filled once by
-                              // launch_tridiag_pivots; takes the divisions out of the per-solve recurrence
+    double* piv;              // optional reciprocal pivots, filled once by launch_tridiag_pivots; takes the divisions out of
+                              // the per-solve recurrence.  Layout (tridiag_piv_rowmajor(nr)): row-major [nsys][nr] like the
+                              // data when a tile of data AND pivots fits in shared memory (the recurrence then runs out of
+                              // shared memory only), else j-major [nr][nsys] (read coalesced over systems on the fly)
 };
 cudaError_t launch_tridiag_rows(const TridiagArgs& a, cudaStream_t st, const char* tag);
 cudaError_t launch_tridiag_pivots(const TridiagArgs& a, cudaStream_t st);
 cudaError_t prepare_tridiag_rows(int nr);
 size_t tridiag_rows_smem(int nr);
+bool tridiag_piv_rowmajor(int nr);
 }  // namespace fdmb
 
 struct fdmb_lapl_cyl {
