@@ -305,6 +305,21 @@ int fdmb_lapl_cube::init()
 
 static int ilog2(int v) { int l = 0; while ((1 << l) < v) l++; return l; }
 
+// FDMB_MG_OVERLAP: z chunks of the x-sweep / transposing-y-sweep overlap of the sharded solve (0 or 1: off)
+static int mg_overlap_chunks(int nranks)
+{
+    const char* e = getenv("FDMB_MG_OVERLAP");
+    return e ? atoi(e) : (nranks <= 2 ? 8 : 4);      // measured (r02p, r02q): 2 GPUs 14.19 -> 13.73 ms, 8 GPUs 4.64 -> 4.37 ms
+}
+// FDMB_MG_SPLIT: SMs the x sweep gets while it runs beside the transposing y sweep.  The y sweep needs SM time in
+// proportion to 1 / nranks of a full sweep but NVLink time that barely shrinks with nranks: the more ranks, the
+// fewer SMs it needs.
+static int mg_overlap_split(int nranks, int sms)
+{
+    if (const char* e = getenv("FDMB_MG_SPLIT")) { int v = atoi(e); if (v > 0 && v < sms) return v; }
+    return nranks <= 2 ? sms / 2 : (nranks == 4 ? (sms * 3) / 8 : sms / 3);
+}
+
 int fdmb_lapl_cube::init_sharded()
 {
     const int J0 = periodic ? 0 : 1;
@@ -397,6 +412,9 @@ fdmb_lapl_cube::~fdmb_lapl_cube()
     }
     if (s_up) cudaStreamDestroy(s_up);
     if (s_dn) cudaStreamDestroy(s_dn);
+    if (s_side) cudaStreamDestroy(s_side);
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    for (auto& e : ev_chunk) if (e) cudaEventDestroy(e);
     if (stream) cudaStreamDestroy(stream);
 }
 
@@ -411,28 +429,57 @@ int fdmb_lapl_cube::solve_device_sharded(double* d_out, const double* d_in, cuda
     const long long plane = (long long)ny * px;
     int rc;
     auto rows = [&](const double* in, double* out, int in_pitch, int out_pitch, double scale, int kind, const char* tag,
-                    int reverse) -> cudaError_t {
+                    int reverse, long long nrows, cudaStream_t s, int max_ctas) -> cudaError_t {
         if (rows_pipe_supported_N(Nx) && (reinterpret_cast<uintptr_t>(in) & 15) == 0) {
             RowsPipeArgs p{};
-            p.in = in; p.out = out; p.nrows = (long long)nzl * ny; p.nvalid = nx; p.in_pitch = in_pitch;
-            p.out_pitch = out_pitch; p.reverse = reverse; p.scale = scale; p.SN = tx.SN; p.WM = tx.WM;
-            return launch_rows_pipe(Nx, kind, p, st, tag);
+            p.in = in; p.out = out; p.nrows = nrows; p.nvalid = nx; p.in_pitch = in_pitch;
+            p.out_pitch = out_pitch; p.reverse = reverse; p.scale = scale; p.SN = tx.SN; p.WM = tx.WM; p.max_ctas = max_ctas;
+            return launch_rows_pipe(Nx, kind, p, s, tag);
         }
         RowsArgs r{};
-        r.in = in; r.out = out; r.nrows = (long long)nzl * ny; r.nvalid = nx; r.in_pitch = in_pitch;
+        r.in = in; r.out = out; r.nrows = nrows; r.nvalid = nx; r.in_pitch = in_pitch;
         r.out_pitch = out_pitch; r.scale = scale; r.SN = tx.SN; r.WM = tx.WM;
-        return launch_rows(Nx, kind, r, st, tag);
+        return launch_rows(Nx, kind, r, s, tag);
     };
-    FDMB_CUDA(rows(d_in, d_work, nx, px, dx * slx, kf, "cube_x_fwd", 0));
-    {   // y forward, transposing into the pencil buffers T_q[z'][y slot & (Sy-1)][x]
+    auto y_fwd_xpose = [&](int o0, int no, int max_ctas) -> cudaError_t {
+        // y forward, transposing into the pencil buffers T_q[z'][y slot & (Sy-1)][x]
         ColsPipeArgs p{};
-        p.out = nullptr; p.nvalid = ny; p.nb = nx; p.no = nzl; p.taxis = 1;
+        p.out = nullptr; p.nvalid = ny; p.nb = nx; p.no = no; p.o0 = o0; p.taxis = 1; p.max_ctas = max_ctas;
         p.reverse = 1; p.scale = dy * sly; p.SN = ty.SN; p.WM = ty.WM;
         OutShard om{};
         for (int q = 0; q < nranks; q++)
             om.base[q] = reinterpret_cast<double*>(reinterpret_cast<char*>(peer_block[q]) + off_T);
         om.logS = ilog2(Sy); om.maskS = Sy - 1; om.sj = px; om.so = (long long)Sy * px; om.o_off = z_first;
-        FDMB_CUDA(launch_cols_pipe_shard(Ny, kf, tm_yw, p, om, st, "cube_y_fwd_xpose"));
+        return launch_cols_pipe_shard(Ny, kf, tm_yw, p, om, st, "cube_y_fwd_xpose");
+    };
+    // The transposing y sweep is bound by its NVLink stores (r01g: ~640 GB/s per direction), not by the SMs: cut the slab
+    // into z chunks and let the x sweep of chunk c+1 run beside the y sweep of chunk c, each on its share of the SMs
+    // (side stream + events; the x sweep gets `split` SMs, the y sweep the rest).  FDMB_MG_OVERLAP = chunks (0: off).
+    int nch = mg_overlap_chunks(nranks);
+    if (preload_only() || nch < 2 || nzl < 2 * nch || nch > 16 || !pipe_supported_N(Nx)) nch = 1;
+    if (nch == 1) {
+        FDMB_CUDA(rows(d_in, d_work, nx, px, dx * slx, kf, "cube_x_fwd", 0, (long long)nzl * ny, st, 0));
+        FDMB_CUDA(y_fwd_xpose(0, nzl, 0));
+    } else {
+        if (!s_side) FDMB_CUDA(cudaStreamCreateWithFlags(&s_side, cudaStreamNonBlocking));
+        if (!ev_fork) FDMB_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+        for (int c = 0; c < nch; c++)
+            if (!ev_chunk[c]) FDMB_CUDA(cudaEventCreateWithFlags(&ev_chunk[c], cudaEventDisableTiming));
+        const int sms = device_sm_count();
+        int split = mg_overlap_split(nranks, sms);
+        FDMB_CUDA(cudaEventRecord(ev_fork, st));
+        FDMB_CUDA(cudaStreamWaitEvent(s_side, ev_fork, 0));
+        for (int c = 0; c < nch; c++) {
+            // even chunk boundaries: the caller's unpitched planes start 16-byte aligned only every other plane
+            const int z0 = (int)((long long)c * nzl / nch) & ~1;
+            const int z1 = c == nch - 1 ? nzl : (int)((long long)(c + 1) * nzl / nch) & ~1;
+            // the first x chunk has the machine to itself
+            FDMB_CUDA(rows(d_in + (long long)z0 * ny * nx, d_work + (long long)z0 * plane, nx, px, dx * slx, kf, "cube_x_fwd", 0,
+                           (long long)(z1 - z0) * ny, s_side, c == 0 ? 0 : split));
+            FDMB_CUDA(cudaEventRecord(ev_chunk[c], s_side));
+            FDMB_CUDA(cudaStreamWaitEvent(st, ev_chunk[c], 0));
+            FDMB_CUDA(y_fwd_xpose(z0, z1 - z0, c == nch - 1 ? 0 : sms - split));
+        }
     }
     if ((rc = barrier(st))) return rc;
     {   // z forward, divide, z inverse; stores go back to the slabs A_r[z slot & (Sz-1)][y'][x]
@@ -452,7 +499,7 @@ int fdmb_lapl_cube::solve_device_sharded(double* d_out, const double* d_in, cuda
         p.reverse = 0; p.scale = sly; p.SN = ty.SN; p.WM = ty.WM;
         FDMB_CUDA(launch_cols_pipe(Ny, ki, tm_y, p, st, "cube_y_inv"));
     }
-    FDMB_CUDA(rows(d_work, d_out, px, nx, slx, ki, "cube_x_inv", 1));
+    FDMB_CUDA(rows(d_work, d_out, px, nx, slx, ki, "cube_x_inv", 1, (long long)nzl * ny, st, 0));
     return FDMB_OK;
 }
 

@@ -84,6 +84,9 @@ struct fdmb_lapl_cube {
     bool attached = false;
     unsigned long long epoch = 0;
     int device = 0;
+    // overlap of the local x sweep with the NVLink-bound transposing y sweep (solve_device_sharded)
+    cudaStream_t s_side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_chunk[16] = {};
 
     int init();
     int init_sharded();

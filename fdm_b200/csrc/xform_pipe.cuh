@@ -141,6 +141,8 @@ struct ColsPipeArgs {
     long long out_so_hi;        // taxis 4: output stride of the outer index's block number (out_so: within a block)
     int reverse;                // walk the tiles back to front (L2 reuse against the previous sweep)
     int mid_o_off;              // added to the outer index handed to the mid functor (sharded sweeps)
+    int o0;                     // first outer index of this launch (a launch may cover a chunk [o0, o0 + no) of the outer axis)
+    int max_ctas;               // > 0: upper bound of the grid (leaves SMs to a kernel running beside this one)
     double scale, scale2;
     const double* SN;
     const cd* WM;
@@ -187,7 +189,7 @@ k_cols_pipe(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUte
 
     auto issue = [&](int t, int s) {
         if (a.reverse) t = ntiles - 1 - t;
-        const int o = t / nbt, b0 = (t % nbt) * B;
+        const int o = t / nbt + a.o0, b0 = (t % nbt) * B;
         mbar_expect_tx(&full[s], tx_bytes);
         double* buf = bufs + s * BUF;
         for (int c = 0; c < a.nchunk; c++) {
@@ -239,7 +241,7 @@ k_cols_pipe(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUte
         const int s = it % NSTAGE;
         const unsigned parity = (it / NSTAGE) & 1;
         const int tt = a.reverse ? ntiles - 1 - t : t;
-        const int o = tt / nbt, b0 = (tt % nbt) * B;
+        const int o = tt / nbt + a.o0, b0 = (tt % nbt) * B;
         const bool bok = b0 + b < a.nb;
         // offset of the outer index in the output: linear, or block number / position in block (taxis 4)
         const long long ooff = (a.taxis == 4)
@@ -303,6 +305,7 @@ struct RowsPipeArgs {
     //   blk = 1 : natural in, blocked out (forward sweep: the caller's array -> work array)
     //   blk = 2 : blocked in, natural out (inverse sweep); a tile is BR consecutive yi of one (yb, z) block
     int blk, blog, ny, nz;
+    int max_ctas;               // > 0: upper bound of the grid (leaves SMs to a kernel running beside this one)
 };
 
 template <int N, int KIND, int NSTAGE>
@@ -474,6 +477,7 @@ inline cudaError_t launch_cols_pipe_t(const CUtensorMap& tm, const CUtensorMap& 
     if (preload_only()) return cudaSuccess;
     const long long ntiles = (long long)((a.nb + C::B - 1) / C::B) * a.no;
     long long grid = (long long)device_sm_count() * per_sm;
+    if (a.max_ctas > 0 && grid > a.max_ctas) grid = a.max_ctas;
     if (grid > ntiles) grid = ntiles;
     if (grid < 1) return cudaSuccess;
     kern<<<(unsigned)grid, C::THREADS_COLS, smem, st>>>(tm, tm2, a, mid, omap);
@@ -499,6 +503,7 @@ inline cudaError_t launch_rows_pipe_t(const RowsPipeArgs& a, cudaStream_t st)
     if (preload_only()) return cudaSuccess;
     const long long ntiles = (a.nrows + C::BR - 1) / C::BR;
     long long grid = (long long)device_sm_count() * per_sm;
+    if (a.max_ctas > 0 && grid > a.max_ctas) grid = a.max_ctas;
     if (grid > ntiles) grid = ntiles;
     if (grid < 1) return cudaSuccess;
     kern<<<(unsigned)grid, C::THREADS, smem, st>>>(a);

@@ -93,7 +93,7 @@ k_cols_ring(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUte
 
     auto issue = [&](int tile, int s) {
         if (a.reverse) tile = ntiles - 1 - tile;
-        const int o = tile / nbt, b0 = (tile % nbt) * B;
+        const int o = tile / nbt + a.o0, b0 = (tile % nbt) * B;
         mbar_expect_tx(&full[s], tx_bytes);
         double* buf = bufs + s * BUF;
         for (int c = 0; c < a.nchunk; c++) {
@@ -145,7 +145,7 @@ k_cols_ring(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUte
         const int s = i % NBUF;
         const unsigned parity = (i / NBUF) & 1;
         const int tt = a.reverse ? ntiles - 1 - (int)tile_l : (int)tile_l;
-        const int o = tt / nbt, b0 = (tt % nbt) * B;
+        const int o = tt / nbt + a.o0, b0 = (tt % nbt) * B;
         const bool bok = b0 + b < a.nb;
         const long long ooff = (a.taxis == 4)
                                    ? (long long)(o >> a.blog) * a.out_so_hi + (long long)(o & ((1 << a.blog) - 1)) * a.out_so
@@ -316,6 +316,7 @@ inline cudaError_t launch_cols_ring_t(const CUtensorMap& tm, const CUtensorMap& 
     if (preload_only()) return cudaSuccess;
     const long long ntiles = (long long)((a.nb + C::B - 1) / C::B) * a.no;
     long long grid = device_sm_count();
+    if (a.max_ctas > 0 && grid > a.max_ctas) grid = a.max_ctas;
     if (grid > (ntiles + 1) / 2) grid = (ntiles + 1) / 2;      // both groups of a CTA get a tile
     if (grid < 1) return cudaSuccess;
     kern<<<(unsigned)grid, C::THREADS, smem, st>>>(tm, tm2, a, mid, omap);
@@ -338,6 +339,7 @@ inline cudaError_t launch_rows_ring_t(const RowsPipeArgs& a, cudaStream_t st)
     if (preload_only()) return cudaSuccess;
     const long long ntiles = (a.nrows + C::B - 1) / C::B;       // (blocked input: an upper bound is enough for the grid)
     long long grid = device_sm_count();
+    if (a.max_ctas > 0 && grid > a.max_ctas) grid = a.max_ctas;
     if (grid > (ntiles + 1) / 2) grid = (ntiles + 1) / 2;
     if (grid < 1) return cudaSuccess;
     kern<<<(unsigned)grid, C::THREADS, smem, st>>>(a);
