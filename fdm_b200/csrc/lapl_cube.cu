@@ -415,6 +415,7 @@ fdmb_lapl_cube::~fdmb_lapl_cube()
     if (s_side) cudaStreamDestroy(s_side);
     if (ev_fork) cudaEventDestroy(ev_fork);
     for (auto& e : ev_chunk) if (e) cudaEventDestroy(e);
+    for (auto& e : ev_done) if (e) cudaEventDestroy(e);
     if (stream) cudaStreamDestroy(stream);
 }
 
@@ -506,15 +507,25 @@ int fdmb_lapl_cube::solve_device_sharded(double* d_out, const double* d_in, cuda
 int fdmb_lapl_cube::solve_device(double* d_out, const double* d_in, cudaStream_t st)
 {
     if (nranks > 1) return solve_device_sharded(d_out, d_in, st);
+    return sweeps(d_out, d_in, st, 7, 0, nz);
+}
+
+// The single-GPU solve in three phases, so that the host-pointer entry point can stream z chunks through it:
+//   phase 1  x and y forward sweeps of the planes [z0, z0 + nzc) of d_in into the work array
+//   phase 2  z forward / divide / inverse over the whole work array
+//   phase 4  y and x inverse sweeps of the planes [z0, z0 + nzc) into d_out
+int fdmb_lapl_cube::sweeps(double* d_out, const double* d_in, cudaStream_t st, int phases, int z0, int nzc)
+{
     const int kf = periodic ? XF_PFWD : XF_DST;
     const int ki = periodic ? XF_PINV : XF_DST;
     const long long plane = (long long)ny * px;
     // x forward: rhs rows -> pitched work
     RowsArgs r{};
-    r.in = d_in; r.out = d_work; r.nrows = (long long)nz * ny; r.nvalid = nx;
-    r.in_pitch = nx; r.out_pitch = px; r.scale = dx * slx; r.SN = tx.SN; r.WM = tx.WM;
+    r.in = d_in ? d_in + (long long)z0 * ny * nx : nullptr; r.out = d_work + (long long)z0 * plane; r.nrows = (long long)nzc * ny;
+    r.nvalid = nx; r.in_pitch = nx; r.out_pitch = px; r.scale = dx * slx; r.SN = tx.SN; r.WM = tx.WM;
     const bool pipe_x = pipe_enabled() && rows_pipe_supported_N(Nx);
     if (blog) {
+        if (phases != 7 || z0 != 0 || nzc != nz) { set_error("LaplCube: the blocked work layout does not stream z chunks"); return FDMB_ERR_INVALID; }
         // blocked work array W[yb][z][yi][x]
         if ((reinterpret_cast<uintptr_t>(d_in) & 15) != 0) {
             set_error("LaplCube: rhs must be 16-byte aligned for grids this large");
@@ -554,25 +565,26 @@ int fdmb_lapl_cube::solve_device(double* d_out, const double* d_in, cudaStream_t
     auto cols_y = [&](const ColsArgs& q, int kind, const char* tag, int reverse) -> cudaError_t {
         if (pipe_y) {
             ColsPipeArgs p{};
-            p.out = q.out; p.out_sj = q.out_sj; p.out_so = q.out_so; p.nvalid = q.nvalid; p.nb = q.nb; p.no = q.no;
-            p.taxis = 1; p.reverse = reverse; p.scale = q.scale;
+            p.out = d_work; p.out_sj = q.out_sj; p.out_so = q.out_so; p.nvalid = q.nvalid; p.nb = q.nb; p.no = q.no;
+            p.o0 = z0; p.taxis = 1; p.reverse = reverse; p.scale = q.scale;
             p.scale2 = q.scale2; p.SN = q.SN; p.WM = q.WM;
             return launch_cols_pipe(Ny, kind, tm_y, p, st, tag);
         }
         return launch_cols(Ny, kind, q, st, tag);
     };
-    FDMB_CUDA(rows(r, kf, "cube_x_fwd", 0));
-    // y forward
+    if (phases & 1) FDMB_CUDA(rows(r, kf, "cube_x_fwd", 0));
+    // y forward (the plain kernel takes the chunk through its pointers, the tensor-map kernel through o0)
     ColsArgs c{};
-    c.in = d_work; c.out = d_work; c.nvalid = ny; c.in_sj = c.out_sj = px; c.nb = nx; c.no = nz;
+    c.out = d_work + (long long)z0 * plane; c.in = c.out; c.nvalid = ny; c.in_sj = c.out_sj = px; c.nb = nx; c.no = nzc;
     c.in_so = c.out_so = plane; c.scale = dy * sly; c.SN = ty.SN; c.WM = ty.WM;
-    FDMB_CUDA(cols_y(c, kf, "cube_y_fwd", 1));
+    if (phases & 1) FDMB_CUDA(cols_y(c, kf, "cube_y_fwd", 1));
     // z forward, divide by -(lm_z+lm_y+lm_x), z inverse
     ColsArgs z{};
     z.in = d_work; z.out = d_work; z.nvalid = nz; z.in_sj = z.out_sj = plane; z.nb = nx; z.no = ny;
     z.in_so = z.out_so = px; z.scale = dz * slz; z.scale2 = slz; z.SN = tz.SN; z.WM = tz.WM;
     MidCubeDivide mid{d_lmz, d_lmx, d_lmy, periodic ? 1 : 0};
-    if (pipe_z) {
+    if (!(phases & 2)) {
+    } else if (pipe_z) {
         ColsPipeArgs p{};
         p.out = z.out; p.out_sj = z.out_sj; p.out_so = z.out_so; p.nvalid = z.nvalid; p.nb = z.nb; p.no = z.no;
         p.taxis = 2; p.reverse = 0; p.scale = z.scale; p.scale2 = z.scale2;
@@ -581,26 +593,73 @@ int fdmb_lapl_cube::solve_device(double* d_out, const double* d_in, cudaStream_t
     } else {
         FDMB_CUDA(launch_cols_cube_divide(Nz, periodic != 0, z, mid, st, "cube_z_fwd_div_inv"));
     }
-    // y inverse
-    c.scale = sly;
-    FDMB_CUDA(cols_y(c, ki, "cube_y_inv", 0));
-    // x inverse: pitched work -> ans rows
-    r.in = d_work; r.out = d_out; r.in_pitch = px; r.out_pitch = nx; r.scale = slx;
-    FDMB_CUDA(rows(r, ki, "cube_x_inv", 1));
+    if (phases & 4) {
+        // y inverse
+        c.scale = sly;
+        FDMB_CUDA(cols_y(c, ki, "cube_y_inv", 0));
+        // x inverse: pitched work -> ans rows
+        r.in = d_work + (long long)z0 * plane; r.out = d_out + (long long)z0 * ny * nx; r.in_pitch = px; r.out_pitch = nx; r.scale = slx;
+        FDMB_CUDA(rows(r, ki, "cube_x_inv", 1));
+    }
     return FDMB_OK;
 }
 
+// Host-pointer solve.  Large single-GPU grids stream through in z chunks: the x / y forward sweeps of chunk c run while
+// chunk c+1 is still crossing PCIe, and the downloads of the finished planes start while the y / x inverse sweeps of the
+// later chunks run; only the z sweep (which needs every plane) and one chunk's worth of sweeps stay exposed.  Chunk
+// boundaries are even (the caller's unpitched planes start 16-byte aligned every other plane).
 int fdmb_lapl_cube::solve_host(double* ans, const double* rhs)
 {
     const size_t bytes = sizeof(double) * (size_t)nx * ny * (nranks > 1 ? nzl : nz);   // this rank's slab
     if (!d_rhs) FDMB_CUDA(cudaMalloc(&d_rhs, bytes));
     if (!d_ans) FDMB_CUDA(cudaMalloc(&d_ans, bytes));
-    FDMB_CUDA(cudaMemcpyAsync(d_rhs, rhs, bytes, cudaMemcpyHostToDevice, stream));
-    int rc = solve_device(d_ans, d_rhs, stream);
-    if (rc) return rc;
-    FDMB_CUDA(cudaMemcpyAsync(ans, d_ans, bytes, cudaMemcpyDeviceToHost, stream));
-    FDMB_CUDA(cudaStreamSynchronize(stream));
-    return FDMB_OK;
+    int nch = 1;
+    if (nranks == 1 && !blog && bytes >= (size_t(64) << 20)) {
+        const char* e = getenv("FDMB_HOST_CHUNKS");
+        nch = e ? atoi(e) : 8;
+        if (nch > 16) nch = 16;
+        if (nch < 1 || nz < 4 * nch) nch = 1;
+    }
+    if (nch == 1) {
+        FDMB_CUDA(cudaMemcpyAsync(d_rhs, rhs, bytes, cudaMemcpyHostToDevice, stream));
+        int rc = solve_device(d_ans, d_rhs, stream);
+        if (rc) { cudaStreamSynchronize(stream); return rc; }
+        FDMB_CUDA(cudaMemcpyAsync(ans, d_ans, bytes, cudaMemcpyDeviceToHost, stream));
+        FDMB_CUDA(cudaStreamSynchronize(stream));
+        return FDMB_OK;
+    }
+    if (!s_up) FDMB_CUDA(cudaStreamCreateWithFlags(&s_up, cudaStreamNonBlocking));
+    if (!s_dn) FDMB_CUDA(cudaStreamCreateWithFlags(&s_dn, cudaStreamNonBlocking));
+    if (!ev_fork) FDMB_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    for (int c = 0; c < nch; c++) {
+        if (!ev_chunk[c]) FDMB_CUDA(cudaEventCreateWithFlags(&ev_chunk[c], cudaEventDisableTiming));
+        if (!ev_done[c]) FDMB_CUDA(cudaEventCreateWithFlags(&ev_done[c], cudaEventDisableTiming));
+    }
+    auto drain = [&]() { cudaStreamSynchronize(s_up); cudaStreamSynchronize(stream); cudaStreamSynchronize(s_dn); };
+    auto bound = [&](int c) { return c >= nch ? nz : (int)((long long)c * nz / nch) & ~1; };
+    const size_t pl = sizeof(double) * (size_t)nx * ny;
+    int rc = FDMB_OK;
+    cudaError_t e = cudaEventRecord(ev_fork, stream);                 // earlier work on the handle's stream owns d_rhs / d_ans
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(s_up, ev_fork, 0);
+    for (int c = 0; c < nch && e == cudaSuccess && !rc; c++) {
+        const int z0 = bound(c), z1 = bound(c + 1);
+        e = cudaMemcpyAsync(d_rhs + (size_t)z0 * nx * ny, rhs + (size_t)z0 * nx * ny, pl * (z1 - z0), cudaMemcpyHostToDevice, s_up);
+        if (e == cudaSuccess) e = cudaEventRecord(ev_chunk[c], s_up);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(stream, ev_chunk[c], 0);
+        if (e == cudaSuccess) rc = sweeps(d_ans, d_rhs, stream, 1, z0, z1 - z0);
+    }
+    if (e == cudaSuccess && !rc) rc = sweeps(d_ans, d_rhs, stream, 2, 0, nz);
+    for (int c = 0; c < nch && e == cudaSuccess && !rc; c++) {
+        const int z0 = bound(c), z1 = bound(c + 1);
+        rc = sweeps(d_ans, d_rhs, stream, 4, z0, z1 - z0);
+        if (!rc) e = cudaEventRecord(ev_done[c], stream);
+        if (e == cudaSuccess && !rc) e = cudaStreamWaitEvent(s_dn, ev_done[c], 0);
+        if (e == cudaSuccess && !rc)
+            e = cudaMemcpyAsync(ans + (size_t)z0 * nx * ny, d_ans + (size_t)z0 * nx * ny, pl * (z1 - z0), cudaMemcpyDeviceToHost, s_dn);
+    }
+    drain();      // every exit waits for the copies: they read and write the caller's arrays
+    if (e != cudaSuccess) { set_error("LaplCube solve (streamed): %s", cudaGetErrorString(e)); return FDMB_ERR_CUDA; }
+    return rc;
 }
 
 // `count` independent solves with host arrays, software-pipelined over two staging pairs: the upload of solve i+1

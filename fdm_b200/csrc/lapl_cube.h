@@ -86,13 +86,14 @@ struct fdmb_lapl_cube {
     int device = 0;
     // overlap of the local x sweep with the NVLink-bound transposing y sweep (solve_device_sharded)
     cudaStream_t s_side = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_chunk[16] = {};
+    cudaEvent_t ev_fork = nullptr, ev_chunk[16] = {}, ev_done[16] = {};
 
     int init();
     int init_sharded();
     int attach(void* const* bases);
     int barrier(cudaStream_t st);
     int solve_device(double* d_out, const double* d_in, cudaStream_t st);
+    int sweeps(double* d_out, const double* d_in, cudaStream_t st, int phases, int z0, int nzc);
     int solve_device_sharded(double* d_out, const double* d_in, cudaStream_t st);
     int solve_host(double* ans, const double* rhs);
     ~fdmb_lapl_cube();

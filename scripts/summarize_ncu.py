@@ -22,6 +22,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 TAGS = [
     (r"k_fgh_rhs", "ns_fgh_rhs"), (r"k_fgh", "ns_fgh"), (r"k_rhs", "ns_rhs"), (r"k_update", "ns_update"),
     (r"k_bound_lid", "ns_bound_lid"), (r"k_bound_mirror", "ns_bound_mirror"), (r"k_bound_p", "ns_bound_p"),
+    (r"k_cyl_fgh<\(bool\)0>|k_cyl_fgh<0>", "nscyl_fgh"), (r"k_cyl_fgh", "nscyl_lfgh"), (r"k_cyl_rhs", "nscyl_rhs"),
+    (r"k_cyl_update", "nscyl_update"), (r"k_cyl_bound_r", "nscyl_bound_r"), (r"k_cyl_bound_z", "nscyl_bound_z"),
+    (r"k_cyl_bound_p", "nscyl_bound_p"), (r"k_tridiag_rows", "cyl_r_tridiag"),
 ]
 
 METRICS = OrderedDict([
@@ -44,6 +47,7 @@ METRICS = OrderedDict([
     ("smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio", "st_mio"),
     ("smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio", "st_math"),
     ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smem_conflicts"),
+    ("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "smem_pipe_pct"),
 ])
 
 
@@ -164,7 +168,7 @@ def main():
     os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     traffic = json.load(open(tpath)) if os.path.exists(tpath) else {}
-    for wl in ("cube127", "cube255", "nscube255", "cube511", "cube1023"):
+    for wl in ("cube127", "cube255", "nscube255", "cube511", "cube1023", "nscyl128", "cyl128"):
         launches(tag, wl)
         full(tag, wl, traffic)
     traffic["_source"] = f"ncu --set full captures of {tag}; bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum)"
