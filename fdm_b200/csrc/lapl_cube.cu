@@ -305,6 +305,20 @@ int fdmb_lapl_cube::init()
 
 static int ilog2(int v) { int l = 0; while ((1 << l) < v) l++; return l; }
 
+const ColsMaps* fdmb_lapl_cube::y_chunk_maps(bool wide, int z0, int nzc)
+{
+    const int nz_here = nranks > 1 ? nzl : nz;
+    if (z0 == 0 && nzc == nz_here) return wide ? &tm_yw : &tm_y;
+    auto& cache = wide ? tm_yw_chunk : tm_y_chunk;
+    auto it = cache.find({z0, nzc});
+    if (it != cache.end()) return &it->second;
+    ColsMaps m{};
+    const unsigned long long plane_b = 8ull * (unsigned long long)ny * px;
+    const int B = wide ? pipe_B_sharded(Ny) : pipe_B(Ny);
+    if (make_cols_maps(&m, d_work + (size_t)z0 * ny * px, Ny, 1, nx, ny, nzc, 8ull * px, plane_b, B)) return nullptr;
+    return &cache.emplace(std::make_pair(z0, nzc), m).first->second;
+}
+
 // FDMB_MG_OVERLAP: z chunks of the x-sweep / transposing-y-sweep overlap of the sharded solve (0 or 1: off)
 static int mg_overlap_chunks(int nranks)
 {
@@ -444,14 +458,16 @@ int fdmb_lapl_cube::solve_device_sharded(double* d_out, const double* d_in, cuda
     };
     auto y_fwd_xpose = [&](int o0, int no, int max_ctas) -> cudaError_t {
         // y forward, transposing into the pencil buffers T_q[z'][y slot & (Sy-1)][x]
+        const ColsMaps* maps = y_chunk_maps(true, o0, no);
+        if (!maps) return cudaErrorInvalidValue;
         ColsPipeArgs p{};
-        p.out = nullptr; p.nvalid = ny; p.nb = nx; p.no = no; p.o0 = o0; p.taxis = 1; p.max_ctas = max_ctas;
+        p.out = nullptr; p.nvalid = ny; p.nb = nx; p.no = no; p.taxis = 1; p.max_ctas = max_ctas;
         p.reverse = 1; p.scale = dy * sly; p.SN = ty.SN; p.WM = ty.WM;
         OutShard om{};
         for (int q = 0; q < nranks; q++)
             om.base[q] = reinterpret_cast<double*>(reinterpret_cast<char*>(peer_block[q]) + off_T);
-        om.logS = ilog2(Sy); om.maskS = Sy - 1; om.sj = px; om.so = (long long)Sy * px; om.o_off = z_first;
-        return launch_cols_pipe_shard(Ny, kf, tm_yw, p, om, st, "cube_y_fwd_xpose");
+        om.logS = ilog2(Sy); om.maskS = Sy - 1; om.sj = px; om.so = (long long)Sy * px; om.o_off = z_first + o0;
+        return launch_cols_pipe_shard(Ny, kf, *maps, p, om, st, "cube_y_fwd_xpose");
     };
     // The transposing y sweep is bound by its NVLink stores (r01g: ~640 GB/s per direction), not by the SMs: cut the slab
     // into z chunks and let the x sweep of chunk c+1 run beside the y sweep of chunk c, each on its share of the SMs
@@ -564,11 +580,13 @@ int fdmb_lapl_cube::sweeps(double* d_out, const double* d_in, cudaStream_t st, i
     };
     auto cols_y = [&](const ColsArgs& q, int kind, const char* tag, int reverse) -> cudaError_t {
         if (pipe_y) {
+            const ColsMaps* maps = y_chunk_maps(false, z0, nzc);     // loads AND stores start at plane z0 (q.out does)
+            if (!maps) return cudaErrorInvalidValue;
             ColsPipeArgs p{};
-            p.out = d_work; p.out_sj = q.out_sj; p.out_so = q.out_so; p.nvalid = q.nvalid; p.nb = q.nb; p.no = q.no;
-            p.o0 = z0; p.taxis = 1; p.reverse = reverse; p.scale = q.scale;
+            p.out = q.out; p.out_sj = q.out_sj; p.out_so = q.out_so; p.nvalid = q.nvalid; p.nb = q.nb; p.no = q.no;
+            p.taxis = 1; p.reverse = reverse; p.scale = q.scale;
             p.scale2 = q.scale2; p.SN = q.SN; p.WM = q.WM;
-            return launch_cols_pipe(Ny, kind, tm_y, p, st, tag);
+            return launch_cols_pipe(Ny, kind, *maps, p, st, tag);
         }
         return launch_cols(Ny, kind, q, st, tag);
     };

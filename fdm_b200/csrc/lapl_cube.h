@@ -1,5 +1,7 @@
 // Internal definition of the LaplCube handle (shared with ns_cube.cu).
 #pragma once
+#include <map>
+#include <utility>
 #include "common.h"
 #include "xform_kernels.cuh"
 #include "xform_pipe.cuh"
@@ -65,6 +67,10 @@ struct fdmb_lapl_cube {
     int solve_batch(int count, double* const* ans, const double* const* rhs);
     bool pipe_y = false, pipe_z = false;         // tensor maps over d_work are valid
     fdmb::ColsMaps tm_y{}, tm_z{}, tm_yw{};      // tm_yw: wide-tile maps of the sharded y forward sweep
+    // y-sweep maps over a chunk [z0, z0 + nzc) of the planes (streamed host solve, x || y overlap of the sharded solve):
+    // the same maps with a shifted base, encoded on first use (a sweep kernel's tiles then start at outer index 0)
+    std::map<std::pair<int, int>, fdmb::ColsMaps> tm_y_chunk, tm_yw_chunk;
+    const fdmb::ColsMaps* y_chunk_maps(bool wide, int z0, int nzc);
     int blog = 0, nyb = 0;                       // blocked work array [yb][z][yi][x], 1 << blog rows per block (0: natural)
 
     // ---- z-slab sharding over `nranks` GPUs (nranks == 1: everything above is the whole problem) ----

@@ -788,23 +788,31 @@ __device__ __forceinline__ void dst_tile_fused_x(double* col, int sj, int g, dou
             // TABROT: slot 2m = 2q + n1 N/8 sits at the angle pi 2q/N + n1 pi/8 (SF[j] = hs sin(pi j/N), cos = SF[N/2 - j])
             double sa = 0, ca = 0, sb = 0, cb = 0;
             if constexpr (TABROT) { sa = SF[2 * q]; ca = SF[N / 2 - 2 * q]; sb = SF[2 * q + 1]; cb = SF[N / 2 - 2 * q - 1]; }
-            auto leg = [&](auto n1c) {
-                constexpr int n1 = decltype(n1c)::value;
-                const int m = q + n1 * S0;
-                // y[j] = hs * (sin(pi j/N)(x[j]+x[N-j]) + (x[j]-x[N-j])/2) for every j in 1..N-1, y[0] = 0;
-                // x[2m] = E[m], x[N-2m] = E[M-m], x[2m+1] = O[m], x[N-2m-1] = O[M-m-1]
-                double a0 = (m == 0) ? 0.0 : in.e(m), c0 = (m == 0) ? 0.0 : in.e(M - m);
-                double a1 = in.o(m), c1 = in.o(M - m - 1);
-                double s0, s1;
-                if constexpr (TABROT) { s0 = rot_sin<n1>(sa, ca); s1 = rot_sin<n1>(sb, cb); }
-                else {
-                    s0 = (n1 < R0 / 2) ? SF[2 * m] : SF[N - 2 * m];
-                    s1 = (n1 < R0 / 2) ? SF[2 * m + 1] : SF[N - 2 * m - 1];
+            if constexpr (TABROT) {
+                auto leg = [&](auto n1c) {
+                    constexpr int n1 = decltype(n1c)::value;
+                    const int m = q + n1 * S0;
+                    double a0 = (m == 0) ? 0.0 : in.e(m), c0 = (m == 0) ? 0.0 : in.e(M - m);
+                    double a1 = in.o(m), c1 = in.o(M - m - 1);
+                    const double s0 = rot_sin<n1>(sa, ca), s1 = rot_sin<n1>(sb, cb);
+                    v[it][n1].x = s0 * (a0 + c0) + h2 * (a0 - c0);
+                    v[it][n1].y = s1 * (a1 + c1) + h2 * (a1 - c1);
+                };
+                static_for<R0>(leg);
+            } else {
+#pragma unroll
+                for (int n1 = 0; n1 < R0; n1++) {
+                    const int m = q + n1 * S0;
+                    // y[j] = hs * (sin(pi j/N)(x[j]+x[N-j]) + (x[j]-x[N-j])/2) for every j in 1..N-1, y[0] = 0;
+                    // x[2m] = E[m], x[N-2m] = E[M-m], x[2m+1] = O[m], x[N-2m-1] = O[M-m-1]
+                    double a0 = (m == 0) ? 0.0 : in.e(m), c0 = (m == 0) ? 0.0 : in.e(M - m);
+                    double a1 = in.o(m), c1 = in.o(M - m - 1);
+                    double s0 = (n1 < R0 / 2) ? SF[2 * m] : SF[N - 2 * m];
+                    double s1 = (n1 < R0 / 2) ? SF[2 * m + 1] : SF[N - 2 * m - 1];
+                    v[it][n1].x = s0 * (a0 + c0) + h2 * (a0 - c0);
+                    v[it][n1].y = s1 * (a1 + c1) + h2 * (a1 - c1);
                 }
-                v[it][n1].x = s0 * (a0 + c0) + h2 * (a0 - c0);
-                v[it][n1].y = s1 * (a1 + c1) + h2 * (a1 - c1);
-            };
-            static_for<R0>(leg);
+            }
         }
         sy.sync();     // every mirrored read is done before anyone overwrites the inputs
 #pragma unroll

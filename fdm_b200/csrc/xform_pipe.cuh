@@ -141,7 +141,6 @@ struct ColsPipeArgs {
     long long out_so_hi;        // taxis 4: output stride of the outer index's block number (out_so: within a block)
     int reverse;                // walk the tiles back to front (L2 reuse against the previous sweep)
     int mid_o_off;              // added to the outer index handed to the mid functor (sharded sweeps)
-    int o0;                     // first outer index of this launch (a launch may cover a chunk [o0, o0 + no) of the outer axis)
     int max_ctas;               // > 0: upper bound of the grid (leaves SMs to a kernel running beside this one)
     double scale, scale2;
     const double* SN;
@@ -189,7 +188,7 @@ k_cols_pipe(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUte
 
     auto issue = [&](int t, int s) {
         if (a.reverse) t = ntiles - 1 - t;
-        const int o = t / nbt + a.o0, b0 = (t % nbt) * B;
+        const int o = t / nbt, b0 = (t % nbt) * B;
         mbar_expect_tx(&full[s], tx_bytes);
         double* buf = bufs + s * BUF;
         for (int c = 0; c < a.nchunk; c++) {
@@ -241,7 +240,7 @@ k_cols_pipe(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUte
         const int s = it % NSTAGE;
         const unsigned parity = (it / NSTAGE) & 1;
         const int tt = a.reverse ? ntiles - 1 - t : t;
-        const int o = tt / nbt + a.o0, b0 = (tt % nbt) * B;
+        const int o = tt / nbt, b0 = (tt % nbt) * B;
         const bool bok = b0 + b < a.nb;
         // offset of the outer index in the output: linear, or block number / position in block (taxis 4)
         const long long ooff = (a.taxis == 4)

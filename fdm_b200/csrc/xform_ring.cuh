@@ -93,7 +93,7 @@ k_cols_ring(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUte
 
     auto issue = [&](int tile, int s) {
         if (a.reverse) tile = ntiles - 1 - tile;
-        const int o = tile / nbt + a.o0, b0 = (tile % nbt) * B;
+        const int o = tile / nbt, b0 = (tile % nbt) * B;
         mbar_expect_tx(&full[s], tx_bytes);
         double* buf = bufs + s * BUF;
         for (int c = 0; c < a.nchunk; c++) {
@@ -145,7 +145,7 @@ k_cols_ring(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUte
         const int s = i % NBUF;
         const unsigned parity = (i / NBUF) & 1;
         const int tt = a.reverse ? ntiles - 1 - (int)tile_l : (int)tile_l;
-        const int o = tt / nbt + a.o0, b0 = (tt % nbt) * B;
+        const int o = tt / nbt, b0 = (tt % nbt) * B;
         const bool bok = b0 + b < a.nb;
         const long long ooff = (a.taxis == 4)
                                    ? (long long)(o >> a.blog) * a.out_so_hi + (long long)(o & ((1 << a.blog) - 1)) * a.out_so
