@@ -6,8 +6,8 @@ C ABI in ``include/fdm_b200.h``; all arithmetic runs in hand-written sm_100a ker
 object construction does, and fails loudly if it is missing.
 """
 from .capi import FdmB200Error, lib  # noqa: F401
-from .lapl_cube import LaplCube, LaplCubeSharded, slab_range  # noqa: F401
-from .ns_cube import NSCube, owned_planes  # noqa: F401
+from .lapl_cube import LaplCube, LaplCubeF32, LaplCubeSharded, slab_range  # noqa: F401
+from .ns_cube import NSCube, NSCubeF32, owned_planes  # noqa: F401
 from .lapl_cyl import LaplCyl3FFT2  # noqa: F401
 from .lapl_rect import LaplRect, LaplRectFFT2  # noqa: F401
 from .ns_cyl import NSCyl  # noqa: F401

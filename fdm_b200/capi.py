@@ -52,6 +52,11 @@ def lib():
     L.fdmb_lapl_cube_export_ipc.argtypes = [C.c_void_p, C.c_void_p]
     L.fdmb_lapl_cube_attach_ipc.argtypes = [C.c_void_p, C.c_void_p]
     L.fdmb_lapl_cube_attach_local.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    fp = C.POINTER(C.c_float)
+    L.fdmb_lapl_cube_f32_create.argtypes = [C.POINTER(C.c_void_p)] + [C.c_double] * 6 + [C.c_int] * 4
+    L.fdmb_lapl_cube_f32_solve.argtypes = [C.c_void_p, fp, fp]
+    L.fdmb_lapl_cube_f32_solve_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.fdmb_lapl_cube_f32_destroy.argtypes = [C.c_void_p]
     _lib = L
     return L
 

@@ -95,6 +95,38 @@ int get_tables(int N, Tables* out)
     return FDMB_OK;
 }
 
+// single-precision tables of the fp32 instantiations: the same values rounded once from long double
+struct TablesF { const float* SN; const cx<float>* WM; };
+static std::map<std::pair<int, int>, TablesF> g_tables_f32;
+
+int get_tables_f32(int N, TablesF* out)
+{
+    int dev = 0;
+    FDMB_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_tab_mutex);
+    auto it = g_tables_f32.find({dev, N});
+    if (it != g_tables_f32.end()) { *out = it->second; return FDMB_OK; }
+    const int M = N / 2;
+    std::vector<float> sn(N / 2 + 1);
+    std::vector<cx<float>> wm(M);
+    const long double pi = 3.141592653589793238462643383279502884L;
+    for (int j = 0; j <= N / 2; j++) sn[j] = (float)sinl(pi * j / N);
+    sn[N / 2] = 1.0f;
+    for (int t = 0; t < M; t++) { wm[t].x = (float)cosl(2 * pi * t / M); wm[t].y = (float)(-sinl(2 * pi * t / M)); }
+    if (M >= 4) { wm[M / 4] = {0.0f, -1.0f}; wm[3 * M / 4] = {0.0f, 1.0f}; }
+    if (M >= 2) wm[M / 2] = {-1.0f, 0.0f};
+    float* d_sn = nullptr;
+    cx<float>* d_wm = nullptr;
+    FDMB_CUDA(cudaMalloc(&d_sn, sizeof(float) * sn.size()));
+    FDMB_CUDA(cudaMalloc(&d_wm, sizeof(cx<float>) * wm.size()));
+    FDMB_CUDA(cudaMemcpy(d_sn, sn.data(), sizeof(float) * sn.size(), cudaMemcpyHostToDevice));
+    FDMB_CUDA(cudaMemcpy(d_wm, wm.data(), sizeof(cx<float>) * wm.size(), cudaMemcpyHostToDevice));
+    TablesF t{d_sn, d_wm};
+    g_tables_f32[{dev, N}] = t;
+    *out = t;
+    return FDMB_OK;
+}
+
 int device_sm_count()
 {
     static int cached[64] = {0};

@@ -23,16 +23,20 @@
 
 namespace fdmb {
 
-// offset-indexed 3-D view, row-major, last index fastest (src/tensor.h:207-219)
-struct Fld {
-    double* p;
+// offset-indexed 3-D view, row-major, last index fastest (src/tensor.h:207-219).  T is the STORAGE type: double on the
+// graded path, float for NSCube<float> (src/ns_cube.cpp:281-282).  The arithmetic of the stencil kernels is double in
+// both cases -- exactly like the reference, whose float instantiation mixes its float fields with double dt, Re, dx in
+// every expression (src/ns_cube.h:19-31) and so rounds to float only when it stores.
+template <typename T> struct FldT {
+    T* p;
     int lz, ly, lx;       // lowest index per axis
     long long sz, sy;     // strides (doubles)
-    __host__ __device__ __forceinline__ double& at(int i, int k, int j) const
+    __host__ __device__ __forceinline__ T& at(int i, int k, int j) const
     {
         return p[(long long)(i - lz) * sz + (long long)(k - ly) * sy + (j - lx)];
     }
 };
+using Fld = FldT<double>;
 
 struct NSGeom {
     int nx, ny, nz;
@@ -47,7 +51,7 @@ struct NSGeom {
 
 // ---- init_bound ---------------------------------------------------------------------
 // lid (ns_cube.cpp:67-72): u[nz+1][k][j] = 2 U0 - u[nz][k][j], k=0..ny+1, j=-1..jmax
-__global__ void k_bound_lid(Fld u, NSGeom g, int jmax)
+template <typename T> __global__ void k_bound_lid(FldT<T> u, NSGeom g, int jmax)
 {
     int j = blockIdx.x * blockDim.x + threadIdx.x - 1;
     int k = blockIdx.y;
@@ -58,7 +62,7 @@ __global__ void k_bound_lid(Fld u, NSGeom g, int jmax)
 // mirror ghosts (ns_cube.cpp:76-95).  blockIdx.z selects the field.  zlo..zhi: the z planes of u and v held by
 // this rank (0..nz+1 on one GPU; own planes + halos when sharded); wbot / wtop: this rank holds the bottom / top
 // z ghost plane of w.
-__global__ void k_bound_mirror(Fld u, Fld v, Fld w, NSGeom g, int zlo, int zhi, int wbot, int wtop)
+template <typename T> __global__ void k_bound_mirror(FldT<T> u, FldT<T> v, FldT<T> w, NSGeom g, int zlo, int zhi, int wbot, int wtop)
 {
     int a = blockIdx.x * blockDim.x + threadIdx.x;   // fast index of the face
     int b = blockIdx.y;                              // slow index of the face
@@ -83,7 +87,7 @@ __global__ void k_bound_mirror(Fld u, Fld v, Fld w, NSGeom g, int zlo, int zhi, 
 }
 
 // pressure ghosts (ns_cube.cpp:98-121).  ilo..ihi: this rank's interior planes (1..nz on one GPU).
-__global__ void k_bound_p(Fld u, Fld v, Fld w, Fld p, NSGeom g, int ilo, int ihi, int wbot, int wtop)
+template <typename T> __global__ void k_bound_p(FldT<T> u, FldT<T> v, FldT<T> w, FldT<T> p, NSGeom g, int ilo, int ihi, int wbot, int wtop)
 {
     int a = blockIdx.x * blockDim.x + threadIdx.x + 1;
     int b = blockIdx.y + 1;
@@ -115,7 +119,7 @@ __global__ void k_bound_p(Fld u, Fld v, Fld w, Fld p, NSGeom g, int ilo, int ihi
 __device__ __forceinline__ double sq(double x) { return x * x; }
 
 // linear element offset of (i,k,j); every field of the graded sizes has < 2^31 elements per axis product
-__device__ __forceinline__ long long lin(const Fld& f, int i, int k, int j)
+template <typename T> __device__ __forceinline__ long long lin(const FldT<T>& f, int i, int k, int j)
 {
     return (long long)(i - f.lz) * f.sz + (long long)(k - f.ly) * f.sy + (j - f.lx);
 }
@@ -126,9 +130,9 @@ __device__ __forceinline__ long long lin(const Fld& f, int i, int k, int j)
 // Interior threads (i,k,j >= 1) read the 27 distinct taps of the three stencils once through
 // row pointers (immediate offsets, no per-tap address arithmetic) and produce F, G and H together;
 // the O(n^2) edge threads take the generic path.
-template <bool F_, bool G_, bool H_>
-__device__ __forceinline__ void fgh_generic(const Fld& u, const Fld& v, const Fld& w, const Fld& F, const Fld& G,
-                                            const Fld& H, const NSGeom& g, int i, int k, int j)
+template <bool F_, bool G_, bool H_, typename T>
+__device__ __forceinline__ void fgh_generic(const FldT<T>& u, const FldT<T>& v, const FldT<T>& w, const FldT<T>& F, const FldT<T>& G,
+                                            const FldT<T>& H, const NSGeom& g, int i, int k, int j)
 {
 #define U(a, b, c) u.at(a, b, c)
 #define V(a, b, c) v.at(a, b, c)
@@ -174,24 +178,24 @@ __device__ __forceinline__ void fgh_generic(const Fld& u, const Fld& v, const Fl
 #undef W
 }
 
-__global__ void __launch_bounds__(256) k_fgh(Fld u, Fld v, Fld w, Fld F, Fld G, Fld H, NSGeom g, int i0, int iFG)
+template <typename T> __global__ void __launch_bounds__(256) k_fgh(FldT<T> u, FldT<T> v, FldT<T> w, FldT<T> F, FldT<T> G, FldT<T> H, NSGeom g, int i0, int iFG)
 {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int k = blockIdx.y * blockDim.y + threadIdx.y;
     const int i = blockIdx.z + i0;
     if (j > g.nx || k > g.ny) return;
     if (i >= iFG && k >= 1 && j >= 1) {
-        const double* __restrict__ uc_ = u.p + lin(u, i, k, j);
-        const double* __restrict__ vc_ = v.p + lin(v, i, k, j);
-        const double* __restrict__ wc_ = w.p + lin(w, i, k, j);
-        const double* __restrict__ ukp = uc_ + u.sy; const double* __restrict__ ukm = uc_ - u.sy;
-        const double* __restrict__ uip = uc_ + u.sz; const double* __restrict__ uim = uc_ - u.sz;
-        const double* __restrict__ vkp = vc_ + v.sy; const double* __restrict__ vkm = vc_ - v.sy;
-        const double* __restrict__ vip = vc_ + v.sz; const double* __restrict__ vim = vc_ - v.sz;
-        const double* __restrict__ vipkm = vip - v.sy;
-        const double* __restrict__ wkp = wc_ + w.sy; const double* __restrict__ wkm = wc_ - w.sy;
-        const double* __restrict__ wip = wc_ + w.sz; const double* __restrict__ wim = wc_ - w.sz;
-        const double* __restrict__ wimkp = wim + w.sy;
+        const T* __restrict__ uc_ = u.p + lin(u, i, k, j);
+        const T* __restrict__ vc_ = v.p + lin(v, i, k, j);
+        const T* __restrict__ wc_ = w.p + lin(w, i, k, j);
+        const T* __restrict__ ukp = uc_ + u.sy; const T* __restrict__ ukm = uc_ - u.sy;
+        const T* __restrict__ uip = uc_ + u.sz; const T* __restrict__ uim = uc_ - u.sz;
+        const T* __restrict__ vkp = vc_ + v.sy; const T* __restrict__ vkm = vc_ - v.sy;
+        const T* __restrict__ vip = vc_ + v.sz; const T* __restrict__ vim = vc_ - v.sz;
+        const T* __restrict__ vipkm = vip - v.sy;
+        const T* __restrict__ wkp = wc_ + w.sy; const T* __restrict__ wkm = wc_ - w.sy;
+        const T* __restrict__ wip = wc_ + w.sz; const T* __restrict__ wim = wc_ - w.sz;
+        const T* __restrict__ wimkp = wim + w.sy;
         // the 27 taps, named by (di,dk,dj) with m = -1, p = +1
         const double u000 = uc_[0], u00p = uc_[1], u00m = uc_[-1], u0p0 = ukp[0], u0pm = ukp[-1], u0m0 = ukm[0];
         const double up00 = uip[0], up0m = uip[-1], um00 = uim[0];
@@ -380,15 +384,15 @@ template <int TJ, int TK> constexpr size_t fgh_rhs_smem()
 }
 
 // ---- poisson RHS (ns_cube.cpp:205-235) ---------------------------------------------------
-__global__ void __launch_bounds__(256) k_rhs(Fld F, Fld G, Fld H, Fld p, Fld R, NSGeom g, int ilo)
+template <typename T> __global__ void __launch_bounds__(256) k_rhs(FldT<T> F, FldT<T> G, FldT<T> H, FldT<T> p, FldT<T> R, NSGeom g, int ilo)
 {
     const int j = blockIdx.x * blockDim.x + threadIdx.x + 1;
     const int k = blockIdx.y * blockDim.y + threadIdx.y + 1;
     const int i = blockIdx.z + ilo;
     if (j > g.nx || k > g.ny) return;
-    const double* __restrict__ Fp = F.p + lin(F, i, k, j);
-    const double* __restrict__ Gp = G.p + lin(G, i, k, j);
-    const double* __restrict__ Hp = H.p + lin(H, i, k, j);
+    const T* __restrict__ Fp = F.p + lin(F, i, k, j);
+    const T* __restrict__ Gp = G.p + lin(G, i, k, j);
+    const T* __restrict__ Hp = H.p + lin(H, i, k, j);
     double r = ((Fp[0] - Fp[-1]) * g.idx + (Gp[0] - Gp[-G.sy]) * g.idy + (Hp[0] - Hp[-H.sz]) * g.idz) * g.idt;
     if (i <= 1 || k <= 1 || j <= 1 || j >= g.nx || k >= g.ny || i >= g.nz) {
         if (i <= 1) r -= p.at(i - 1, k, j) * g.idz2;
@@ -402,13 +406,13 @@ __global__ void __launch_bounds__(256) k_rhs(Fld F, Fld G, Fld H, Fld p, Fld R, 
 }
 
 // ---- update_uvwp (ns_cube.cpp:241-277) ---------------------------------------------------
-__global__ void __launch_bounds__(256) k_update(Fld u, Fld v, Fld w, Fld p, Fld x, Fld F, Fld G, Fld H, NSGeom g, int ilo)
+template <typename T> __global__ void __launch_bounds__(256) k_update(FldT<T> u, FldT<T> v, FldT<T> w, FldT<T> p, FldT<T> x, FldT<T> F, FldT<T> G, FldT<T> H, NSGeom g, int ilo)
 {
     const int j = blockIdx.x * blockDim.x + threadIdx.x + 1;
     const int k = blockIdx.y * blockDim.y + threadIdx.y + 1;
     const int i = blockIdx.z + ilo;
     if (j > g.nx || k > g.ny) return;
-    const double* __restrict__ xp = x.p + lin(x, i, k, j);
+    const T* __restrict__ xp = x.p + lin(x, i, k, j);
     const double xc = xp[0];
     if (j < g.nx) u.p[lin(u, i, k, j)] = F.p[lin(F, i, k, j)] - g.dtdx * (xp[1] - xc);
     if (k < g.ny) v.p[lin(v, i, k, j)] = G.p[lin(G, i, k, j)] - g.dtdy * (xp[x.sy] - xc);
@@ -562,14 +566,14 @@ int fdmb_ns_cube::init()
         // so a first-use load behind it deadlocks when several ranks are driven by one host thread.
         cudaFuncAttributes fa;
         FDMB_CUDA(cudaFuncGetAttributes(&fa, k_pull));
-        FDMB_CUDA(cudaFuncGetAttributes(&fa, k_fgh));
-        FDMB_CUDA(cudaFuncGetAttributes(&fa, k_rhs));
+        FDMB_CUDA(cudaFuncGetAttributes(&fa, k_fgh<double>));
+        FDMB_CUDA(cudaFuncGetAttributes(&fa, k_rhs<double>));
         FDMB_CUDA(cudaFuncSetAttribute(k_fgh_rhs<64, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fgh_rhs_smem<64, 8>()));
         FDMB_CUDA(cudaFuncGetAttributes(&fa, k_fgh_rhs<64, 8>));
-        FDMB_CUDA(cudaFuncGetAttributes(&fa, k_update));
-        FDMB_CUDA(cudaFuncGetAttributes(&fa, k_bound_lid));
-        FDMB_CUDA(cudaFuncGetAttributes(&fa, k_bound_mirror));
-        FDMB_CUDA(cudaFuncGetAttributes(&fa, k_bound_p));
+        FDMB_CUDA(cudaFuncGetAttributes(&fa, k_update<double>));
+        FDMB_CUDA(cudaFuncGetAttributes(&fa, k_bound_lid<double>));
+        FDMB_CUDA(cudaFuncGetAttributes(&fa, k_bound_mirror<double>));
+        FDMB_CUDA(cudaFuncGetAttributes(&fa, k_bound_p<double>));
     }
     ns_layout(nx, ny, nz, rank, nranks, &lay);
     FDMB_CUDA(cudaMalloc(&block, lay.bytes));
@@ -667,20 +671,20 @@ int fdmb_ns_cube::step_once(cudaStream_t st)
             int jmax = (nz + 1 < nx + 1) ? nz + 1 : nx + 1;
             LaunchScope sc("ns_bound_lid", st);
             dim3 grid((jmax + 2 + 127) / 128, ny + 2);
-            k_bound_lid<<<grid, 128, 0, st>>>(u, g, jmax);
+            k_bound_lid<double><<<grid, 128, 0, st>>>(u, g, jmax);
         }
         {
             LaunchScope sc("ns_bound_mirror", st);
             const int zlo = lay.wlo[0], zhi = lay.whi[0];
             const int rows = (zhi - zlo + 1) > ny + 2 ? (zhi - zlo + 1) : ny + 2;
             dim3 grid((nmax + 2 + 127) / 128, rows, 3);
-            k_bound_mirror<<<grid, 128, 0, st>>>(u, v, w, g, zlo, zhi, bot ? 1 : 0, top ? 1 : 0);
+            k_bound_mirror<double><<<grid, 128, 0, st>>>(u, v, w, g, zlo, zhi, bot ? 1 : 0, top ? 1 : 0);
         }
         {
             LaunchScope sc("ns_bound_p", st);
             const int rows = nzl > ny ? nzl : ny;
             dim3 grid((nmax + 127) / 128, rows, 3);
-            k_bound_p<<<grid, 128, 0, st>>>(u, v, w, p, g, ilo, ihi, bot ? 1 : 0, top ? 1 : 0);
+            k_bound_p<double><<<grid, 128, 0, st>>>(u, v, w, p, g, ilo, ihi, bot ? 1 : 0, top ? 1 : 0);
         }
         if (fused) {
             LaunchScope sc("ns_fgh_rhs", st);
@@ -701,13 +705,13 @@ int fdmb_ns_cube::step_once(cudaStream_t st)
                 dim3 block(64, 4);
                 const int i0 = lay.wlo[7];                 // first plane of H
                 dim3 grid((nx + 1 + 63) / 64, (ny + 1 + 3) / 4, ihi - i0 + 1);
-                k_fgh<<<grid, block, 0, st>>>(u, v, w, F, G, H, g, i0, ilo);
+                k_fgh<double><<<grid, block, 0, st>>>(u, v, w, F, G, H, g, i0, ilo);
             }
             {
                 LaunchScope sc("ns_rhs", st);
                 dim3 block(64, 4);
                 dim3 grid((nx + 63) / 64, (ny + 3) / 4, nzl);
-                k_rhs<<<grid, block, 0, st>>>(F, G, H, p, R, g, ilo);
+                k_rhs<double><<<grid, block, 0, st>>>(F, G, H, p, R, g, ilo);
             }
         }
         FDMB_CHECK_LAUNCH();
@@ -725,7 +729,7 @@ int fdmb_ns_cube::step_once(cudaStream_t st)
             LaunchScope sc("ns_update", st);
             dim3 block(64, 4);
             dim3 grid((nx + 63) / 64, (ny + 3) / 4, nzl);
-            k_update<<<grid, block, 0, st>>>(u, v, w, p, x, F, G, H, g, ilo);
+            k_update<double><<<grid, block, 0, st>>>(u, v, w, p, x, F, G, H, g, ilo);
         }
         FDMB_CHECK_LAUNCH();
     }
@@ -920,6 +924,173 @@ int fdmb_ns_cube_field_device_ptr(fdmb_ns_cube* h, int field, void** dptr)
 long long fdmb_ns_cube_time_index(fdmb_ns_cube* h) { return h ? h->time_index : -1; }
 
 int fdmb_ns_cube_destroy(fdmb_ns_cube* h)
+{
+    delete h;
+    return FDMB_OK;
+}
+
+}  // extern "C"
+
+// =====================================================================================================================
+// NSCube<float> (reference instantiations src/ns_cube.cpp:281-282).  Float STORAGE for all nine fields and a float
+// pressure solve (fdmb_lapl_cube_f32: the reference's member is LaplCube<T,check>, src/ns_cube.h:34), so a step moves
+// half the bytes; the stencil arithmetic is double like the reference's own mixed expressions (see FldT).  Single GPU.
+// =====================================================================================================================
+typedef struct fdmb_lapl_cube_f32 fdmb_lapl_cube_f32;
+extern "C" {
+int fdmb_lapl_cube_f32_create(fdmb_lapl_cube_f32** h, double dx, double dy, double dz, double lx, double ly, double lz,
+                              int nx, int ny, int nz, int periodic);
+int fdmb_lapl_cube_f32_solve_device(fdmb_lapl_cube_f32* h, float* d_ans, const float* d_rhs, void* stream);
+int fdmb_lapl_cube_f32_destroy(fdmb_lapl_cube_f32* h);
+}
+
+struct fdmb_ns_cube_f32 {
+    fdmb_ns_cube_params prm{};
+    int nx = 0, ny = 0, nz = 0;
+    NSGeom g{};
+    FldT<float> f[9]{};
+    long long count[9] = {};
+    fdmb_lapl_cube_f32* lapl = nullptr;
+    cudaStream_t stream = nullptr;
+    long long time_index = 0;
+    void* block = nullptr;
+    StepGraph graph;
+
+    int init();
+    int step_once(cudaStream_t st);
+    ~fdmb_ns_cube_f32()
+    {
+        cudaFree(block);
+        if (lapl) fdmb_lapl_cube_f32_destroy(lapl);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+int fdmb_ns_cube_f32::init()
+{
+    nx = prm.nx; ny = prm.nx /* ns_cube.h:58 */; nz = prm.nz;
+    if (nx < 3 || nz < 3) { set_error("NSCube<float>: nx, nz must be >= 3"); return FDMB_ERR_INVALID; }
+    const double dx = (prm.x2 - prm.x1) / nx, dy = (prm.y2 - prm.y1) / ny, dz = (prm.z2 - prm.z1) / nz;
+    const double dx2 = dx * dx, dy2 = dy * dy, dz2 = dz * dz;
+    int rc = fdmb_lapl_cube_f32_create(&lapl, dx, dy, dz, prm.x2 - prm.x1 + dx, prm.y2 - prm.y1 + dy, prm.z2 - prm.z1 + dz,
+                                       nx, ny, nz, 0);
+    if (rc) return rc;
+    FDMB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    NSLayout lay;
+    ns_layout(nx, ny, nz, 0, 1, &lay);
+    size_t off[9], o = 0;
+    for (int k = 0; k < 9; k++) { off[k] = o; count[k] = lay.count[k]; o += (sizeof(float) * (size_t)lay.count[k] + 255) & ~(size_t)255; }
+    FDMB_CUDA(cudaMalloc(&block, o));
+    FDMB_CUDA(cudaMemset(block, 0, o));
+    FDMB_CUDA(cudaDeviceSynchronize());
+    static const int Y0[9] = {0, -1, 0, 0, 1, 1, 0, 1, 1}, X0[9] = {-1, 0, 0, 0, 1, 0, 1, 1, 1};
+    for (int k = 0; k < 9; k++) {
+        f[k].p = reinterpret_cast<float*>(static_cast<char*>(block) + off[k]);
+        f[k].lz = lay.wlo[k]; f[k].ly = Y0[k]; f[k].lx = X0[k];
+        f[k].sy = lay.sy[k]; f[k].sz = lay.sz[k];
+    }
+    g.nx = nx; g.ny = ny; g.nz = nz; g.U0 = prm.u0; g.dt = prm.dt;
+    const double Re = prm.Re;
+    g.cRx = 1.0 / Re / dx2; g.cRy = 1.0 / Re / dy2; g.cRz = 1.0 / Re / dz2;
+    g.idx = 1.0 / dx; g.idy = 1.0 / dy; g.idz = 1.0 / dz;
+    g.iRdx = 1.0 / Re / dx; g.iRdy = 1.0 / Re / dy; g.iRdz = 1.0 / Re / dz;
+    g.idx2 = 1.0 / dx2; g.idy2 = 1.0 / dy2; g.idz2 = 1.0 / dz2;
+    g.idt = 1.0 / prm.dt;
+    g.dtdx = prm.dt / dx; g.dtdy = prm.dt / dy; g.dtdz = prm.dt / dz;
+    return FDMB_OK;
+}
+
+int fdmb_ns_cube_f32::step_once(cudaStream_t st)
+{
+    const FldT<float> &u = f[0], &v = f[1], &w = f[2], &p = f[3], &x = f[4], &F = f[5], &G = f[6], &H = f[7], &R = f[8];
+    const int nmax = nx > ny ? (nx > nz ? nx : nz) : (ny > nz ? ny : nz);
+    {
+        int jmax = (nz + 1 < nx + 1) ? nz + 1 : nx + 1;
+        LaunchScope sc("ns32_bound_lid", st);
+        k_bound_lid<float><<<dim3((jmax + 2 + 127) / 128, ny + 2), 128, 0, st>>>(u, g, jmax);
+    }
+    {
+        LaunchScope sc("ns32_bound_mirror", st);
+        const int rows = (nz + 2) > ny + 2 ? (nz + 2) : ny + 2;
+        k_bound_mirror<float><<<dim3((nmax + 2 + 127) / 128, rows, 3), 128, 0, st>>>(u, v, w, g, 0, nz + 1, 1, 1);
+    }
+    {
+        LaunchScope sc("ns32_bound_p", st);
+        const int rows = nz > ny ? nz : ny;
+        k_bound_p<float><<<dim3((nmax + 127) / 128, rows, 3), 128, 0, st>>>(u, v, w, p, g, 1, nz, 1, 1);
+    }
+    {
+        LaunchScope sc("ns32_fgh", st);
+        k_fgh<float><<<dim3((nx + 1 + 63) / 64, (ny + 1 + 3) / 4, nz + 1), dim3(64, 4), 0, st>>>(u, v, w, F, G, H, g, 0, 1);
+    }
+    {
+        LaunchScope sc("ns32_rhs", st);
+        k_rhs<float><<<dim3((nx + 63) / 64, (ny + 3) / 4, nz), dim3(64, 4), 0, st>>>(F, G, H, p, R, g, 1);
+    }
+    FDMB_CHECK_LAUNCH();
+    int rc = fdmb_lapl_cube_f32_solve_device(lapl, x.p, R.p, st);
+    if (rc) return rc;
+    {
+        LaunchScope sc("ns32_update", st);
+        k_update<float><<<dim3((nx + 63) / 64, (ny + 3) / 4, nz), dim3(64, 4), 0, st>>>(u, v, w, p, x, F, G, H, g, 1);
+    }
+    FDMB_CHECK_LAUNCH();
+    return FDMB_OK;
+}
+
+extern "C" {
+
+int fdmb_ns_cube_f32_create(fdmb_ns_cube_f32** out, const fdmb_ns_cube_params* p)
+{
+    if (!out || !p) { set_error("null argument"); return FDMB_ERR_INVALID; }
+    *out = nullptr;
+    auto* h = new (std::nothrow) fdmb_ns_cube_f32();
+    if (!h) { set_error("out of host memory"); return FDMB_ERR_NOMEM; }
+    h->prm = *p;
+    int rc = h->init();
+    if (rc) { delete h; return rc; }
+    *out = h;
+    return FDMB_OK;
+}
+
+int fdmb_ns_cube_f32_step(fdmb_ns_cube_f32* h, int nsteps)
+{
+    if (!h || nsteps < 0) { set_error("bad argument"); return FDMB_ERR_INVALID; }
+    for (int s = 0; s < nsteps; s++) {
+        int rc = h->graph.run(h->stream, h, nullptr, [&]() { return h->step_once(h->stream); });
+        if (rc) { cudaStreamSynchronize(h->stream); return rc; }
+        h->time_index++;
+    }
+    FDMB_CUDA(cudaStreamSynchronize(h->stream));
+    return FDMB_OK;
+}
+
+int fdmb_ns_cube_f32_field_size(fdmb_ns_cube_f32* h, int field, long long* count)
+{
+    if (!h || field < 0 || field > 8 || !count) { set_error("bad field id"); return FDMB_ERR_INVALID; }
+    *count = h->count[field];
+    return FDMB_OK;
+}
+
+int fdmb_ns_cube_f32_get_field(fdmb_ns_cube_f32* h, int field, float* host)
+{
+    if (!h || field < 0 || field > 8 || !host) { set_error("bad field id"); return FDMB_ERR_INVALID; }
+    FDMB_CUDA(cudaStreamSynchronize(h->stream));
+    FDMB_CUDA(cudaMemcpy(host, h->f[field].p, sizeof(float) * (size_t)h->count[field], cudaMemcpyDeviceToHost));
+    return FDMB_OK;
+}
+
+int fdmb_ns_cube_f32_set_field(fdmb_ns_cube_f32* h, int field, const float* host)
+{
+    if (!h || field < 0 || field > 8 || !host) { set_error("bad field id"); return FDMB_ERR_INVALID; }
+    FDMB_CUDA(cudaStreamSynchronize(h->stream));
+    FDMB_CUDA(cudaMemcpy(h->f[field].p, host, sizeof(float) * (size_t)h->count[field], cudaMemcpyHostToDevice));
+    return FDMB_OK;
+}
+
+long long fdmb_ns_cube_f32_time_index(fdmb_ns_cube_f32* h) { return h ? h->time_index : -1; }
+
+int fdmb_ns_cube_f32_destroy(fdmb_ns_cube_f32* h)
 {
     delete h;
     return FDMB_OK;

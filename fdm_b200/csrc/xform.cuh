@@ -48,11 +48,14 @@ namespace fdmb {
 
 enum XformKind { XF_DST = 0, XF_PFWD = 1, XF_PINV = 2, XF_DCT = 3 };
 
-struct cd { double x, y; };
-__device__ __forceinline__ cd operator+(cd a, cd b) { return {a.x + b.x, a.y + b.y}; }
-__device__ __forceinline__ cd operator-(cd a, cd b) { return {a.x - b.x, a.y - b.y}; }
-__device__ __forceinline__ cd cmul(cd a, cd w) { return {a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x}; }
-__device__ __forceinline__ cd mul_mi(cd a) { return {a.y, -a.x}; }  // a * (-i)
+// complex value of real type T (T = double everywhere on the graded path; float for the fp32 instantiations of the
+// reference, src/lapl_cube.cpp:176-177, which run the plain tile transforms below in single precision)
+template <typename T> struct cx { T x, y; };
+using cd = cx<double>;
+template <typename T> __device__ __forceinline__ cx<T> operator+(cx<T> a, cx<T> b) { return {a.x + b.x, a.y + b.y}; }
+template <typename T> __device__ __forceinline__ cx<T> operator-(cx<T> a, cx<T> b) { return {a.x - b.x, a.y - b.y}; }
+template <typename T> __device__ __forceinline__ cx<T> cmul(cx<T> a, cx<T> w) { return {a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x}; }
+template <typename T> __device__ __forceinline__ cx<T> mul_mi(cx<T> a) { return {a.y, -a.x}; }  // a * (-i)
 
 // compile-time loop: f(std::integral_constant<int, i>) for i = 0..n-1
 template <int I_> struct IntC { static constexpr int value = I_; };
@@ -65,21 +68,21 @@ template <int n, int i = 0, typename F> __device__ __forceinline__ void static_f
 template <int R> struct Dft;
 
 template <> struct Dft<2> {
-    static __device__ __forceinline__ void run(cd* v) {
-        cd a = v[0] + v[1], b = v[0] - v[1];
+    template <typename T> static __device__ __forceinline__ void run(cx<T>* v) {
+        cx<T> a = v[0] + v[1], b = v[0] - v[1];
         v[0] = a; v[1] = b;
     }
 };
 template <> struct Dft<4> {
-    static __device__ __forceinline__ void run(cd* v) {
-        cd t0 = v[0] + v[2], t1 = v[0] - v[2], t2 = v[1] + v[3], t3 = mul_mi(v[1] - v[3]);
+    template <typename T> static __device__ __forceinline__ void run(cx<T>* v) {
+        cx<T> t0 = v[0] + v[2], t1 = v[0] - v[2], t2 = v[1] + v[3], t3 = mul_mi(v[1] - v[3]);
         v[0] = t0 + t2; v[2] = t0 - t2; v[1] = t1 + t3; v[3] = t1 - t3;
     }
 };
 template <> struct Dft<8> {
-    static __device__ __forceinline__ void run(cd* v) {
-        constexpr double h = 0.70710678118654752440;
-        cd u[4], w[4];
+    template <typename T> static __device__ __forceinline__ void run(cx<T>* v) {
+        constexpr T h = T(0.70710678118654752440);
+        cx<T> u[4], w[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) { u[j] = v[j] + v[j + 4]; w[j] = v[j] - v[j + 4]; }
         w[1] = {h * (w[1].x + w[1].y), h * (w[1].y - w[1].x)};
@@ -91,20 +94,20 @@ template <> struct Dft<8> {
     }
 };
 template <> struct Dft<16> {
-    static __device__ __forceinline__ void run(cd* v) {
-        constexpr double h = 0.70710678118654752440;
-        constexpr double c1 = 0.92387953251128675613;  // cos(pi/8)
-        constexpr double s1 = 0.38268343236508977173;  // sin(pi/8)
-        cd u[8], w[8];
+    template <typename T> static __device__ __forceinline__ void run(cx<T>* v) {
+        constexpr T h = T(0.70710678118654752440);
+        constexpr T c1 = T(0.92387953251128675613);  // cos(pi/8)
+        constexpr T s1 = T(0.38268343236508977173);  // sin(pi/8)
+        cx<T> u[8], w[8];
 #pragma unroll
         for (int j = 0; j < 8; j++) { u[j] = v[j] + v[j + 8]; w[j] = v[j] - v[j + 8]; }
-        w[1] = cmul(w[1], cd{c1, -s1});
+        w[1] = cmul(w[1], cx<T>{c1, -s1});
         w[2] = {h * (w[2].x + w[2].y), h * (w[2].y - w[2].x)};
-        w[3] = cmul(w[3], cd{s1, -c1});
+        w[3] = cmul(w[3], cx<T>{s1, -c1});
         w[4] = mul_mi(w[4]);
-        w[5] = cmul(w[5], cd{-s1, -c1});
+        w[5] = cmul(w[5], cx<T>{-s1, -c1});
         w[6] = {h * (w[6].y - w[6].x), -h * (w[6].x + w[6].y)};
-        w[7] = cmul(w[7], cd{-c1, -s1});
+        w[7] = cmul(w[7], cx<T>{-c1, -s1});
         Dft<8>::run(u); Dft<8>::run(w);
 #pragma unroll
         for (int k = 0; k < 8; k++) { v[2 * k] = u[k]; v[2 * k + 1] = w[k]; }
@@ -160,8 +163,8 @@ template <int N> __device__ __forceinline__ int fft_pos(int k)
 
 // One in-place DIF pass over sub-blocks of length L with radix R.
 // WM[t] = (cos(2 pi t/M), -sin(2 pi t/M)), t = 0..M-1.
-template <int M, int L, int R, int G>
-__device__ __forceinline__ void fft_pass(double* col, int sj, int g, const cd* __restrict__ WM)
+template <int M, int L, int R, int G, typename T>
+__device__ __forceinline__ void fft_pass(T* col, int sj, int g, const cx<T>* __restrict__ WM)
 {
     constexpr int S = L / R;      // distance between butterfly legs (complex elements)
     constexpr int NBF = M / R;    // butterflies per column
@@ -172,7 +175,7 @@ __device__ __forceinline__ void fft_pass(double* col, int sj, int g, const cd* _
         if (NBF % G != 0 && q >= NBF) break;
         int blk = q / S, n2 = q % S;
         int base = blk * L + n2;
-        cd v[R];
+        cx<T> v[R];
 #pragma unroll
         for (int n1 = 0; n1 < R; n1++) {
             int idx = 2 * (base + n1 * S);
@@ -182,9 +185,9 @@ __device__ __forceinline__ void fft_pass(double* col, int sj, int g, const cd* _
         Dft<R>::run(v);
 #pragma unroll
         for (int k1 = 0; k1 < R; k1++) {
-            cd o = v[k1];
+            cx<T> o = v[k1];
             if (S > 1 && k1 > 0) {
-                cd w = WM[n2 * k1 * (M / L)];
+                cx<T> w = WM[n2 * k1 * (M / L)];
                 o = cmul(o, w);
             }
             int idx = 2 * (base + k1 * S);
@@ -196,8 +199,8 @@ __device__ __forceinline__ void fft_pass(double* col, int sj, int g, const cd* _
 
 // Complex FFT of length M = N/2 on (col[2m*sj], col[(2m+1)*sj]); output digit-reversed.
 // Ends with __syncthreads().
-template <int N, int G>
-__device__ __forceinline__ void fft_inplace(double* col, int sj, int g, const cd* __restrict__ WM)
+template <int N, int G, typename T>
+__device__ __forceinline__ void fft_inplace(T* col, int sj, int g, const cx<T>* __restrict__ WM)
 {
     using P = Plan<N>;
     constexpr int M = P::M;
@@ -216,19 +219,19 @@ __device__ __forceinline__ void fft_inplace(double* col, int sj, int g, const cd
 // Untangle one (k, M-k) pair of the half-length FFT of a real sequence.
 // Y[k] = A_k - i B_k is the length-N DFT bin; returns A_k, B_k, A_{M-k}, B_{M-k}.
 // SN[j] = sin(pi j / N), j = 0..N/2.
-template <int N>
-__device__ __forceinline__ void untangle(const double* col, int sj, int k, const double* __restrict__ SN,
-                                         double scale, double& Ak, double& Bk, double& Am, double& Bm)
+template <int N, typename T>
+__device__ __forceinline__ void untangle(const T* col, int sj, int k, const T* __restrict__ SN,
+                                         T scale, T& Ak, T& Bk, T& Am, T& Bm)
 {
     constexpr int M = N / 2;
     int pk = fft_pos<N>(k), pm = fft_pos<N>((M - k) & (M - 1));
-    cd zk = {col[(2 * pk) * sj], col[(2 * pk + 1) * sj]};
-    cd zm = {col[(2 * pm) * sj], col[(2 * pm + 1) * sj]};
-    double c = SN[M - 2 * k], s = SN[2 * k];      // cos, sin of 2 pi k / N
-    double hs = 0.5 * scale;
-    double ex = hs * (zk.x + zm.x), ey = hs * (zk.y - zm.y);
-    double ox = hs * (zk.y + zm.y), oy = -hs * (zk.x - zm.x);
-    double wx = c * ox + s * oy, wy = c * oy - s * ox;
+    cx<T> zk = {col[(2 * pk) * sj], col[(2 * pk + 1) * sj]};
+    cx<T> zm = {col[(2 * pm) * sj], col[(2 * pm + 1) * sj]};
+    T c = SN[M - 2 * k], s = SN[2 * k];      // cos, sin of 2 pi k / N
+    T hs = T(0.5) * scale;
+    T ex = hs * (zk.x + zm.x), ey = hs * (zk.y - zm.y);
+    T ox = hs * (zk.y + zm.y), oy = -hs * (zk.x - zm.x);
+    T wx = c * ox + s * oy, wy = c * oy - s * ox;
     Ak = ex + wx; Bk = -(ey + wy);
     Am = ex - wx; Bm = ey - wy;
 }
@@ -239,10 +242,10 @@ __device__ __forceinline__ void untangle(const double* col, int sj, int k, const
 // scr: scratch of at least (G + G/8 + 1) * scr_s doubles per CTA, column b at scr[b].
 // ---------------------------------------------------------------------------------
 // PREFOLD: the caller already applied the fold below while staging the tile (k_rows_pipe).
-template <int N, int G, bool PREFOLD = false>
-__device__ __forceinline__ void dst_tile(double* col, int sj, int g, double scale,
-                                         const double* __restrict__ SN, const cd* __restrict__ WM,
-                                         double* scr, int scr_s)
+template <int N, int G, bool PREFOLD = false, typename T>
+__device__ __forceinline__ void dst_tile(T* col, int sj, int g, T scale,
+                                         const T* __restrict__ SN, const cx<T>* __restrict__ WM,
+                                         T* scr, int scr_s)
 {
     constexpr int M = N / 2;
     static_assert(G <= M / 2 || M == 2, "too many threads per column");
@@ -250,12 +253,12 @@ __device__ __forceinline__ void dst_tile(double* col, int sj, int g, double scal
         // fold: y[j] = sin(pi j/N)(x[j]+x[N-j]) + (x[j]-x[N-j])/2
 #pragma unroll
         for (int j = g + 1; j < M; j += G) {
-            double a = col[j * sj], c = col[(N - j) * sj];
-            double y1 = SN[j] * (a + c), y2 = 0.5 * (a - c);
+            T a = col[j * sj], c = col[(N - j) * sj];
+            T y1 = SN[j] * (a + c), y2 = T(0.5) * (a - c);
             col[j * sj] = y1 + y2;
             col[(N - j) * sj] = y1 - y2;
         }
-        if (g == 0) { col[0] = 0.0; col[M * sj] = 2.0 * col[M * sj]; }
+        if (g == 0) { col[0] = T(0); col[M * sj] = T(2) * col[M * sj]; }
         __syncthreads();
     }
 
@@ -263,14 +266,14 @@ __device__ __forceinline__ void dst_tile(double* col, int sj, int g, double scal
 
     // untangle into natural order: even slot 2k <- S[2k] = B_k, odd slot 2k+1 <- A_k
     constexpr int HP = (M / 2 >= G) ? (M / 2) / G : 1;   // pairs per thread
-    double r[HP][4];
+    T r[HP][4];
 #pragma unroll
     for (int i = 0; i < HP; i++) {
         int k = g + i * G;
         if (k < M / 2)
             untangle<N>(col, sj, k, SN, scale, r[i][0], r[i][1], r[i][2], r[i][3]);
     }
-    double zh_x = 0, zh_y = 0;   // bin M/2 (self-paired), handled by g == 0
+    T zh_x = 0, zh_y = 0;   // bin M/2 (self-paired), handled by g == 0
     if (g == 0) {
         int ph = fft_pos<N>(M / 2);
         zh_x = scale * col[(2 * ph) * sj];
@@ -281,8 +284,8 @@ __device__ __forceinline__ void dst_tile(double* col, int sj, int g, double scal
     for (int i = 0; i < HP; i++) {
         int k = g + i * G;
         if (k == 0) {
-            col[0] = 0.0;
-            col[sj] = 0.5 * r[i][0];             // A_0 / 2 seeds the running sum
+            col[0] = T(0);
+            col[sj] = T(0.5) * r[i][0];             // A_0 / 2 seeds the running sum
         } else if (k < M / 2) {
             col[(2 * k) * sj] = r[i][1];
             col[(2 * k + 1) * sj] = r[i][0];
@@ -298,15 +301,15 @@ __device__ __forceinline__ void dst_tile(double* col, int sj, int g, double scal
 
     // inclusive prefix sum over the odd slots: S[2k+1] = sum_{m<=k} A'_m
     constexpr int CS = M / G;     // contiguous chunk per thread
-    double a[CS];
-    double run = 0.0;
+    T a[CS];
+    T run = T(0);
 #pragma unroll
     for (int i = 0; i < CS; i++) {
         int k = g * CS + i;
         run += col[(2 * k + 1) * sj];
         a[i] = run;
     }
-    double off = 0.0;
+    T off = T(0);
     if constexpr (G > 1) {
         scr[g * scr_s] = run;
         __syncthreads();
@@ -314,9 +317,9 @@ __device__ __forceinline__ void dst_tile(double* col, int sj, int g, double scal
 #pragma unroll
             for (int q = 0; q < G; q++) if (q < g) off += scr[q * scr_s];
         } else {
-            double* scr2 = scr + G * scr_s;
+            T* scr2 = scr + G * scr_s;
             if ((g & 7) == 0) {
-                double t = 0.0;
+                T t = T(0);
 #pragma unroll
                 for (int q = 0; q < 8; q++) t += scr[(g + q) * scr_s];
                 scr2[(g >> 3) * scr_s] = t;
@@ -339,21 +342,21 @@ __device__ __forceinline__ void dst_tile(double* col, int sj, int g, double scal
 // ---------------------------------------------------------------------------------
 // Periodic forward transform (pFFT_1) over slots 0..N-1.  Ends with __syncthreads().
 // ---------------------------------------------------------------------------------
-template <int N, int G>
-__device__ __forceinline__ void pfwd_tile(double* col, int sj, int g, double scale,
-                                          const double* __restrict__ SN, const cd* __restrict__ WM)
+template <int N, int G, typename T>
+__device__ __forceinline__ void pfwd_tile(T* col, int sj, int g, T scale,
+                                          const T* __restrict__ SN, const cx<T>* __restrict__ WM)
 {
     constexpr int M = N / 2;
     fft_inplace<N, G>(col, sj, g, WM);
     constexpr int HP = (M / 2 >= G) ? (M / 2) / G : 1;
-    double r[HP][4];
+    T r[HP][4];
 #pragma unroll
     for (int i = 0; i < HP; i++) {
         int k = g + i * G;
         if (k < M / 2)
             untangle<N>(col, sj, k, SN, scale, r[i][0], r[i][1], r[i][2], r[i][3]);
     }
-    double zh_x = 0, zh_y = 0;
+    T zh_x = 0, zh_y = 0;
     if (g == 0) {
         int ph = fft_pos<N>(M / 2);
         zh_x = scale * col[(2 * ph) * sj];
@@ -383,37 +386,37 @@ __device__ __forceinline__ void pfwd_tile(double* col, int sj, int g, double sca
 // ---------------------------------------------------------------------------------
 // Periodic inverse transform (pFFT) over slots 0..N-1.  Ends with __syncthreads().
 // ---------------------------------------------------------------------------------
-template <int N, int G>
-__device__ __forceinline__ void pinv_tile(double* col, int sj, int g, double scale,
-                                          const double* __restrict__ SN, const cd* __restrict__ WM)
+template <int N, int G, typename T>
+__device__ __forceinline__ void pinv_tile(T* col, int sj, int g, T scale,
+                                          const T* __restrict__ SN, const cx<T>* __restrict__ WM)
 {
     constexpr int M = N / 2;
     constexpr int HP = (M / 2 >= G) ? (M / 2) / G : 1;
     // inverse untangle: build conj(Z[k]), Z[k] = Ze[k] + i Zo[k]
-    double r[HP][4];
+    T r[HP][4];
 #pragma unroll
     for (int i = 0; i < HP; i++) {
         int k = g + i * G;
         if (k == 0) {
-            double a0 = col[0], aM = col[M * sj];
+            T a0 = col[0], aM = col[M * sj];
             r[i][0] = a0 + aM; r[i][1] = -(a0 - aM);
         } else if (k < M / 2) {
-            double ak = col[k * sj], bk = col[(N - k) * sj];
-            double am = col[(M - k) * sj], bm = col[(M + k) * sj];
+            T ak = col[k * sj], bk = col[(N - k) * sj];
+            T am = col[(M - k) * sj], bm = col[(M + k) * sj];
             // X_k = ak - i bk ; conj X_{M-k} = am + i bm
-            double ex = ak + am, ey = -bk + bm;          // Ze = X_k + conj X_{M-k}
-            double dx_ = ak - am, dy_ = -bk - bm;        // X_k - conj X_{M-k}
-            double c = SN[M - 2 * k], s = SN[2 * k];     // e^{+2 pi i k/N} = c + i s
-            double ox = dx_ * c - dy_ * s, oy = dx_ * s + dy_ * c;   // Zo
+            T ex = ak + am, ey = -bk + bm;          // Ze = X_k + conj X_{M-k}
+            T dx_ = ak - am, dy_ = -bk - bm;        // X_k - conj X_{M-k}
+            T c = SN[M - 2 * k], s = SN[2 * k];     // e^{+2 pi i k/N} = c + i s
+            T ox = dx_ * c - dy_ * s, oy = dx_ * s + dy_ * c;   // Zo
             // Z[k] = Ze + i Zo = (ex - oy) + i (ey + ox); Z[M-k] = conj(Ze) + i conj(Zo) = (ex + oy) + i(-ey + ox)
             r[i][0] = ex - oy; r[i][1] = -(ey + ox);     // conj Z[k]
             r[i][2] = ex + oy; r[i][3] = -(-ey + ox);    // conj Z[M-k]
         }
     }
-    double zh_x = 0, zh_y = 0;
+    T zh_x = 0, zh_y = 0;
     if (g == 0 && M >= 2) {
-        double a = col[(M / 2) * sj], b = col[(N - M / 2) * sj];
-        zh_x = 2.0 * a; zh_y = -2.0 * b;                 // conj(2a + 2ib)
+        T a = col[(M / 2) * sj], b = col[(N - M / 2) * sj];
+        zh_x = T(2) * a; zh_y = -T(2) * b;                 // conj(2a + 2ib)
     }
     __syncthreads();
 #pragma unroll
@@ -433,8 +436,8 @@ __device__ __forceinline__ void pinv_tile(double* col, int sj, int g, double sca
 
     // undo the digit reversal: y[2m] = Re F[pos(m)], y[2m+1] = -Im F[pos(m)]
     constexpr int CS = M / G;
-    double o[CS][2];
-    double hs = 0.5 * scale;
+    T o[CS][2];
+    T hs = T(0.5) * scale;
 #pragma unroll
     for (int i = 0; i < CS; i++) {
         int m = g + i * G;
@@ -458,33 +461,33 @@ __device__ __forceinline__ void pinv_tile(double* col, int sj, int g, double sca
 // S[2k+1] = S[2k-1] - Im Y[k], seeded with S[1] = (x[0]-x[N])/2 + sum x[j] cos(pi j/N),
 // which the fold accumulates on the way.  Ends with __syncthreads().
 // ---------------------------------------------------------------------------------
-template <int N, int G>
-__device__ __forceinline__ void dct_tile(double* col, int sj, int g, double scale,
-                                         const double* __restrict__ SN, const cd* __restrict__ WM,
-                                         double* scr, int scr_s)
+template <int N, int G, typename T>
+__device__ __forceinline__ void dct_tile(T* col, int sj, int g, T scale,
+                                         const T* __restrict__ SN, const cx<T>* __restrict__ WM,
+                                         T* scr, int scr_s)
 {
     constexpr int M = N / 2;
     static_assert(G <= M / 2 || M == 2, "too many threads per column");
-    double part = 0.0;
+    T part = T(0);
 #pragma unroll
     for (int j = g + 1; j < M; j += G) {
-        double a = col[j * sj], c = col[(N - j) * sj];
-        double y1 = 0.5 * (a + c), y2 = SN[j] * (a - c);
+        T a = col[j * sj], c = col[(N - j) * sj];
+        T y1 = T(0.5) * (a + c), y2 = SN[j] * (a - c);
         col[j * sj] = y1 - y2;
         col[(N - j) * sj] = y1 + y2;
         part += SN[M - j] * (a - c);              // cos(pi j/N) x[j] + cos(pi (N-j)/N) x[N-j]
     }
     if (g == 0) {
-        double x0 = col[0], xn = col[N * sj];
-        col[0] = 0.5 * (x0 + xn);
-        part += 0.5 * (x0 - xn);
+        T x0 = col[0], xn = col[N * sj];
+        col[0] = T(0.5) * (x0 + xn);
+        part += T(0.5) * (x0 - xn);
     }
     // S[1] / scale, parked in scratch slot G until the untangle (keeps a register free across the FFT passes)
     if constexpr (G > 1) {
         scr[g * scr_s] = part;
         __syncthreads();
         if (g == 0) {
-            double c1 = 0.0;
+            T c1 = T(0);
 #pragma unroll 8
             for (int q = 0; q < G; q++) c1 += scr[q * scr_s];
             scr[G * scr_s] = c1;
@@ -497,14 +500,14 @@ __device__ __forceinline__ void dct_tile(double* col, int sj, int g, double scal
     fft_inplace<N, G>(col, sj, g, WM);
 
     constexpr int HP = (M / 2 >= G) ? (M / 2) / G : 1;
-    double r[HP][4];
+    T r[HP][4];
 #pragma unroll
     for (int i = 0; i < HP; i++) {
         int k = g + i * G;
         if (k < M / 2)
             untangle<N>(col, sj, k, SN, scale, r[i][0], r[i][1], r[i][2], r[i][3]);
     }
-    double zh_x = 0, zh_y = 0;
+    T zh_x = 0, zh_y = 0;
     if (g == 0) {
         int ph = fft_pos<N>(M / 2);
         zh_x = scale * col[(2 * ph) * sj];
@@ -533,15 +536,15 @@ __device__ __forceinline__ void dct_tile(double* col, int sj, int g, double scal
 
     // inclusive prefix sum over the odd slots
     constexpr int CS = M / G;
-    double a[CS];
-    double run = 0.0;
+    T a[CS];
+    T run = T(0);
 #pragma unroll
     for (int i = 0; i < CS; i++) {
         int k = g * CS + i;
         run += col[(2 * k + 1) * sj];
         a[i] = run;
     }
-    double off = 0.0;
+    T off = T(0);
     if constexpr (G > 1) {
         scr[g * scr_s] = run;
         __syncthreads();
@@ -556,10 +559,10 @@ __device__ __forceinline__ void dct_tile(double* col, int sj, int g, double scal
     __syncthreads();
 }
 
-template <int N, int G, int KIND, bool PREFOLD = false>
-__device__ __forceinline__ void xform_tile(double* col, int sj, int g, double scale,
-                                           const double* __restrict__ SN, const cd* __restrict__ WM,
-                                           double* scr, int scr_s)
+template <int N, int G, int KIND, bool PREFOLD = false, typename T>
+__device__ __forceinline__ void xform_tile(T* col, int sj, int g, T scale,
+                                           const T* __restrict__ SN, const cx<T>* __restrict__ WM,
+                                           T* scr, int scr_s)
 {
     if constexpr (KIND == XF_DST) dst_tile<N, G, PREFOLD>(col, sj, g, scale, SN, WM, scr, scr_s);
     else if constexpr (KIND == XF_PFWD) pfwd_tile<N, G>(col, sj, g, scale, SN, WM);

@@ -13,47 +13,55 @@
 
 namespace fdmb {
 
-template <int N> struct TileCfg {
+template <int N, typename T = double> struct TileCfg {
     // columns per CTA in k_cols / rows per CTA in k_rows
     static constexpr int B = (N <= 64) ? 32 : (N <= 1024 ? 16 : 8);
     static constexpr int G = Plan<N>::G;
     static constexpr int THREADS = B * G;
-    static constexpr int SCR = (G + G / 8 + 1) * B;                  // scan scratch (doubles)
-    static constexpr size_t SMEM_COLS = sizeof(double) * (size_t)(N * B + SCR);
-    static constexpr size_t SMEM_ROWS = sizeof(double) * (size_t)((N + 1) * B + SCR);
+    static constexpr int SCR = (G + G / 8 + 1) * B;                  // scan scratch (elements)
+    static constexpr size_t SMEM_COLS = sizeof(T) * (size_t)((N + 1) * B + SCR);
+    static constexpr size_t SMEM_ROWS = sizeof(T) * (size_t)((N + 1) * B + SCR);
 };
 
-struct RowsArgs {
-    const double* in;
-    double* out;
+// T = double on the graded path; float for the reference's single-precision instantiations (lapl_cube_f32.cu)
+template <typename T> struct RowsArgsT {
+    const T* in;
+    T* out;
     long long nrows;       // total rows
-    int nvalid;            // meaningful entries per row (N-1 for DST, N for periodic)
-    long long in_pitch;    // doubles between consecutive rows
+    int nvalid;            // meaningful entries per row (N-1 for DST, N for periodic, N+1 for the DCT)
+    long long in_pitch;    // elements between consecutive rows
     long long out_pitch;
-    double scale;
-    const double* SN;
-    const cd* WM;
+    T scale;
+    const T* SN;
+    const cx<T>* WM;
 };
+using RowsArgs = RowsArgsT<double>;
 
-template <int N, int KIND>
-__global__ void __launch_bounds__(TileCfg<N>::THREADS) k_rows(RowsArgs a)
+template <typename T> __device__ __forceinline__ T* dyn_smem()
 {
-    using C = TileCfg<N>;
+    extern __shared__ __align__(16) unsigned char smem_bytes[];
+    return reinterpret_cast<T*>(smem_bytes);
+}
+
+template <int N, int KIND, typename T = double>
+__global__ void __launch_bounds__(TileCfg<N>::THREADS) k_rows(RowsArgsT<T> a)
+{
+    using C = TileCfg<N, T>;
     constexpr int BR = C::B, G = C::G, P = N + 1;
     constexpr int J0 = (KIND == XF_DST) ? 1 : 0;
-    extern __shared__ double smem[];
-    double* tile = smem;
-    double* scr = smem + P * BR;
+    T* smem = dyn_smem<T>();
+    T* tile = smem;
+    T* scr = smem + P * BR;
     const int tid = threadIdx.x;
     const long long row0 = (long long)blockIdx.x * BR;
     constexpr int NW = C::THREADS / 32 > 0 ? C::THREADS / 32 : 1;
     const int warp = tid >> 5, lane = tid & 31;
     for (int r = warp; r < BR; r += NW) {
         long long row = row0 + r;
-        const double* src = a.in + row * a.in_pitch;
+        const T* src = a.in + row * a.in_pitch;
         bool ok = row < a.nrows;
         for (int x = lane; x < a.nvalid; x += 32)
-            tile[r * P + x + J0] = ok ? src[x] : 0.0;
+            tile[r * P + x + J0] = ok ? src[x] : T(0);
     }
     __syncthreads();
     const int b = tid % BR, g = tid / BR;
@@ -61,7 +69,7 @@ __global__ void __launch_bounds__(TileCfg<N>::THREADS) k_rows(RowsArgs a)
     for (int r = warp; r < BR; r += NW) {
         long long row = row0 + r;
         if (row >= a.nrows) continue;
-        double* dst = a.out + row * a.out_pitch;
+        T* dst = a.out + row * a.out_pitch;
         for (int x = lane; x < a.nvalid; x += 32) dst[x] = tile[r * P + x + J0];
     }
 }
@@ -71,9 +79,23 @@ __global__ void __launch_bounds__(TileCfg<N>::THREADS) k_rows(RowsArgs a)
 struct MidNone {
     static constexpr bool active = false;
     struct Ctx {};
-    __device__ __forceinline__ double operator()(double v, int, int, int) const { return v; }
+    template <typename T> __device__ __forceinline__ T operator()(T v, int, int, int) const { return v; }
     __device__ __forceinline__ Ctx ctx(int, int) const { return Ctx{}; }
     __device__ __forceinline__ double apply(double v, int, const Ctx&) const { return v; }
+};
+// single-precision spectral divide of the plain sweep: the reference's LaplCube<float> divides in float too
+// (src/lapl_cube.cpp:74-77 with T = float)
+struct MidCubeDivideF {
+    static constexpr bool active = true;
+    const float* lm_j;
+    const float* lm_b;
+    const float* lm_o;
+    int zero_null;
+    __device__ __forceinline__ float operator()(float v, int j, int b, int o) const
+    {
+        if (zero_null && j == 0 && b == 0 && o == 0) return 0.0f;
+        return v / -(lm_j[j] + lm_b[b] + lm_o[o]);
+    }
 };
 
 // 1/d to within an ulp: hardware seed (MUFU.RCP64H, ~20 bits) + two Newton steps.  d is a sum of
@@ -115,50 +137,51 @@ struct MidCubeDivide {
     }
 };
 
-struct ColsArgs {
-    const double* in;
-    double* out;
+template <typename T> struct ColsArgsT {
+    const T* in;
+    T* out;
     int nvalid;               // entries along the transform axis
-    long long in_sj, out_sj;  // stride (doubles) along the transform axis
+    long long in_sj, out_sj;  // stride (elements) along the transform axis
     int nb;                   // extent of the contiguous axis
     int no;                   // extent of the outer axis
     long long in_so, out_so;  // stride along the outer axis
-    double scale, scale2;     // forward / second transform scale
-    const double* SN;
-    const cd* WM;
+    T scale, scale2;          // forward / second transform scale
+    const T* SN;
+    const cx<T>* WM;
 };
+using ColsArgs = ColsArgsT<double>;
 
-template <int N, int KIND, typename MID, int KIND2>
-__global__ void __launch_bounds__(TileCfg<N>::THREADS) k_cols(ColsArgs a, MID mid)
+template <int N, int KIND, typename MID, int KIND2, typename T = double>
+__global__ void __launch_bounds__(TileCfg<N>::THREADS) k_cols(ColsArgsT<T> a, MID mid)
 {
-    using C = TileCfg<N>;
+    using C = TileCfg<N, T>;
     constexpr int B = C::B, G = C::G;
     constexpr int J0 = (KIND == XF_DST) ? 1 : 0;
-    extern __shared__ double smem[];
-    double* tile = smem;
-    double* scr = smem + N * B;
+    T* smem = dyn_smem<T>();
+    T* tile = smem;
+    T* scr = smem + (N + 1) * B;
     const int tid = threadIdx.x;
     const int b0 = blockIdx.x * B;
     const int o = blockIdx.y;
     const int b = tid % B, g = tid / B;
     const bool bok = b0 + b < a.nb;
     {
-        const double* src = a.in + (long long)o * a.in_so + b0 + b;
+        const T* src = a.in + (long long)o * a.in_so + b0 + b;
         for (int j = g; j < a.nvalid; j += G)
-            tile[(j + J0) * B + b] = bok ? src[j * a.in_sj] : 0.0;
+            tile[(j + J0) * B + b] = bok ? src[j * a.in_sj] : T(0);
     }
     __syncthreads();
     xform_tile<N, G, KIND>(tile + b, B, g, a.scale, a.SN, a.WM, scr + b, B);
     if constexpr (MID::active) {
         for (int j = g; j < a.nvalid; j += G) {
-            double v = tile[(j + J0) * B + b];
-            tile[(j + J0) * B + b] = bok ? mid(v, j + J0, b0 + b + J0, o + J0) : 0.0;
+            T v = tile[(j + J0) * B + b];
+            tile[(j + J0) * B + b] = bok ? mid(v, j + J0, b0 + b + J0, o + J0) : T(0);
         }
         __syncthreads();
         xform_tile<N, G, KIND2>(tile + b, B, g, a.scale2, a.SN, a.WM, scr + b, B);
     }
     if (bok) {
-        double* dst = a.out + (long long)o * a.out_so + b0 + b;
+        T* dst = a.out + (long long)o * a.out_so + b0 + b;
         for (int j = g; j < a.nvalid; j += G) dst[j * a.out_sj] = tile[(j + J0) * B + b];
     }
 }
@@ -168,11 +191,11 @@ int current_device_slot();   // cudaGetDevice() clamped to [0, 63]
 // ---- host-side dispatch over the instantiated transform lengths -----------------
 #define FDMB_FOR_EACH_N(X) X(4) X(8) X(16) X(32) X(64) X(128) X(256) X(512) X(1024) X(2048)
 
-template <int N, int KIND>
-inline cudaError_t launch_rows_t(const RowsArgs& a, cudaStream_t st)
+template <int N, int KIND, typename T = double>
+inline cudaError_t launch_rows_t(const RowsArgsT<T>& a, cudaStream_t st)
 {
-    using C = TileCfg<N>;
-    auto kern = k_rows<N, KIND>;
+    using C = TileCfg<N, T>;
+    auto kern = k_rows<N, KIND, T>;
     static bool attr_set_dev[64] = {false};   // function attributes are per device
     bool& attr_set = attr_set_dev[current_device_slot()];
     if (!attr_set) {
@@ -184,11 +207,11 @@ inline cudaError_t launch_rows_t(const RowsArgs& a, cudaStream_t st)
     return cudaGetLastError();
 }
 
-template <int N, int KIND, typename MID, int KIND2>
-inline cudaError_t launch_cols_t(const ColsArgs& a, const MID& mid, cudaStream_t st)
+template <int N, int KIND, typename MID, int KIND2, typename T = double>
+inline cudaError_t launch_cols_t(const ColsArgsT<T>& a, const MID& mid, cudaStream_t st)
 {
-    using C = TileCfg<N>;
-    auto kern = k_cols<N, KIND, MID, KIND2>;
+    using C = TileCfg<N, T>;
+    auto kern = k_cols<N, KIND, MID, KIND2, T>;
     static bool attr_set_dev[64] = {false};   // function attributes are per device
     bool& attr_set = attr_set_dev[current_device_slot()];
     if (!attr_set) {

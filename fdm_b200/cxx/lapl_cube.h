@@ -67,9 +67,18 @@ public:
           zpoints(periodic ? nz : nz + 1), ypoints(periodic ? ny : ny + 1), xpoints(periodic ? nx : nx + 1),
           nx(nx), ny(ny), nz(nz), mxdim(std::max({nx + 1, ny + 1, nz + 1})), indices({1, nz, 1, ny, 1, nx})
     {
-        FDMB_VERIFY(fdmb_lapl_cube_create(&handle, dx, dy, dz, lx, ly, lz, nx, ny, nz, periodic ? 1 : 0));
+        if constexpr (std::is_same<T, float>::value) {
+            // single precision all the way: float arrays, tables and butterflies on the device (fdmb_lapl_cube_f32_*)
+            FDMB_VERIFY(fdmb_lapl_cube_f32_create(&handle32, dx, dy, dz, lx, ly, lz, nx, ny, nz, periodic ? 1 : 0));
+        } else {
+            FDMB_VERIFY(fdmb_lapl_cube_create(&handle, dx, dy, dz, lx, ly, lz, nx, ny, nz, periodic ? 1 : 0));
+        }
     }
-    ~LaplCube() { if (handle) fdmb_lapl_cube_destroy(handle); }
+    ~LaplCube()
+    {
+        if (handle) fdmb_lapl_cube_destroy(handle);
+        if (handle32) fdmb_lapl_cube_f32_destroy(handle32);
+    }
     LaplCube(const LaplCube&) = delete;
     LaplCube& operator=(const LaplCube&) = delete;
 
@@ -78,6 +87,8 @@ public:
     {
         if constexpr (std::is_same<T, double>::value) {
             FDMB_VERIFY(fdmb_lapl_cube_solve(handle, ans, rhs));
+        } else if constexpr (std::is_same<T, float>::value) {
+            FDMB_VERIFY(fdmb_lapl_cube_f32_solve(handle32, ans, rhs));
         } else {
             const size_t n = (size_t)nx * ny * nz;
             cvt_in.assign(rhs, rhs + n);
@@ -102,7 +113,8 @@ public:
 
 private:
     fdmb_lapl_cube* handle = nullptr;
-    std::vector<double> cvt_in, cvt_out;
+    fdmb_lapl_cube_f32* handle32 = nullptr;      // T = float
+    std::vector<double> cvt_in, cvt_out;         // other element types: widened to fp64 at the boundary
 };
 
 }  // namespace fdm

@@ -64,11 +64,19 @@ public:
         FDMB_VERIFY(fdmb_ns_cube_default_params(&prm));
         prm.x1 = x1; prm.y1 = y1; prm.z1 = z1; prm.x2 = x2; prm.y2 = y2; prm.z2 = z2;
         prm.u0 = U0; prm.Re = Re; prm.dt = dt; prm.nx = nx; prm.nz = nz; prm.verbose = verbose;
-        FDMB_VERIFY(fdmb_ns_cube_create(&handle, &prm));
+        if constexpr (std::is_same<T, float>::value) {
+            FDMB_VERIFY(fdmb_ns_cube_f32_create(&handle32, &prm));    // float fields + float pressure solve on the device
+        } else {
+            FDMB_VERIFY(fdmb_ns_cube_create(&handle, &prm));
+        }
         tensor* all[9] = {&u, &v, &w, &p, &x, &F, &G, &H, &RHS};
         for (int id = 0; id < 9; id++) dig[id] = digest(all[id]->vec, (long long)all[id]->size);
     }
-    ~NSCube() { if (handle) fdmb_ns_cube_destroy(handle); }
+    ~NSCube()
+    {
+        if (handle) fdmb_ns_cube_destroy(handle);
+        if (handle32) fdmb_ns_cube_f32_destroy(handle32);
+    }
     NSCube(const NSCube&) = delete;
     NSCube& operator=(const NSCube&) = delete;
 
@@ -80,7 +88,11 @@ public:
             push_if_changed(FDMB_FIELD_U, u); push_if_changed(FDMB_FIELD_V, v); push_if_changed(FDMB_FIELD_W, w);
             push_if_changed(FDMB_FIELD_P, p);
         }
-        FDMB_VERIFY(fdmb_ns_cube_step(handle, n));
+        if constexpr (std::is_same<T, float>::value) {
+            FDMB_VERIFY(fdmb_ns_cube_f32_step(handle32, n));
+        } else {
+            FDMB_VERIFY(fdmb_ns_cube_step(handle, n));
+        }
         time_index += n;
         if (auto_sync) sync_to_host(false);
     }
@@ -100,6 +112,7 @@ public:
 
 private:
     fdmb_ns_cube* handle = nullptr;
+    fdmb_ns_cube_f32* handle32 = nullptr;    // T = float
     std::vector<double> cvt;
     unsigned long long dig[9] = {};          // digest of each mirror when it last agreed with the device (by field id)
 
@@ -128,6 +141,8 @@ private:
     {
         if constexpr (std::is_same<T, double>::value) {
             FDMB_VERIFY(fdmb_ns_cube_get_field(handle, id, t.vec));
+        } else if constexpr (std::is_same<T, float>::value) {
+            FDMB_VERIFY(fdmb_ns_cube_f32_get_field(handle32, id, t.vec));
         } else {
             cvt.resize((size_t)t.size);
             FDMB_VERIFY(fdmb_ns_cube_get_field(handle, id, cvt.data()));
@@ -139,6 +154,8 @@ private:
     {
         if constexpr (std::is_same<T, double>::value) {
             FDMB_VERIFY(fdmb_ns_cube_set_field(handle, id, t.vec));
+        } else if constexpr (std::is_same<T, float>::value) {
+            FDMB_VERIFY(fdmb_ns_cube_f32_set_field(handle32, id, t.vec));
         } else {
             cvt.assign(t.vec, t.vec + t.size);
             FDMB_VERIFY(fdmb_ns_cube_set_field(handle, id, cvt.data()));

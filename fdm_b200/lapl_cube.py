@@ -80,6 +80,53 @@ class LaplCube:
             pass
 
 
+class LaplCubeF32:
+    """``fdm::LaplCube<float,check,F>`` (src/lapl_cube.cpp:176-177,181-182): same constructor and ``solve`` as
+    :class:`LaplCube` with float32 arrays; the device arrays, tables and butterflies are float32 (single GPU)."""
+
+    def __init__(self, dx, dy, dz, lx, ly, lz, nx, ny, nz, periodic=False):
+        self.nx, self.ny, self.nz = int(nx), int(ny), int(nz)
+        self.periodic = bool(periodic)
+        self._h = C.c_void_p()
+        capi.check(capi.lib().fdmb_lapl_cube_f32_create(C.byref(self._h), float(dx), float(dy), float(dz), float(lx),
+                                                        float(ly), float(lz), self.nx, self.ny, self.nz,
+                                                        int(self.periodic)), "LaplCube<float> create")
+
+    @property
+    def shape(self):
+        return (self.nz, self.ny, self.nx)
+
+    def solve(self, ans, rhs=None):
+        if rhs is None:
+            rhs, ans = ans, None
+        rhs = np.ascontiguousarray(rhs, dtype=np.float32)
+        if rhs.size != self.nx * self.ny * self.nz:
+            raise ValueError(f"rhs has {rhs.size} elements, expected {self.nx * self.ny * self.nz}")
+        if ans is None:
+            ans = np.empty(self.shape, dtype=np.float32)
+        if not (isinstance(ans, np.ndarray) and ans.dtype == np.float32 and ans.flags.c_contiguous and ans.size == rhs.size):
+            raise ValueError("ans must be a C-contiguous float32 array of the same size as rhs")
+        fp = C.POINTER(C.c_float)
+        capi.check(capi.lib().fdmb_lapl_cube_f32_solve(self._h, ans.ctypes.data_as(fp), rhs.ctypes.data_as(fp)),
+                   "LaplCube<float> solve")
+        return ans
+
+    def solve_device(self, d_ans, d_rhs, stream=0):
+        capi.check(capi.lib().fdmb_lapl_cube_f32_solve_device(self._h, C.c_void_p(d_ans), C.c_void_p(d_rhs),
+                                                             C.c_void_p(stream)), "LaplCube<float> solve_device")
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            capi.lib().fdmb_lapl_cube_f32_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 IPC_HANDLE_BYTES = 64
 
 

@@ -46,6 +46,15 @@ def _bind(L):
     L.fdmb_ns_cube_attach_ipc.argtypes = [C.c_void_p, C.c_void_p]
     L.fdmb_ns_cube_attach_local.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
     L.fdmb_ns_cube_synchronize.argtypes = [C.c_void_p]
+    fp = C.POINTER(C.c_float)
+    L.fdmb_ns_cube_f32_create.argtypes = [C.POINTER(C.c_void_p), P]
+    L.fdmb_ns_cube_f32_step.argtypes = [C.c_void_p, C.c_int]
+    L.fdmb_ns_cube_f32_field_size.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_longlong)]
+    L.fdmb_ns_cube_f32_get_field.argtypes = [C.c_void_p, C.c_int, fp]
+    L.fdmb_ns_cube_f32_set_field.argtypes = [C.c_void_p, C.c_int, fp]
+    L.fdmb_ns_cube_f32_time_index.argtypes = [C.c_void_p]
+    L.fdmb_ns_cube_f32_time_index.restype = C.c_longlong
+    L.fdmb_ns_cube_f32_destroy.argtypes = [C.c_void_p]
     L._ns_cube_bound = True
 
 
@@ -165,6 +174,56 @@ class NSCube:
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
             capi.lib().fdmb_ns_cube_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class NSCubeF32:
+    """``fdm::NSCube<float,check>`` (src/ns_cube.cpp:281-282): float32 fields and pressure solve, same keywords,
+    field names and extents as :class:`NSCube` (single GPU)."""
+
+    def __init__(self, nx=32, nz=32, Re=1.0, dt=0.001, u0=1.0,
+                 x1=-math.pi, y1=-math.pi, z1=-math.pi, x2=math.pi, y2=math.pi, z2=math.pi, verbose=0):
+        L = capi.lib()
+        _bind(L)
+        self.params = NSCubeParams(x1, y1, z1, x2, y2, z2, u0, Re, dt, int(nx), int(nz), int(verbose))
+        self.nx, self.ny, self.nz = int(nx), int(nx), int(nz)
+        self._h = C.c_void_p()
+        capi.check(L.fdmb_ns_cube_f32_create(C.byref(self._h), C.byref(self.params)), "NSCube<float> create")
+
+    def step(self, nsteps=1):
+        capi.check(capi.lib().fdmb_ns_cube_f32_step(self._h, int(nsteps)), "NSCube<float> step")
+
+    @property
+    def time_index(self):
+        return capi.lib().fdmb_ns_cube_f32_time_index(self._h)
+
+    def field_size(self, name):
+        n = C.c_longlong()
+        capi.check(capi.lib().fdmb_ns_cube_f32_field_size(self._h, FIELD_IDS[name], C.byref(n)), "field_size")
+        return n.value
+
+    def field(self, name):
+        out = np.empty(self.field_size(name), dtype=np.float32)
+        capi.check(capi.lib().fdmb_ns_cube_f32_get_field(self._h, FIELD_IDS[name], out.ctypes.data_as(C.POINTER(C.c_float))),
+                   "get_field")
+        return out
+
+    def set_field(self, name, a):
+        a = np.ascontiguousarray(a, dtype=np.float32).ravel()
+        if a.size != self.field_size(name):
+            raise ValueError(f"field {name} has {self.field_size(name)} elements, got {a.size}")
+        capi.check(capi.lib().fdmb_ns_cube_f32_set_field(self._h, FIELD_IDS[name], a.ctypes.data_as(C.POINTER(C.c_float))),
+                   "set_field")
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            capi.lib().fdmb_ns_cube_f32_destroy(self._h)
             self._h = C.c_void_p()
 
     def __del__(self):

@@ -88,6 +88,16 @@ int fdmb_lapl_cube_solve_device(fdmb_lapl_cube* h, double* d_ans, const double* 
 int fdmb_lapl_cube_solve_batch(fdmb_lapl_cube* h, int count, double* const* ans, const double* const* rhs);
 int fdmb_lapl_cube_destroy(fdmb_lapl_cube* h);
 
+/* Single precision: fdm::LaplCube<float,check,F> (the instantiations of src/lapl_cube.cpp:176-177,181-182).  Same
+ * arguments and meaning as above with float arrays; the device arrays, the tables and every butterfly are float (the
+ * reference stores its eigenvalue tables as T too, src/lapl_cube.h:53-54).  Single GPU.                          */
+typedef struct fdmb_lapl_cube_f32 fdmb_lapl_cube_f32;
+int fdmb_lapl_cube_f32_create(fdmb_lapl_cube_f32** h, double dx, double dy, double dz,
+                              double lx, double ly, double lz, int nx, int ny, int nz, int periodic);
+int fdmb_lapl_cube_f32_solve(fdmb_lapl_cube_f32* h, float* ans, const float* rhs);
+int fdmb_lapl_cube_f32_solve_device(fdmb_lapl_cube_f32* h, float* d_ans, const float* d_rhs, void* stream);
+int fdmb_lapl_cube_f32_destroy(fdmb_lapl_cube_f32* h);
+
 /* Multi-GPU LaplCube: the grid is cut into z-slabs, one rank (= one GPU, normally one process) per
  * slab.  The reference has no distributed solver; this is the slab decomposition of the same
  * solve() (src/lapl_cube.cpp:9-142): x and y transforms are local to a slab, the z transform runs
@@ -207,6 +217,18 @@ int fdmb_ns_cube_export_ipc(fdmb_ns_cube* h, void* handles);
 int fdmb_ns_cube_attach_ipc(fdmb_ns_cube* h, const void* handles);
 int fdmb_ns_cube_attach_local(fdmb_ns_cube* h, fdmb_ns_cube* const* all);
 int fdmb_ns_cube_synchronize(fdmb_ns_cube* h);
+
+/* Single precision: fdm::NSCube<float,check> (src/ns_cube.cpp:281-282).  Float fields and a float pressure solve
+ * (the member LaplCube<T,check>, src/ns_cube.h:34); the stencil arithmetic is double, like the reference's own mixed
+ * float / double expressions.  Same params, field ids and extents as above; single GPU.                          */
+typedef struct fdmb_ns_cube_f32 fdmb_ns_cube_f32;
+int fdmb_ns_cube_f32_create(fdmb_ns_cube_f32** h, const fdmb_ns_cube_params* p);
+int fdmb_ns_cube_f32_step(fdmb_ns_cube_f32* h, int nsteps);
+int fdmb_ns_cube_f32_field_size(fdmb_ns_cube_f32* h, int field, long long* count);
+int fdmb_ns_cube_f32_get_field(fdmb_ns_cube_f32* h, int field, float* host);
+int fdmb_ns_cube_f32_set_field(fdmb_ns_cube_f32* h, int field, const float* host);
+long long fdmb_ns_cube_f32_time_index(fdmb_ns_cube_f32* h);
+int fdmb_ns_cube_f32_destroy(fdmb_ns_cube_f32* h);
 
 /* ---- NSCyl ----------------------------------------------------------------------
  * Replaces fdm::NSCyl<double,check,zflag> (src/ns_cyl.h:17-132, src/ns_cyl.cpp:23-484): flow between

@@ -68,6 +68,17 @@ def lib():
         L.ref_ns_cyl_set_field.argtypes = [C.c_void_p, C.c_int, _dp]
         L.ref_ns_cyl_destroy.argtypes = [C.c_void_p]
         L.ref_ns_cyl_set_u0.argtypes = [C.c_void_p, C.c_double]
+        fp = C.POINTER(C.c_float)
+        L.ref_lapl_cube_f32_create.restype = C.c_void_p
+        L.ref_lapl_cube_f32_create.argtypes = [C.c_double] * 6 + [C.c_int] * 4
+        L.ref_lapl_cube_f32_solve.argtypes = [C.c_void_p, fp, fp]
+        L.ref_lapl_cube_f32_destroy.argtypes = [C.c_void_p]
+        L.ref_ns_cube_f32_create.restype = C.c_void_p
+        L.ref_ns_cube_f32_create.argtypes = [C.c_int, C.POINTER(C.c_char_p)]
+        L.ref_ns_cube_f32_step.argtypes = [C.c_void_p, C.c_int]
+        L.ref_ns_cube_f32_field_size.argtypes = [C.c_void_p, C.c_int]
+        L.ref_ns_cube_f32_get_field.argtypes = [C.c_void_p, C.c_int, fp]
+        L.ref_ns_cube_f32_destroy.argtypes = [C.c_void_p]
         L.ref_nbody_create.restype = C.c_void_p
         L.ref_nbody_create.argtypes = [C.c_double] * 4 + [C.c_int] * 3 + [C.c_double] * 3 + [C.c_int] * 2
         L.ref_nbody_count.argtypes = [C.c_void_p]
@@ -134,6 +145,49 @@ class LaplCube:
     def __del__(self):
         if getattr(self, "h", None):
             lib().ref_lapl_cube_destroy(self.h)
+            self.h = None
+
+
+class LaplCubeF32:
+    """The unmodified fdm::LaplCube<float,false,F> (src/lapl_cube.cpp:176-177,181-182)."""
+
+    def __init__(self, dx, dy, dz, lx, ly, lz, nx, ny, nz, periodic=False):
+        self.shape = (nz, ny, nx)
+        self.h = lib().ref_lapl_cube_f32_create(dx, dy, dz, lx, ly, lz, nx, ny, nz, int(periodic))
+
+    def solve(self, rhs):
+        rhs = np.ascontiguousarray(rhs, dtype=np.float32).reshape(self.shape).copy()
+        ans = np.empty_like(rhs)
+        fp = C.POINTER(C.c_float)
+        lib().ref_lapl_cube_f32_solve(self.h, ans.ctypes.data_as(fp), rhs.ctypes.data_as(fp))
+        return ans
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().ref_lapl_cube_f32_destroy(self.h)
+            self.h = None
+
+
+class NSCubeF32:
+    """The unmodified fdm::NSCube<float,false> (src/ns_cube.cpp:281-282)."""
+
+    def __init__(self, **params):
+        n, arr, self._keep = _kv(params)
+        self.h = lib().ref_ns_cube_f32_create(n, arr)
+
+    def step(self, nsteps=1):
+        lib().ref_ns_cube_f32_step(self.h, nsteps)
+
+    def field(self, name):
+        fid = FIELD_IDS[name]
+        n = lib().ref_ns_cube_f32_field_size(self.h, fid)
+        out = np.empty(n, dtype=np.float32)
+        lib().ref_ns_cube_f32_get_field(self.h, fid, out.ctypes.data_as(C.POINTER(C.c_float)))
+        return out
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().ref_ns_cube_f32_destroy(self.h)
             self.h = None
 
 

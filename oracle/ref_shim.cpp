@@ -82,8 +82,8 @@ Config make_config(int nkv, const char** kv)
     return c;
 }
 
-template <typename NS>
-int ns_field(NS* ns, int id, double** ptr)
+template <typename NS, typename T = double>
+int ns_field(NS* ns, int id, T** ptr)
 {
     switch (id) {
     case 0: *ptr = ns->u.vec; return ns->u.size;
@@ -267,6 +267,53 @@ int ref_ns_cube_set_field(void* vh, int id, const double* in)
     return n;
 }
 void ref_ns_cube_destroy(void* vh) { delete (NSCube<double, false>*)vh; }
+
+// ---- single-precision instantiations (src/lapl_cube.cpp:176-177,181-182; src/ns_cube.cpp:281-282) -------------
+struct CubeHF {
+    int periodic;
+    LaplCube<float, false, F3d>* d = nullptr;
+    LaplCube<float, false, F3p>* p = nullptr;
+};
+void* ref_lapl_cube_f32_create(double dx, double dy, double dz, double lx, double ly, double lz,
+                               int nx, int ny, int nz, int periodic)
+{
+    auto* h = new CubeHF;
+    h->periodic = periodic;
+    if (periodic) h->p = new LaplCube<float, false, F3p>(dx, dy, dz, lx, ly, lz, nx, ny, nz);
+    else h->d = new LaplCube<float, false, F3d>(dx, dy, dz, lx, ly, lz, nx, ny, nz);
+    return h;
+}
+void ref_lapl_cube_f32_solve(void* vh, float* ans, float* rhs)
+{
+    auto* h = (CubeHF*)vh;
+    if (h->periodic) h->p->solve(ans, rhs); else h->d->solve(ans, rhs);
+}
+void ref_lapl_cube_f32_destroy(void* vh)
+{
+    auto* h = (CubeHF*)vh;
+    delete h->p; delete h->d; delete h;
+}
+void* ref_ns_cube_f32_create(int nkv, const char** kv)
+{
+    Config c = make_config(nkv, kv);
+    return new NSCube<float, false>(c);
+}
+void ref_ns_cube_f32_step(void* vh, int nsteps)
+{
+    auto* ns = (NSCube<float, false>*)vh;
+    for (int i = 0; i < nsteps; i++) ns->step();
+}
+int ref_ns_cube_f32_field_size(void* vh, int id)
+{
+    float* p; return ns_field((NSCube<float, false>*)vh, id, &p);
+}
+int ref_ns_cube_f32_get_field(void* vh, int id, float* out)
+{
+    float* p; int n = ns_field((NSCube<float, false>*)vh, id, &p);
+    if (n > 0) std::memcpy(out, p, sizeof(float) * n);
+    return n;
+}
+void ref_ns_cube_f32_destroy(void* vh) { delete (NSCube<float, false>*)vh; }
 
 // ---- NSCyl ---------------------------------------------------------------------
 void* ref_ns_cyl_create(int nkv, const char** kv, int zperiodic)

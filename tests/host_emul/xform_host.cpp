@@ -49,6 +49,41 @@ static void run_one(double* data, int sj, double scale)
     for (auto& t : th) t.join();
 }
 
+// the same tile transforms in single precision (the fp32 instantiations: lapl_cube_f32.cu)
+template <int N, int KIND>
+static void run_one_f32(float* data, int sj, float scale)
+{
+    constexpr int G = Plan<N>::G;
+    std::vector<double> snd; std::vector<cd> wmd;
+    make_tables(N, snd, wmd);
+    std::vector<float> sn(snd.begin(), snd.end());
+    std::vector<cx<float>> wm(wmd.size());
+    for (size_t i = 0; i < wmd.size(); i++) wm[i] = {(float)wmd[i].x, (float)wmd[i].y};
+    std::vector<float> scr((G + G / 8 + 2));
+    std::barrier<> bar(G);
+    std::vector<std::thread> th;
+    for (int g = 0; g < G; g++)
+        th.emplace_back([&, g] {
+            tl_barrier = &bar;
+            xform_tile<N, G, KIND>(data, sj, g, scale, (const float*)sn.data(), (const cx<float>*)wm.data(), scr.data(), 1);
+        });
+    for (auto& t : th) t.join();
+}
+
+extern "C" int emul_xform_f32(int kind, int N, float* data, int sj, float scale)
+{
+#define X(NN)                                                          \
+    case NN:                                                           \
+        if (kind == 0) run_one_f32<NN, XF_DST>(data, sj, scale);       \
+        else if (kind == 1) run_one_f32<NN, XF_PFWD>(data, sj, scale); \
+        else if (kind == 3) run_one_f32<NN, XF_DCT>(data, sj, scale);  \
+        else run_one_f32<NN, XF_PINV>(data, sj, scale);                \
+        return 0;
+    switch (N) { X(4) X(8) X(16) X(32) X(64) X(128) X(256) X(512) X(1024) }
+#undef X
+    return -1;
+}
+
 // fused DST (dst_tile_fused) on the planar tile layout: mode 0 = OutTile, 1 = OutGlobal-like policy
 // writing to a separate array, 2 = PREFOLD (fold applied by the caller, like k_rows_pipe's first touch).
 // swz selects the 8-column-tile swizzles (three-pass plans only).  data: natural slots 0..N-1, stride sj.

@@ -24,6 +24,7 @@ def emul():
                        check=True)
     L = C.CDLL(LIB)
     L.emul_xform.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double), C.c_int, C.c_double]
+    L.emul_xform_f32.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_float), C.c_int, C.c_float]
     L.emul_dst_fused.argtypes = [C.c_int, C.POINTER(C.c_double), C.c_int, C.c_double, C.c_int, C.POINTER(C.c_double), C.c_int]
     L.emul_dst_fused_half.argtypes = [C.POINTER(C.c_double), C.c_int, C.c_double, C.c_int, C.POINTER(C.c_double), C.c_int]
     return L
@@ -95,3 +96,27 @@ def test_fused_dst_1024_half_threads(emul, mode, swz):
     assert emul.emul_dst_fused_half(p(d), sj, 0.37, mode, p(sep), swz) == 0
     got = sep if mode == 1 else d[sj::sj][: N - 1]
     assert O.rel_l2(got, O.sFFT(x, 0.37)) < 2e-14
+
+
+@pytest.mark.parametrize("N", [4, 8, 16, 32, 64, 128, 256, 512, 1024])
+def test_tile_transforms_single_precision(emul, N):
+    """The same tile transforms instantiated for float (fdm::FFT<float>, src/fft.cpp:481): single-precision accuracy
+    against the double oracle, growing like sqrt(log N) as a float FFT does."""
+    rng = np.random.default_rng(7 * N)
+    pf = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))
+    tol = 4e-7 * (2 + np.log2(N))
+    x = rng.uniform(-1, 1, N - 1).astype(np.float32)
+    d = np.zeros(N, dtype=np.float32); d[1:] = x
+    assert emul.emul_xform_f32(0, N, pf(d), 1, 0.37) == 0
+    assert O.rel_l2(d[1:], O.sFFT(x.astype(np.float64), 0.37)) < tol
+    x = rng.uniform(-1, 1, N).astype(np.float32)
+    d = x.copy()
+    assert emul.emul_xform_f32(1, N, pf(d), 1, 0.37) == 0
+    assert O.rel_l2(d, O.pFFT_1(x.astype(np.float64), 0.37)) < tol
+    d = x.copy()
+    assert emul.emul_xform_f32(2, N, pf(d), 1, 0.37) == 0
+    assert O.rel_l2(d, O.pFFT(x.astype(np.float64), 0.37)) < tol
+    x = rng.uniform(-1, 1, N + 1).astype(np.float32)
+    d = x.copy()
+    assert emul.emul_xform_f32(3, N, pf(d), 1, 0.37) == 0
+    assert O.rel_l2(d, O.cFFT(x.astype(np.float64), 0.37)) < tol
