@@ -319,6 +319,13 @@ const ColsMaps* fdmb_lapl_cube::y_chunk_maps(bool wide, int z0, int nzc)
     return &cache.emplace(std::make_pair(z0, nzc), m).first->second;
 }
 
+static bool xinv_inplace()
+{
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("FDMB_XINV_INPLACE"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v != 0;
+}
+
 // FDMB_MG_OVERLAP: z chunks of the x-sweep / transposing-y-sweep overlap of the sharded solve (0 or 1: off)
 static int mg_overlap_chunks(int nranks)
 {
@@ -612,11 +619,22 @@ int fdmb_lapl_cube::sweeps(double* d_out, const double* d_in, cudaStream_t st, i
         FDMB_CUDA(launch_cols_cube_divide(Nz, periodic != 0, z, mid, st, "cube_z_fwd_div_inv"));
     }
     if (phases & 4) {
+        double* out_z0 = d_out + (long long)z0 * ny * nx;
+        // Where the ring row sweep runs (Nx = 1024), the y inverse sweep stores straight into the caller's UNPITCHED ans
+        // rows and the x inverse sweep transforms them in place: rows of odd pitch land at offsets of both parities,
+        // which is what makes the row sweep's dense reads conflict-free (xform_ring.cuh); the pitched work array's rows
+        // cannot (all 16-byte aligned).  Measured (r02x): the row sweep gains 0.5 ms (4.30 -> 3.80 ms), but the column
+        // sweep's 64-byte segments no longer start on sector boundaries in rows of 8184 bytes and its stores turn into
+        // read-modify-write traffic: 3.54 -> 9.64 ms.  OFF unless FDMB_XINV_INPLACE=1.
+        const bool inplace = pipe_x && pipe_y && Nx == 1024 && !periodic && ring_enabled() && xinv_inplace() &&
+                             (reinterpret_cast<uintptr_t>(out_z0) & 15) == 0;
         // y inverse
         c.scale = sly;
+        if (inplace) { c.out = out_z0; c.out_sj = nx; c.out_so = (long long)ny * nx; }
         FDMB_CUDA(cols_y(c, ki, "cube_y_inv", 0));
-        // x inverse: pitched work -> ans rows
-        r.in = d_work + (long long)z0 * plane; r.out = d_out + (long long)z0 * ny * nx; r.in_pitch = px; r.out_pitch = nx; r.scale = slx;
+        // x inverse: pitched work (or ans itself) -> ans rows
+        r.in = inplace ? out_z0 : d_work + (long long)z0 * plane; r.out = out_z0;
+        r.in_pitch = inplace ? nx : px; r.out_pitch = nx; r.scale = slx;
         FDMB_CUDA(rows(r, ki, "cube_x_inv", 1));
     }
     return FDMB_OK;

@@ -203,12 +203,22 @@ __global__ void __launch_bounds__(RingCfg<N>::THREADS, 1) k_rows_ring(RowsPipeAr
     const int YB = 1 << a.blog, SUB = YB / B > 0 ? YB / B : 1;   // blk = 2: B divides YB
     const int nyb = (a.ny + YB - 1) >> a.blog;
     const long long ntiles = (a.blk == 2) ? (long long)a.nz * nyb * SUB : (a.nrows + B - 1) / B;
-    // landing: pitched inputs (even pitch: every row starts 16-byte aligned) get one bulk copy per row and a skewed
-    // shared-memory pitch (a pitch that is a multiple of 16 doubles would put the 8 rows of a half-warp into one bank);
-    // odd pitches (the caller's unpitched N-1 arrays) land as ONE contiguous chunk with the pitch they have
+    // Landing of the 8 dense rows of a tile (stage A reads them with lanes = (row b, thread g): a half-warp's 16 accesses
+    // sit at off[b] + 2 g' + const, so it needs row offsets that cover BOTH parities to reach all 16 double-banks):
+    //   parity  the caller's unpitched arrays (pitch = N - 1, odd): row r of a tile starts 16-byte aligned for even r
+    //           and 8 bytes off for odd r.  One bulk copy per row of N doubles -- odd rows from one element earlier --
+    //           lands element j of row r at off[r] + j with off[r] = 1040 r + 4 (r >> 1) + (r & 1), i.e.
+    //           off[r] mod 16 = 0, 1, 4, 5, 8, 9, 12, 13: conflict-free (r02d: the chunk landing below was 2-way
+    //           conflicted, 32 % of the kernel's wavefronts).  The last row of the whole array is copied two doubles
+    //           short and patched (the copy would run past the allocation).
+    //   per_row pitched inputs (even pitch: every row 16-byte aligned): one copy per row, pitch skewed by 2 doubles;
+    //           all offsets even, so a half-warp reaches 8 banks: 2-way conflicts remain (work array -> ans sweep)
+    //   chunk   any other odd pitch: ONE contiguous copy with the pitch it has
+    const bool land_par = (a.in_pitch & 1) && a.in_pitch == N - 1 && a.nvalid == N - 1 && a.blk == 0;
     const bool per_row = (a.in_pitch & 1) == 0;
-    const int LP = (per_row && (a.in_pitch & 15) == 0) ? a.in_pitch + 2 : a.in_pitch;
+    const int LP = land_par ? 1040 : ((per_row && (a.in_pitch & 15) == 0) ? a.in_pitch + 2 : a.in_pitch);
     const unsigned row_bytes = (unsigned)a.in_pitch * 8u;
+    auto row_off = [&](int r) { return land_par ? r * 1040 + 4 * (r >> 1) + (r & 1) : r * LP; };
 
     auto locate = [&](long long tl, long long& in_row0, long long& nat_row0, int& rows) {
         if (a.reverse) tl = ntiles - 1 - tl;
@@ -238,7 +248,15 @@ __global__ void __launch_bounds__(RingCfg<N>::THREADS, 1) k_rows_ring(RowsPipeAr
         locate(tl, in_row0, nat_row0, rows);
         double* buf = bufs + s * BUF;
         const double* src = a.in + in_row0 * a.in_pitch;
-        if (per_row) {
+        if (land_par) {
+            unsigned total = 0;
+            for (int r = 0; r < rows; r++) total += (in_row0 + r == a.nrows - 1 && !(r & 1)) ? (N - 2) * 8u : N * 8u;
+            mbar_expect_tx(&full[s], total);
+            for (int r = 0; r < rows; r++) {
+                const unsigned bytes = (in_row0 + r == a.nrows - 1 && !(r & 1)) ? (N - 2) * 8u : N * 8u;
+                bulk_load_1d(buf + row_off(r) - (r & 1), src + (long long)r * a.in_pitch - (r & 1), bytes, &full[s]);
+            }
+        } else if (per_row) {
             mbar_expect_tx(&full[s], (unsigned)rows * row_bytes);
             for (int r = 0; r < rows; r++) bulk_load_1d(buf + r * LP, src + (long long)r * a.in_pitch, row_bytes, &full[s]);
         } else {
@@ -273,7 +291,13 @@ __global__ void __launch_bounds__(RingCfg<N>::THREADS, 1) k_rows_ring(RowsPipeAr
         double* buf = bufs + s * BUF;
         mbar_wait(&armed[s], parity);
         mbar_wait(&full[s], parity);
-        if (!per_row) {   // an odd tail (rows * pitch odd) leaves one double outside the 16-byte granularity of the bulk copy
+        if (land_par) {   // the array's last row (even position in its tile) was copied two doubles short: element N - 2
+            const int r = (int)(a.nrows - 1 - in_row0);
+            if (r >= 0 && r < B && !(r & 1)) {
+                if (t == 0) buf[row_off(r) + N - 2] = a.in[(a.nrows - 1) * a.in_pitch + N - 2];
+                gs.sync();
+            }
+        } else if (!per_row) {   // an odd tail (rows * pitch odd) leaves one double outside the 16-byte granularity of the bulk copy
             const long long cnt = (long long)rows * a.in_pitch;
             if (cnt & 1) {
                 if (t == 0) buf[cnt - 1] = a.in[in_row0 * a.in_pitch + cnt - 1];
@@ -283,7 +307,7 @@ __global__ void __launch_bounds__(RingCfg<N>::THREADS, 1) k_rows_ring(RowsPipeAr
         // fold + three radix passes + untangle + running sum, in place: dense rows in, planar rows [B][P] out
         dst_tile_fused_x<N, G, GAP, false, true, false>(buf + b * P, 1, g, hs, SNs, SF1, WMs, scr + b, B,
                                                         OutTile<N, GAP>{buf + b * P, 1}, (double*)nullptr, gs,
-                                                        InDense{buf + b * LP, b < rows});
+                                                        InDense{buf + row_off(b), b < rows});
         // copy-out: one warp per row, lanes along the row
         if (warp < rows) {
             double* dst = a.out + out_row(row0 + warp) * a.out_pitch;
@@ -351,7 +375,9 @@ template <int N> inline bool rows_ring_fits(const RowsPipeArgs& a)
 {
     using C = RingCfg<N>;
     const bool per_row = (a.in_pitch & 1) == 0;
-    const int LP = (per_row && (a.in_pitch & 15) == 0) ? a.in_pitch + 2 : a.in_pitch;
+    const bool parity = (a.in_pitch & 1) && a.in_pitch == N - 1 && a.blk == 0;
+    const int LP = parity ? 1040 : ((per_row && (a.in_pitch & 15) == 0) ? a.in_pitch + 2 : a.in_pitch);
+    static_assert(7 * 1040 + 12 + 1 + N <= C::ROWS_BUF || N != 1024, "parity landing fits the tile buffer");
     return a.nvalid == N - 1 && a.in_pitch >= a.nvalid && (long long)C::B * LP <= C::ROWS_BUF &&
            (reinterpret_cast<uintptr_t>(a.in) & 15) == 0;
 }
