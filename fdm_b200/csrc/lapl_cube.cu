@@ -166,6 +166,29 @@ cudaError_t launch_cols_pipe_cube_divide_shard(int N, bool periodic, const ColsM
     return cudaErrorInvalidValue;
 }
 
+cudaError_t launch_cols_pipe_shard_tma(int N, const ColsMaps& tm, ColsPipeArgs a, const OutShardTma& om, cudaStream_t st,
+                                       const char* tag)
+{
+    LaunchScope scope(tag, st);
+    MidNone mid;
+    FDMB_PICK_MAPS(true)
+#define X(NN) case NN: return launch_cols_pipe_t<NN, XF_DST, MidNone, XF_DST, OutShardTma>(m1, m2, a, mid, st, om);
+    switch (N) { FDMB_FOR_EACH_ROWS_PIPE_N(X) }        // lengths up to 1024: 16-column, unswizzled tiles
+#undef X
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_cols_pipe_cube_divide_shard_tma(int N, const ColsMaps& tm, ColsPipeArgs a, const MidCubeDivide& mid,
+                                                   const OutShardTma& om, cudaStream_t st, const char* tag)
+{
+    LaunchScope scope(tag, st);
+    FDMB_PICK_MAPS(true)
+#define X(NN) case NN: return launch_cols_pipe_t<NN, XF_DST, MidCubeDivide, XF_DST, OutShardTma>(m1, m2, a, mid, st, om);
+    switch (N) { FDMB_FOR_EACH_ROWS_PIPE_N(X) }
+#undef X
+    return cudaErrorInvalidValue;
+}
+
 // ---- cross-GPU barrier on the handle's stream -----------------------------------------------------
 // Thread t publishes this rank's arrival epoch into rank t's flag array (release, system scope: all
 // peer stores of the kernels that ran before on this stream are complete at the kernel boundary),
@@ -399,6 +422,44 @@ int fdmb_lapl_cube::attach(void* const* bases)
     for (int q = 0; q < nranks; q++)
         if (q != rank) peer_block[q] = bases[q];
     attached = true;
+    return build_store_maps();
+}
+
+// FDMB_MG_TMA_STORE=1: the transposing sweeps hand their finished tiles to the TMA unit (OutShardTma) instead of storing
+// every value from the transform's registers (EmitShard).  Parity-green, but measured SLOWER on 2 GPUs (r02p: 14.93 vs
+// 13.71 ms per solve; y forward 733 vs 584 us per chunk): with one 128 KB tile per CTA the tile has to be written to
+// shared memory, read by the TMA unit and released before the next load can start, while the register stores stream out
+// during the last two transform stages; and the NVLink packets are the same 128-byte rows either way.  Off by default.
+static bool mg_tma_store()
+{
+    const char* e = getenv("FDMB_MG_TMA_STORE");
+    return e && e[0] == '1';
+}
+
+// Tensor maps over every rank's pencil buffer T_q[z'][y slot][x] and slab A_q[z slot][y'][x], split into the views of
+// the odd and the even local slots (a planar tile holds a rank's odd slots and its even slots as two contiguous row
+// blocks).  Dirichlet sweeps only (the planar layout); boxes hold half a rank's slots (<= 256 rows).
+int fdmb_lapl_cube::build_store_maps()
+{
+    st_ready = false;
+    if (periodic || !mg_tma_store() || Sy / 2 > 256 || Sz / 2 > 256 || Sy < 2 || Sz < 2 || Ny > 1024 || Nz > 1024) return FDMB_OK;
+    const unsigned long long row = 8ull * px, plane_b = 8ull * (unsigned long long)ny * px;
+    const unsigned By = pipe_B_sharded(Ny), Bz = pipe_B_sharded(Nz);
+    int rc;
+    for (int q = 0; q < nranks; q++) {
+        char* T = reinterpret_cast<char*>(peer_block[q]) + off_T;
+        char* A = reinterpret_cast<char*>(peer_block[q]);
+        // y forward: destination rows are y slots (stride px), planes are z' (stride Sy * px)
+        if ((rc = make_tensor_map_3d(&st_y.even[q], T, nx, Sy / 2, nz, 2 * row, (unsigned long long)Sy * row, By, Sy / 2, 1))) return rc;
+        if ((rc = make_tensor_map_3d(&st_y.odd[q], T + row, nx, Sy / 2, nz, 2 * row, (unsigned long long)Sy * row, By, Sy / 2, 1))) return rc;
+        // z sweep: destination "rows" are z slots (stride one plane), the middle index is y'
+        if ((rc = make_tensor_map_3d(&st_z.even[q], A, nx, ny, Sz / 2, row, 2 * plane_b, Bz, 1, Sz / 2))) return rc;
+        if ((rc = make_tensor_map_3d(&st_z.odd[q], A + plane_b, nx, ny, Sz / 2, row, 2 * plane_b, Bz, 1, Sz / 2))) return rc;
+    }
+    st_y.nranks = st_z.nranks = nranks;
+    st_y.half = Sy / 2; st_y.taxis = 1; st_y.o_off = z_first;
+    st_z.half = Sz / 2; st_z.taxis = 2; st_z.o_off = y_first;
+    st_ready = true;
     return FDMB_OK;
 }
 
@@ -470,6 +531,11 @@ int fdmb_lapl_cube::solve_device_sharded(double* d_out, const double* d_in, cuda
         ColsPipeArgs p{};
         p.out = nullptr; p.nvalid = ny; p.nb = nx; p.no = no; p.taxis = 1; p.max_ctas = max_ctas;
         p.reverse = 1; p.scale = dy * sly; p.SN = ty.SN; p.WM = ty.WM;
+        if (kf == XF_DST && (st_ready || (preload_only() && Ny <= 1024 && Nz <= 1024)) && mg_tma_store()) {
+            OutShardTma ot = st_y;
+            ot.o_off = z_first + o0;
+            return launch_cols_pipe_shard_tma(Ny, *maps, p, ot, st, "cube_y_fwd_xpose");
+        }
         OutShard om{};
         for (int q = 0; q < nranks; q++)
             om.base[q] = reinterpret_cast<double*>(reinterpret_cast<char*>(peer_block[q]) + off_T);
@@ -511,10 +577,14 @@ int fdmb_lapl_cube::solve_device_sharded(double* d_out, const double* d_in, cuda
         p.out = nullptr; p.nvalid = nz; p.nb = nx; p.no = nyl; p.taxis = 2;
         p.reverse = 0; p.mid_o_off = y_first; p.scale = dz * slz; p.scale2 = slz; p.SN = tz.SN; p.WM = tz.WM;
         MidCubeDivide mid{d_lmz, d_lmx, d_lmy, periodic ? 1 : 0};
+        if (!periodic && (st_ready || (preload_only() && Ny <= 1024 && Nz <= 1024)) && mg_tma_store()) {
+            FDMB_CUDA(launch_cols_pipe_cube_divide_shard_tma(Nz, tm_z, p, mid, st_z, st, "cube_z_fwd_div_inv_xpose"));
+        } else {
         OutShard om{};
         for (int q = 0; q < nranks; q++) om.base[q] = reinterpret_cast<double*>(peer_block[q]);
         om.logS = ilog2(Sz); om.maskS = Sz - 1; om.sj = plane; om.so = px; om.o_off = y_first;
         FDMB_CUDA(launch_cols_pipe_cube_divide_shard(Nz, periodic != 0, tm_z, p, mid, om, st, "cube_z_fwd_div_inv_xpose"));
+        }
     }
     if ((rc = barrier(st))) return rc;
     {   // y inverse (local)

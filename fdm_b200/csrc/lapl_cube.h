@@ -36,6 +36,11 @@ cudaError_t launch_cols_pipe_shard(int N, int kind, const ColsMaps& tm, ColsPipe
 cudaError_t launch_cols_pipe_cube_divide_shard(int N, bool periodic, const ColsMaps& tm, ColsPipeArgs a,
                                                const MidCubeDivide& mid, const OutShard& om, cudaStream_t st,
                                                const char* tag);
+// DST sweeps whose finished tiles leave as TMA tile stores (OutShardTma)
+cudaError_t launch_cols_pipe_shard_tma(int N, const ColsMaps& tm, ColsPipeArgs a, const OutShardTma& om, cudaStream_t st,
+                                       const char* tag);
+cudaError_t launch_cols_pipe_cube_divide_shard_tma(int N, const ColsMaps& tm, ColsPipeArgs a, const MidCubeDivide& mid,
+                                                   const OutShardTma& om, cudaStream_t st, const char* tag);
 
 // Even split of the N index slots of one axis over P ranks (N, P powers of two).  Slot 0 of a
 // Dirichlet axis is the implicit zero boundary, so rank 0 owns one interior entry fewer.
@@ -90,6 +95,10 @@ struct fdmb_lapl_cube {
     bool attached = false;
     unsigned long long epoch = 0;
     int device = 0;
+    // TMA tile-store views of every rank's pencil buffer (y forward sweep) and slab (z sweep), built at attach()
+    fdmb::OutShardTma st_y{}, st_z{};
+    bool st_ready = false;
+    int build_store_maps();
     // overlap of the local x sweep with the NVLink-bound transposing y sweep (solve_device_sharded)
     cudaStream_t s_side = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_chunk[16] = {}, ev_done[16] = {};

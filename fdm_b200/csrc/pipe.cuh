@@ -87,6 +87,19 @@ __device__ __forceinline__ void tma_load_3d_hint(void* smem_dst, const CUtensorM
         "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)), "l"(pol)
         : "memory");
 }
+// shared -> global (tensor map, 3-D tile), bulk async-group completion; elements outside the tensor are not written
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, const void* smem_src, int c0, int c1, int c2)
+{
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(tm), "r"(c0), "r"(c1),
+                 "r"(c2), "r"(smem_u32(smem_src))
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all committed bulk groups of this thread have finished READING their shared-memory sources
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// ... have completed altogether (their global writes are performed)
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm)
 {
     asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");

@@ -128,6 +128,21 @@ struct OutShard {
     }
 };
 
+// The transposing sweeps' stores as TMA tile stores out of the finished planar tile (DST sweeps): per destination rank
+// one box of its odd slots and one of its even slots (the same strided views the planar LOADS use).  The SMs only
+// issue 2 * nranks descriptors per tile; the NVLink writes drain in the background while the CTA fetches and
+// transforms its next tile -- with per-value st.global the store instructions themselves stalled on the link.
+struct OutShardTma {
+    static constexpr bool sharded = true;
+    static constexpr bool tma_store = true;
+    CUtensorMap odd[FDMB_MAX_RANKS], even[FDMB_MAX_RANKS];   // destination views of rank q: local slots 1,3,.. / 0,2,..
+    int nranks, half;               // half = slots per rank / 2 = rows per box
+    int taxis;                      // 1: box (cols, rows, 1), coordinates (b0, 0, o + o_off); 2: box (cols, 1, rows), (b0, o + o_off, 0)
+    int o_off;
+};
+template <typename OMAP, typename = void> struct UsesTmaStore { static constexpr bool value = false; };
+template <typename OMAP> struct UsesTmaStore<OMAP, decltype((void)OMAP::tma_store)> { static constexpr bool value = OMAP::tma_store; };
+
 struct ColsPipeArgs {
     double* out;
     long long out_sj, out_so;   // output strides (doubles) along the transform / outer axis
@@ -249,7 +264,37 @@ k_cols_pipe(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUte
         double* tile = bufs + s * BUF;
         mbar_wait(&full[s], parity);
 
-        if constexpr (FUSED) {
+        if constexpr (FUSED && UsesTmaStore<OMAP>::value) {
+            // transposing sweep: the last transform leaves its spectrum in the planar tile, one thread hands the tile to
+            // the TMA unit as 2 * nranks boxes (odd / even slots of every destination rank)
+            static_assert(!C::SWZ && !SEP, "TMA tile stores need the unswizzled single-tile layout");
+            const OutTile<N, GAP> ot{tile + b, B};
+            if constexpr (MID::active) {
+                const OutMidTile<N, GAP, MID> om{tile + b, B, mid, mid.ctx(bok ? b0 + b + 1 : 0, o + a.mid_o_off + 1), bok};
+                dst_tile_fused<N, G, GAP, false, false, false>(tile + b, B, g, 0.5 * a.scale, SNs, SF1, WMs, scr + b, B, om);
+                dst_tile_fused<N, G, GAP, false, false, false>(tile + b, B, g, 0.5 * a.scale2, SNs, SF2, WMs, scr + b, B, ot);
+            } else {
+                dst_tile_fused<N, G, GAP, false, false, false>(tile + b, B, g, 0.5 * a.scale, SNs, SF1, WMs, scr + b, B, ot);
+            }
+            fence_proxy_async();          // the transform's generic-proxy writes, before the async proxy reads the tile
+            __syncthreads();
+            if (tid == 0) {
+                const int oc = o + omap.o_off;
+                for (int q = 0; q < omap.nranks; q++) {
+                    const double* so = tile + (size_t)(q * omap.half) * B;                    // O[k]: slot 2k + 1
+                    const double* se = tile + (size_t)(M + GAP + q * omap.half) * B;          // E[k]: slot 2k
+                    if (omap.taxis == 1) {
+                        tma_store_3d(&omap.odd[q], so, b0, 0, oc);
+                        tma_store_3d(&omap.even[q], se, b0, 0, oc);
+                    } else {
+                        tma_store_3d(&omap.odd[q], so, b0, oc, 0);
+                        tma_store_3d(&omap.even[q], se, b0, oc, 0);
+                    }
+                }
+                bulk_commit();
+                bulk_wait_read();         // the tile may be overwritten once the TMA unit has read it
+            }
+        } else if constexpr (FUSED) {
             // smem-lean path: finished spectral values leave the registers straight to global memory
             const auto og = omap.emitter(a.out, a.out_sj, ooff, J0, o, b0 + b, bok);
             if constexpr (MID::active) {
@@ -286,6 +331,9 @@ k_cols_pipe(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUte
         __syncthreads();
         const int tn = t + NSTAGE * gridDim.x;
         if (tid == 0 && tn < ntiles) issue(tn, s);
+    }
+    if constexpr (UsesTmaStore<OMAP>::value) {
+        if (tid == 0) bulk_wait_all();    // the tile stores are performed before the CTA (and the kernel) ends
     }
 }
 

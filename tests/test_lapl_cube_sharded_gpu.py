@@ -149,6 +149,19 @@ def test_sharded_eigenvector_kat_device(fb, n):
         assert (num / den) ** 0.5 < TOL, f"P={P}"
 
 
+@pytest.mark.parametrize("shape", [(63, 63, 63), (127, 255, 31), (1023, 63, 31), (63, 1023, 31)], ids=lambda s: "x".join(map(str, s)))
+def test_sharded_tma_tile_stores(fb, monkeypatch, shape):
+    """FDMB_MG_TMA_STORE=1 (off by default, see lapl_cube.cu): the transposing sweeps leave their tiles through TMA tile
+    stores into the peers' buffers -- odd / even slot views per destination rank -- instead of per-value peer stores."""
+    monkeypatch.setenv("FDMB_MG_TMA_STORE", "1")
+    nz, ny, nx = shape
+    rhs = O.synthetic_rhs(shape, seed=sum(shape) + 1)
+    args = (0.1, 0.2, 0.3, 0.1 * (nx + 1), 0.2 * (ny + 1), 0.3 * (nz + 1), nx, ny, nz)
+    want = O.LaplCube(*args).solve(rhs)
+    for P in ranks_available(fb):
+        assert O.rel_l2(solve_in_process(fb, args, rhs, P, repeats=2), want) < TOL, f"P={P}"
+
+
 def test_sharded_rejects_bad_split(fb):
     with pytest.raises(fb.FdmB200Error):
         fb.LaplCubeSharded(1, 1, 1, 16, 16, 16, 15, 15, 15, rank=0, nranks=2)     # transform length 16 < 32
