@@ -195,9 +195,20 @@ cudaError_t launch_cols_pipe_cube_divide_shard_tma(int N, const ColsMaps& tm, Co
 // then waits until rank t's epoch has arrived here.  A lost peer traps after ~30 s instead of hanging.
 struct PeerFlags { unsigned long long* f[FDMB_MAX_RANKS]; };
 
-__global__ void k_mg_barrier(PeerFlags pf, int rank, int nranks, unsigned long long epoch)
+// The epoch is NOT a kernel argument: every rank counts its own barriers in device memory (slot FDMB_MAX_RANKS of its
+// flag array; all ranks execute the same sequence of barriers, so the counters agree).  A launch sequence that contains
+// barriers can therefore be captured once and replayed as a CUDA graph (the sharded NS steps).
+__global__ void k_mg_barrier(PeerFlags pf, int rank, int nranks)
 {
+    __shared__ unsigned long long s_epoch;
     const int t = threadIdx.x;
+    if (t == 0) {
+        unsigned long long* cnt = pf.f[rank] + FDMB_MAX_RANKS;
+        s_epoch = *cnt + 1;
+        *cnt = s_epoch;
+    }
+    __syncthreads();
+    const unsigned long long epoch = s_epoch;
     if (t < nranks) {
         __threadfence_system();
         unsigned long long* dst = pf.f[t] + rank;
@@ -217,14 +228,13 @@ __global__ void k_mg_barrier(PeerFlags pf, int rank, int nranks, unsigned long l
     __threadfence_system();
 }
 
-int launch_mg_barrier(void* const* peer_blocks, size_t off_flags, int rank, int nranks, unsigned long long epoch,
-                      cudaStream_t st)
+int launch_mg_barrier(void* const* peer_blocks, size_t off_flags, int rank, int nranks, cudaStream_t st)
 {
     PeerFlags pf{};
     for (int q = 0; q < nranks; q++)
         pf.f[q] = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(peer_blocks[q]) + off_flags);
     LaunchScope scope("mg_barrier", st);
-    k_mg_barrier<<<1, 32, 0, st>>>(pf, rank, nranks, epoch);
+    k_mg_barrier<<<1, 32, 0, st>>>(pf, rank, nranks);
     FDMB_CHECK_LAUNCH();
     return FDMB_OK;
 }
@@ -469,9 +479,8 @@ int fdmb_lapl_cube::barrier(cudaStream_t st)
     PeerFlags pf{};
     for (int q = 0; q < nranks; q++)
         pf.f[q] = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(peer_block[q]) + off_flags);
-    epoch++;
     LaunchScope scope("cube_mg_barrier", st);
-    k_mg_barrier<<<1, 32, 0, st>>>(pf, rank, nranks, epoch);
+    k_mg_barrier<<<1, 32, 0, st>>>(pf, rank, nranks);
     FDMB_CHECK_LAUNCH();
     return FDMB_OK;
 }
@@ -546,6 +555,10 @@ int fdmb_lapl_cube::solve_device_sharded(double* d_out, const double* d_in, cuda
     // into z chunks and let the x sweep of chunk c+1 run beside the y sweep of chunk c, each on its share of the SMs
     // (side stream + events; the x sweep gets `split` SMs, the y sweep the rest).  FDMB_MG_OVERLAP = chunks (0: off).
     int nch = mg_overlap_chunks(nranks);
+    {   // a chunk has to be worth two launches: at least 16 M points (1023^3: 4-8 chunks; 255^3: none)
+        const long long by_size = (long long)nzl * ny * nx / (16ll << 20);
+        if (nch > by_size) nch = (int)by_size;
+    }
     if (preload_only() || nch < 2 || nzl < 2 * nch || nch > 16 || !pipe_supported_N(Nx)) nch = 1;
     if (nch == 1) {
         FDMB_CUDA(rows(d_in, d_work, nx, px, dx * slx, kf, "cube_x_fwd", 0, (long long)nzl * ny, st, 0));

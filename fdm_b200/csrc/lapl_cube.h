@@ -19,9 +19,9 @@ inline bool rows_pipe_supported_N(int N) { return pipe_supported_N(N) && N <= 10
 inline int pipe_B(int N) { return N <= 512 ? 16 : 8; }
 bool ring_enabled();     // FDMB_RING=0 selects the one-tile-per-CTA sweeps at N = 1024 (A/B measurements)
 // cross-GPU barrier on a stream over the flag arrays at `off_flags` inside every rank's peer-mapped block
-// (FDMB_MAX_RANKS u64 epochs each, zero-initialised); epoch must increase by one per call on every rank
-int launch_mg_barrier(void* const* peer_blocks, size_t off_flags, int rank, int nranks, unsigned long long epoch,
-                      cudaStream_t st);
+// (FDMB_MAX_RANKS u64 arrival epochs + this rank's own barrier count, zero-initialised; every rank must run the same
+// sequence of barriers)
+int launch_mg_barrier(void* const* peer_blocks, size_t off_flags, int rank, int nranks, cudaStream_t st);
 int preload_mg_barrier();
 inline int pipe_B_sharded(int N) { return N <= 1024 ? 16 : 8; }     // PipeCfg<N, true>::B
 cudaError_t launch_rows_pipe(int N, int kind, const RowsPipeArgs& a, cudaStream_t st, const char* tag);
@@ -93,7 +93,6 @@ struct fdmb_lapl_cube {
     void* peer_block[fdmb::FDMB_MAX_RANKS] = {};           // mapped bases of every rank's mg_block (own included)
     bool peer_ipc[fdmb::FDMB_MAX_RANKS] = {};
     bool attached = false;
-    unsigned long long epoch = 0;
     int device = 0;
     // TMA tile-store views of every rank's pencil buffer (y forward sweep) and slab (z sweep), built at attach()
     fdmb::OutShardTma st_y{}, st_z{};

@@ -448,8 +448,7 @@ int fdmb_lapl_cyl::init_sharded()
 int fdmb_lapl_cyl::barrier(cudaStream_t st)
 {
     if (preload_only()) return FDMB_OK;
-    epoch++;
-    return launch_mg_barrier(peer_block, off_flags, rank, nranks, epoch, st);
+    return launch_mg_barrier(peer_block, off_flags, rank, nranks, st);
 }
 
 // d_in / d_out: this rank's phi-slab [Sphi][nz][nr] of the caller's arrays

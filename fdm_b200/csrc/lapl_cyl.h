@@ -59,7 +59,6 @@ struct fdmb_lapl_cyl {
     void* peer_block[fdmb::FDMB_MAX_RANKS] = {};
     bool peer_ipc[fdmb::FDMB_MAX_RANKS] = {};
     bool attached = false;
-    unsigned long long epoch = 0;
     fdmb::ColsMaps tm_tphi{}, tm_tphi_l{}, tm_za{};   // phi sweeps over the local pencils (wide tiles for the transposing
                                                       // one, normal tiles for the local one), z inverse over the slab
     int init_sharded();

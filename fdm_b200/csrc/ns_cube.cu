@@ -637,8 +637,8 @@ int fdmb_ns_cube::step(int nsteps, cudaStream_t st)
 {
     if (nranks > 1 && !attached) { set_error("NSCube: sharded handle used before attach_ipc/attach_local"); return FDMB_ERR_COMM; }
     for (int s = 0; s < nsteps; s++) {
-        // sharded steps carry the barrier epoch as a kernel argument: they are launched kernel by kernel
-        const int rc = nranks > 1 ? step_once(st) : graph.run(st, this, nullptr, [&]() { return step_once(st); });
+        // (sharded steps too: the cross-GPU barriers keep their epoch in device memory, so the sequence replays)
+        const int rc = graph.run(st, this, nullptr, [&]() { return step_once(st); });
         if (rc) return rc;
         time_index++;
     }

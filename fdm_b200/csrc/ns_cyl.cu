@@ -603,9 +603,8 @@ int fdmb_ns_cyl::step(int nsteps, int linear, cudaStream_t st)
 {
     if (nranks > 1 && !attached) { set_error("NSCyl: sharded handle used before attach_ipc/attach_local"); return FDMB_ERR_COMM; }
     for (int s = 0; s < nsteps; s++) {
-        // sharded steps carry the barrier epoch as a kernel argument: they are launched kernel by kernel
-        const int rc = nranks > 1 ? step_once(linear, st)
-                                  : graph[linear ? 1 : 0].run(st, this, nullptr, [&]() { return step_once(linear, st); });
+        // (sharded steps too: the cross-GPU barriers keep their epoch in device memory, so the sequence replays)
+        const int rc = graph[linear ? 1 : 0].run(st, this, nullptr, [&]() { return step_once(linear, st); });
         if (rc) return rc;
         time_index++;
     }
