@@ -90,10 +90,21 @@ cudaError_t launch_rows_pipe(int N, int kind, const RowsPipeArgs& a, cudaStream_
     return cudaErrorInvalidValue;
 }
 
+// FDMB_RING_PAIR (bit 0: y sweeps, bit 1: z sweep): the two groups of a ring CTA take ADJACENT tiles (the two 64-byte
+// halves of the same lines and pages) instead of tiles a grid stride apart.  Measured (r02x): 22.25-22.31 ms against
+// 22.42-22.43 ms -- within the run-to-run noise; off.
+static int ring_pair()
+{
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("FDMB_RING_PAIR"); v = e ? atoi(e) : 0; }
+    return v;
+}
+
 cudaError_t launch_cols_pipe(int N, int kind, const ColsMaps& tm, ColsPipeArgs a, cudaStream_t st, const char* tag)
 {
     LaunchScope scope(tag, st);
     MidNone mid;
+    a.pair_tiles = ring_pair() & 1;
     FDMB_PICK_MAPS(kind == XF_DST)
     if (N == 1024 && kind == XF_DST && ring_enabled()) return launch_cols_ring_t<1024, MidNone>(m1, m2, a, mid, st);
 #define X(NN)                                                                                          \
@@ -124,6 +135,7 @@ cudaError_t launch_cols_pipe_cube_divide(int N, bool periodic, const ColsMaps& t
                                          const MidCubeDivide& mid, cudaStream_t st, const char* tag)
 {
     LaunchScope scope(tag, st);
+    a.pair_tiles = (ring_pair() >> 1) & 1;
     FDMB_PICK_MAPS(!periodic)
     if (N == 1024 && !periodic && ring_enabled()) return launch_cols_ring_t<1024, MidCubeDivide>(m1, m2, a, mid, st);
 #define X(NN)                                                                                              \

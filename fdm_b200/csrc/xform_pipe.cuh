@@ -157,6 +157,8 @@ struct ColsPipeArgs {
     int reverse;                // walk the tiles back to front (L2 reuse against the previous sweep)
     int mid_o_off;              // added to the outer index handed to the mid functor (sharded sweeps)
     int max_ctas;               // > 0: upper bound of the grid (leaves SMs to a kernel running beside this one)
+    int pair_tiles;             // ring sweeps: the two groups of a CTA take ADJACENT tiles (the two 64-byte halves of the
+                                // same 128-byte lines, the same pages) instead of tiles a whole grid stride apart
     double scale, scale2;
     const double* SN;
     const cd* WM;

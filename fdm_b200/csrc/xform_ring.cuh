@@ -132,15 +132,20 @@ k_cols_ring(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUte
     load_fold_table<N>(SF1, a.SN, 0.5 * a.scale);
     if constexpr (MID::active) load_fold_table<N>(SF2, a.SN, 0.5 * a.scale2);
     __syncthreads();
+    // tile of this CTA's i-th slot: grid-strided, or in adjacent pairs (i even / odd = the two groups)
+    auto tile_of = [&](int i) -> long long {
+        return a.pair_tiles ? 2ll * blockIdx.x + (i & 1) + (long long)(i >> 1) * 2 * gridDim.x
+                            : blockIdx.x + (long long)i * gridDim.x;
+    };
     if (tid == 0) {
         for (int i = 0; i < NBUF; i++) {
-            const long long tile = blockIdx.x + (long long)i * gridDim.x;
+            const long long tile = tile_of(i);
             if (tile < ntiles) issue((int)tile, i);
         }
     }
 
     for (int i = grp;; i += C::NG) {
-        const long long tile_l = blockIdx.x + (long long)i * gridDim.x;
+        const long long tile_l = tile_of(i);
         if (tile_l >= ntiles) break;
         const int s = i % NBUF;
         const unsigned parity = (i / NBUF) & 1;
@@ -170,7 +175,7 @@ k_cols_ring(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUte
         // async-proxy writes of the tile that lands here next (consumed by the other group)
         fence_proxy_async();
         gs.sync();
-        const long long tn = tile_l + (long long)NBUF * gridDim.x;
+        const long long tn = tile_of(i + NBUF);
         if (t == 0 && tn < ntiles) issue((int)tn, s);
     }
 }
