@@ -47,6 +47,8 @@ struct NSGeom {
     double idx2, idy2, idz2; // 1/dx2 ...
     double idt;
     double dtdx, dtdy, dtdz; // dt/dx ...
+    double dcx, dcy, dcz, dcc; // dt/Re/dx2 ..., -2 (dcx + dcy + dcz)     (k_fgh_div)
+    double qx, qy, qz;         // dt/(4 dx) ...
 };
 
 // ---- init_bound ---------------------------------------------------------------------
@@ -239,148 +241,172 @@ template <typename T> __global__ void __launch_bounds__(256) k_fgh(FldT<T> u, Fl
 }
 
 // ---- FGH + divergence in one sweep (ns_cube.cpp:126-200 and 204-235) -------------------------------------------
-// z-marching, shared-memory staged.  A block owns a (TK-1) x (TJ-1) core of (k, j) points and marches over a chunk of
-// z planes; its TK x TJ threads cover the core plus one row below and one column to the left, where only the G / F
-// values the core's divergence needs are produced.  Per plane:
-//   * the (TK+2) x (TJ+2) halo tiles of u, v, w of planes i-1, i, i+1 sit in a ring of FOUR shared-memory planes per
-//     field: every value is fetched from global memory once per block, and plane i+2 streams into the fourth slot with
-//     asynchronous copies (cp.async, zero-filled outside the field) while plane i is computed;
-//   * every thread evaluates F, G, H at its point from the staged taps and publishes F, G in shared memory;
-//   * the core threads form RHS = ((F - F[j-1])/dx + (G - G[k-1])/dy + (H - H[i-1])/dz)/dt - ghost pressures, with H[i-1]
-//     carried in a register from the previous plane (the chunk's first plane i = ia - 1 only produces it).
+// z-marching with the taps in registers, warps independent of each other (no shared memory, no barrier).  A warp owns
+// 31 consecutive j of one row k (lane 0 is the column to the left, where only F is produced) and marches over a chunk of
+// z planes.  Of the taps of a plane's stencils, twelve are last step's registers (the five taps of plane i+1 become
+// centre taps, seven centre taps become taps of plane i-1), so a step loads 20 values per point through row pointers
+// that advance by one plane.
+//   RHS = ((F - F[j-1])/dx + (G - G[k-1])/dy + (H - H[i-1])/dz)/dt - ghost pressures:
+//   F[j-1] comes from the lane to the left (shuffle), H[i-1] is the thread's own value of the previous plane (the chunk's
+//   first plane i = ia - 1 only produces it), and G[k-1] is evaluated a second time by the thread itself with the
+//   k-shifted taps (three more loads and one more stencil, +28 % fp64 work): exchanging it between warps costs a
+//   barrier per plane, which serialises the load and compute phases of a block (measured: 404 us against 388 us for
+//   k_fgh + k_rhs at 255^3).
 // Traffic: u, v, w read once, F, G, H, RHS written once = 56 B per point, against 80 B for k_fgh + k_rhs.
-// The same kernel serves a z-slab of the sharded step: it starts one plane below the slab like k_fgh did.
-template <int TJ, int TK>
-__global__ void __launch_bounds__(TJ * TK, 2)
-k_fgh_rhs(Fld u, Fld v, Fld w, Fld p, Fld F, Fld G, Fld H, Fld R, NSGeom g, int ia0, int ib0, int zchunk)
+// The same kernel serves a z-slab of the sharded step: it starts one plane below the slab like k_fgh does.
+// Addresses of taps a thread does not use stay inside the allocation: rows k-1 of u and w fall back to row k where
+// k = 0 (row k-2 of v to row k-1), and v / w at j-1 = -1 (lane 0 of the first block column, F only) is the element
+// before the row.
+// one momentum stencil with dt folded into the coefficients:
+//   c + dcx sx + dcy sy + dcz sz + dcc c  =  c + dt (second differences)/Re       (sx = the two x neighbours' sum ...)
+//   - qa (a^2 - b^2)                      =  - dt ((a/2)^2 - (b/2)^2)/d           (the squared face averages)
+//   - q1 d1 - q2 d2                       =  - dt/4 (product differences)/d       (the two cross terms)
+// 9 fused operations instead of the 20 of the reference's order of evaluation; differs from it by a few ulps.
+__device__ __forceinline__ double fgh_combine(const NSGeom& g, double c, double sx, double sy, double sz, double a, double b,
+                                              double qa, double d1, double q1, double d2, double q2)
 {
-    constexpr int NT = TJ * TK;
-    constexpr int PW = TJ + 2 + 1;                 // tile pitch (odd: rows start in different banks)
-    constexpr int PLANE = (TK + 2) * PW;
-    extern __shared__ double fgh_smem[];
-    double (*su)[PLANE] = reinterpret_cast<double (*)[PLANE]>(fgh_smem);
-    double (*sv)[PLANE] = su + 4;
-    double (*sw)[PLANE] = sv + 4;
-    double (*sF)[TJ + 1] = reinterpret_cast<double (*)[TJ + 1]>(fgh_smem + 12 * PLANE);
-    double (*sG)[TJ + 1] = sF + TK;
-    const int tj = threadIdx.x, tk = threadIdx.y, tid = tk * TJ + tj;
-    const int j0 = 1 + blockIdx.x * (TJ - 1), k0 = 1 + blockIdx.y * (TK - 1);
-    const int ia = ia0 + blockIdx.z * zchunk;
-    const int ib = (ia + zchunk - 1 < ib0) ? ia + zchunk - 1 : ib0;
-    const int j = j0 - 1 + tj, k = k0 - 1 + tk;
-    const int nx = g.nx, ny = g.ny, nz = g.nz;
-    // global extents of the three fields (ns_cube.h:66-68); z: the planes this rank holds start at f.lz
-    // one element of a halo tile: asynchronous 8-byte copy, zero-filled outside the field (z: the planes this rank
-    // holds start at f.lz)
-    auto stage = [&](double* dst, const Fld& f, int i, int kk, int jj) {
-        const bool in = i >= f.lz && i <= nz + 1 && kk >= f.ly && kk <= ny + 1 && jj >= f.lx && jj <= nx + 1;
-        const double* src = in ? &f.at(i, kk, jj) : f.p;
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src),
-                     "r"(in ? 8 : 0)
-                     : "memory");
-    };
-    auto load_plane = [&](int i) {
-        const int s = (i + 4) & 3;
-        for (int e = tid; e < (TK + 2) * (TJ + 2); e += NT) {
-            const int r = e / (TJ + 2), c = e - r * (TJ + 2);
-            const int kk = k0 - 2 + r, jj = j0 - 2 + c, off = r * PW + c;
-            stage(&su[s][off], u, i, kk, jj);
-            stage(&sv[s][off], v, i, kk, jj);
-            stage(&sw[s][off], w, i, kk, jj);
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    load_plane(ia - 2); load_plane(ia - 1); load_plane(ia);
-    const bool core = tk >= 1 && tj >= 1 && k <= ny && j <= nx;
-    const bool doF = k >= 1 && k <= ny && j <= nx;            // j >= 0 always
-    const bool doG = j >= 1 && j <= nx && k <= ny;            // k >= 0 always
-    double hprev = 0.0;
-    for (int i = ia - 1; i <= ib; i++) {
-        // planes up to i + 1 have landed for everybody; plane i + 2 (needed from the next iteration on) streams into the
-        // slot plane i - 2 left, which nobody reads any more (the barrier at the end of the previous iteration)
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncthreads();
-        if (i + 1 <= ib) load_plane(i + 2);
-        double fv = 0.0, gv = 0.0, hv = 0.0;
-        const bool fg = i >= ia;
-        {
-            // the 27 distinct taps of the three stencils, read once (every thread's 3 x 3 x 3 neighbourhood lies inside
-            // the staged tiles), named by (di,dk,dj) with m = -1, p = +1 like k_fgh
-            const int c0 = (tk + 1) * PW + (tj + 1);
-            const double* __restrict__ uc_ = su[(i + 4) & 3] + c0;
-            const double* __restrict__ uip = su[(i + 5) & 3] + c0;
-            const double* __restrict__ uim = su[(i + 3) & 3] + c0;
-            const double* __restrict__ vc_ = sv[(i + 4) & 3] + c0;
-            const double* __restrict__ vip = sv[(i + 5) & 3] + c0;
-            const double* __restrict__ vim = sv[(i + 3) & 3] + c0;
-            const double* __restrict__ wc_ = sw[(i + 4) & 3] + c0;
-            const double* __restrict__ wip = sw[(i + 5) & 3] + c0;
-            const double* __restrict__ wim = sw[(i + 3) & 3] + c0;
-            const double u000 = uc_[0], u00p = uc_[1], u00m = uc_[-1], u0p0 = uc_[PW], u0pm = uc_[PW - 1], u0m0 = uc_[-PW];
-            const double up00 = uip[0], up0m = uip[-1], um00 = uim[0];
-            const double v000 = vc_[0], v00p = vc_[1], v00m = vc_[-1], v0p0 = vc_[PW], v0m0 = vc_[-PW], v0mp = vc_[-PW + 1];
-            const double vp00 = vip[0], vpm0 = vip[-PW], vm00 = vim[0];
-            const double w000 = wc_[0], w00p = wc_[1], w00m = wc_[-1], w0p0 = wc_[PW], w0m0 = wc_[-PW];
-            const double wp00 = wip[0], wm00 = wim[0], wm0p = wim[1], wmp0 = wim[PW];
-            if (fg && doF)
-                fv = u000 + g.dt * (
-                    (u00p - 2 * u000 + u00m) * g.cRx +
-                    (u0p0 - 2 * u000 + u0m0) * g.cRy +
-                    (up00 - 2 * u000 + um00) * g.cRz -
-                    (sq(0.5 * (u000 + u00p)) - sq(0.5 * (u00m + u000))) * g.idx -
-                    0.25 * ((u000 + u0p0) * (v00p + v000) -
-                            (u0m0 + u000) * (v0mp + v0m0)) * g.idy -
-                    0.25 * ((u000 + up00) * (w00p + w000) -
-                            (um00 + u000) * (wm0p + wm00)) * g.idz);
-            if (fg && doG)
-                gv = v000 + g.dt * (
-                    (v00p - 2 * v000 + v00m) * g.cRx +
-                    (v0p0 - 2 * v000 + v0m0) * g.cRy +
-                    (vp00 - 2 * v000 + vm00) * g.cRz -
-                    (sq(0.5 * (v000 + v0p0)) - sq(0.5 * (v0m0 + v000))) * g.idy -
-                    0.25 * ((u000 + u0p0) * (v00p + v000) -
-                            (u00m + u0pm) * (v000 + v00m)) * g.idx -
-                    0.25 * ((w000 + w0p0) * (v000 + vp00) -
-                            (wm00 + wmp0) * (vm00 + v000)) * g.idz);
-            if (core)
-                hv = w000 + g.dt * (
-                    (w00p - 2 * w000 + w00m) * g.cRx +
-                    (w0p0 - 2 * w000 + w0m0) * g.cRy +
-                    (wp00 - 2 * w000 + wm00) * g.cRz -
-                    (sq(0.5 * (wp00 + w000)) - sq(0.5 * (wm00 + w000))) * g.idz -
-                    0.25 * ((up00 + u000) * (w00p + w000) -
-                            (up0m + u00m) * (w000 + w00m)) * g.idx -
-                    0.25 * ((w000 + w0p0) * (v000 + vp00) -
-                            (w0m0 + w000) * (v0m0 + vpm0)) * g.idy);
-        }
-        sF[tk][tj] = fv; sG[tk][tj] = gv;
-        __syncthreads();
-        if (fg) {
-            if (doF && (tj >= 1 || j == 0)) F.p[lin(F, i, k, j)] = fv;
-            if (doG && (tk >= 1 || k == 0)) G.p[lin(G, i, k, j)] = gv;
-        }
-        if (core) {
-            if (fg || i == 0) H.p[lin(H, i, k, j)] = hv;         // (plane ia - 1 belongs to the chunk below, except H[0])
-            if (fg) {
-                double r = ((fv - sF[tk][tj - 1]) * g.idx + (gv - sG[tk - 1][tj]) * g.idy + (hv - hprev) * g.idz) * g.idt;
-                if (i <= 1 || k <= 1 || j <= 1 || j >= nx || k >= ny || i >= nz) {
-                    if (i <= 1) r -= p.at(i - 1, k, j) * g.idz2;
-                    if (k <= 1) r -= p.at(i, k - 1, j) * g.idy2;
-                    if (j <= 1) r -= p.at(i, k, j - 1) * g.idx2;
-                    if (j >= nx) r -= p.at(i, k, j + 1) * g.idx2;
-                    if (k >= ny) r -= p.at(i, k + 1, j) * g.idy2;
-                    if (i >= nz) r -= p.at(i + 1, k, j) * g.idz2;
-                }
-                R.p[lin(R, i, k, j)] = r;
-            }
-            hprev = hv;
-        }
-    }
+    double acc = fma(g.dcc, c, c);
+    acc = fma(g.dcx, sx, acc);
+    acc = fma(g.dcy, sy, acc);
+    acc = fma(g.dcz, sz, acc);
+    double t = a * a;
+    t = fma(-b, b, t);
+    acc = fma(-qa, t, acc);
+    acc = fma(-q1, d1, acc);
+    return fma(-q2, d2, acc);
 }
 
-template <int TJ, int TK> constexpr size_t fgh_rhs_smem()
+constexpr int FGH_TK = 4, FGH_MINB = 3;      // 128-thread blocks (4 rows), 168 registers: two register sets of taps
+template <int TK, int MINB, int PF>
+__global__ void __launch_bounds__(32 * TK, MINB)
+k_fgh_div(Fld u, Fld v, Fld w, Fld p, Fld F, Fld G, Fld H, Fld R, NSGeom g, int ia0, int ib0, int zchunk)
 {
-    return sizeof(double) * (size_t)(12 * (TK + 2) * (TJ + 3) + 2 * TK * (TJ + 1));
+    const int tj = threadIdx.x;
+    const int nx = g.nx, ny = g.ny, nz = g.nz;
+    const int j_ = blockIdx.x * 31 + tj, k = blockIdx.y * TK + threadIdx.y;
+    if (k > ny) return;                              // (whole warps)
+    const bool inb = j_ <= nx;
+    const int j = inb ? j_ : nx;                     // out-of-range lanes shadow the last column, store nothing
+    const int ia = ia0 + blockIdx.z * zchunk;
+    const int ib = (ia + zchunk - 1 < ib0) ? ia + zchunk - 1 : ib0;
+    const bool core = inb && k >= 1 && tj >= 1;
+    const bool stF = inb && k >= 1 && (tj >= 1 || j == 0);   // (lane 0 repeats the last column of the block to the left)
+    const bool stG = inb && tj >= 1;                 // j >= 1; k >= 0
+    const bool edge_kj = k <= 1 || j <= 1 || j >= nx || k >= ny;
+
+    // row pointers at plane ia - 1 (the priming plane)
+    const double* __restrict__ uc_ = u.p + lin(u, ia - 1, k, j);
+    const double* __restrict__ vc_ = v.p + lin(v, ia - 1, k, j);
+    const double* __restrict__ wc_ = w.p + lin(w, ia - 1, k, j);
+    const long long usy = u.sy, vsy = v.sy, wsy = w.sy, usz = u.sz, vsz = v.sz, wsz = w.sz;
+    const long long ukm_o = k >= 1 ? -usy : 0, wkm_o = k >= 1 ? -wsy : 0, vkM_o = k >= 1 ? -2 * vsy : -vsy;
+    double* __restrict__ Fp = F.p + lin(F, ia - 1, k, j);
+    double* __restrict__ Gp = G.p + lin(G, ia - 1, k, j);
+    double* __restrict__ Hp = H.p + lin(H, ia - 1, k, j);
+    double* __restrict__ Rp = R.p + lin(R, ia - 1, k, j);
+    const double* __restrict__ pp = p.p + lin(p, ia - 1, k, j);     // ghost pressures of the boundary cells
+    const long long psy = p.sy, psz = p.sz;
+
+    // the twenty values a step loads: fifteen taps of its centre plane and the five taps of the plane above
+    struct Ld {
+        double u00p, u0p0, u0pm, u0m0, u0mm, v00p, v00m, v0p0, v0mp, v0mm, v0M0, w00p, w0p0, w0m0, w00m;
+        double up00, up0m, vp00, vpm0, wp00;
+    };
+    auto load = [&](Ld& L, const bool pf) {     // centre plane = the plane uc_, vc_, wc_ point at; advances them
+        L.u00p = uc_[1]; L.u0p0 = uc_[usy]; L.u0pm = uc_[usy - 1]; L.u0m0 = uc_[ukm_o]; L.u0mm = uc_[ukm_o - 1];
+        L.v00p = vc_[1]; L.v00m = vc_[-1]; L.v0p0 = vc_[vsy]; L.v0mp = vc_[-vsy + 1]; L.v0mm = vc_[-vsy - 1]; L.v0M0 = vc_[vkM_o];
+        L.w00p = wc_[1]; L.w0p0 = wc_[wsy]; L.w0m0 = wc_[wkm_o]; L.w00m = wc_[-1];
+        L.up00 = uc_[usz]; L.up0m = uc_[usz - 1]; L.vp00 = vc_[vsz]; L.vpm0 = vc_[vsz - vsy]; L.wp00 = wc_[wsz];
+        uc_ += usz; vc_ += vsz; wc_ += wsz;
+        if (PF && pf) {   // the first-touch rows of the load after the next (three planes above this centre) on their way to L2
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(uc_ + 2 * usz));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(vc_ + 2 * vsz));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(wc_ + 2 * wsz));
+        }
+    };
+    // carried registers: the centre taps that were last step's plane-above taps, and the taps of the plane below that
+    // were last step's centre taps.  As seen from centre plane ia - 2 only what the priming step (H alone) consumes
+    // is real.
+    double u000 = uc_[0], u00m = uc_[-1], v000 = vc_[0], v0m0 = vc_[-vsy], w000 = wc_[0];
+    double um00 = 0.0, vm00 = 0.0, wm00 = wc_[-wsz], wm0p = 0.0, wmp0 = 0.0, vmm0 = 0.0, wmm0 = 0.0;
+    double hprev = 0.0;
+    auto step = [&](const int i, const Ld& L) {
+        const bool fg = i >= ia;
+        // ghost pressures of the boundary cells (ns_cube.cpp:216-232): loaded before the stencils, consumed after them
+        const bool edge = fg && core && (edge_kj || i <= 1 || i >= nz);
+        double pzm = 0.0, pzp = 0.0, pym = 0.0, pyp = 0.0, pxm = 0.0, pxp = 0.0;
+        if (edge) {
+            if (i <= 1) pzm = pp[-psz];
+            if (i >= nz) pzp = pp[psz];
+            if (k <= 1) pym = pp[-psy];
+            if (k >= ny) pyp = pp[psy];
+            if (j <= 1) pxm = pp[-1];
+            if (j >= nx) pxp = pp[1];
+            asm volatile("" ::: "memory");
+        }
+        // every thread evaluates all four stencils (the stores are predicated); the eleven distinct products of face sums
+        // are formed once: F and G share Puv1, F and H Puw1, G and H Pwv1, G[k-1] shares Puv2 with F and Pwv2 with H
+        const double Puv1 = (u000 + L.u0p0) * (L.v00p + v000), Puv2 = (L.u0m0 + u000) * (L.v0mp + v0m0);
+        const double Puw1 = (u000 + L.up00) * (L.w00p + w000), Puw2 = (um00 + u000) * (wm0p + wm00);
+        const double Pwv1 = (w000 + L.w0p0) * (v000 + L.vp00), Pwv2 = (L.w0m0 + w000) * (v0m0 + L.vpm0);
+        const double Pg2 = (u00m + L.u0pm) * (v000 + L.v00m), Pg4 = (wm00 + wmp0) * (vm00 + v000);
+        const double Pm2 = (L.u0mm + u00m) * (v0m0 + L.v0mm), Pm4 = (wmm0 + wm00) * (vmm0 + v0m0);
+        const double Ph2 = (L.up0m + u00m) * (w000 + L.w00m);
+        const double fv = fgh_combine(g, u000, L.u00p + u00m, L.u0p0 + L.u0m0, L.up00 + um00, u000 + L.u00p, u00m + u000, g.qx,
+                                      Puv1 - Puv2, g.qy, Puw1 - Puw2, g.qz);                   // ns_cube.cpp:136-149
+        const double gv = fgh_combine(g, v000, L.v00p + L.v00m, L.v0p0 + v0m0, L.vp00 + vm00, v000 + L.v0p0, v0m0 + v000, g.qy,
+                                      Puv1 - Pg2, g.qx, Pwv1 - Pg4, g.qz);                     // :156-169
+        const double gm = fgh_combine(g, v0m0, L.v0mp + L.v0mm, v000 + L.v0M0, L.vpm0 + vmm0, v0m0 + v000, L.v0M0 + v0m0, g.qy,
+                                      Puv2 - Pm2, g.qx, Pwv2 - Pm4, g.qz);                     // the same at (i, k-1, j)
+        const double hv = fgh_combine(g, w000, L.w00p + L.w00m, L.w0p0 + L.w0m0, L.wp00 + wm00, L.wp00 + w000, wm00 + w000, g.qz,
+                                      Puw1 - Ph2, g.qx, Pwv1 - Pwv2, g.qy);                    // :176-189
+        if (fg) {
+            const double fm = __shfl_up_sync(0xffffffffu, fv, 1);
+            if (stF) *Fp = fv;
+            if (stG) *Gp = gv;
+            if (core) {
+                *Hp = hv;
+                double r = ((fv - fm) * g.idx + (gv - gm) * g.idy + (hv - hprev) * g.idz) * g.idt;
+                if (edge) {
+                    if (i <= 1) r -= pzm * g.idz2;
+                    if (k <= 1) r -= pym * g.idy2;
+                    if (j <= 1) r -= pxm * g.idx2;
+                    if (j >= nx) r -= pxp * g.idx2;
+                    if (k >= ny) r -= pyp * g.idy2;
+                    if (i >= nz) r -= pzp * g.idz2;
+                }
+                *Rp = r;
+            }
+        } else if (core && i == 0) {
+            *Hp = hv;              // (plane ia - 1 belongs to the chunk below, except H[0])
+        }
+        hprev = hv;
+        // shift: centre -> plane below, plane above -> centre
+        um00 = u000; vm00 = v000; wm00 = w000; wm0p = L.w00p; wmp0 = L.w0p0; vmm0 = v0m0; wmm0 = L.w0m0;
+        u000 = L.up00; u00m = L.up0m; v000 = L.vp00; v0m0 = L.vpm0; w000 = L.wp00;
+        Fp += F.sz; Gp += G.sz; Hp += H.sz; Rp += R.sz; pp += psz;
+    };
+    // software pipeline: the loads of plane i + 1 are in flight while plane i is evaluated (two register sets)
+    Ld A, B;
+    load(A, ia - 1 <= ib - 2);
+    int i = ia - 1;
+#pragma unroll 1
+    for (; i + 2 <= ib; i += 2) {      // (unconditional loads: the compiler keeps them ahead of the arithmetic)
+        load(B, i + 1 <= ib - 2);
+        asm volatile("" ::: "memory");
+        step(i, A);
+        load(A, i + 2 <= ib - 2);
+        asm volatile("" ::: "memory");
+        step(i + 1, B);
+    }
+    if (i + 1 <= ib) {
+        load(B, false);
+        asm volatile("" ::: "memory");
+        step(i, A);
+        step(i + 1, B);
+    } else {
+        step(i, A);
+    }
 }
 
 // ---- poisson RHS (ns_cube.cpp:205-235) ---------------------------------------------------
@@ -443,15 +469,23 @@ __global__ void __launch_bounds__(256) k_pull(PullList pl)
 
 using namespace fdmb;
 
-// FDMB_FGH_FUSED=1 selects the fused, shared-memory staged FGH + divergence sweep (k_fgh_rhs) for handles created
-// afterwards.  Measured at 255^3 (r02j/k): 625 us against 279 + 109 us for k_fgh + k_rhs -- both variants are bound by
-// instruction issue, not by DRAM (k_fgh: 34 % of peak DRAM throughput), so the 80 -> 56 B/pt of traffic the fusion
-// saves buys nothing while the per-element staging and the two barriers per plane cost issue slots.  Off by default;
-// parity-tested (tests/test_ns_cube_gpu.py::test_fused_fgh_rhs_matches).
-static bool fused_fgh_rhs_requested()
+// FGH + divergence run as ONE sweep (k_fgh_div) by default; FDMB_FGH_FUSED=0 selects k_fgh + k_rhs for handles created
+// afterwards.  Measured at 255^3 (r02fgh): 274 us against 278 + 110 us, step 0.919 -> 0.810 ms.  History of the fused
+// sweep: shared-memory staged tiles with cp.async 625 us (issue-bound staging); register marching with a G exchange
+// through shared memory and a barrier per plane 404 us (the barrier serialises a block's load and compute phases);
+// independent warps that evaluate G[k-1] themselves 346 us (half the stall samples on the first use of a plane's loads);
+// the same with the next plane's loads in flight during the stencils 300 us; ghost-pressure loads hoisted and dt folded
+// into the coefficients (11 shared products, 9 fused operations per stencil) 274 us.
+static int fgh_chunks_per_sm()
+{
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("FDMB_FGH_CHUNKS"); v = e ? atoi(e) : 32; if (v < 1) v = 32; }
+    return v;
+}
+static int fused_fgh_rhs_requested()
 {
     const char* e = getenv("FDMB_FGH_FUSED");
-    return e && e[0] == '1';
+    return e ? atoi(e) : 1;
 }
 
 // global z range of field `fld` (u v w p x F G H RHS), ns_cube.h:66-75
@@ -524,7 +558,7 @@ struct fdmb_ns_cube {
     bool attached = false;
 
     StepGraph graph;            // one time step as a replayed CUDA graph (single-GPU handles)
-    bool fused = false;         // FGH + divergence in one sweep (k_fgh_rhs)
+    int fused = 0;              // FGH + divergence in one sweep (k_fgh_div), 0 = k_fgh + k_rhs
 
     int init();
     int step(int nsteps, cudaStream_t st);
@@ -568,8 +602,7 @@ int fdmb_ns_cube::init()
         FDMB_CUDA(cudaFuncGetAttributes(&fa, k_pull));
         FDMB_CUDA(cudaFuncGetAttributes(&fa, k_fgh<double>));
         FDMB_CUDA(cudaFuncGetAttributes(&fa, k_rhs<double>));
-        FDMB_CUDA(cudaFuncSetAttribute(k_fgh_rhs<64, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fgh_rhs_smem<64, 8>()));
-        FDMB_CUDA(cudaFuncGetAttributes(&fa, k_fgh_rhs<64, 8>));
+        FDMB_CUDA(cudaFuncGetAttributes(&fa, k_fgh_div<FGH_TK, FGH_MINB, 1>));
         FDMB_CUDA(cudaFuncGetAttributes(&fa, k_update<double>));
         FDMB_CUDA(cudaFuncGetAttributes(&fa, k_bound_lid<double>));
         FDMB_CUDA(cudaFuncGetAttributes(&fa, k_bound_mirror<double>));
@@ -596,6 +629,8 @@ int fdmb_ns_cube::init()
     g.idx2 = 1.0 / dx2; g.idy2 = 1.0 / dy2; g.idz2 = 1.0 / dz2;
     g.idt = 1.0 / prm.dt;
     g.dtdx = prm.dt / dx; g.dtdy = prm.dt / dy; g.dtdz = prm.dt / dz;
+    g.dcx = prm.dt * g.cRx; g.dcy = prm.dt * g.cRy; g.dcz = prm.dt * g.cRz; g.dcc = -2.0 * (g.dcx + g.dcy + g.dcz);
+    g.qx = 0.25 * prm.dt * g.idx; g.qy = 0.25 * prm.dt * g.idy; g.qz = 0.25 * prm.dt * g.idz;
     return FDMB_OK;
 }
 
@@ -688,17 +723,16 @@ int fdmb_ns_cube::step_once(cudaStream_t st)
         }
         if (fused) {
             LaunchScope sc("ns_fgh_rhs", st);
-            constexpr int TJ = 64, TK = 8;
-            // z chunks: enough blocks for two waves of two resident blocks per SM, not more (each chunk recomputes one
-            // plane of H and reloads two planes)
-            const int tiles = ((nx + TJ - 2) / (TJ - 1)) * ((ny + TK - 2) / (TK - 1));
-            int nch = (4 * device_sm_count() + tiles - 1) / tiles;
+            // z chunks: about 32 warps' worth of work per SM and chunk wave, not more (each chunk recomputes one plane
+            // of H and loads one plane's full tap set)
+            const int bx = (nx + 1 + 30) / 31, by = (ny + 1 + FGH_TK - 1) / FGH_TK;
+            int nch = (fgh_chunks_per_sm() * device_sm_count() * 4 / FGH_TK + bx * by - 1) / (bx * by);
             if (nch < 1) nch = 1;
             if (nch > nzl) nch = nzl;
             const int zchunk = (nzl + nch - 1) / nch;
-            dim3 block(TJ, TK);
-            dim3 grid((nx + TJ - 2) / (TJ - 1), (ny + TK - 2) / (TK - 1), (nzl + zchunk - 1) / zchunk);
-            k_fgh_rhs<TJ, TK><<<grid, block, fgh_rhs_smem<TJ, TK>(), st>>>(u, v, w, p, F, G, H, R, g, ilo, ihi, zchunk);
+            dim3 block(32, FGH_TK);
+            dim3 grid(bx, by, (nzl + zchunk - 1) / zchunk);
+            k_fgh_div<FGH_TK, FGH_MINB, 1><<<grid, block, 0, st>>>(u, v, w, p, F, G, H, R, g, ilo, ihi, zchunk);
         } else {
             {
                 LaunchScope sc("ns_fgh", st);

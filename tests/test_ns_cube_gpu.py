@@ -122,11 +122,13 @@ def test_ns_errors(fb):
         fb.NSCube(nx=32, nz=32)    # the README size: reference aborts in FFTTable (fft.cpp:67)
 
 
+@pytest.mark.parametrize("fused", ["1", "0"])
 @pytest.mark.parametrize("n,steps", [(15, 5), (31, 20), (63, 6), (127, 3)])
-def test_fused_fgh_rhs_matches(fb, ref, monkeypatch, n, steps):
-    """FDMB_FGH_FUSED=1: the z-marching, shared-memory staged FGH + divergence sweep (k_fgh_rhs; off by default, see
-    ns_cube.cu) against the compiled reference, all nine public fields (F, G, H, RHS included)."""
-    monkeypatch.setenv("FDMB_FGH_FUSED", "1")
+def test_fused_fgh_rhs_matches(fb, ref, monkeypatch, n, steps, fused):
+    """Both FGH + divergence paths against the compiled reference on all nine public fields (F, G, H, RHS included):
+    the default register-marching single sweep (k_fgh_div, ns_cube.cu) and the two-kernel fallback FDMB_FGH_FUSED=0
+    (k_fgh + k_rhs, the reference's own order of evaluation)."""
+    monkeypatch.setenv("FDMB_FGH_FUSED", fused)
     ns = fb.NSCube(nx=n, nz=n, Re=400.0, dt=0.005)
     R = ref.NSCube(nx=n, nz=n, Re=400.0, dt=0.005)
     ns.step(steps); R.step(steps)
