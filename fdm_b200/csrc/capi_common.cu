@@ -159,6 +159,12 @@ bool pipe_enabled()
 
 bool profiling_on() { return g_prof_on.load(std::memory_order_relaxed); }
 
+int pdl_mode()
+{
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("FDMB_PDL"); v = e ? atoi(e) : 1; if (v < 0 || v > 2) v = 1; }
+    return v;
+}
 bool graphs_enabled()
 {
     static int v = -1;

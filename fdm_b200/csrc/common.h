@@ -5,9 +5,11 @@
 #include <atomic>
 #include <cstdarg>
 #include <string>
+#include <utility>
 
 #include "../../include/fdm_b200.h"
 #include "xform.cuh"
+#include "pdl.cuh"
 
 namespace fdmb {
 

@@ -634,6 +634,7 @@ int fdmb_lapl_cube::solve_device(double* d_out, const double* d_in, cudaStream_t
 //   phase 4  y and x inverse sweeps of the planes [z0, z0 + nzc) into d_out
 int fdmb_lapl_cube::sweeps(double* d_out, const double* d_in, cudaStream_t st, int phases, int z0, int nzc)
 {
+    PdlScope pdl(pdl_small_grid((long long)nx * ny * nz));    // launch-bound sizes: programmatic dependent launch (pdl.cuh)
     const int kf = periodic ? XF_PFWD : XF_DST;
     const int ki = periodic ? XF_PINV : XF_DST;
     const long long plane = (long long)ny * px;

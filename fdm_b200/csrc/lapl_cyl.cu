@@ -31,6 +31,8 @@ constexpr int TS = 32;
 
 __global__ void __launch_bounds__(128) k_tridiag_rows(TridiagArgs a, int ts)
 {
+    pdl_wait();
+    pdl_trigger();
     extern __shared__ double smem[];
     const int P = a.nr | 1;                    // odd pitch
     double* tb = smem;                         // rhs / solution
@@ -118,6 +120,8 @@ constexpr int TSS = 32;
 
 __global__ void __launch_bounds__(128) k_tridiag_rows_pivs(TridiagArgs a)
 {
+    pdl_wait();
+    pdl_trigger();
     extern __shared__ double smem[];
     const int P = a.nr | 1;                    // odd pitch: lane s walks row s without bank conflicts
     double* tb = smem;                         // rhs / solution
@@ -168,6 +172,8 @@ constexpr int TSP = 64;       // systems per CTA of the pivot-table variant
 
 __global__ void __launch_bounds__(256) k_tridiag_rows_piv(TridiagArgs a, int ts)
 {
+    pdl_wait();
+    pdl_trigger();
     extern __shared__ double smem[];
     const int P = a.nr | 1;                    // odd pitch
     double* tb = smem;                         // rhs / solution
@@ -299,18 +305,15 @@ cudaError_t launch_tridiag_rows(const TridiagArgs& a, cudaStream_t st, const cha
     cudaError_t e = prepare_tridiag_rows(a.nr);
     if (e != cudaSuccess) return e;
     if (a.piv && tridiag_piv_rowmajor(a.nr)) {
-        k_tridiag_rows_pivs<<<(unsigned)((a.nsys + TSS - 1) / TSS), tridiag_variant() == 3 ? 32 : 128, rows_pivs_smem(a.nr), st>>>(a);
-        return cudaGetLastError();
+        return launch_pdl(k_tridiag_rows_pivs, dim3((unsigned)((a.nsys + TSS - 1) / TSS)), dim3(tridiag_variant() == 3 ? 32 : 128), rows_pivs_smem(a.nr), st, a);
     }
     if (a.piv) {
         const int ts = tridiag_tile_rows(a.nr, true);
         const int nt = (tridiag_variant() == 1 && ts >= 32) ? ts : 256;      // 1: every thread of the CTA owns a system
-        k_tridiag_rows_piv<<<(unsigned)((a.nsys + ts - 1) / ts), nt, rows_piv_smem(a.nr, ts), st>>>(a, ts);
-        return cudaGetLastError();
+        return launch_pdl(k_tridiag_rows_piv, dim3((unsigned)((a.nsys + ts - 1) / ts)), dim3(nt), rows_piv_smem(a.nr, ts), st, a, ts);
     }
     const int ts = tridiag_tile_rows(a.nr, false);
-    k_tridiag_rows<<<(unsigned)((a.nsys + ts - 1) / ts), 128, rows_smem(a.nr, ts), st>>>(a, ts);
-    return cudaGetLastError();
+    return launch_pdl(k_tridiag_rows, dim3((unsigned)((a.nsys + ts - 1) / ts)), dim3(128), rows_smem(a.nr, ts), st, a, ts);
 }
 
 }  // namespace fdmb
@@ -532,6 +535,7 @@ int fdmb_lapl_cyl::solve_device(double* d_out, const double* d_in, cudaStream_t 
     const long long wplane = (long long)nz * pr;      // work-array stride between phi planes
     const long long uplane = (long long)nz * nr;      // caller-array stride between phi planes
     const int kzf = zperiodic ? XF_PFWD : XF_DST, kzi = zperiodic ? XF_PINV : XF_DST;
+    PdlScope pdl(pdl_small_grid((long long)nr * nz * nphi));    // launch-bound sizes (pdl.cuh)
     int rc;
     // phi forward: caller rhs -> work.  TMA-fed when the caller's rows are 16-byte multiples.
     {

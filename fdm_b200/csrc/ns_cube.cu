@@ -55,6 +55,8 @@ struct NSGeom {
 // lid (ns_cube.cpp:67-72): u[nz+1][k][j] = 2 U0 - u[nz][k][j], k=0..ny+1, j=-1..jmax
 template <typename T> __global__ void k_bound_lid(FldT<T> u, NSGeom g, int jmax)
 {
+    pdl_wait();
+    pdl_trigger();
     int j = blockIdx.x * blockDim.x + threadIdx.x - 1;
     int k = blockIdx.y;
     if (j > jmax) return;
@@ -66,6 +68,8 @@ template <typename T> __global__ void k_bound_lid(FldT<T> u, NSGeom g, int jmax)
 // z ghost plane of w.
 template <typename T> __global__ void k_bound_mirror(FldT<T> u, FldT<T> v, FldT<T> w, NSGeom g, int zlo, int zhi, int wbot, int wtop)
 {
+    pdl_wait();
+    pdl_trigger();
     int a = blockIdx.x * blockDim.x + threadIdx.x;   // fast index of the face
     int b = blockIdx.y;                              // slow index of the face
     if (blockIdx.z == 0) {          // u: i = b in zlo..zhi, k = a in 0..ny+1
@@ -91,6 +95,8 @@ template <typename T> __global__ void k_bound_mirror(FldT<T> u, FldT<T> v, FldT<
 // pressure ghosts (ns_cube.cpp:98-121).  ilo..ihi: this rank's interior planes (1..nz on one GPU).
 template <typename T> __global__ void k_bound_p(FldT<T> u, FldT<T> v, FldT<T> w, FldT<T> p, NSGeom g, int ilo, int ihi, int wbot, int wtop)
 {
+    pdl_wait();
+    pdl_trigger();
     int a = blockIdx.x * blockDim.x + threadIdx.x + 1;
     int b = blockIdx.y + 1;
     const int nx = g.nx, ny = g.ny, nz = g.nz;
@@ -182,6 +188,8 @@ __device__ __forceinline__ void fgh_generic(const FldT<T>& u, const FldT<T>& v, 
 
 template <typename T> __global__ void __launch_bounds__(256) k_fgh(FldT<T> u, FldT<T> v, FldT<T> w, FldT<T> F, FldT<T> G, FldT<T> H, NSGeom g, int i0, int iFG)
 {
+    pdl_wait();
+    pdl_trigger();
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int k = blockIdx.y * blockDim.y + threadIdx.y;
     const int i = blockIdx.z + i0;
@@ -281,6 +289,8 @@ template <int TK, int MINB, int PF>
 __global__ void __launch_bounds__(32 * TK, MINB)
 k_fgh_div(Fld u, Fld v, Fld w, Fld p, Fld F, Fld G, Fld H, Fld R, NSGeom g, int ia0, int ib0, int zchunk)
 {
+    pdl_wait();
+    pdl_trigger();
     const int tj = threadIdx.x;
     const int nx = g.nx, ny = g.ny, nz = g.nz;
     const int j_ = blockIdx.x * 31 + tj, k = blockIdx.y * TK + threadIdx.y;
@@ -412,6 +422,8 @@ k_fgh_div(Fld u, Fld v, Fld w, Fld p, Fld F, Fld G, Fld H, Fld R, NSGeom g, int 
 // ---- poisson RHS (ns_cube.cpp:205-235) ---------------------------------------------------
 template <typename T> __global__ void __launch_bounds__(256) k_rhs(FldT<T> F, FldT<T> G, FldT<T> H, FldT<T> p, FldT<T> R, NSGeom g, int ilo)
 {
+    pdl_wait();
+    pdl_trigger();
     const int j = blockIdx.x * blockDim.x + threadIdx.x + 1;
     const int k = blockIdx.y * blockDim.y + threadIdx.y + 1;
     const int i = blockIdx.z + ilo;
@@ -434,6 +446,8 @@ template <typename T> __global__ void __launch_bounds__(256) k_rhs(FldT<T> F, Fl
 // ---- update_uvwp (ns_cube.cpp:241-277) ---------------------------------------------------
 template <typename T> __global__ void __launch_bounds__(256) k_update(FldT<T> u, FldT<T> v, FldT<T> w, FldT<T> p, FldT<T> x, FldT<T> F, FldT<T> G, FldT<T> H, NSGeom g, int ilo)
 {
+    pdl_wait();
+    pdl_trigger();
     const int j = blockIdx.x * blockDim.x + threadIdx.x + 1;
     const int k = blockIdx.y * blockDim.y + threadIdx.y + 1;
     const int i = blockIdx.z + ilo;
@@ -686,6 +700,7 @@ int fdmb_ns_cube::step_once(cudaStream_t st)
     const int nmax = nx > ny ? (nx > nz ? nx : nz) : (ny > nz ? ny : nz);
     const bool bot = rank == 0, top = rank == nranks - 1;
     const int nzl = ihi - ilo + 1;
+    PdlScope pdl(nranks == 1 && pdl_small_grid((long long)nx * ny * nz));   // launch-bound sizes (pdl.cuh)
     int rc;
     {
         if (nranks > 1) {
@@ -706,20 +721,20 @@ int fdmb_ns_cube::step_once(cudaStream_t st)
             int jmax = (nz + 1 < nx + 1) ? nz + 1 : nx + 1;
             LaunchScope sc("ns_bound_lid", st);
             dim3 grid((jmax + 2 + 127) / 128, ny + 2);
-            k_bound_lid<double><<<grid, 128, 0, st>>>(u, g, jmax);
+            launch_pdl(k_bound_lid<double>, grid, dim3(128), 0, st, u, g, jmax);
         }
         {
             LaunchScope sc("ns_bound_mirror", st);
             const int zlo = lay.wlo[0], zhi = lay.whi[0];
             const int rows = (zhi - zlo + 1) > ny + 2 ? (zhi - zlo + 1) : ny + 2;
             dim3 grid((nmax + 2 + 127) / 128, rows, 3);
-            k_bound_mirror<double><<<grid, 128, 0, st>>>(u, v, w, g, zlo, zhi, bot ? 1 : 0, top ? 1 : 0);
+            launch_pdl(k_bound_mirror<double>, grid, dim3(128), 0, st, u, v, w, g, zlo, zhi, bot ? 1 : 0, top ? 1 : 0);
         }
         {
             LaunchScope sc("ns_bound_p", st);
             const int rows = nzl > ny ? nzl : ny;
             dim3 grid((nmax + 127) / 128, rows, 3);
-            k_bound_p<double><<<grid, 128, 0, st>>>(u, v, w, p, g, ilo, ihi, bot ? 1 : 0, top ? 1 : 0);
+            launch_pdl(k_bound_p<double>, grid, dim3(128), 0, st, u, v, w, p, g, ilo, ihi, bot ? 1 : 0, top ? 1 : 0);
         }
         if (fused) {
             LaunchScope sc("ns_fgh_rhs", st);
@@ -732,20 +747,20 @@ int fdmb_ns_cube::step_once(cudaStream_t st)
             const int zchunk = (nzl + nch - 1) / nch;
             dim3 block(32, FGH_TK);
             dim3 grid(bx, by, (nzl + zchunk - 1) / zchunk);
-            k_fgh_div<FGH_TK, FGH_MINB, 1><<<grid, block, 0, st>>>(u, v, w, p, F, G, H, R, g, ilo, ihi, zchunk);
+            launch_pdl(k_fgh_div<FGH_TK, FGH_MINB, 1>, grid, block, 0, st, u, v, w, p, F, G, H, R, g, ilo, ihi, zchunk);
         } else {
             {
                 LaunchScope sc("ns_fgh", st);
                 dim3 block(64, 4);
                 const int i0 = lay.wlo[7];                 // first plane of H
                 dim3 grid((nx + 1 + 63) / 64, (ny + 1 + 3) / 4, ihi - i0 + 1);
-                k_fgh<double><<<grid, block, 0, st>>>(u, v, w, F, G, H, g, i0, ilo);
+                launch_pdl(k_fgh<double>, grid, block, 0, st, u, v, w, F, G, H, g, i0, ilo);
             }
             {
                 LaunchScope sc("ns_rhs", st);
                 dim3 block(64, 4);
                 dim3 grid((nx + 63) / 64, (ny + 3) / 4, nzl);
-                k_rhs<double><<<grid, block, 0, st>>>(F, G, H, p, R, g, ilo);
+                launch_pdl(k_rhs<double>, grid, block, 0, st, F, G, H, p, R, g, ilo);
             }
         }
         FDMB_CHECK_LAUNCH();
@@ -763,7 +778,7 @@ int fdmb_ns_cube::step_once(cudaStream_t st)
             LaunchScope sc("ns_update", st);
             dim3 block(64, 4);
             dim3 grid((nx + 63) / 64, (ny + 3) / 4, nzl);
-            k_update<double><<<grid, block, 0, st>>>(u, v, w, p, x, F, G, H, g, ilo);
+            launch_pdl(k_update<double>, grid, block, 0, st, u, v, w, p, x, F, G, H, g, ilo);
         }
         FDMB_CHECK_LAUNCH();
     }

@@ -60,6 +60,8 @@ struct CylGeom {
 // r-direction ghosts of w, v, u (ns_cyl.cpp:83-104): one thread per (phi, z row)
 __global__ void k_cyl_bound_r(CFld u, CFld v, CFld w, CylGeom g, int i0)
 {
+    pdl_wait();
+    pdl_trigger();
     const int k = blockIdx.x * blockDim.x + threadIdx.x + g.z_;
     const int i = blockIdx.y + i0;
     if (k > g.znn) return;
@@ -80,6 +82,8 @@ __global__ void k_cyl_bound_r(CFld u, CFld v, CFld w, CylGeom g, int i0)
 // z0..znn (ns_cyl.cpp:108) -- reproduced, clamped to the allocated r range.
 __global__ void k_cyl_bound_z(CFld u, CFld v, CFld w, CylGeom g, int jmax_v, int i0)
 {
+    pdl_wait();
+    pdl_trigger();
     const int j = blockIdx.x * blockDim.x + threadIdx.x - 1;   // -1 .. nr+1
     const int i = blockIdx.y + i0;
     const int nr = g.nr, nz = g.nz;
@@ -99,6 +103,8 @@ __global__ void k_cyl_bound_z(CFld u, CFld v, CFld w, CylGeom g, int jmax_v, int
 // pressure ghosts (ns_cyl.cpp:132-171); blockIdx.z = 0: r faces, 1: z faces (Dirichlet z)
 __global__ void k_cyl_bound_p(CFld u, CFld v, CFld p, CylGeom g, int i0)
 {
+    pdl_wait();
+    pdl_trigger();
     const int a = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = blockIdx.y + i0;
     const int nr = g.nr, nz = g.nz;
@@ -133,6 +139,8 @@ template <bool LIN>
 __global__ void __launch_bounds__(256, LIN ? 1 : 3)
 k_cyl_fgh(CFld u, CFld v, CFld w, CFld u0, CFld v0, CFld w0, CFld F, CFld G, CFld H, CylGeom g, int i0)
 {
+    pdl_wait();
+    pdl_trigger();
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int k = blockIdx.y * blockDim.y + threadIdx.y + g.z0;
     const int i = blockIdx.z + i0;
@@ -333,6 +341,8 @@ k_cyl_fgh(CFld u, CFld v, CFld w, CFld u0, CFld v0, CFld w0, CFld F, CFld G, CFl
 // ---- poisson RHS (ns_cyl.cpp:408-439) --------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_cyl_rhs(CFld F, CFld G, CFld H, CFld p, CFld R, CylGeom g, int i0)
 {
+    pdl_wait();
+    pdl_trigger();
     const int j = blockIdx.x * blockDim.x + threadIdx.x + 1;
     const int k = blockIdx.y * blockDim.y + threadIdx.y + g.z1;
     const int i = blockIdx.z + i0;
@@ -355,6 +365,8 @@ __global__ void __launch_bounds__(256) k_cyl_rhs(CFld F, CFld G, CFld H, CFld p,
 __global__ void __launch_bounds__(256)
 k_cyl_update(CFld u, CFld v, CFld w, CFld p, CFld x, CFld F, CFld G, CFld H, CylGeom g, int i0)
 {
+    pdl_wait();
+    pdl_trigger();
     const int j = blockIdx.x * blockDim.x + threadIdx.x + 1;
     const int k = blockIdx.y * blockDim.y + threadIdx.y + g.z1;
     const int i = blockIdx.z + i0;
@@ -619,6 +631,7 @@ int fdmb_ns_cyl::step_once(int linear, cudaStream_t st)
     const int nown = phi - plo + 1;
     const int wlo = lay.wlo[0], nwin = lay.whi[0] - lay.wlo[0] + 1;     // planes of u, v, w held here (own + halos)
     const int prev = (rank + nranks - 1) % nranks, next = (rank + 1) % nranks;
+    PdlScope pdl(nranks == 1 && pdl_small_grid((long long)g.nr * g.nz * g.nphi));   // launch-bound sizes (pdl.cuh)
     int rc;
     {
         if (nranks > 1) {
@@ -642,26 +655,26 @@ int fdmb_ns_cyl::step_once(int linear, cudaStream_t st)
         {
             LaunchScope sc("nscyl_bound_r", st);
             dim3 grid((nzrows + 127) / 128, nwin);
-            k_cyl_bound_r<<<grid, 128, 0, st>>>(u, v, w, g, wlo);
+            launch_pdl(k_cyl_bound_r, grid, dim3(128), 0, st, u, v, w, g, wlo);
         }
         if (!zper) {
             LaunchScope sc("nscyl_bound_z", st);
             const int jmax_v = g.znn < nr + 1 ? g.znn : nr + 1;
             dim3 grid((nr + 3 + 127) / 128, nwin);
-            k_cyl_bound_z<<<grid, 128, 0, st>>>(u, v, w, g, jmax_v, wlo);
+            launch_pdl(k_cyl_bound_z, grid, dim3(128), 0, st, u, v, w, g, jmax_v, wlo);
         }
         {
             LaunchScope sc("nscyl_bound_p", st);
             const int na = (g.zn - g.z1 + 1) > nr ? (g.zn - g.z1 + 1) : nr;
             dim3 grid((na + 127) / 128, nown, zper ? 1 : 2);
-            k_cyl_bound_p<<<grid, 128, 0, st>>>(u, v, p, g, plo);
+            launch_pdl(k_cyl_bound_p, grid, dim3(128), 0, st, u, v, p, g, plo);
         }
         {
             LaunchScope sc(linear ? "nscyl_lfgh" : "nscyl_fgh", st);
             dim3 block(64, 4);
             dim3 grid((nr + 1 + 63) / 64, (g.zn - g.z0 + 1 + 3) / 4, nown);
-            if (linear) k_cyl_fgh<true><<<grid, block, 0, st>>>(u, v, w, u0, v0, w0, F, G, H, g, plo);
-            else k_cyl_fgh<false><<<grid, block, 0, st>>>(u, v, w, u0, v0, w0, F, G, H, g, plo);
+            if (linear) launch_pdl(k_cyl_fgh<true>, grid, block, 0, st, u, v, w, u0, v0, w0, F, G, H, g, plo);
+            else launch_pdl(k_cyl_fgh<false>, grid, block, 0, st, u, v, w, u0, v0, w0, F, G, H, g, plo);
         }
         if (nranks > 1) {
             // the divergence reads H on the plane below the slab: fetch it from its owner
@@ -673,7 +686,7 @@ int fdmb_ns_cyl::step_once(int linear, cudaStream_t st)
             LaunchScope sc("nscyl_rhs", st);
             dim3 block(64, 4);
             dim3 grid((nr + 63) / 64, (g.zn - g.z1 + 1 + 3) / 4, nown);
-            k_cyl_rhs<<<grid, block, 0, st>>>(F, G, H, p, R, g, plo);
+            launch_pdl(k_cyl_rhs, grid, block, 0, st, F, G, H, p, R, g, plo);
         }
         FDMB_CHECK_LAUNCH();
         rc = lapl->solve_device(x.p, R.p, st);      // ns_cyl.cpp:441
@@ -688,7 +701,7 @@ int fdmb_ns_cyl::step_once(int linear, cudaStream_t st)
             LaunchScope sc("nscyl_update", st);
             dim3 block(64, 4);
             dim3 grid((nr + 63) / 64, (g.zn - g.z1 + 1 + 3) / 4, nown);
-            k_cyl_update<<<grid, block, 0, st>>>(u, v, w, p, x, F, G, H, g, plo);
+            launch_pdl(k_cyl_update, grid, block, 0, st, u, v, w, p, x, F, G, H, g, plo);
         }
         FDMB_CHECK_LAUNCH();
     }

@@ -10,6 +10,7 @@
 //            read+write sweep (the third-axis sweep of LaplCube).
 #pragma once
 #include "xform.cuh"
+#include "pdl.cuh"
 
 namespace fdmb {
 
@@ -53,6 +54,8 @@ __global__ void __launch_bounds__(TileCfg<N>::THREADS) k_rows(RowsArgsT<T> a)
     T* tile = smem;
     T* scr = smem + P * BR;
     const int tid = threadIdx.x;
+    pdl_wait();
+    pdl_trigger();
     const long long row0 = (long long)blockIdx.x * BR;
     constexpr int NW = C::THREADS / 32 > 0 ? C::THREADS / 32 : 1;
     const int warp = tid >> 5, lane = tid & 31;
@@ -161,6 +164,8 @@ __global__ void __launch_bounds__(TileCfg<N>::THREADS) k_cols(ColsArgsT<T> a, MI
     T* tile = smem;
     T* scr = smem + (N + 1) * B;
     const int tid = threadIdx.x;
+    pdl_wait();
+    pdl_trigger();
     const int b0 = blockIdx.x * B;
     const int o = blockIdx.y;
     const int b = tid % B, g = tid / B;
@@ -203,8 +208,7 @@ inline cudaError_t launch_rows_t(const RowsArgsT<T>& a, cudaStream_t st)
         attr_set = true;
     }
     unsigned grid = (unsigned)((a.nrows + C::B - 1) / C::B);
-    kern<<<grid, C::THREADS, C::SMEM_ROWS, st>>>(a);
-    return cudaGetLastError();
+    return launch_pdl(kern, dim3(grid), dim3(C::THREADS), C::SMEM_ROWS, st, a);
 }
 
 template <int N, int KIND, typename MID, int KIND2, typename T = double>
@@ -219,8 +223,7 @@ inline cudaError_t launch_cols_t(const ColsArgsT<T>& a, const MID& mid, cudaStre
         attr_set = true;
     }
     dim3 grid((a.nb + C::B - 1) / C::B, a.no);
-    kern<<<grid, C::THREADS, C::SMEM_COLS, st>>>(a, mid);
-    return cudaGetLastError();
+    return launch_pdl(kern, grid, dim3(C::THREADS), C::SMEM_COLS, st, a, mid);
 }
 
 }  // namespace fdmb

@@ -245,6 +245,8 @@ k_cols_pipe(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUte
         if constexpr (MID::active) load_fold_table<N>(SF2, a.SN, 0.5 * a.scale2);
     }
     __syncthreads();
+    pdl_wait();      // everything above is independent of the previous kernel's output (pdl.cuh)
+    pdl_trigger();
     if (tid == 0) {
         for (int s = 0; s < NSTAGE; s++) {
             int t = blockIdx.x + s * gridDim.x;
@@ -425,6 +427,8 @@ __global__ void __launch_bounds__(PipeCfg<N>::THREADS) k_rows_pipe(RowsPipeArgs 
     load_tables<N>(SNs, WMs, a.SN, a.WM);
     if constexpr (KIND == XF_DST) load_fold_table<N>(SF1, a.SN, hs);
     __syncthreads();
+    pdl_wait();      // everything above is independent of the previous kernel's output (pdl.cuh)
+    pdl_trigger();
     if (tid == 0) {
         for (int s = 0; s < NSTAGE; s++) {
             long long t = blockIdx.x + (long long)s * gridDim.x;
@@ -529,8 +533,7 @@ inline cudaError_t launch_cols_pipe_t(const CUtensorMap& tm, const CUtensorMap& 
     if (a.max_ctas > 0 && grid > a.max_ctas) grid = a.max_ctas;
     if (grid > ntiles) grid = ntiles;
     if (grid < 1) return cudaSuccess;
-    kern<<<(unsigned)grid, C::THREADS_COLS, smem, st>>>(tm, tm2, a, mid, omap);
-    return cudaGetLastError();
+    return launch_pdl(kern, dim3((unsigned)grid), dim3(C::THREADS_COLS), smem, st, tm, tm2, a, mid, omap);
 }
 
 template <int N, int KIND>
@@ -555,8 +558,7 @@ inline cudaError_t launch_rows_pipe_t(const RowsPipeArgs& a, cudaStream_t st)
     if (a.max_ctas > 0 && grid > a.max_ctas) grid = a.max_ctas;
     if (grid > ntiles) grid = ntiles;
     if (grid < 1) return cudaSuccess;
-    kern<<<(unsigned)grid, C::THREADS, smem, st>>>(a);
-    return cudaGetLastError();
+    return launch_pdl(kern, dim3((unsigned)grid), dim3(C::THREADS), smem, st, a);
 }
 
 }  // namespace fdmb

@@ -132,6 +132,8 @@ k_cols_ring(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUte
     load_fold_table<N>(SF1, a.SN, 0.5 * a.scale);
     if constexpr (MID::active) load_fold_table<N>(SF2, a.SN, 0.5 * a.scale2);
     __syncthreads();
+    pdl_wait();      // everything above is independent of the previous kernel's output (pdl.cuh)
+    pdl_trigger();
     // tile of this CTA's i-th slot: grid-strided, or in adjacent pairs (i even / odd = the two groups)
     auto tile_of = [&](int i) -> long long {
         return a.pair_tiles ? 2ll * blockIdx.x + (i & 1) + (long long)(i >> 1) * 2 * gridDim.x
@@ -279,6 +281,8 @@ __global__ void __launch_bounds__(RingCfg<N>::THREADS, 1) k_rows_ring(RowsPipeAr
     load_tables<N>(SNs, WMs, a.SN, a.WM);
     load_fold_table<N>(SF1, a.SN, hs);
     __syncthreads();
+    pdl_wait();      // everything above is independent of the previous kernel's output (pdl.cuh)
+    pdl_trigger();
     if (tid == 0) {
         for (int i = 0; i < NBUF; i++) {
             const long long tl = blockIdx.x + (long long)i * gridDim.x;
@@ -348,8 +352,7 @@ inline cudaError_t launch_cols_ring_t(const CUtensorMap& tm, const CUtensorMap& 
     if (a.max_ctas > 0 && grid > a.max_ctas) grid = a.max_ctas;
     if (grid > (ntiles + 1) / 2) grid = (ntiles + 1) / 2;      // both groups of a CTA get a tile
     if (grid < 1) return cudaSuccess;
-    kern<<<(unsigned)grid, C::THREADS, smem, st>>>(tm, tm2, a, mid, omap);
-    return cudaGetLastError();
+    return launch_pdl(kern, dim3((unsigned)grid), dim3(C::THREADS), smem, st, tm, tm2, a, mid, omap);
 }
 
 template <int N>
@@ -371,8 +374,7 @@ inline cudaError_t launch_rows_ring_t(const RowsPipeArgs& a, cudaStream_t st)
     if (a.max_ctas > 0 && grid > a.max_ctas) grid = a.max_ctas;
     if (grid > (ntiles + 1) / 2) grid = (ntiles + 1) / 2;
     if (grid < 1) return cudaSuccess;
-    kern<<<(unsigned)grid, C::THREADS, smem, st>>>(a);
-    return cudaGetLastError();
+    return launch_pdl(kern, dim3((unsigned)grid), dim3(C::THREADS), smem, st, a);
 }
 
 // can the rows ring kernel take this sweep?  (dense rows + planar rows must fit the tile buffer)
