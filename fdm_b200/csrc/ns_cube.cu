@@ -10,9 +10,9 @@
 //   barrier -> pull u,v,w halos -> init_bound -> FGH (H also on the plane below the slab, recomputed instead of
 //   exchanged) -> RHS -> sharded solve -> barrier -> pull the x plane above the slab -> update
 //
-//   step() = init_bound (ns_cube.cpp:65-122)  -> k_bound_lid, k_bound_mirror, k_bound_p
-//            FGH        (ns_cube.cpp:126-200) -> k_fgh
-//            poisson    (ns_cube.cpp:204-238) -> k_rhs + LaplCube solve
+//   step() = init_bound (ns_cube.cpp:65-122)  -> k_bound_all (single precision: k_bound_lid, k_bound_mirror, k_bound_p)
+//            FGH        (ns_cube.cpp:126-200) -> k_fgh_div, which also forms the divergence (FDMB_FGH_FUSED=0: k_fgh)
+//            poisson    (ns_cube.cpp:204-238) -> (k_rhs +) LaplCube solve
 //            update_uvwp(ns_cube.cpp:241-277) -> k_update
 #include <cmath>
 #include <cstring>
@@ -121,6 +121,76 @@ template <typename T> __global__ void k_bound_p(FldT<T> u, FldT<T> v, FldT<T> w,
             if (wtop)
                 p.at(nz + 1, k, j) = p.at(nz, k, j) - (w.at(nz + 1, k, j) - 2 * w.at(nz, k, j) + w.at(nz - 1, k, j)) * g.iRdz;
         }
+    }
+}
+
+// init_bound in ONE launch (the double-precision step).  The three ordered fills above depend on each other only through
+// values a thread can form itself: the mirror of u on the lid plane reads what the lid fill has just written there
+// (2 U0 - u[nz], where the lid loop reaches), and the pressure ghosts read mirrored ghosts (u[-1] = u[1], u[nx+1] =
+// u[nx-1], ... on planes the lid never touches).  With those substitutions every role writes a set of elements nobody
+// else reads or writes: blockIdx.z = 0 lid (j = 0..min(jmax, nx); j = -1 and nx+1 of that plane belong to the u mirror),
+// 1..3 mirrors of u, v, w, 4..6 pressure ghosts on the x, y, z faces.  Same expressions, same operands: bit-identical to
+// the three-kernel sequence (which the single-precision step keeps).
+template <typename T>
+__global__ void k_bound_all(FldT<T> u, FldT<T> v, FldT<T> w, FldT<T> p, NSGeom g, int jmax, int zlo, int zhi, int ilo, int ihi,
+                            int wbot, int wtop)
+{
+    pdl_wait();
+    pdl_trigger();
+    const int nx = g.nx, ny = g.ny, nz = g.nz;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    switch (blockIdx.z) {
+    case 0: {        // lid (ns_cube.cpp:67-72), top rank: k = r in 0..ny+1, j = t in 0..min(jmax, nx)
+        if (!wtop || r > ny + 1 || t > jmax || t > nx) return;
+        u.at(nz + 1, r, t) = 2 * g.U0 - u.at(nz, r, t);
+        return;
+    }
+    case 1: {        // u mirror (:76-81): i = zlo + r, k = t in 0..ny+1
+        const int i = zlo + r, k = t;
+        if (i > zhi || k > ny + 1) return;
+        const bool lid = wtop && i == nz + 1;       // that plane's interior is being rewritten by role 0
+        const T a = (lid && 1 <= jmax) ? (T)(2 * g.U0 - u.at(nz, k, 1)) : u.at(i, k, 1);
+        const T b = (lid && nx - 1 <= jmax) ? (T)(2 * g.U0 - u.at(nz, k, nx - 1)) : u.at(i, k, nx - 1);
+        u.at(i, k, -1) = a;
+        u.at(i, k, nx + 1) = b;
+        return;
+    }
+    case 2: {        // v mirror (:83-88): i = zlo + r, j = t in 0..nx+1
+        const int i = zlo + r, j = t;
+        if (i > zhi || j > nx + 1) return;
+        v.at(i, -1, j) = v.at(i, 1, j);
+        v.at(i, ny + 1, j) = v.at(i, ny - 1, j);
+        return;
+    }
+    case 3: {        // w mirror (:90-95): k = r in 0..ny+1, j = t in 0..nx+1
+        if (r > ny + 1 || t > nx + 1) return;
+        if (wbot) w.at(-1, r, t) = w.at(1, r, t);
+        if (wtop) w.at(nz + 1, r, t) = w.at(nz - 1, r, t);
+        return;
+    }
+    case 4: {        // pressure ghosts, x faces (:98-104): i = ilo + r, k = t + 1 in 1..ny; u[-1] = u[1], u[nx+1] = u[nx-1]
+        const int i = ilo + r, k = t + 1;
+        if (i > ihi || k > ny) return;
+        p.at(i, k, 0) = p.at(i, k, 1) - (u.at(i, k, 1) - 2 * u.at(i, k, 0) + u.at(i, k, 1)) * g.iRdx;
+        p.at(i, k, nx + 1) = p.at(i, k, nx) - (u.at(i, k, nx - 1) - 2 * u.at(i, k, nx) + u.at(i, k, nx - 1)) * g.iRdx;
+        return;
+    }
+    case 5: {        // y faces (:106-112): i = ilo + r, j = t + 1 in 1..nx; v[-1] = v[1], v[ny+1] = v[ny-1]
+        const int i = ilo + r, j = t + 1;
+        if (i > ihi || j > nx) return;
+        p.at(i, 0, j) = p.at(i, 1, j) - (v.at(i, 1, j) - 2 * v.at(i, 0, j) + v.at(i, 1, j)) * g.iRdy;
+        p.at(i, ny + 1, j) = p.at(i, ny, j) - (v.at(i, ny - 1, j) - 2 * v.at(i, ny, j) + v.at(i, ny - 1, j)) * g.iRdy;
+        return;
+    }
+    default: {       // z faces (:114-121): k = r + 1 in 1..ny, j = t + 1 in 1..nx; w[-1] = w[1], w[nz+1] = w[nz-1]
+        const int k = r + 1, j = t + 1;
+        if (k > ny || j > nx) return;
+        if (wbot) p.at(0, k, j) = p.at(1, k, j) - (w.at(1, k, j) - 2 * w.at(0, k, j) + w.at(1, k, j)) * g.iRdz;
+        if (wtop)
+            p.at(nz + 1, k, j) = p.at(nz, k, j) - (w.at(nz - 1, k, j) - 2 * w.at(nz, k, j) + w.at(nz - 1, k, j)) * g.iRdz;
+        return;
+    }
     }
 }
 
@@ -618,9 +688,7 @@ int fdmb_ns_cube::init()
         FDMB_CUDA(cudaFuncGetAttributes(&fa, k_rhs<double>));
         FDMB_CUDA(cudaFuncGetAttributes(&fa, k_fgh_div<FGH_TK, FGH_MINB, 1>));
         FDMB_CUDA(cudaFuncGetAttributes(&fa, k_update<double>));
-        FDMB_CUDA(cudaFuncGetAttributes(&fa, k_bound_lid<double>));
-        FDMB_CUDA(cudaFuncGetAttributes(&fa, k_bound_mirror<double>));
-        FDMB_CUDA(cudaFuncGetAttributes(&fa, k_bound_p<double>));
+        FDMB_CUDA(cudaFuncGetAttributes(&fa, k_bound_all<double>));
     }
     ns_layout(nx, ny, nz, rank, nranks, &lay);
     FDMB_CUDA(cudaMalloc(&block, lay.bytes));
@@ -717,24 +785,14 @@ int fdmb_ns_cube::step_once(cudaStream_t st)
             }
             if ((rc = pull(flds, lo, hi, from, n, st))) return rc;
         }
-        if (top) {   // the reference loops j = -1..nz+1 (ns_cube.cpp:68); clamp to the allocated x range
-            int jmax = (nz + 1 < nx + 1) ? nz + 1 : nx + 1;
-            LaunchScope sc("ns_bound_lid", st);
-            dim3 grid((jmax + 2 + 127) / 128, ny + 2);
-            launch_pdl(k_bound_lid<double>, grid, dim3(128), 0, st, u, g, jmax);
-        }
-        {
-            LaunchScope sc("ns_bound_mirror", st);
+        {   // init_bound, one launch (k_bound_all).  The reference's lid loop runs j = -1..nz+1 (ns_cube.cpp:68): clamped
+            // to the allocated x range
+            LaunchScope sc("ns_bound", st);
+            const int jmax = (nz + 1 < nx + 1) ? nz + 1 : nx + 1;
             const int zlo = lay.wlo[0], zhi = lay.whi[0];
             const int rows = (zhi - zlo + 1) > ny + 2 ? (zhi - zlo + 1) : ny + 2;
-            dim3 grid((nmax + 2 + 127) / 128, rows, 3);
-            launch_pdl(k_bound_mirror<double>, grid, dim3(128), 0, st, u, v, w, g, zlo, zhi, bot ? 1 : 0, top ? 1 : 0);
-        }
-        {
-            LaunchScope sc("ns_bound_p", st);
-            const int rows = nzl > ny ? nzl : ny;
-            dim3 grid((nmax + 127) / 128, rows, 3);
-            launch_pdl(k_bound_p<double>, grid, dim3(128), 0, st, u, v, w, p, g, ilo, ihi, bot ? 1 : 0, top ? 1 : 0);
+            dim3 grid((nmax + 2 + 127) / 128, rows, 7);
+            launch_pdl(k_bound_all<double>, grid, dim3(128), 0, st, u, v, w, p, g, jmax, zlo, zhi, ilo, ihi, bot ? 1 : 0, top ? 1 : 0);
         }
         if (fused) {
             LaunchScope sc("ns_fgh_rhs", st);
