@@ -40,6 +40,7 @@ SOLVE_BYTES_PER_PT = 48.0        # 3 sweeps
 NS_BYTES_PER_PT = 168.0
 
 WORKLOADS = {
+    "cube63": dict(kind="cube", n=63, label="LaplCube Dirichlet 63^3 fp64 solve"),
     "cube127": dict(kind="cube", n=127, label="LaplCube Dirichlet 127^3 fp64 solve (BASELINE configs[1])"),
     "cube255": dict(kind="cube", n=255, label="LaplCube Dirichlet 255^3 fp64 solve"),
     "cube511": dict(kind="cube", n=511, label="LaplCube Dirichlet 511^3 fp64 solve"),

@@ -14,7 +14,7 @@ ncu --set full --clock-control none --import-source on -k regex:'k_cols_pipe|k_r
     python bench.py --workload cube1023 --steps 2 --warmup 3 $B > $out/full_cube1023.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:'k_cols_pipe|k_rows_pipe' -s 15 -c 5 -o $rep/full_cube255 -f \
     python bench.py --workload cube255 --steps 2 --warmup 3 $B > $out/full_cube255.log 2>&1
-FDMB_GRAPH=0 ncu --set full --clock-control none --import-source on -k regex:'k_fgh|k_rhs|k_update|k_bound' -s 18 -c 6 -o $rep/full_nscube255 -f \
+FDMB_GRAPH=0 ncu --set full --clock-control none --import-source on -k regex:'k_fgh|k_rhs|k_update|k_bound' -s 9 -c 3 -o $rep/full_nscube255 -f \
     python bench.py --workload nscube255 --steps 2 --warmup 3 $B > $out/full_nscube255.log 2>&1
 FDMB_GRAPH=0 ncu --set full --clock-control none --import-source on -k regex:'k_cyl|k_tridiag|k_cols|k_rows' -s 33 -c 11 -o $rep/full_nscyl128 -f \
     python bench.py --workload nscyl128 --steps 2 --warmup 3 $B > $out/full_nscyl128.log 2>&1
