@@ -40,3 +40,24 @@ def test_sass_uses_tma_and_no_tensor_cores():
     assert count("DFMA") > 10000
     for mma in ("HMMA", "IMMA", "DMMA", "UTCHMMA", "UTCQMMA"):
         assert count(mma) == 0, mma
+
+
+@pytest.mark.skipif(shutil.which("cuobjdump") is None, reason="cuobjdump not on PATH")
+def test_sass_dependent_launch_and_marching_fgh():
+    """Programmatic dependent launch is compiled into every sweep / NS kernel (griddepcontrol.wait = ACQBULK,
+    launch_dependents = PREEXIT), and the fused FGH + divergence sweep is the barrier-free register-marching kernel
+    DESIGN 4.3 describes: warp shuffles for F[j-1], L2 prefetches, no CTA barrier, no shared memory."""
+    if not os.path.exists(LIB):
+        pytest.skip("library not built")
+    sass = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True, timeout=600).stdout
+    count = lambda mn, text=sass: len(re.findall(r"\b" + mn + r"\b", text))      # noqa: E731
+    assert count("ACQBULK") >= 100 and count("PREEXIT") >= 100
+    # the body of k_fgh_div: from its "Function :" header to the next one
+    m = re.search(r"Function : (\S*k_fgh_div\S*)(.*?)(?=\n\s*Function : |\Z)", sass, re.S)
+    assert m, "k_fgh_div not in the library"
+    body = m.group(2)
+    assert count("ACQBULK", body) == 1 and count("PREEXIT", body) == 1
+    assert len(re.findall(r"SHFL\.UP", body)) >= 2            # F[j-1] from the lane to the left (two 32-bit halves)
+    assert len(re.findall(r"CCTL\.E\.PF2", body)) >= 3        # prefetch.global.L2 of the first-touch rows
+    assert len(re.findall(r"BAR\.SYNC", body)) == 0 and count("LDS", body) == 0 and count("STS", body) == 0
+    assert count("DFMA", body) > 100
