@@ -59,6 +59,9 @@ want = [("UTMALDG", "tensor-map tile loads (TMA, `cp.async.bulk.tensor`): the co
         ("LDS", "shared-memory loads"), ("STS", "shared-memory stores"), ("LDG", "global loads"), ("STG", "global stores"),
         ("REDG", "global fp64 reductions (`REDG.E.ADD.F64`: `atomicAdd` without return, the PM deposit)"),
         ("ATOMG", "global atomics with return"),
+        ("ACQBULK", "`griddepcontrol.wait`: programmatic dependent launch, every sweep / tridiagonal / NS kernel waits after its prologue"),
+        ("PREEXIT", "`griddepcontrol.launch_dependents`: issued right after that wait"),
+        ("SHFL", "warp shuffles (F[j-1] of the fused FGH + divergence sweep; the radix stages exchange through shared memory)"),
         ("HMMA", "tensor-core MMA (none expected: nothing on this path is a dense contraction)"),
         ("UTCHMMA", "tcgen05 MMA (none expected)")]
 print("| SASS mnemonic | static count | what it is here |")
